@@ -1,0 +1,167 @@
+/*
+ * metada_cuda_c_api.h -- thin C ABI of the B200 (sm_100a) backend for METADA's ensemble Kalman
+ * analysis step (LETKF / ETKF / EnKF).
+ *
+ * This is the drop-in boundary: the C++ host classes in metada_b200/host (CudaBackendTag traits,
+ * CudaState, CudaObservation, CudaObsOperator, device Ensemble store, LETKF/ETKF/EnKF policies)
+ * call only these entry points; so does the Python ctypes binding used by tests and bench.py.
+ * Conventions follow the reference's own native bridges (opaque handles with create/destroy as in
+ * backends/lorenz63/state/lorenz63/state_c_api.h:7-16; int return code, 0 = success, caller-owned
+ * output buffers as in backends/common/obsoperator/WRFDAObsOperator_c_api.h:35-130).
+ *
+ *   - extern "C", plain pointers and sizes; no C++/torch types.
+ *   - every call returns 0 on success, non-zero on failure; mdc_last_error(ctx) has the message.
+ *   - one context per device; handles are not thread-safe; all work is queued on the context's
+ *     stream; calls that fill HOST buffers synchronise before returning.
+ *   - there is NO CPU fallback: without a CUDA device mdc_ctx_create fails.
+ *
+ * Reference paths below are relative to /root/reference/src.
+ */
+#ifndef METADA_CUDA_C_API_H
+#define METADA_CUDA_C_API_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct mdc_ctx mdc_ctx;
+typedef struct mdc_ens mdc_ens;
+typedef struct mdc_obs mdc_obs;
+
+#define MDC_OK 0
+#define MDC_ERR_INVALID 1
+#define MDC_ERR_CUDA 2
+#define MDC_ERR_NUMERIC 3
+#define MDC_ERR_UNSUPPORTED 4
+
+/* ---- context ---------------------------------------------------------------------------- */
+int mdc_ctx_create(int device, mdc_ctx** out);
+int mdc_ctx_destroy(mdc_ctx* ctx);
+const char* mdc_last_error(const mdc_ctx* ctx);
+int mdc_ctx_sync(mdc_ctx* ctx);
+/* cudaStream_t of the context, for interop (e.g. torch.cuda.ExternalStream) */
+void* mdc_ctx_stream(mdc_ctx* ctx);
+/* CUDA-event stopwatch on the context's stream: start, ... work ..., stop -> elapsed ms */
+int mdc_timer_start(mdc_ctx* ctx);
+int mdc_timer_stop(mdc_ctx* ctx, float* ms);
+/* number of kernels this library has launched on ctx since creation (bench.py gpu_launches) */
+int64_t mdc_ctx_launch_count(const mdc_ctx* ctx);
+int mdc_ctx_sm_count(const mdc_ctx* ctx);
+/* writes > L2-size bytes to evict the L2 between timed iterations */
+int mdc_ctx_flush_l2(mdc_ctx* ctx);
+
+/* ---- ensemble store: replaces framework/adapters/Ensemble.hpp:42-194 (vector<State>) ------
+ * Device layout: X[col][lev][member], col = y*nx + x  (one contiguous nz*k block per column).
+ * Host layout of one member (State::getDataPtr<double>, State.hpp:229-242; SimpleState.hpp:73-80):
+ *   [lev][y][x].
+ * (nx, ny) is the LOCAL grid including any read-only halo; set_domain places it in the global
+ * grid for multi-GPU column sharding (default: the local grid is the whole domain). */
+int mdc_ens_create(mdc_ctx* ctx, int nx, int ny, int nz, int k, mdc_ens** out);
+int mdc_ens_destroy(mdc_ens* ens);
+int mdc_ens_set_domain(mdc_ens* ens, int gx0, int gy0, int gnx, int gny, int own_nx, int own_ny);
+int mdc_ens_upload_member(mdc_ens* ens, int m, const double* host);
+int mdc_ens_download_member(mdc_ens* ens, int m, double* host);
+/* batched variants (coalesced transposes): members m0..m0+count-1, one host pointer each */
+int mdc_ens_upload_members(mdc_ens* ens, int m0, int count, const double* const* hosts);
+int mdc_ens_download_members(mdc_ens* ens, int m0, int count, double* const* hosts);
+/* seeded synthetic ensemble generated on the device (bit-identical to
+ * metada_b200.synthetic.member on the host); coordinates are global. */
+int mdc_ens_fill_synthetic(mdc_ens* ens, uint64_t seed);
+/* Ensemble::RecomputeMean (Ensemble.hpp:105-114) on the device; host_mean [lev][y][x] or NULL */
+int mdc_ens_mean(mdc_ens* ens, double* host_mean);
+/* sum over members/levels/columns of X and X^2 -- cheap whole-state checksum for big runs */
+int mdc_ens_checksum(mdc_ens* ens, double* sum, double* sumsq);
+double* mdc_ens_devptr(mdc_ens* ens);
+int64_t mdc_ens_bytes(const mdc_ens* ens);
+
+/* ---- observations: replaces backends/common/observation/GridObservation.hpp (AoS) ---------
+ * SoA on the device. GRID coordinates (Location(int,int,int), Location.hpp:66-67) are GLOBAL.
+ * err is the standard deviation; variance = err*err (GridObservation.hpp:239-252); invalid obs
+ * have H(x) = 0 (IdentityObsOperator.hpp:165-168) and infinite variance.
+ * gid: global observation ids (NULL = 0..P-1); they define the summation order. */
+int mdc_obs_create(mdc_ctx* ctx, int64_t P, const int32_t* x, const int32_t* y, const int32_t* z,
+                   const double* value, const double* err, const uint8_t* valid,
+                   const int64_t* gid, mdc_obs** out);
+int mdc_obs_destroy(mdc_obs* obs);
+int64_t mdc_obs_size(const mdc_obs* obs);       /* own + halo rows */
+
+/* ---- H(x), Y' and d: replaces k calls of ObsOperator::apply (ObsOperator.hpp:255-259 ->
+ * IdentityObsOperator.hpp:154-180, 594-676) + LETKF.hpp:209-211 / ETKF.hpp:135-141 ---------- */
+int mdc_hx_idw4(mdc_ens* ens, mdc_obs* obs);
+/* any output may be NULL; Y, Yp are [P][k] row-major */
+int mdc_hx_download(mdc_obs* obs, double* Y, double* ybar, double* Yp, double* d);
+
+/* ---- multi-GPU observation halo (column sharding) ------------------------------------------
+ * Rows are (k + 8) doubles: Y'[k], d, value, err, valid, x, y, z, gid.  pack selects own obs with
+ * ylo <= y < yhi into a DEVICE buffer; append adds received rows as halo obs. */
+int mdc_obs_pack_rows(mdc_obs* obs, int ylo, int yhi, double* dev_rows, int64_t cap, int64_t* n);
+int mdc_obs_append_rows(mdc_obs* obs, const double* dev_rows, int64_t n);
+int mdc_obs_row_doubles(const mdc_obs* obs);
+
+/* ---- bucketed spatial index: replaces the O(P) scan of LETKF.hpp:159-165 -------------------
+ * cell <= 0 picks ceil(radius). Selection is bit-identical to
+ * Location::distance_to(...) <= radius (Location.hpp:204-211). */
+int mdc_obs_index_build(mdc_obs* obs, int cell);
+int mdc_obs_index_query_counts(mdc_obs* obs, mdc_ens* ens, double radius, int32_t* host_counts);
+/* lists[c*cap .. ) = global obs ids of column cols[c] in kernel order; counts[c] = full count */
+int mdc_obs_index_query_lists(mdc_obs* obs, mdc_ens* ens, double radius, const int64_t* cols,
+                              int64_t ncols, int32_t cap, int64_t* host_lists,
+                              int32_t* host_counts);
+
+/* ---- LETKF: replaces LETKF<Tag>::Analyse / updateGridPoint (LETKF.hpp:63-119, 152-243) ----- */
+enum { MDC_MODE_REF_COMPAT = 0, MDC_MODE_REF_ETKF = 1, MDC_MODE_CANONICAL = 2 };
+enum { MDC_LOC_CUTOFF = 0, MDC_LOC_GASPARI_COHN = 1 };
+
+typedef struct {
+  double radius;      /* horizontal selection radius (inclusive) = Gaspari-Cohn support       */
+  double radius_v;    /* vertical radius in levels; <= 0: none (one transform per column)     */
+  double inflation;
+  int mode;           /* MDC_MODE_*                                                           */
+  int loc;            /* MDC_LOC_* (CANONICAL)                                                */
+  int use_R;          /* CANONICAL: 1 -> R = diag(err^2), 0 -> R = I                          */
+  int max_sweeps;     /* Jacobi sweep cap (<= 0: 40)                                          */
+  double jacobi_tol;  /* stop when a sweep's max |g_p.g_q|/(|g_p||g_q|) < tol (<= 0: 1e-9)    */
+  int reserved[4];
+} mdc_letkf_params;
+
+typedef struct {
+  float ms_hx, ms_index, ms_columns, ms_total;
+  int64_t columns;        /* analysed columns                                                 */
+  int64_t sum_local_obs;  /* sum over columns of p_loc                                        */
+  int32_t max_local_obs;
+  int32_t max_sweeps;     /* max Jacobi sweeps used by a column                               */
+  int64_t sum_sweeps;
+  int32_t numeric_failures;
+  int32_t reserved;
+} mdc_letkf_stats;
+
+int mdc_letkf_analyse(mdc_ens* ens, mdc_obs* obs, const mdc_letkf_params* params,
+                      mdc_letkf_stats* stats);
+/* transform W (k x k row-major; REF_COMPAT: s_i in row 0) of column `col` at level 0, for tests */
+int mdc_letkf_column_transform(mdc_ens* ens, mdc_obs* obs, const mdc_letkf_params* params,
+                               int64_t col, double* host_W);
+
+/* ---- global ETKF: replaces ETKF<Tag>::Analyse (ETKF.hpp:100-179) --------------------------- */
+int mdc_etkf_analyse(mdc_ens* ens, mdc_obs* obs, double inflation);
+
+/* ---- global stochastic EnKF: replaces EnKF<Tag>::Analyse (EnKF.hpp:139-256) ---------------- */
+typedef struct {
+  double innovation_norm, background_spread, analysis_spread;
+  double max_kalman_gain, min_kalman_gain, condition_number;
+} mdc_enkf_diag;
+/* Z: host [P][k] standard-normal draws (obs_pert = sqrt(R_ii) Z, EnKF.hpp:340-361), or NULL to
+ * draw them on the device from `seed`. want_gain_stats: stream max/min of K without storing it. */
+int mdc_enkf_analyse(mdc_ens* ens, mdc_obs* obs, double inflation, const double* Z, uint64_t seed,
+                     int want_gain_stats, mdc_enkf_diag* diag);
+
+/* ---- microbenchmarks used for the roofline denominators (profiles/) ------------------------ */
+int mdc_bench_fp64_fma(mdc_ctx* ctx, double* tflops);
+int mdc_bench_fp64_dmma(mdc_ctx* ctx, double* tflops);
+int mdc_bench_hbm_copy(mdc_ctx* ctx, double* gbs);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

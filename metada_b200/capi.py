@@ -1,0 +1,376 @@
+"""ctypes binding of include/metada_cuda_c_api.h (the product's C ABI).
+
+Everything here is a 1:1 wrapper; no arithmetic happens in Python.  No fallback of any kind:
+``load_library`` raises if the shared library is missing, ``Context`` raises without a GPU.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import re
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_ROOT = os.path.dirname(_HERE)
+_LIB = os.path.join(_HERE, "libmetada_cuda.so")
+_SRC = os.path.join(_HERE, "csrc", "mdc_api.cu")
+_HEADER = os.path.join(_ROOT, "include", "metada_cuda_c_api.h")
+
+MODE_REF_COMPAT, MODE_REF_ETKF, MODE_CANONICAL = 0, 1, 2
+LOC_CUTOFF, LOC_GASPARI_COHN = 0, 1
+
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+              "-shared", "-Xcompiler", "-fPIC", "-cudart", "shared",
+              "-Xlinker", "-rpath=/usr/local/cuda/lib64"]
+
+
+class MdcError(RuntimeError):
+    pass
+
+
+class LetkfParams(C.Structure):
+    _fields_ = [("radius", C.c_double), ("radius_v", C.c_double), ("inflation", C.c_double),
+                ("mode", C.c_int), ("loc", C.c_int), ("use_R", C.c_int), ("max_sweeps", C.c_int),
+                ("jacobi_tol", C.c_double), ("reserved", C.c_int * 4)]
+
+
+class LetkfStats(C.Structure):
+    _fields_ = [("ms_hx", C.c_float), ("ms_index", C.c_float), ("ms_columns", C.c_float),
+                ("ms_total", C.c_float), ("columns", C.c_int64), ("sum_local_obs", C.c_int64),
+                ("max_local_obs", C.c_int32), ("max_sweeps", C.c_int32), ("sum_sweeps", C.c_int64),
+                ("numeric_failures", C.c_int32), ("reserved", C.c_int32)]
+
+    def asdict(self):
+        return {n: getattr(self, n) for n, _ in self._fields_ if n != "reserved"}
+
+
+class EnkfDiag(C.Structure):
+    _fields_ = [(n, C.c_double) for n in (
+        "innovation_norm", "background_spread", "analysis_spread",
+        "max_kalman_gain", "min_kalman_gain", "condition_number")]
+
+    def asdict(self):
+        return {n: getattr(self, n) for n, _ in self._fields_}
+
+
+def lib_path() -> str:
+    return _LIB
+
+
+def build_library(force: bool = False, verbose: bool = False) -> str:
+    """nvcc cross-compiles for sm_100a (works without a GPU)."""
+    srcs = [os.path.join(_HERE, "csrc", f) for f in os.listdir(os.path.join(_HERE, "csrc"))] + [_HEADER]
+    newest = max(os.path.getmtime(s) for s in srcs)
+    if force or not os.path.exists(_LIB) or os.path.getmtime(_LIB) < newest:
+        cmd = ["nvcc", *NVCC_FLAGS, "-o", _LIB, _SRC]
+        if verbose:
+            cmd.insert(1, "-Xptxas=-v")
+        subprocess.check_call(cmd)
+    return _LIB
+
+
+def exported_symbols() -> list[str]:
+    """extern "C" entry points declared in the public header."""
+    txt = open(_HEADER).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    return sorted(set(re.findall(r"\b(mdc_[a-z0-9_]+)\s*\(", txt)))
+
+
+_lib = None
+
+
+def load_library() -> C.CDLL:
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(_LIB):
+        raise MdcError(f"{_LIB} is missing: build it with metada_b200.build_library() "
+                       "(__graft_entry__.build()); there is no CPU fallback")
+    L = C.CDLL(_LIB)
+    vp, i64, dbl = C.c_void_p, C.c_int64, C.c_double
+    pd = C.POINTER(C.c_double)
+    sig = {
+        "mdc_ctx_create": (C.c_int, [C.c_int, C.POINTER(vp)]),
+        "mdc_ctx_destroy": (C.c_int, [vp]),
+        "mdc_last_error": (C.c_char_p, [vp]),
+        "mdc_ctx_sync": (C.c_int, [vp]),
+        "mdc_ctx_stream": (vp, [vp]),
+        "mdc_timer_start": (C.c_int, [vp]),
+        "mdc_timer_stop": (C.c_int, [vp, C.POINTER(C.c_float)]),
+        "mdc_ctx_launch_count": (i64, [vp]),
+        "mdc_ctx_sm_count": (C.c_int, [vp]),
+        "mdc_ctx_flush_l2": (C.c_int, [vp]),
+        "mdc_ens_create": (C.c_int, [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(vp)]),
+        "mdc_ens_destroy": (C.c_int, [vp]),
+        "mdc_ens_set_domain": (C.c_int, [vp] + [C.c_int] * 6),
+        "mdc_ens_upload_member": (C.c_int, [vp, C.c_int, vp]),
+        "mdc_ens_download_member": (C.c_int, [vp, C.c_int, vp]),
+        "mdc_ens_upload_members": (C.c_int, [vp, C.c_int, C.c_int, C.POINTER(vp)]),
+        "mdc_ens_download_members": (C.c_int, [vp, C.c_int, C.c_int, C.POINTER(vp)]),
+        "mdc_ens_fill_synthetic": (C.c_int, [vp, C.c_uint64]),
+        "mdc_ens_mean": (C.c_int, [vp, vp]),
+        "mdc_ens_checksum": (C.c_int, [vp, pd, pd]),
+        "mdc_ens_devptr": (vp, [vp]),
+        "mdc_ens_bytes": (i64, [vp]),
+        "mdc_obs_create": (C.c_int, [vp, i64, vp, vp, vp, vp, vp, vp, vp, C.POINTER(vp)]),
+        "mdc_obs_destroy": (C.c_int, [vp]),
+        "mdc_obs_size": (i64, [vp]),
+        "mdc_hx_idw4": (C.c_int, [vp, vp]),
+        "mdc_hx_download": (C.c_int, [vp, vp, vp, vp, vp]),
+        "mdc_obs_pack_rows": (C.c_int, [vp, C.c_int, C.c_int, vp, i64, C.POINTER(i64)]),
+        "mdc_obs_append_rows": (C.c_int, [vp, vp, i64]),
+        "mdc_obs_row_doubles": (C.c_int, [vp]),
+        "mdc_obs_index_build": (C.c_int, [vp, C.c_int]),
+        "mdc_obs_index_query_counts": (C.c_int, [vp, vp, dbl, vp]),
+        "mdc_obs_index_query_lists": (C.c_int, [vp, vp, dbl, vp, i64, C.c_int32, vp, vp]),
+        "mdc_letkf_analyse": (C.c_int, [vp, vp, C.POINTER(LetkfParams), C.POINTER(LetkfStats)]),
+        "mdc_letkf_column_transform": (C.c_int, [vp, vp, C.POINTER(LetkfParams), i64, vp]),
+        "mdc_etkf_analyse": (C.c_int, [vp, vp, dbl]),
+        "mdc_enkf_analyse": (C.c_int, [vp, vp, dbl, vp, C.c_uint64, C.c_int, C.POINTER(EnkfDiag)]),
+        "mdc_bench_fp64_fma": (C.c_int, [vp, pd]),
+        "mdc_bench_fp64_dmma": (C.c_int, [vp, pd]),
+        "mdc_bench_hbm_copy": (C.c_int, [vp, pd]),
+    }
+    for name, (res, args) in sig.items():
+        fn = getattr(L, name)
+        fn.restype = res
+        fn.argtypes = args
+    _lib = L
+    return L
+
+
+def _ptr(a):
+    return C.c_void_p(a.ctypes.data) if a is not None else C.c_void_p(0)
+
+
+class Context:
+    def __init__(self, device: int = 0):
+        self.L = load_library()
+        h = C.c_void_p()
+        rc = self.L.mdc_ctx_create(device, C.byref(h))
+        if rc:
+            raise MdcError(f"mdc_ctx_create(device={device}) failed rc={rc}: no usable CUDA device "
+                           "(this backend has no CPU fallback)")
+        self.h = h
+        self.device = device
+
+    def check(self, rc: int):
+        if rc:
+            raise MdcError(f"rc={rc}: {self.L.mdc_last_error(self.h).decode()}")
+
+    def sync(self):
+        self.check(self.L.mdc_ctx_sync(self.h))
+
+    def stream_ptr(self) -> int:
+        return int(self.L.mdc_ctx_stream(self.h) or 0)
+
+    def timer_start(self):
+        self.check(self.L.mdc_timer_start(self.h))
+
+    def timer_stop(self) -> float:
+        ms = C.c_float()
+        self.check(self.L.mdc_timer_stop(self.h, C.byref(ms)))
+        return ms.value
+
+    def launch_count(self) -> int:
+        return int(self.L.mdc_ctx_launch_count(self.h))
+
+    def sm_count(self) -> int:
+        return int(self.L.mdc_ctx_sm_count(self.h))
+
+    def flush_l2(self):
+        self.check(self.L.mdc_ctx_flush_l2(self.h))
+
+    def bench_fp64_fma(self) -> float:
+        v = C.c_double()
+        self.check(self.L.mdc_bench_fp64_fma(self.h, C.byref(v)))
+        return v.value
+
+    def bench_fp64_dmma(self) -> float:
+        v = C.c_double()
+        self.check(self.L.mdc_bench_fp64_dmma(self.h, C.byref(v)))
+        return v.value
+
+    def bench_hbm_copy(self) -> float:
+        v = C.c_double()
+        self.check(self.L.mdc_bench_hbm_copy(self.h, C.byref(v)))
+        return v.value
+
+    def close(self):
+        if self.h:
+            self.L.mdc_ctx_destroy(self.h)
+            self.h = None
+
+
+class Ensemble:
+    """Device-resident ensemble store, layout [col][lev][member]."""
+
+    def __init__(self, ctx: Context, nx: int, ny: int, nz: int, k: int):
+        self.ctx, self.nx, self.ny, self.nz, self.k = ctx, nx, ny, nz, k
+        h = C.c_void_p()
+        ctx.check(ctx.L.mdc_ens_create(ctx.h, nx, ny, nz, k, C.byref(h)))
+        self.h = h
+
+    def set_domain(self, gx0, gy0, gnx, gny, own_nx, own_ny):
+        self.ctx.check(self.ctx.L.mdc_ens_set_domain(self.h, gx0, gy0, gnx, gny, own_nx, own_ny))
+
+    def upload(self, X: np.ndarray):
+        """X: [k, nz, ny, nx] float64 (any host memory)."""
+        X = np.ascontiguousarray(X, dtype=np.float64)
+        assert X.shape == (self.k, self.nz, self.ny, self.nx), X.shape
+        self.upload_ptrs(0, [X[m].ctypes.data for m in range(self.k)])
+        self.ctx.sync()
+
+    def upload_ptrs(self, m0: int, ptrs):
+        arr = (C.c_void_p * len(ptrs))(*ptrs)
+        self.ctx.check(self.ctx.L.mdc_ens_upload_members(self.h, m0, len(ptrs), arr))
+
+    def download_ptrs(self, m0: int, ptrs):
+        arr = (C.c_void_p * len(ptrs))(*ptrs)
+        self.ctx.check(self.ctx.L.mdc_ens_download_members(self.h, m0, len(ptrs), arr))
+
+    def download(self) -> np.ndarray:
+        out = np.empty((self.k, self.nz, self.ny, self.nx))
+        self.download_ptrs(0, [out[m].ctypes.data for m in range(self.k)])
+        return out
+
+    def upload_member(self, m: int, x: np.ndarray):
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        self.ctx.check(self.ctx.L.mdc_ens_upload_member(self.h, m, _ptr(x)))
+        self.ctx.sync()
+
+    def download_member(self, m: int) -> np.ndarray:
+        out = np.empty((self.nz, self.ny, self.nx))
+        self.ctx.check(self.ctx.L.mdc_ens_download_member(self.h, m, _ptr(out)))
+        return out
+
+    def fill_synthetic(self, seed: int = 1000):
+        self.ctx.check(self.ctx.L.mdc_ens_fill_synthetic(self.h, seed))
+
+    def mean(self) -> np.ndarray:
+        out = np.empty((self.nz, self.ny, self.nx))
+        self.ctx.check(self.ctx.L.mdc_ens_mean(self.h, _ptr(out)))
+        return out
+
+    def checksum(self):
+        s, s2 = C.c_double(), C.c_double()
+        self.ctx.check(self.ctx.L.mdc_ens_checksum(self.h, C.byref(s), C.byref(s2)))
+        return s.value, s2.value
+
+    def devptr(self) -> int:
+        return int(self.ctx.L.mdc_ens_devptr(self.h))
+
+    def nbytes(self) -> int:
+        return int(self.ctx.L.mdc_ens_bytes(self.h))
+
+    def close(self):
+        if self.h:
+            self.ctx.L.mdc_ens_destroy(self.h)
+            self.h = None
+
+
+class Observations:
+    """Device SoA of GRID observations (+ Y', d after hx)."""
+
+    def __init__(self, ctx: Context, x, y, z, value, err, valid=None, gid=None):
+        self.ctx = ctx
+        x = np.ascontiguousarray(x, dtype=np.int32)
+        y = np.ascontiguousarray(y, dtype=np.int32)
+        z = np.ascontiguousarray(z, dtype=np.int32) if z is not None else None
+        value = np.ascontiguousarray(value, dtype=np.float64)
+        err = np.ascontiguousarray(err, dtype=np.float64)
+        valid = np.ascontiguousarray(valid, dtype=np.uint8) if valid is not None else None
+        gid = np.ascontiguousarray(gid, dtype=np.int64) if gid is not None else None
+        h = C.c_void_p()
+        ctx.check(ctx.L.mdc_obs_create(ctx.h, len(x), _ptr(x), _ptr(y), _ptr(z), _ptr(value),
+                                       _ptr(err), _ptr(valid), _ptr(gid), C.byref(h)))
+        self.h = h
+
+    def size(self) -> int:
+        return int(self.ctx.L.mdc_obs_size(self.h))
+
+    def hx(self, ens: Ensemble):
+        self.ctx.check(self.ctx.L.mdc_hx_idw4(ens.h, self.h))
+        self._k = ens.k
+
+    def hx_download(self, want=("Y", "ybar", "Yp", "d")):
+        P, k = self.size(), self._k
+        out = {}
+        if "Y" in want:
+            out["Y"] = np.empty((P, k))
+        if "ybar" in want:
+            out["ybar"] = np.empty(P)
+        if "Yp" in want:
+            out["Yp"] = np.empty((P, k))
+        if "d" in want:
+            out["d"] = np.empty(P)
+        self.ctx.check(self.ctx.L.mdc_hx_download(self.h, _ptr(out.get("Y")), _ptr(out.get("ybar")),
+                                                  _ptr(out.get("Yp")), _ptr(out.get("d"))))
+        return out
+
+    def row_doubles(self) -> int:
+        return int(self.ctx.L.mdc_obs_row_doubles(self.h))
+
+    def pack_rows(self, ylo: int, yhi: int, dev_ptr: int, cap: int) -> int:
+        n = C.c_int64()
+        self.ctx.check(self.ctx.L.mdc_obs_pack_rows(self.h, ylo, yhi, C.c_void_p(dev_ptr), cap, C.byref(n)))
+        return n.value
+
+    def append_rows(self, dev_ptr: int, n: int):
+        self.ctx.check(self.ctx.L.mdc_obs_append_rows(self.h, C.c_void_p(dev_ptr), n))
+
+    def index_build(self, cell: int):
+        self.ctx.check(self.ctx.L.mdc_obs_index_build(self.h, cell))
+
+    def query_counts(self, ens: Ensemble, radius: float) -> np.ndarray:
+        out = np.empty(ens.nx * ens.ny, dtype=np.int32)
+        self.ctx.check(self.ctx.L.mdc_obs_index_query_counts(self.h, ens.h, radius, _ptr(out)))
+        return out.reshape(ens.ny, ens.nx)
+
+    def query_lists(self, ens: Ensemble, radius: float, cols, cap: int):
+        cols = np.ascontiguousarray(cols, dtype=np.int64)
+        lists = np.empty((len(cols), cap), dtype=np.int64)
+        counts = np.empty(len(cols), dtype=np.int32)
+        self.ctx.check(self.ctx.L.mdc_obs_index_query_lists(self.h, ens.h, radius, _ptr(cols), len(cols),
+                                                            cap, _ptr(lists), _ptr(counts)))
+        return [lists[i, :min(counts[i], cap)].copy() for i in range(len(cols))], counts
+
+    def close(self):
+        if self.h:
+            self.ctx.L.mdc_obs_destroy(self.h)
+            self.h = None
+
+
+def make_params(radius, inflation=1.0, mode=MODE_CANONICAL, loc=LOC_GASPARI_COHN, use_R=1,
+                radius_v=0.0, max_sweeps=0, jacobi_tol=0.0) -> LetkfParams:
+    p = LetkfParams()
+    p.radius, p.radius_v, p.inflation = radius, radius_v, inflation
+    p.mode, p.loc, p.use_R, p.max_sweeps, p.jacobi_tol = mode, loc, use_R, max_sweeps, jacobi_tol
+    return p
+
+
+def letkf_analyse(ens: Ensemble, obs: Observations, params: LetkfParams) -> dict:
+    st = LetkfStats()
+    ens.ctx.check(ens.ctx.L.mdc_letkf_analyse(ens.h, obs.h, C.byref(params), C.byref(st)))
+    return st.asdict()
+
+
+def letkf_column_transform(ens: Ensemble, obs: Observations, params: LetkfParams, col: int) -> np.ndarray:
+    W = np.empty((ens.k, ens.k))
+    ens.ctx.check(ens.ctx.L.mdc_letkf_column_transform(ens.h, obs.h, C.byref(params), col, _ptr(W)))
+    return W
+
+
+def etkf_analyse(ens: Ensemble, obs: Observations, inflation: float):
+    ens.ctx.check(ens.ctx.L.mdc_etkf_analyse(ens.h, obs.h, inflation))
+
+
+def enkf_analyse(ens: Ensemble, obs: Observations, inflation: float, Z=None, seed: int = 7,
+                 want_gain_stats: bool = False) -> dict:
+    Zc = np.ascontiguousarray(Z, dtype=np.float64) if Z is not None else None
+    d = EnkfDiag()
+    ens.ctx.check(ens.ctx.L.mdc_enkf_analyse(ens.h, obs.h, inflation, _ptr(Zc), seed,
+                                             int(want_gain_stats), C.byref(d)))
+    return d.asdict()

@@ -1,0 +1,759 @@
+// C ABI of the sm_100a METADA analysis backend (see include/metada_cuda_c_api.h).
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -shared ...
+#include <algorithm>
+#include <climits>
+#include <cmath>
+#include <new>
+#include <vector>
+
+#include "bench_kernels.cuh"
+#include "ens_kernels.cuh"
+#include "global_kernels.cuh"
+#include "hx_kernels.cuh"
+#include "index_kernels.cuh"
+#include "letkf_kernels.cuh"
+#include "mdc_internal.cuh"
+
+namespace {
+
+constexpr size_t kStageBytes = 512ull << 20;  // staging for host<->device member transposes
+constexpr int kMemberBatch = 8;
+
+int grid_for(mdc_ctx* ctx, int64_t work_items, int threads, int per_sm = 8) {
+  int64_t blocks = (work_items + threads - 1) / threads;
+  int64_t cap = (int64_t)ctx->sm_count * per_sm;
+  return (int)std::max<int64_t>(1, std::min(blocks, cap));
+}
+
+template <typename T>
+int dev_alloc(mdc_ctx* ctx, T** p, size_t n) {
+  *p = nullptr;
+  if (n == 0) n = 1;
+  MDC_CUDA(ctx, cudaMalloc((void**)p, n * sizeof(T)));
+  return MDC_OK;
+}
+
+int ensure_stage(mdc_ens* e, size_t elems) {
+  if (e->stage_elems >= elems) return MDC_OK;
+  if (e->stage) cudaFree(e->stage);
+  e->stage = nullptr;
+  e->stage_elems = 0;
+  MDC_CUDA(e->ctx, cudaMalloc((void**)&e->stage, elems * sizeof(double)));
+  e->stage_elems = elems;
+  return MDC_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+// ------------------------------------------------------------------------------ context
+int mdc_ctx_create(int device, mdc_ctx** out) {
+  if (!out) return MDC_ERR_INVALID;
+  *out = nullptr;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) return MDC_ERR_CUDA;  // no CPU fallback
+  if (device < 0 || device >= ndev) return MDC_ERR_INVALID;
+  mdc_ctx* ctx = new (std::nothrow) mdc_ctx();
+  if (!ctx) return MDC_ERR_INVALID;
+  ctx->device = device;
+  if (cudaSetDevice(device) != cudaSuccess) { delete ctx; return MDC_ERR_CUDA; }
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { delete ctx; return MDC_ERR_CUDA; }
+  ctx->sm_count = prop.multiProcessorCount;
+  ctx->max_smem_optin = (int)prop.sharedMemPerBlockOptin;
+  if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return MDC_ERR_CUDA; }
+  cudaEventCreate(&ctx->ev0);
+  cudaEventCreate(&ctx->ev1);
+  for (auto& e : ctx->pe) cudaEventCreate(&e);
+  if (cudaMalloc((void**)&ctx->d_flags, 16 * sizeof(int)) != cudaSuccess ||
+      cudaMalloc((void**)&ctx->d_stats, 16 * sizeof(long long)) != cudaSuccess) {
+    delete ctx;
+    return MDC_ERR_CUDA;
+  }
+  cudaMemset(ctx->d_flags, 0, 16 * sizeof(int));
+  cudaMemset(ctx->d_stats, 0, 16 * sizeof(long long));
+  *out = ctx;
+  return MDC_OK;
+}
+
+int mdc_ctx_destroy(mdc_ctx* ctx) {
+  if (!ctx) return MDC_OK;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  if (ctx->flush_buf) cudaFree(ctx->flush_buf);
+  cudaFree(ctx->d_flags);
+  cudaFree(ctx->d_stats);
+  cudaEventDestroy(ctx->ev0);
+  cudaEventDestroy(ctx->ev1);
+  for (auto& e : ctx->pe) cudaEventDestroy(e);
+  cudaStreamDestroy(ctx->stream);
+  delete ctx;
+  return MDC_OK;
+}
+
+const char* mdc_last_error(const mdc_ctx* ctx) { return ctx ? ctx->err : "null context"; }
+
+int mdc_ctx_sync(mdc_ctx* ctx) {
+  MDC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return MDC_OK;
+}
+void* mdc_ctx_stream(mdc_ctx* ctx) { return (void*)ctx->stream; }
+int mdc_timer_start(mdc_ctx* ctx) {
+  MDC_CUDA(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
+  return MDC_OK;
+}
+int mdc_timer_stop(mdc_ctx* ctx, float* ms) {
+  MDC_CUDA(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
+  MDC_CUDA(ctx, cudaEventSynchronize(ctx->ev1));
+  MDC_CUDA(ctx, cudaEventElapsedTime(ms, ctx->ev0, ctx->ev1));
+  return MDC_OK;
+}
+int64_t mdc_ctx_launch_count(const mdc_ctx* ctx) { return ctx->launches; }
+int mdc_ctx_sm_count(const mdc_ctx* ctx) { return ctx->sm_count; }
+
+int mdc_ctx_flush_l2(mdc_ctx* ctx) {
+  MDC_CUDA(ctx, cudaSetDevice(ctx->device));
+  if (!ctx->flush_buf) {
+    ctx->flush_bytes = 256ull << 20;  // 2x the 126 MB L2
+    MDC_CUDA(ctx, cudaMalloc(&ctx->flush_buf, ctx->flush_bytes));
+  }
+  int64_t n = (int64_t)(ctx->flush_bytes / sizeof(float4));
+  flush_l2_kernel<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>((float4*)ctx->flush_buf, n);
+  MDC_LAUNCH_CHECK(ctx);
+  return MDC_OK;
+}
+
+// ------------------------------------------------------------------------------ ensemble
+int mdc_ens_create(mdc_ctx* ctx, int nx, int ny, int nz, int k, mdc_ens** out) {
+  if (!ctx || !out) return MDC_ERR_INVALID;
+  *out = nullptr;
+  if (nx <= 0 || ny <= 0 || nz <= 0 || k <= 1) MDC_FAIL(ctx, MDC_ERR_INVALID, "mdc_ens_create: bad dims %d %d %d k=%d", nx, ny, nz, k);
+  MDC_CUDA(ctx, cudaSetDevice(ctx->device));
+  mdc_ens* e = new (std::nothrow) mdc_ens();
+  if (!e) MDC_FAIL(ctx, MDC_ERR_INVALID, "out of host memory");
+  e->ctx = ctx;
+  e->nx = nx; e->ny = ny; e->nz = nz; e->k = k;
+  e->gx0 = 0; e->gy0 = 0; e->gnx = nx; e->gny = ny; e->own_nx = nx; e->own_ny = ny;
+  size_t total = (size_t)nx * ny * nz * k;
+  cudaError_t ce = cudaMalloc((void**)&e->X, total * sizeof(double));
+  if (ce != cudaSuccess) {
+    delete e;
+    MDC_FAIL(ctx, MDC_ERR_CUDA, "mdc_ens_create: cudaMalloc(%zu bytes) failed: %s", total * sizeof(double), cudaGetErrorString(ce));
+  }
+  *out = e;
+  return MDC_OK;
+}
+
+int mdc_ens_destroy(mdc_ens* e) {
+  if (!e) return MDC_OK;
+  cudaSetDevice(e->ctx->device);
+  cudaStreamSynchronize(e->ctx->stream);
+  cudaFree(e->X);
+  if (e->mean) cudaFree(e->mean);
+  if (e->stage) cudaFree(e->stage);
+  delete e;
+  return MDC_OK;
+}
+
+int mdc_ens_set_domain(mdc_ens* e, int gx0, int gy0, int gnx, int gny, int own_nx, int own_ny) {
+  mdc_ctx* ctx = e->ctx;
+  if (gnx <= 0 || gny <= 0 || gx0 < 0 || gy0 < 0 || gx0 + e->nx > gnx || gy0 + e->ny > gny ||
+      own_nx <= 0 || own_ny <= 0 || own_nx > e->nx || own_ny > e->ny)
+    MDC_FAIL(ctx, MDC_ERR_INVALID, "mdc_ens_set_domain: inconsistent domain");
+  e->gx0 = gx0; e->gy0 = gy0; e->gnx = gnx; e->gny = gny; e->own_nx = own_nx; e->own_ny = own_ny;
+  return MDC_OK;
+}
+
+int mdc_ens_upload_members(mdc_ens* e, int m0, int count, const double* const* hosts) {
+  mdc_ctx* ctx = e->ctx;
+  if (m0 < 0 || count <= 0 || m0 + count > e->k) MDC_FAIL(ctx, MDC_ERR_INVALID, "upload: member range [%d,%d) out of range", m0, m0 + count);
+  MDC_CUDA(ctx, cudaSetDevice(ctx->device));
+  const int64_t G = (int64_t)e->nx * e->ny, n = G * e->nz;
+  for (int mb = 0; mb < count; mb += kMemberBatch) {
+    const int cb = std::min(kMemberBatch, count - mb);
+    const int64_t piece = std::min<int64_t>(n, (int64_t)(kStageBytes / sizeof(double)) / cb);
+    if (int rc = ensure_stage(e, (size_t)piece * cb)) return rc;
+    for (int64_t p0 = 0; p0 < n; p0 += piece) {
+      const int64_t np = std::min(piece, n - p0);
+      for (int c = 0; c < cb; ++c)
+        MDC_CUDA(ctx, cudaMemcpyAsync(e->stage + (int64_t)c * np, hosts[mb + c] + p0, np * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+      ens_scatter_members_kernel<<<mdc_div_up(np, 256), 256, 0, ctx->stream>>>(e->X, e->stage, p0, np, G, e->nz, e->k, m0 + mb, cb);
+      MDC_LAUNCH_CHECK(ctx);
+    }
+  }
+  return MDC_OK;
+}
+
+int mdc_ens_upload_member(mdc_ens* e, int m, const double* host) {
+  const double* h[1] = {host};
+  return mdc_ens_upload_members(e, m, 1, h);
+}
+
+int mdc_ens_download_members(mdc_ens* e, int m0, int count, double* const* hosts) {
+  mdc_ctx* ctx = e->ctx;
+  if (m0 < 0 || count <= 0 || m0 + count > e->k) MDC_FAIL(ctx, MDC_ERR_INVALID, "download: member range out of range");
+  MDC_CUDA(ctx, cudaSetDevice(ctx->device));
+  const int64_t G = (int64_t)e->nx * e->ny, n = G * e->nz;
+  for (int mb = 0; mb < count; mb += kMemberBatch) {
+    const int cb = std::min(kMemberBatch, count - mb);
+    const int64_t piece = std::min<int64_t>(n, (int64_t)(kStageBytes / sizeof(double)) / cb);
+    if (int rc = ensure_stage(e, (size_t)piece * cb)) return rc;
+    for (int64_t p0 = 0; p0 < n; p0 += piece) {
+      const int64_t np = std::min(piece, n - p0);
+      ens_gather_members_kernel<<<mdc_div_up(np, 256), 256, 0, ctx->stream>>>(e->X, e->stage, p0, np, G, e->nz, e->k, m0 + mb, cb);
+      MDC_LAUNCH_CHECK(ctx);
+      for (int c = 0; c < cb; ++c)
+        MDC_CUDA(ctx, cudaMemcpyAsync(hosts[mb + c] + p0, e->stage + (int64_t)c * np, np * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+      // the staging buffer is reused by the next piece: same stream => ordered
+    }
+  }
+  MDC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return MDC_OK;
+}
+
+int mdc_ens_download_member(mdc_ens* e, int m, double* host) {
+  double* h[1] = {host};
+  return mdc_ens_download_members(e, m, 1, h);
+}
+
+int mdc_ens_fill_synthetic(mdc_ens* e, uint64_t seed) {
+  mdc_ctx* ctx = e->ctx;
+  MDC_CUDA(ctx, cudaSetDevice(ctx->device));
+  int64_t total = (int64_t)e->nx * e->ny * e->nz * e->k;
+  ens_fill_synthetic_kernel<<<grid_for(ctx, total, 256, 16), 256, 0, ctx->stream>>>(
+      e->X, e->nx, e->ny, e->nz, e->k, e->gx0, e->gy0, e->gnx, e->gny, seed);
+  MDC_LAUNCH_CHECK(ctx);
+  return MDC_OK;
+}
+
+static int ens_mean_device(mdc_ens* e) {
+  mdc_ctx* ctx = e->ctx;
+  const int64_t npts = (int64_t)e->nx * e->ny * e->nz;
+  if (!e->mean) MDC_CUDA(ctx, cudaMalloc((void**)&e->mean, npts * sizeof(double)));
+  constexpr int W = 4;
+  size_t smem = (size_t)W * 32 * (e->k | 1) * sizeof(double);
+  MDC_CUDA(ctx, cudaFuncSetAttribute(ens_mean_kernel<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int grid = (int)std::max<int64_t>(1, std::min<int64_t>((npts + W * 32 - 1) / (W * 32), (int64_t)ctx->sm_count * 4));
+  ens_mean_kernel<W><<<grid, W * 32, smem, ctx->stream>>>(e->X, e->mean, npts, e->k);
+  MDC_LAUNCH_CHECK(ctx);
+  return MDC_OK;
+}
+
+int mdc_ens_mean(mdc_ens* e, double* host_mean) {
+  mdc_ctx* ctx = e->ctx;
+  MDC_CUDA(ctx, cudaSetDevice(ctx->device));
+  if (int rc = ens_mean_device(e)) return rc;
+  if (host_mean) {
+    const int64_t G = (int64_t)e->nx * e->ny, npts = G * e->nz;
+    if (int rc = ensure_stage(e, (size_t)npts)) return rc;
+    mean_to_host_order_kernel<<<mdc_div_up(npts, 256), 256, 0, ctx->stream>>>(e->mean, e->stage, G, e->nz);
+    MDC_LAUNCH_CHECK(ctx);
+    MDC_CUDA(ctx, cudaMemcpyAsync(host_mean, e->stage, npts * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    MDC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  }
+  return MDC_OK;
+}
+
+int mdc_ens_checksum(mdc_ens* e, double* sum, double* sumsq) {
+  mdc_ctx* ctx = e->ctx;
+  MDC_CUDA(ctx, cudaSetDevice(ctx->device));
+  double* d2 = nullptr;
+  MDC_CUDA(ctx, cudaMalloc((void**)&d2, 2 * sizeof(double)));
+  MDC_CUDA(ctx, cudaMemsetAsync(d2, 0, 2 * sizeof(double), ctx->stream));
+  int64_t total = (int64_t)e->nx * e->ny * e->nz * e->k;
+  ens_checksum_kernel<<<grid_for(ctx, total, 256, 8), 256, 0, ctx->stream>>>(e->X, total, d2);
+  MDC_LAUNCH_CHECK(ctx);
+  double h[2];
+  MDC_CUDA(ctx, cudaMemcpyAsync(h, d2, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
+  MDC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  cudaFree(d2);
+  if (sum) *sum = h[0];
+  if (sumsq) *sumsq = h[1];
+  return MDC_OK;
+}
+
+double* mdc_ens_devptr(mdc_ens* e) { return e->X; }
+int64_t mdc_ens_bytes(const mdc_ens* e) { return (int64_t)e->nx * e->ny * e->nz * e->k * 8; }
+
+// ------------------------------------------------------------------------------ observations
+static void obs_free_arrays(mdc_obs* o) {
+  cudaFree(o->x); cudaFree(o->y); cudaFree(o->z); cudaFree(o->gid); cudaFree(o->val);
+  cudaFree(o->err); cudaFree(o->valid); cudaFree(o->Y); cudaFree(o->ybar); cudaFree(o->Yp);
+  cudaFree(o->d);
+}
+
+// grow row capacity (and the k-wide arrays once k is known), preserving contents
+static int obs_reserve(mdc_obs* o, int64_t cap, int k) {
+  mdc_ctx* ctx = o->ctx;
+  if (cap <= o->cap && (k == o->k || k == 0)) return MDC_OK;
+  const int64_t ncap = std::max(cap, o->cap);
+  const int nk = k ? k : o->k;
+  mdc_obs n = *o;
+  auto mv = [&](auto** dst, auto* src, size_t elems_new, size_t elems_old) -> int {
+    using T = std::remove_pointer_t<std::remove_pointer_t<decltype(dst)>>;
+    if (int rc = dev_alloc<T>(ctx, dst, elems_new)) return rc;
+    if (src && elems_old) MDC_CUDA(ctx, cudaMemcpyAsync(*dst, src, elems_old * sizeof(T), cudaMemcpyDeviceToDevice, ctx->stream));
+    return MDC_OK;
+  };
+  const size_t P = (size_t)o->P;
+  if (mv(&n.x, o->x, ncap, P) || mv(&n.y, o->y, ncap, P) || mv(&n.z, o->z, ncap, P) ||
+      mv(&n.gid, o->gid, ncap, P) || mv(&n.val, o->val, ncap, P) || mv(&n.err, o->err, ncap, P) ||
+      mv(&n.valid, o->valid, ncap, P) || mv(&n.ybar, o->ybar, ncap, P) || mv(&n.d, o->d, ncap, P))
+    return MDC_ERR_CUDA;
+  const size_t kold = (o->k == nk) ? P * (size_t)nk : 0;
+  if (nk > 0) {
+    if (mv(&n.Y, o->Y, (size_t)ncap * nk, kold) || mv(&n.Yp, o->Yp, (size_t)ncap * nk, kold)) return MDC_ERR_CUDA;
+  } else {
+    n.Y = nullptr; n.Yp = nullptr;
+  }
+  MDC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  obs_free_arrays(o);
+  o->x = n.x; o->y = n.y; o->z = n.z; o->gid = n.gid; o->val = n.val; o->err = n.err;
+  o->valid = n.valid; o->Y = n.Y; o->ybar = n.ybar; o->Yp = n.Yp; o->d = n.d;
+  o->cap = ncap;
+  o->k = nk;
+  return MDC_OK;
+}
+
+int mdc_obs_create(mdc_ctx* ctx, int64_t P, const int32_t* x, const int32_t* y, const int32_t* z,
+                   const double* value, const double* err, const uint8_t* valid,
+                   const int64_t* gid, mdc_obs** out) {
+  if (!ctx || !out) return MDC_ERR_INVALID;
+  *out = nullptr;
+  if (P < 0 || P > INT32_MAX / 2) MDC_FAIL(ctx, MDC_ERR_INVALID, "mdc_obs_create: bad P");
+  if (P > 0 && (!x || !y || !value || !err)) MDC_FAIL(ctx, MDC_ERR_INVALID, "mdc_obs_create: null arrays");
+  MDC_CUDA(ctx, cudaSetDevice(ctx->device));
+  mdc_obs* o = new (std::nothrow) mdc_obs();
+  if (!o) MDC_FAIL(ctx, MDC_ERR_INVALID, "out of host memory");
+  o->ctx = ctx;
+  if (int rc = obs_reserve(o, std::max<int64_t>(P, 1), 0)) { delete o; return rc; }
+  o->P = o->P_own = P;
+  if (P > 0) {
+    std::vector<int32_t> zz;
+    if (!z) { zz.assign((size_t)P, 0); z = zz.data(); }
+    std::vector<uint8_t> vv;
+    if (!valid) { vv.assign((size_t)P, 1); valid = vv.data(); }
+    std::vector<int64_t> gg;
+    if (!gid) { gg.resize((size_t)P); for (int64_t i = 0; i < P; ++i) gg[(size_t)i] = i; gid = gg.data(); }
+    cudaStream_t s = ctx->stream;
+    MDC_CUDA(ctx, cudaMemcpyAsync(o->x, x, P * 4, cudaMemcpyHostToDevice, s));
+    MDC_CUDA(ctx, cudaMemcpyAsync(o->y, y, P * 4, cudaMemcpyHostToDevice, s));
+    MDC_CUDA(ctx, cudaMemcpyAsync(o->z, z, P * 4, cudaMemcpyHostToDevice, s));
+    MDC_CUDA(ctx, cudaMemcpyAsync(o->gid, gid, P * 8, cudaMemcpyHostToDevice, s));
+    MDC_CUDA(ctx, cudaMemcpyAsync(o->val, value, P * 8, cudaMemcpyHostToDevice, s));
+    MDC_CUDA(ctx, cudaMemcpyAsync(o->err, err, P * 8, cudaMemcpyHostToDevice, s));
+    MDC_CUDA(ctx, cudaMemcpyAsync(o->valid, valid, P, cudaMemcpyHostToDevice, s));
+    MDC_CUDA(ctx, cudaStreamSynchronize(s));  // temporaries above go out of scope
+  }
+  *out = o;
+  return MDC_OK;
+}
+
+int mdc_obs_destroy(mdc_obs* o) {
+  if (!o) return MDC_OK;
+  cudaSetDevice(o->ctx->device);
+  cudaStreamSynchronize(o->ctx->stream);
+  obs_free_arrays(o);
+  cudaFree(o->cell_start); cudaFree(o->cell_fill); cudaFree(o->sorted_row);
+  cudaFree(o->sx); cudaFree(o->sy); cudaFree(o->sz); cudaFree(o->key);
+  delete o;
+  return MDC_OK;
+}
+
+int64_t mdc_obs_size(const mdc_obs* o) { return o->P; }
+int mdc_obs_row_doubles(const mdc_obs* o) { return o->k + 8; }
+
+// ------------------------------------------------------------------------------ H(x)
+int mdc_hx_idw4(mdc_ens* e, mdc_obs* o) {
+  mdc_ctx* ctx = e->ctx;
+  if (o->ctx != ctx) MDC_FAIL(ctx, MDC_ERR_INVALID, "hx: ens/obs belong to different contexts");
+  MDC_CUDA(ctx, cudaSetDevice(ctx->device));
+  if (o->P != o->P_own) MDC_FAIL(ctx, MDC_ERR_INVALID, "hx: halo rows already appended; H(x) applies to own obs only");
+  if (int rc = obs_reserve(o, o->cap, e->k)) return rc;
+  if (o->P == 0) { o->have_hx = true; return MDC_OK; }
+  constexpr int W = 8;
+  HxGeom g{e->nx, e->ny, e->nz, e->k, e->gx0, e->gy0, e->gnx, e->gny};
+  MDC_CUDA(ctx, cudaMemsetAsync(ctx->d_flags, 0, sizeof(int), ctx->stream));
+  size_t smem = (size_t)W * e->k * sizeof(double);
+  int grid = (int)std::max<int64_t>(1, std::min<int64_t>((o->P + W - 1) / W, (int64_t)ctx->sm_count * 8));
+  hx_idw4_kernel<W><<<grid, W * 32, smem, ctx->stream>>>(e->X, g, o->P, o->x, o->y, o->z, o->valid, o->val, o->Y, o->ybar, o->Yp, o->d, ctx->d_flags);
+  MDC_LAUNCH_CHECK(ctx);
+  int flag = 0;
+  MDC_CUDA(ctx, cudaMemcpyAsync(&flag, ctx->d_flags, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  MDC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  if (flag) MDC_FAIL(ctx, MDC_ERR_INVALID, "hx: an observation needs state outside this ensemble's local grid (+halo)");
+  o->have_hx = true;
+  return MDC_OK;
+}
+
+int mdc_hx_download(mdc_obs* o, double* Y, double* ybar, double* Yp, double* d) {
+  mdc_ctx* ctx = o->ctx;
+  if (!o->have_hx) MDC_FAIL(ctx, MDC_ERR_INVALID, "hx_download: call mdc_hx_idw4 first");
+  MDC_CUDA(ctx, cudaSetDevice(ctx->device));
+  const size_t P = (size_t)o->P, k = (size_t)o->k;
+  cudaStream_t s = ctx->stream;
+  if (Y) MDC_CUDA(ctx, cudaMemcpyAsync(Y, o->Y, P * k * 8, cudaMemcpyDeviceToHost, s));
+  if (Yp) MDC_CUDA(ctx, cudaMemcpyAsync(Yp, o->Yp, P * k * 8, cudaMemcpyDeviceToHost, s));
+  if (ybar) MDC_CUDA(ctx, cudaMemcpyAsync(ybar, o->ybar, P * 8, cudaMemcpyDeviceToHost, s));
+  if (d) MDC_CUDA(ctx, cudaMemcpyAsync(d, o->d, P * 8, cudaMemcpyDeviceToHost, s));
+  MDC_CUDA(ctx, cudaStreamSynchronize(s));
+  return MDC_OK;
+}
+
+// ------------------------------------------------------------------------------ obs halo rows
+__global__ void obs_pack_rows_kernel(int64_t P, int k, const int32_t* x, const int32_t* y,
+                                     const int32_t* z, const int64_t* gid, const double* val,
+                                     const double* err, const uint8_t* valid, const double* Yp,
+                                     const double* d, int ylo, int yhi, double* rows, int64_t cap,
+                                     unsigned long long* counter) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp_global = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  const int rd = k + 8;
+  for (int64_t i = warp_global; i < P; i += nwarps) {
+    if (y[i] < ylo || y[i] >= yhi) continue;
+    unsigned long long slot = 0;
+    if (lane == 0) slot = atomicAdd(counter, 1ull);
+    slot = __shfl_sync(0xffffffffu, slot, 0);
+    if ((int64_t)slot >= cap) continue;
+    double* r = rows + slot * rd;
+    for (int j = lane; j < k; j += 32) r[j] = Yp[i * k + j];
+    if (lane == 0) {
+      r[k + 0] = d[i]; r[k + 1] = val[i]; r[k + 2] = err[i]; r[k + 3] = (double)valid[i];
+      r[k + 4] = (double)x[i]; r[k + 5] = (double)y[i]; r[k + 6] = (double)z[i];
+      r[k + 7] = (double)gid[i];
+    }
+  }
+}
+
+__global__ void obs_unpack_rows_kernel(int64_t n, int k, const double* rows, int64_t base,
+                                       int32_t* x, int32_t* y, int32_t* z, int64_t* gid,
+                                       double* val, double* err, uint8_t* valid, double* Yp,
+                                       double* d) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp_global = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  const int rd = k + 8;
+  for (int64_t i = warp_global; i < n; i += nwarps) {
+    const double* r = rows + i * rd;
+    const int64_t o = base + i;
+    for (int j = lane; j < k; j += 32) Yp[o * k + j] = r[j];
+    if (lane == 0) {
+      d[o] = r[k + 0]; val[o] = r[k + 1]; err[o] = r[k + 2]; valid[o] = (uint8_t)(r[k + 3] != 0.0);
+      x[o] = (int32_t)r[k + 4]; y[o] = (int32_t)r[k + 5]; z[o] = (int32_t)r[k + 6];
+      gid[o] = (int64_t)r[k + 7];
+    }
+  }
+}
+
+int mdc_obs_pack_rows(mdc_obs* o, int ylo, int yhi, double* dev_rows, int64_t cap, int64_t* n) {
+  mdc_ctx* ctx = o->ctx;
+  if (!o->have_hx) MDC_FAIL(ctx, MDC_ERR_INVALID, "pack_rows: call mdc_hx_idw4 first");
+  MDC_CUDA(ctx, cudaSetDevice(ctx->device));
+  unsigned long long* counter = (unsigned long long*)ctx->d_stats;
+  MDC_CUDA(ctx, cudaMemsetAsync(counter, 0, sizeof(unsigned long long), ctx->stream));
+  if (o->P_own > 0) {
+    obs_pack_rows_kernel<<<grid_for(ctx, o->P_own * 32, 256, 8), 256, 0, ctx->stream>>>(
+        o->P_own, o->k, o->x, o->y, o->z, o->gid, o->val, o->err, o->valid, o->Yp, o->d, ylo, yhi, dev_rows, cap, counter);
+    MDC_LAUNCH_CHECK(ctx);
+  }
+  unsigned long long h = 0;
+  MDC_CUDA(ctx, cudaMemcpyAsync(&h, counter, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
+  MDC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  if (n) *n = (int64_t)h;   // caller compares with cap; rows beyond cap were dropped
+  return MDC_OK;
+}
+
+int mdc_obs_append_rows(mdc_obs* o, const double* dev_rows, int64_t n) {
+  mdc_ctx* ctx = o->ctx;
+  if (!o->have_hx) MDC_FAIL(ctx, MDC_ERR_INVALID, "append_rows: call mdc_hx_idw4 first (defines k)");
+  if (n <= 0) return MDC_OK;
+  MDC_CUDA(ctx, cudaSetDevice(ctx->device));
+  if (int rc = obs_reserve(o, o->P + n, o->k)) return rc;
+  obs_unpack_rows_kernel<<<grid_for(ctx, n * 32, 256, 8), 256, 0, ctx->stream>>>(
+      n, o->k, dev_rows, o->P, o->x, o->y, o->z, o->gid, o->val, o->err, o->valid, o->Yp, o->d);
+  MDC_LAUNCH_CHECK(ctx);
+  o->P += n;
+  o->index_valid = false;
+  return MDC_OK;
+}
+
+// ------------------------------------------------------------------------------ bucket index
+int mdc_obs_index_build(mdc_obs* o, int cell) {
+  mdc_ctx* ctx = o->ctx;
+  MDC_CUDA(ctx, cudaSetDevice(ctx->device));
+  if (cell <= 0) MDC_FAIL(ctx, MDC_ERR_INVALID, "index_build: cell must be > 0");
+  cudaStream_t s = ctx->stream;
+  const int64_t P = o->P;
+  o->cell = cell;
+  o->index_P = P;
+  int bbox[4] = {0, 0, 0, 0};
+  if (P > 0) {
+    int init[4] = {INT_MAX, INT_MAX, INT_MIN, INT_MIN};
+    MDC_CUDA(ctx, cudaMemcpyAsync(ctx->d_flags + 4, init, sizeof(init), cudaMemcpyHostToDevice, s));
+    index_bbox_kernel<<<grid_for(ctx, P, 256, 4), 256, 0, s>>>(o->x, o->y, P, ctx->d_flags + 4);
+    MDC_LAUNCH_CHECK(ctx);
+    MDC_CUDA(ctx, cudaMemcpyAsync(bbox, ctx->d_flags + 4, sizeof(bbox), cudaMemcpyDeviceToHost, s));
+    MDC_CUDA(ctx, cudaStreamSynchronize(s));
+  }
+  o->xmin = bbox[0]; o->ymin = bbox[1];
+  const int64_t ncx = ((int64_t)bbox[2] - bbox[0]) / cell + 1, ncy = ((int64_t)bbox[3] - bbox[1]) / cell + 1;
+  if (ncx * ncy > (1ll << 28)) MDC_FAIL(ctx, MDC_ERR_INVALID, "index_build: %lld x %lld cells is too many; use a larger cell", (long long)ncx, (long long)ncy);
+  o->ncx = (int)ncx; o->ncy = (int)ncy;
+  const size_t ncell = (size_t)(ncx * ncy);
+  if (ncell + 1 > o->cell_cap) {
+    cudaFree(o->cell_start); cudaFree(o->cell_fill);
+    if (dev_alloc(ctx, &o->cell_start, ncell + 1) || dev_alloc(ctx, &o->cell_fill, ncell)) return MDC_ERR_CUDA;
+    o->cell_cap = ncell + 1;
+  }
+  if ((size_t)P > o->sorted_cap) {
+    cudaFree(o->sorted_row); cudaFree(o->sx); cudaFree(o->sy); cudaFree(o->sz); cudaFree(o->key);
+    if (dev_alloc(ctx, &o->sorted_row, (size_t)P) || dev_alloc(ctx, &o->sx, (size_t)P) || dev_alloc(ctx, &o->sy, (size_t)P) ||
+        dev_alloc(ctx, &o->sz, (size_t)P) || dev_alloc(ctx, &o->key, (size_t)P))
+      return MDC_ERR_CUDA;
+    o->sorted_cap = (size_t)P;
+  }
+  MDC_CUDA(ctx, cudaMemsetAsync(o->cell_fill, 0, ncell * sizeof(int32_t), s));
+  MDC_CUDA(ctx, cudaMemsetAsync(o->cell_start, 0, (ncell + 1) * sizeof(int32_t), s));
+  if (P > 0) {
+    // histogram into cell_fill, scan into cell_start, clear cell_fill, scatter, per-cell id sort
+    index_key_hist_kernel<<<grid_for(ctx, P, 256, 8), 256, 0, s>>>(o->x, o->y, P, o->xmin, o->ymin, cell, o->ncx, o->key, o->cell_fill);
+    MDC_LAUNCH_CHECK(ctx);
+    index_scan_kernel<<<1, 1024, 0, s>>>(o->cell_fill, o->cell_start, (int)ncell);
+    MDC_LAUNCH_CHECK(ctx);
+    MDC_CUDA(ctx, cudaMemsetAsync(o->cell_fill, 0, ncell * sizeof(int32_t), s));
+    index_scatter_kernel<<<grid_for(ctx, P, 256, 8), 256, 0, s>>>(o->key, P, o->cell_start, o->cell_fill, o->sorted_row);
+    MDC_LAUNCH_CHECK(ctx);
+    index_cell_sort_kernel<<<mdc_div_up((int64_t)ncell, 128), 128, 0, s>>>(o->cell_start, (int)ncell, o->sorted_row, o->gid, o->x, o->y, o->z, o->sx, o->sy, o->sz);
+    MDC_LAUNCH_CHECK(ctx);
+  }
+  o->index_valid = true;
+  return MDC_OK;
+}
+
+static IndexView index_view(const mdc_obs* o) {
+  IndexView iv;
+  iv.cell_start = o->cell_start; iv.sorted_row = o->sorted_row;
+  iv.sx = o->sx; iv.sy = o->sy; iv.sz = o->sz;
+  iv.cell = o->cell; iv.ncx = o->ncx; iv.ncy = o->ncy; iv.xmin = o->xmin; iv.ymin = o->ymin;
+  return iv;
+}
+
+static int ensure_index(mdc_obs* o, double radius) {
+  if (o->index_valid && o->index_P == o->P) return MDC_OK;
+  int cell = (int)std::ceil(radius);
+  if (cell < 1) cell = 1;
+  return mdc_obs_index_build(o, cell);
+}
+
+int mdc_obs_index_query_counts(mdc_obs* o, mdc_ens* e, double radius, int32_t* host_counts) {
+  mdc_ctx* ctx = o->ctx;
+  MDC_CUDA(ctx, cudaSetDevice(ctx->device));
+  if (int rc = ensure_index(o, radius)) return rc;
+  const int64_t G = (int64_t)e->nx * e->ny;
+  int32_t* dc = nullptr;
+  if (dev_alloc(ctx, &dc, (size_t)G)) return MDC_ERR_CUDA;
+  MDC_CUDA(ctx, cudaMemsetAsync(dc, 0xff, G * sizeof(int32_t), ctx->stream));
+  const int64_t nown = (int64_t)e->own_nx * e->own_ny;
+  index_query_counts_kernel<<<mdc_div_up(nown, 128), 128, 0, ctx->stream>>>(index_view(o), e->nx, e->own_nx, e->own_ny, e->gx0, e->gy0, radius, dc);
+  MDC_LAUNCH_CHECK(ctx);
+  MDC_CUDA(ctx, cudaMemcpyAsync(host_counts, dc, G * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+  MDC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  cudaFree(dc);
+  return MDC_OK;
+}
+
+int mdc_obs_index_query_lists(mdc_obs* o, mdc_ens* e, double radius, const int64_t* cols,
+                              int64_t ncols, int32_t cap, int64_t* host_lists,
+                              int32_t* host_counts) {
+  mdc_ctx* ctx = o->ctx;
+  MDC_CUDA(ctx, cudaSetDevice(ctx->device));
+  if (ncols <= 0 || cap <= 0) return MDC_OK;
+  if (int rc = ensure_index(o, radius)) return rc;
+  int64_t *dcols = nullptr, *dl = nullptr;
+  int32_t* dc = nullptr;
+  if (dev_alloc(ctx, &dcols, (size_t)ncols) || dev_alloc(ctx, &dl, (size_t)ncols * cap) || dev_alloc(ctx, &dc, (size_t)ncols)) return MDC_ERR_CUDA;
+  MDC_CUDA(ctx, cudaMemcpyAsync(dcols, cols, ncols * 8, cudaMemcpyHostToDevice, ctx->stream));
+  MDC_CUDA(ctx, cudaMemsetAsync(dl, 0xff, (size_t)ncols * cap * 8, ctx->stream));
+  index_query_lists_kernel<<<mdc_div_up(ncols, 64), 64, 0, ctx->stream>>>(index_view(o), o->gid, e->nx, e->gx0, e->gy0, radius, dcols, ncols, cap, dl, dc);
+  MDC_LAUNCH_CHECK(ctx);
+  MDC_CUDA(ctx, cudaMemcpyAsync(host_lists, dl, (size_t)ncols * cap * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  MDC_CUDA(ctx, cudaMemcpyAsync(host_counts, dc, ncols * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  MDC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  cudaFree(dcols); cudaFree(dl); cudaFree(dc);
+  return MDC_OK;
+}
+
+// ------------------------------------------------------------------------------ LETKF
+static int letkf_launch(mdc_ens* e, mdc_obs* o, const mdc_letkf_params* p, const long long* dcols,
+                        long long ncols, double* dW, long long w_col) {
+  mdc_ctx* ctx = e->ctx;
+  const int k = e->k;
+  if (k > 128) MDC_FAIL(ctx, MDC_ERR_UNSUPPORTED, "letkf: k=%d > 128 members not supported", k);
+  if (p->mode < 0 || p->mode > 2) MDC_FAIL(ctx, MDC_ERR_INVALID, "letkf: bad mode");
+  if (!(p->inflation > 0.0)) MDC_FAIL(ctx, MDC_ERR_INVALID, "letkf: inflation must be > 0");
+  const size_t smem = lk_smem_bytes(k, p->mode);
+  if ((int)smem > ctx->max_smem_optin)
+    MDC_FAIL(ctx, MDC_ERR_UNSUPPORTED, "letkf: k=%d mode=%d needs %zu B shared memory > %d available", k, p->mode, smem, ctx->max_smem_optin);
+  ColParams cp;
+  cp.X = e->X;
+  if (!e->mean) MDC_CUDA(ctx, cudaMalloc((void**)&e->mean, (size_t)e->nx * e->ny * e->nz * sizeof(double)));
+  cp.mean_out = e->mean;
+  cp.nx = e->nx; cp.ny = e->ny; cp.nz = e->nz; cp.k = k; cp.own_nx = e->own_nx; cp.own_ny = e->own_ny;
+  cp.gx0 = e->gx0; cp.gy0 = e->gy0;
+  cp.iv = index_view(o);
+  cp.Yp = o->Yp; cp.d = o->d; cp.err = o->err; cp.valid = o->valid;
+  cp.radius = p->radius; cp.radius_v = p->radius_v; cp.inflation = p->inflation;
+  cp.mode = p->mode; cp.loc = p->loc; cp.use_R = p->use_R;
+  cp.max_sweeps = p->max_sweeps > 0 ? p->max_sweeps : 40;
+  cp.jtol = p->jacobi_tol > 0.0 ? p->jacobi_tol : 1e-9;
+  cp.stats = ctx->d_stats;
+  cp.W_out = dW; cp.w_col = w_col;
+  cp.cols = dcols; cp.ncols = ncols;
+  const long long total_cols = dcols ? ncols : (long long)e->own_nx * e->own_ny;
+  const int nr = (k + 31) / 32;
+  auto launch = [&](auto kern) -> int {
+    MDC_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int occ = 1;
+    MDC_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, LK_THREADS, smem));
+    if (occ < 1) occ = 1;
+    int grid = (int)std::max<long long>(1, std::min<long long>(total_cols, (long long)ctx->sm_count * occ));
+    kern<<<grid, LK_THREADS, smem, ctx->stream>>>(cp);
+    MDC_LAUNCH_CHECK(ctx);
+    return MDC_OK;
+  };
+  switch (nr) {
+    case 1: return launch(letkf_column_kernel<1>);
+    case 2: return launch(letkf_column_kernel<2>);
+    case 3: return launch(letkf_column_kernel<3>);
+    default: return launch(letkf_column_kernel<4>);
+  }
+}
+
+int mdc_letkf_analyse(mdc_ens* e, mdc_obs* o, const mdc_letkf_params* p, mdc_letkf_stats* st) {
+  mdc_ctx* ctx = e->ctx;
+  if (o->ctx != ctx) MDC_FAIL(ctx, MDC_ERR_INVALID, "letkf: ens/obs belong to different contexts");
+  MDC_CUDA(ctx, cudaSetDevice(ctx->device));
+  cudaStream_t s = ctx->stream;
+  MDC_CUDA(ctx, cudaEventRecord(ctx->pe[0], s));
+  // K2/K3: Y' = H(X) - mean once from the background ensemble (snapshot semantics), unless the
+  // caller already ran H (multi-GPU: H, then halo exchange, then analyse)
+  if (!o->have_hx) {
+    if (int rc = mdc_hx_idw4(e, o)) return rc;
+  } else if (o->k != e->k) {
+    MDC_FAIL(ctx, MDC_ERR_INVALID, "letkf: Y' has k=%d, ensemble has k=%d", o->k, e->k);
+  }
+  MDC_CUDA(ctx, cudaEventRecord(ctx->pe[1], s));
+  if (int rc = ensure_index(o, p->radius)) return rc;
+  MDC_CUDA(ctx, cudaEventRecord(ctx->pe[2], s));
+  MDC_CUDA(ctx, cudaMemsetAsync(ctx->d_stats, 0, 16 * sizeof(long long), s));
+  if (int rc = letkf_launch(e, o, p, nullptr, 0, nullptr, -1)) return rc;
+  MDC_CUDA(ctx, cudaEventRecord(ctx->pe[3], s));
+  long long h[16];
+  MDC_CUDA(ctx, cudaMemcpyAsync(h, ctx->d_stats, sizeof(h), cudaMemcpyDeviceToHost, s));
+  MDC_CUDA(ctx, cudaStreamSynchronize(s));
+  o->have_hx = false;  // the ensemble changed: Y' is stale for a next cycle
+  if (st) {
+    memset(st, 0, sizeof(*st));
+    cudaEventElapsedTime(&st->ms_hx, ctx->pe[0], ctx->pe[1]);
+    cudaEventElapsedTime(&st->ms_index, ctx->pe[1], ctx->pe[2]);
+    cudaEventElapsedTime(&st->ms_columns, ctx->pe[2], ctx->pe[3]);
+    cudaEventElapsedTime(&st->ms_total, ctx->pe[0], ctx->pe[3]);
+    st->columns = h[5];
+    st->sum_local_obs = h[0];
+    st->max_local_obs = (int32_t)h[1];
+    st->sum_sweeps = h[2];
+    st->max_sweeps = (int32_t)h[3];
+    st->numeric_failures = (int32_t)h[4];
+  }
+  if (h[4]) MDC_FAIL(ctx, MDC_ERR_NUMERIC, "letkf: %lld column transforms failed (non-SPD matrix); those columns were left unchanged", h[4]);
+  return MDC_OK;
+}
+
+int mdc_letkf_column_transform(mdc_ens* e, mdc_obs* o, const mdc_letkf_params* p, int64_t col,
+                               double* host_W) {
+  // Debug/test entry: runs the column kernel on ONE column and returns its W. The column's state
+  // IS updated (callers use a scratch ensemble).
+  mdc_ctx* ctx = e->ctx;
+  MDC_CUDA(ctx, cudaSetDevice(ctx->device));
+  if (!o->have_hx) { if (int rc = mdc_hx_idw4(e, o)) return rc; }
+  if (int rc = ensure_index(o, p->radius)) return rc;
+  double* dW = nullptr;
+  long long* dcol = nullptr;
+  if (dev_alloc(ctx, &dW, (size_t)e->k * e->k) || dev_alloc(ctx, &dcol, 1)) return MDC_ERR_CUDA;
+  long long c = col;
+  MDC_CUDA(ctx, cudaMemcpyAsync(dcol, &c, 8, cudaMemcpyHostToDevice, ctx->stream));
+  MDC_CUDA(ctx, cudaMemsetAsync(ctx->d_stats, 0, 16 * sizeof(long long), ctx->stream));
+  int rc = letkf_launch(e, o, p, dcol, 1, dW, c);
+  if (!rc) {
+    MDC_CUDA(ctx, cudaMemcpyAsync(host_W, dW, (size_t)e->k * e->k * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    MDC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  }
+  cudaFree(dW); cudaFree(dcol);
+  return rc;
+}
+
+// ------------------------------------------------------------------------------ microbenchmarks
+int mdc_bench_fp64_fma(mdc_ctx* ctx, double* tflops) {
+  MDC_CUDA(ctx, cudaSetDevice(ctx->device));
+  double* d = nullptr;
+  if (dev_alloc(ctx, &d, 8)) return MDC_ERR_CUDA;
+  const int grid = ctx->sm_count * 8;
+  float best = 1e30f;
+  for (int it = 0; it < 5; ++it) {
+    mdc_timer_start(ctx);
+    mb_fp64_fma_kernel<<<grid, 256, 0, ctx->stream>>>(d, 1.0000001, 1e-9);
+    MDC_LAUNCH_CHECK(ctx);
+    float ms;
+    mdc_timer_stop(ctx, &ms);
+    if (it > 0) best = std::min(best, ms);
+  }
+  *tflops = 2.0 * (double)grid * 256 * MB_ITERS * MB_ILP / (best * 1e-3) / 1e12;
+  cudaFree(d);
+  return MDC_OK;
+}
+
+int mdc_bench_fp64_dmma(mdc_ctx* ctx, double* tflops) {
+  MDC_CUDA(ctx, cudaSetDevice(ctx->device));
+  double* d = nullptr;
+  if (dev_alloc(ctx, &d, 8)) return MDC_ERR_CUDA;
+  const int grid = ctx->sm_count * 8;
+  float best = 1e30f;
+  for (int it = 0; it < 5; ++it) {
+    mdc_timer_start(ctx);
+    mb_fp64_dmma_kernel<<<grid, 256, 0, ctx->stream>>>(d, 1.0000001, 1e-9);
+    MDC_LAUNCH_CHECK(ctx);
+    float ms;
+    mdc_timer_stop(ctx, &ms);
+    if (it > 0) best = std::min(best, ms);
+  }
+  // one m8n8k4 mma per warp = 8*8*4 FMAs = 512 flops
+  *tflops = 512.0 * (double)grid * (256 / 32) * MB_ITERS * MB_ILP / (best * 1e-3) / 1e12;
+  cudaFree(d);
+  return MDC_OK;
+}
+
+int mdc_bench_hbm_copy(mdc_ctx* ctx, double* gbs) {
+  MDC_CUDA(ctx, cudaSetDevice(ctx->device));
+  const int64_t n = (1ll << 30) / sizeof(double2);  // 1 GiB each way
+  double2 *a = nullptr, *b = nullptr;
+  if (dev_alloc(ctx, &a, (size_t)n) || dev_alloc(ctx, &b, (size_t)n)) return MDC_ERR_CUDA;
+  MDC_CUDA(ctx, cudaMemsetAsync(a, 0, n * sizeof(double2), ctx->stream));
+  float best = 1e30f;
+  for (int it = 0; it < 6; ++it) {
+    mdc_timer_start(ctx);
+    mb_copy_kernel<<<ctx->sm_count * 16, 256, 0, ctx->stream>>>(a, b, n);
+    MDC_LAUNCH_CHECK(ctx);
+    float ms;
+    mdc_timer_stop(ctx, &ms);
+    if (it > 0) best = std::min(best, ms);
+  }
+  *gbs = 2.0 * (double)n * sizeof(double2) / (best * 1e-3) / 1e9;
+  cudaFree(a); cudaFree(b);
+  return MDC_OK;
+}
+
+}  // extern "C"
+
+#include "global_api.inl"

@@ -1,0 +1,95 @@
+// Internal structures of the sm_100a METADA analysis backend (not part of the C ABI).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/metada_cuda_c_api.h"
+
+struct mdc_ctx {
+  int device = 0;
+  int sm_count = 148;
+  int max_smem_optin = 0;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;   // public stopwatch
+  cudaEvent_t pe[4] = {nullptr, nullptr, nullptr, nullptr};  // per-phase timers
+  int64_t launches = 0;
+  char err[512] = {0};
+  void* flush_buf = nullptr;
+  size_t flush_bytes = 0;
+  int* d_flags = nullptr;      // [16] device scratch for error flags / counters
+  long long* d_stats = nullptr;  // [16]
+};
+
+struct mdc_ens {
+  mdc_ctx* ctx = nullptr;
+  int nx = 0, ny = 0, nz = 0, k = 0;           // local grid (incl. halo)
+  int gx0 = 0, gy0 = 0, gnx = 0, gny = 0;      // placement in the global grid
+  int own_nx = 0, own_ny = 0;                  // analysed columns: x < own_nx, y < own_ny
+  double* X = nullptr;                         // [col][lev][member]
+  double* mean = nullptr;                      // [col][lev] (lazily allocated)
+  double* stage = nullptr;                     // staging for member-major host transfers
+  size_t stage_elems = 0;
+  double* host_pinned = nullptr;               // pinned bounce buffer for pageable callers
+};
+
+struct mdc_obs {
+  mdc_ctx* ctx = nullptr;
+  int64_t P = 0;       // rows in use (own + halo)
+  int64_t P_own = 0;
+  int64_t cap = 0;
+  int k = 0;           // members of Y (set by hx / append)
+  int32_t *x = nullptr, *y = nullptr, *z = nullptr;
+  int64_t* gid = nullptr;
+  double *val = nullptr, *err = nullptr;
+  uint8_t* valid = nullptr;
+  double *Y = nullptr, *ybar = nullptr, *Yp = nullptr, *d = nullptr;  // Y,Yp: [P][k]
+  bool have_hx = false;
+  // bucket index
+  bool index_valid = false;
+  int cell = 0, ncx = 0, ncy = 0, xmin = 0, ymin = 0;
+  int64_t index_P = 0;
+  int32_t* cell_start = nullptr;   // [ncx*ncy + 1]
+  int32_t* cell_fill = nullptr;    // [ncx*ncy]
+  size_t cell_cap = 0;
+  int32_t* sorted_row = nullptr;   // [P] sorted position -> obs row
+  int32_t *sx = nullptr, *sy = nullptr, *sz = nullptr;  // coordinates in sorted order
+  int32_t* key = nullptr;          // [P]
+  size_t sorted_cap = 0;
+};
+
+#define MDC_FAIL(ctx, code, ...)                              \
+  do {                                                        \
+    snprintf((ctx)->err, sizeof((ctx)->err), __VA_ARGS__);    \
+    return (code);                                            \
+  } while (0)
+
+#define MDC_CUDA(ctx, call)                                                              \
+  do {                                                                                   \
+    cudaError_t e_ = (call);                                                             \
+    if (e_ != cudaSuccess) {                                                             \
+      snprintf((ctx)->err, sizeof((ctx)->err), "%s failed at %s:%d: %s", #call, __FILE__, \
+               __LINE__, cudaGetErrorString(e_));                                        \
+      return MDC_ERR_CUDA;                                                               \
+    }                                                                                    \
+  } while (0)
+
+#define MDC_LAUNCH_CHECK(ctx)                  \
+  do {                                         \
+    (ctx)->launches++;                         \
+    MDC_CUDA(ctx, cudaGetLastError());         \
+  } while (0)
+
+static inline int mdc_div_up(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
+
+// ---- synthetic data: pure integer hash + exact FP64 ops (bit-identical on host/numpy) ----
+__host__ __device__ inline uint64_t mdc_splitmix64(uint64_t z) {
+  z += 0x9E3779B97F4A7C15ull;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  return z ^ (z >> 31);
+}
+__host__ __device__ inline uint64_t mdc_hash(uint64_t seed, uint64_t idx) {
+  return mdc_splitmix64(seed * 0xD1342543DE82EF95ull + idx);
+}

@@ -1,0 +1,231 @@
+"""ctypes loader for the CPU oracle (oracle/libmetada_oracle.so).
+
+TEST INFRASTRUCTURE ONLY: imported by tests/, __graft_entry__.smoke() and bench.py's
+cpu_baseline / ``--impl reference`` legs -- never by the product package ``metada_b200``.
+
+Array conventions (the reference's member-major layout):
+    X      float64 [k, nz, ny, nx]  (C-contiguous)
+    ox/oy/oz int32 [P]; oval, oerr float64 [P]; valid uint8 [P]
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "libmetada_oracle.so")
+
+MODE_REF_COMPAT, MODE_REF_ETKF, MODE_CANONICAL = 0, 1, 2
+LOC_CUTOFF, LOC_GASPARI_COHN = 0, 1
+SEM_SNAPSHOT, SEM_AS_WRITTEN = 0, 1
+
+
+class LetkfParams(C.Structure):
+    _fields_ = [
+        ("nx", C.c_int), ("ny", C.c_int), ("nz", C.c_int), ("k", C.c_int),
+        ("P", C.c_int64),
+        ("radius", C.c_double), ("radius_v", C.c_double), ("inflation", C.c_double),
+        ("mode", C.c_int), ("loc", C.c_int), ("use_R", C.c_int), ("semantics", C.c_int),
+        ("nthreads", C.c_int),
+    ]
+
+
+class EnkfDiag(C.Structure):
+    _fields_ = [(n, C.c_double) for n in (
+        "innovation_norm", "background_spread", "analysis_spread",
+        "max_kalman_gain", "min_kalman_gain", "condition_number")]
+
+
+def build(force: bool = False) -> str:
+    """Compile the oracle with gcc (seconds)."""
+    src = os.path.join(_HERE, "metada_oracle.c")
+    if force or not os.path.exists(_LIB_PATH) or os.path.getmtime(_LIB_PATH) < os.path.getmtime(src):
+        subprocess.check_call(["make", "-C", _HERE, "libmetada_oracle.so"], stdout=subprocess.DEVNULL)
+    return _LIB_PATH
+
+
+_lib = None
+
+
+def lib() -> C.CDLL:
+    global _lib
+    if _lib is None:
+        build()
+        _lib = C.CDLL(_LIB_PATH)
+        _lib.orc_distance_grid.restype = C.c_double
+        _lib.orc_distance_grid.argtypes = [C.c_int] * 4
+        _lib.orc_gaspari_cohn.restype = C.c_double
+        _lib.orc_gaspari_cohn.argtypes = [C.c_double]
+        _lib.orc_select_local.restype = C.c_int64
+        _lib.orc_max_threads.restype = C.c_int
+    return _lib
+
+
+def _p(a, t):
+    return a.ctypes.data_as(C.POINTER(t)) if a is not None else None
+
+
+def _i32(a):
+    return np.ascontiguousarray(a, dtype=np.int32)
+
+
+def _f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def max_threads() -> int:
+    return lib().orc_max_threads()
+
+
+def gaspari_cohn(z: float) -> float:
+    return lib().orc_gaspari_cohn(float(z))
+
+
+def select_local(gx, gy, ox, oy, radius):
+    ox, oy = _i32(ox), _i32(oy)
+    out = np.empty(len(ox), dtype=np.int32)
+    c = lib().orc_select_local(C.c_int(gx), C.c_int(gy), C.c_int64(len(ox)), _p(ox, C.c_int32),
+                               _p(oy, C.c_int32), C.c_double(radius), _p(out, C.c_int32))
+    return out[:c].copy()
+
+
+def select_counts(nx, ny, ox, oy, radius, nthreads=0):
+    ox, oy = _i32(ox), _i32(oy)
+    out = np.empty(nx * ny, dtype=np.int32)
+    lib().orc_select_counts(C.c_int(nx), C.c_int(ny), C.c_int64(len(ox)), _p(ox, C.c_int32),
+                            _p(oy, C.c_int32), C.c_double(radius), _p(out, C.c_int32),
+                            C.c_int(nthreads))
+    return out.reshape(ny, nx)
+
+
+def hx_idw4(member, ox, oy, oz=None, valid=None):
+    member = _f64(member)
+    if member.ndim == 2:
+        member = member[None]
+    nz, ny, nx = member.shape
+    ox, oy = _i32(ox), _i32(oy)
+    oz = _i32(oz) if oz is not None else np.zeros(len(ox), np.int32)
+    v = np.ascontiguousarray(valid, dtype=np.uint8) if valid is not None else None
+    out = np.empty(len(ox))
+    lib().orc_hx_idw4(_p(member, C.c_double), C.c_int(nx), C.c_int(ny), C.c_int(nz),
+                      C.c_int64(len(ox)), _p(ox, C.c_int32), _p(oy, C.c_int32), _p(oz, C.c_int32),
+                      _p(v, C.c_uint8), _p(out, C.c_double))
+    return out
+
+
+def ensemble_mean(X):
+    X = _f64(X)
+    k = X.shape[0]
+    n = X[0].size
+    out = np.empty(X.shape[1:])
+    lib().orc_ensemble_mean(_p(X, C.c_double), C.c_int(k), C.c_int64(n), _p(out, C.c_double))
+    return out
+
+
+def obs_space(X, ox, oy, oz, oval, valid=None):
+    """Returns Y, ybar, Yp, d."""
+    X = _f64(X)
+    k, nz, ny, nx = X.shape
+    ox, oy, oz, oval = _i32(ox), _i32(oy), _i32(oz), _f64(oval)
+    P = len(ox)
+    v = np.ascontiguousarray(valid, dtype=np.uint8) if valid is not None else None
+    Y, Yp = np.empty((P, k)), np.empty((P, k))
+    ybar, d = np.empty(P), np.empty(P)
+    lib().orc_obs_space(_p(X, C.c_double), C.c_int(nx), C.c_int(ny), C.c_int(nz), C.c_int(k),
+                        C.c_int64(P), _p(ox, C.c_int32), _p(oy, C.c_int32), _p(oz, C.c_int32),
+                        _p(v, C.c_uint8), _p(oval, C.c_double), _p(Y, C.c_double),
+                        _p(ybar, C.c_double), _p(Yp, C.c_double), _p(d, C.c_double))
+    return Y, ybar, Yp, d
+
+
+def letkf(X, ox, oy, oz, oval, oerr, valid=None, *, radius, inflation=1.0, mode=MODE_CANONICAL,
+          loc=LOC_GASPARI_COHN, use_R=1, radius_v=0.0, semantics=SEM_SNAPSHOT, nthreads=0,
+          cols=None, want_W=False):
+    """Returns dict(Xa, counts[, W]).  X is not modified."""
+    Xa = _f64(X).copy()
+    k, nz, ny, nx = Xa.shape
+    ox, oy, oz = _i32(ox), _i32(oy), _i32(oz)
+    oval, oerr = _f64(oval), _f64(oerr)
+    P = len(ox)
+    v = np.ascontiguousarray(valid, dtype=np.uint8) if valid is not None else None
+    prm = LetkfParams(nx, ny, nz, k, P, radius, radius_v, inflation, mode, loc, use_R, semantics,
+                      nthreads)
+    counts = np.full(nx * ny, -1, dtype=np.int32)
+    cs = np.ascontiguousarray(cols, dtype=np.int64) if cols is not None else None
+    ncols = len(cs) if cs is not None else nx * ny
+    W = np.zeros((ncols, k, k)) if want_W else None
+    rc = lib().orc_letkf(C.byref(prm), _p(Xa, C.c_double), _p(ox, C.c_int32), _p(oy, C.c_int32),
+                         _p(oz, C.c_int32), _p(oval, C.c_double), _p(oerr, C.c_double),
+                         _p(v, C.c_uint8), _p(cs, C.c_int64), C.c_int64(ncols if cs is not None else 0),
+                         _p(counts, C.c_int32), _p(W, C.c_double))
+    if rc:
+        raise RuntimeError(f"orc_letkf failed rc={rc}")
+    out = {"Xa": Xa, "counts": counts.reshape(ny, nx)}
+    if want_W:
+        out["W"] = W
+    return out
+
+
+def etkf(X, ox, oy, oz, oval, oerr, valid=None, *, inflation=1.0):
+    Xa = _f64(X).copy()
+    k, nz, ny, nx = Xa.shape
+    ox, oy, oz = _i32(ox), _i32(oy), _i32(oz)
+    oval, oerr = _f64(oval), _f64(oerr)
+    v = np.ascontiguousarray(valid, dtype=np.uint8) if valid is not None else None
+    rc = lib().orc_etkf(_p(Xa, C.c_double), C.c_int(nx), C.c_int(ny), C.c_int(nz), C.c_int(k),
+                        C.c_int64(len(ox)), _p(ox, C.c_int32), _p(oy, C.c_int32), _p(oz, C.c_int32),
+                        _p(oval, C.c_double), _p(oerr, C.c_double), _p(v, C.c_uint8),
+                        C.c_double(inflation))
+    if rc:
+        raise RuntimeError(f"orc_etkf failed rc={rc}")
+    return Xa
+
+
+def enkf(X, ox, oy, oz, oval, oerr, Z, valid=None, *, inflation=1.0, want_gain_stats=False,
+         nthreads=0):
+    Xa = _f64(X).copy()
+    k, nz, ny, nx = Xa.shape
+    ox, oy, oz = _i32(ox), _i32(oy), _i32(oz)
+    oval, oerr, Z = _f64(oval), _f64(oerr), _f64(Z)
+    assert Z.shape == (len(ox), k)
+    v = np.ascontiguousarray(valid, dtype=np.uint8) if valid is not None else None
+    diag = EnkfDiag()
+    rc = lib().orc_enkf(_p(Xa, C.c_double), C.c_int(nx), C.c_int(ny), C.c_int(nz), C.c_int(k),
+                        C.c_int64(len(ox)), _p(ox, C.c_int32), _p(oy, C.c_int32), _p(oz, C.c_int32),
+                        _p(oval, C.c_double), _p(oerr, C.c_double), _p(v, C.c_uint8),
+                        C.c_double(inflation), _p(Z, C.c_double), C.c_int(int(want_gain_stats)),
+                        C.c_int(nthreads), C.byref(diag))
+    if rc:
+        raise RuntimeError(f"orc_enkf failed rc={rc}")
+    return Xa, {n: getattr(diag, n) for n, _ in EnkfDiag._fields_}
+
+
+def jacobi_eigh(A):
+    A = _f64(A)
+    k = A.shape[0]
+    ev, V = np.empty(k), np.empty((k, k))
+    sw = C.c_int(0)
+    rc = lib().orc_jacobi_eigh(C.c_int(k), _p(A, C.c_double), _p(ev, C.c_double), _p(V, C.c_double),
+                               C.byref(sw))
+    if rc:
+        raise RuntimeError("jacobi failed")
+    return ev, V, sw.value
+
+
+def lu_inverse(A):
+    A = _f64(A)
+    out = np.empty_like(A)
+    if lib().orc_lu_inverse(C.c_int(A.shape[0]), _p(A, C.c_double), _p(out, C.c_double)):
+        raise RuntimeError("singular")
+    return out
+
+
+def cholesky_lower(A):
+    A = _f64(A)
+    out = np.empty_like(A)
+    if lib().orc_cholesky_lower(C.c_int(A.shape[0]), _p(A, C.c_double), _p(out, C.c_double)):
+        raise RuntimeError("not SPD")
+    return out

@@ -1,0 +1,194 @@
+"""GPU parity: the CUDA path (through the C ABI) against the CPU oracle on identical seeded inputs.
+
+Bars: local-obs selection sets/counts bit-exact; Y/Y'/d bit-exact (same
+operation order, no FMA contraction); analysis mean and perturbations relative <= 1e-10.
+"""
+import numpy as np
+import pytest
+
+import metada_b200 as mb
+from metada_b200 import capi, synthetic as syn
+from oracle import orc
+from tests.common import analysis_errors, make_case, rel_err
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-10
+
+
+def _setup(ctx, X, o):
+    k, nz, ny, nx = X.shape
+    ens = mb.Ensemble(ctx, nx, ny, nz, k)
+    ens.upload(X)
+    obs = mb.Observations(ctx, o["x"], o["y"], o["z"], o["value"], o["err"], o["valid"])
+    return ens, obs
+
+
+def test_upload_download_roundtrip_and_mean(ctx):
+    X, _ = make_case(13, 7, 3, 11, 5, seed=1)
+    ens = mb.Ensemble(ctx, 13, 7, 3, 11)
+    ens.upload(X)
+    assert np.array_equal(ens.download(), X)
+    assert np.array_equal(ens.download_member(4), X[4])
+    assert np.array_equal(ens.mean(), orc.ensemble_mean(X))     # Ensemble.hpp:105-114, bit-exact
+    s, s2 = ens.checksum()
+    assert abs(s - X.sum()) < 1e-9 * abs(X).sum() and abs(s2 - (X * X).sum()) < 1e-9 * (X * X).sum()
+    ens.close()
+
+
+def test_synthetic_fill_bit_identical_to_host(ctx):
+    ens = mb.Ensemble(ctx, 21, 10, 4, 6)
+    ens.fill_synthetic(1234)
+    assert np.array_equal(ens.download(), syn.ensemble(6, 21, 10, 4, seed=1234))
+    # a sub-domain placed inside a larger global grid reproduces the global field
+    sub = mb.Ensemble(ctx, 8, 5, 4, 6)
+    sub.set_domain(3, 2, 21, 10, 8, 5)
+    sub.fill_synthetic(1234)
+    assert np.array_equal(sub.download(), syn.ensemble(6, 21, 10, 4, seed=1234)[:, :, 2:7, 3:11])
+    ens.close(); sub.close()
+
+
+@pytest.mark.parametrize("nz", [1, 3])
+def test_hx_bit_exact(ctx, nz):
+    X, o = make_case(19, 12, nz, 9, 200, seed=2, invalid_frac=0.1, out_of_grid=10)
+    ens, obs = _setup(ctx, X, o)
+    obs.hx(ens)
+    got = obs.hx_download()
+    Y, ybar, Yp, d = orc.obs_space(X, o["x"], o["y"], o["z"], o["value"], o["valid"])
+    assert np.array_equal(got["Y"], Y)
+    assert np.array_equal(got["ybar"], ybar)
+    assert np.array_equal(got["Yp"], Yp)
+    assert np.array_equal(got["d"], d)
+    ens.close(); obs.close()
+
+
+@pytest.mark.parametrize("radius", [0.0, 1.0, 2.9999, 5.0, 7.5])
+def test_selection_counts_and_sets_bit_exact(ctx, radius):
+    X, o = make_case(40, 33, 1, 2, 700, seed=3, out_of_grid=20)
+    ens, obs = _setup(ctx, X, o)
+    counts = obs.query_counts(ens, radius)
+    ref = orc.select_counts(40, 33, o["x"], o["y"], radius)
+    assert np.array_equal(counts, ref)
+    cols = np.array([0, 39, 40 * 16 + 20, 40 * 33 - 1, 777], np.int64)
+    lists, cnt = obs.query_lists(ens, radius, cols, cap=700)
+    for c, lst, n in zip(cols, lists, cnt):
+        want = orc.select_local(int(c % 40), int(c // 40), o["x"], o["y"], radius)
+        assert n == len(want)
+        assert sorted(lst.tolist()) == want.tolist()          # same SET, bit-exact
+    ens.close(); obs.close()
+
+
+@pytest.mark.parametrize("mode,loc", [(mb.MODE_REF_COMPAT, 0), (mb.MODE_REF_ETKF, 0),
+                                      (mb.MODE_CANONICAL, mb.LOC_GASPARI_COHN), (mb.MODE_CANONICAL, mb.LOC_CUTOFF)])
+@pytest.mark.parametrize("k,nz,infl", [(20, 1, 1.0), (9, 3, 1.1), (40, 2, 1.0)])
+def test_letkf_matches_oracle(ctx, mode, loc, k, nz, infl):
+    X, o = make_case(24, 20, nz, k, 120, seed=4 + k, invalid_frac=0.05, out_of_grid=4)
+    ens, obs = _setup(ctx, X, o)
+    radius = 4.0
+    st = capi.letkf_analyse(ens, obs, capi.make_params(radius, infl, mode, loc))
+    Xa = ens.download()
+    ref = orc.letkf(X, o["x"], o["y"], o["z"], o["value"], o["err"], o["valid"], radius=radius,
+                    inflation=infl, mode=mode, loc=loc)
+    em, ep = analysis_errors(Xa, ref["Xa"])
+    assert em < TOL and ep < TOL, (em, ep)
+    assert st["columns"] == 24 * 20
+    assert st["sum_local_obs"] == int(ref["counts"].sum())
+    assert st["max_local_obs"] == int(ref["counts"].max())
+    # analysis mean kept on the device (LETKF.hpp:116 RecomputeMean)
+    assert rel_err(ens.mean(), Xa.sum(0) / k) < 1e-14
+    ens.close(); obs.close()
+
+
+def test_letkf_k80_and_k128_canonical(ctx):
+    for k, P in ((80, 150), (128, 100)):
+        X, o = make_case(12, 10, 2, k, P, seed=k)
+        ens, obs = _setup(ctx, X, o)
+        capi.letkf_analyse(ens, obs, capi.make_params(5.0, 1.05, mb.MODE_CANONICAL, mb.LOC_GASPARI_COHN))
+        ref = orc.letkf(X, o["x"], o["y"], o["z"], o["value"], o["err"], radius=5.0, inflation=1.05)
+        em, ep = analysis_errors(ens.download(), ref["Xa"])
+        assert em < TOL and ep < TOL, (k, em, ep)
+        ens.close(); obs.close()
+
+
+def test_letkf_vertical_localisation(ctx):
+    X, o = make_case(14, 12, 6, 10, 150, seed=9)
+    ens, obs = _setup(ctx, X, o)
+    p = capi.make_params(4.0, 1.0, mb.MODE_CANONICAL, mb.LOC_GASPARI_COHN, radius_v=2.0)
+    capi.letkf_analyse(ens, obs, p)
+    ref = orc.letkf(X, o["x"], o["y"], o["z"], o["value"], o["err"], radius=4.0, radius_v=2.0)
+    em, ep = analysis_errors(ens.download(), ref["Xa"])
+    assert em < TOL and ep < TOL, (em, ep)
+    ens.close(); obs.close()
+
+
+def test_letkf_no_obs_in_reach_only_inflates(ctx):
+    # LETKF.hpp:167-190: empty local set -> mean kept, perturbations * sqrt(inflation)
+    X, o = make_case(16, 16, 2, 8, 3, seed=5)
+    o["x"][:] = 0; o["y"][:] = 0
+    ens, obs = _setup(ctx, X, o)
+    capi.letkf_analyse(ens, obs, capi.make_params(2.0, 1.44, mb.MODE_CANONICAL))
+    Xa = ens.download()
+    far = np.s_[:, :, 8:, 8:]
+    m = X[far].mean(0)
+    assert rel_err(Xa[far], m + (X[far] - m) * 1.2) < 1e-14
+    ens.close(); obs.close()
+
+
+def test_letkf_dense_cluster_exceeds_selection_buffer(ctx):
+    # > LK_SELCAP (512) local obs in one column's reach: exercises the chunked flush path
+    nx = ny = 12
+    k = 12
+    X, _ = make_case(nx, ny, 1, k, 4, seed=6)
+    o = syn.observations(1500, nx, ny, 1, seed=77)
+    ens, obs = _setup(ctx, X, o)
+    st = capi.letkf_analyse(ens, obs, capi.make_params(9.0, 1.0, mb.MODE_CANONICAL, mb.LOC_GASPARI_COHN))
+    assert st["max_local_obs"] > 512
+    ref = orc.letkf(X, o["x"], o["y"], o["z"], o["value"], o["err"], radius=9.0)
+    em, ep = analysis_errors(ens.download(), ref["Xa"])
+    assert em < TOL and ep < TOL, (em, ep)
+    ens.close(); obs.close()
+
+
+def test_letkf_column_transform_matches_oracle_W(ctx):
+    X, o = make_case(15, 13, 1, 16, 90, seed=8)
+    col = 13 * 6 + 7
+    for mode in (mb.MODE_CANONICAL, mb.MODE_REF_ETKF, mb.MODE_REF_COMPAT):
+        ens, obs = _setup(ctx, X, o)
+        W = capi.letkf_column_transform(ens, obs, capi.make_params(4.0, 1.0, mode, mb.LOC_GASPARI_COHN), col)
+        ref = orc.letkf(X, o["x"], o["y"], o["z"], o["value"], o["err"], radius=4.0, mode=mode,
+                        cols=[col], want_W=True)["W"][0]
+        assert rel_err(W, ref) < TOL
+        ens.close(); obs.close()
+
+
+def test_etkf_matches_oracle(ctx):
+    X, o = make_case(30, 20, 2, 12, 80, seed=10, invalid_frac=0.05)
+    ens, obs = _setup(ctx, X, o)
+    capi.etkf_analyse(ens, obs, 1.05)
+    ref = orc.etkf(X, o["x"], o["y"], o["z"], o["value"], o["err"], o["valid"], inflation=1.05)
+    em, ep = analysis_errors(ens.download(), ref)
+    assert em < TOL and ep < TOL, (em, ep)
+    ens.close(); obs.close()
+
+
+def test_enkf_matches_oracle_with_supplied_perturbations(ctx):
+    X, o = make_case(25, 16, 1, 10, 120, seed=11)
+    ens, obs = _setup(ctx, X, o)
+    Z = np.random.default_rng(7).standard_normal((120, 10))
+    diag = capi.enkf_analyse(ens, obs, 1.1, Z=Z, want_gain_stats=True)
+    ref, rdiag = orc.enkf(X, o["x"], o["y"], o["z"], o["value"], o["err"], Z, inflation=1.1, want_gain_stats=True)
+    em, ep = analysis_errors(ens.download(), ref)
+    assert em < TOL and ep < 1e-9, (em, ep)
+    for key in ("innovation_norm", "background_spread", "analysis_spread", "max_kalman_gain",
+                "min_kalman_gain", "condition_number"):
+        assert abs(diag[key] - rdiag[key]) <= 1e-9 * abs(rdiag[key]), (key, diag[key], rdiag[key])
+    ens.close(); obs.close()
+
+
+def test_errors_are_reported_not_swallowed(ctx):
+    with pytest.raises(mb.MdcError):
+        mb.Ensemble(ctx, 0, 4, 1, 4)
+    X, o = make_case(8, 8, 1, 4, 10, seed=12)
+    ens, obs = _setup(ctx, X, o)
+    with pytest.raises(mb.MdcError):
+        capi.letkf_analyse(ens, obs, capi.make_params(3.0, -1.0))
+    ens.close(); obs.close()

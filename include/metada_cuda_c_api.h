@@ -122,7 +122,7 @@ typedef struct {
   int loc;            /* MDC_LOC_* (CANONICAL)                                                */
   int use_R;          /* CANONICAL: 1 -> R = diag(err^2), 0 -> R = I                          */
   int max_sweeps;     /* Jacobi sweep cap (<= 0: 40)                                          */
-  double jacobi_tol;  /* stop when a sweep's max |g_p.g_q|/(|g_p||g_q|) < tol (<= 0: 1e-9)    */
+  double jacobi_tol;  /* stop when a sweep's max |g_p.g_q|/(|g_p||g_q|) < tol (<= 0: 1e-12)    */
   int reserved[4];
 } mdc_letkf_params;
 

@@ -3,6 +3,7 @@
 #include <algorithm>
 #include <climits>
 #include <cmath>
+#include <cstdlib>
 #include <new>
 #include <vector>
 
@@ -12,6 +13,7 @@
 #include "hx_kernels.cuh"
 #include "index_kernels.cuh"
 #include "letkf_kernels.cuh"
+#include "letkf_v2.cuh"
 #include "mdc_internal.cuh"
 
 namespace {
@@ -607,11 +609,37 @@ static int letkf_launch(mdc_ens* e, mdc_obs* o, const mdc_letkf_params* p, const
   cp.radius = p->radius; cp.radius_v = p->radius_v; cp.inflation = p->inflation;
   cp.mode = p->mode; cp.loc = p->loc; cp.use_R = p->use_R;
   cp.max_sweeps = p->max_sweeps > 0 ? p->max_sweeps : 40;
-  cp.jtol = p->jacobi_tol > 0.0 ? p->jacobi_tol : 1e-9;
+  cp.jtol = p->jacobi_tol > 0.0 ? p->jacobi_tol : 1e-11;
   cp.stats = ctx->d_stats;
   cp.W_out = dW; cp.w_col = w_col;
   cp.cols = dcols; cp.ncols = ncols;
   const long long total_cols = dcols ? ncols : (long long)e->own_nx * e->own_ny;
+  if (p->mode == MDC_MODE_CANONICAL && !getenv("MDC_LETKF_V1")) {
+    // optimised canonical kernel: level-chunk sized so that two CTAs fit one SM when k allows
+    const int lchmax = std::max(4, 2560 / k);
+    const int nchunk = (e->nz + lchmax - 1) / lchmax;
+    const int lch = (e->nz + nchunk - 1) / nchunk;
+    const size_t smem2 = v2_smem_bytes(k, lch);
+    if ((int)smem2 > ctx->max_smem_optin)
+      MDC_FAIL(ctx, MDC_ERR_UNSUPPORTED, "letkf: k=%d needs %zu B shared memory > %d available", k, smem2, ctx->max_smem_optin);
+    auto launch2 = [&](auto kern, int nt) -> int {
+      MDC_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+      int occ = 1;
+      MDC_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, nt, smem2));
+      if (occ < 1) occ = 1;
+      int grid = (int)std::max<long long>(1, std::min<long long>(total_cols, (long long)ctx->sm_count * occ));
+      kern<<<grid, nt, smem2, ctx->stream>>>(cp, lch);
+      MDC_LAUNCH_CHECK(ctx);
+      return MDC_OK;
+    };
+    // <NT, MINB, LG, RPL, TM, TMY>: NT = (k/8 block pairs) * LG lanes rounded up to whole warps
+    if (k <= 16) return launch2(letkf_canonical_kernel<32, 8, 4, 4, 1, 8>, 32);
+    if (k <= 24) return launch2(letkf_canonical_kernel<32, 8, 4, 6, 2, 12>, 32);
+    if (k <= 40) return launch2(letkf_canonical_kernel<64, 4, 8, 5, 3, 10>, 64);
+    if (k <= 64) return launch2(letkf_canonical_kernel<64, 4, 8, 8, 4, 16>, 64);
+    if (k <= 80) return launch2(letkf_canonical_kernel<160, 2, 16, 5, 5, 8>, 160);
+    return launch2(letkf_canonical_kernel<256, 1, 16, 8, 8, 8>, 256);
+  }
   const int nr = (k + 31) / 32;
   auto launch = [&](auto kern) -> int {
     MDC_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -1,0 +1,199 @@
+"""Column sharding of the LETKF across the GPUs of one node (host-side plumbing only).
+
+LETKF columns are independent once Y' = H(X) - mean is known (snapshot semantics), so the column
+grid is cut into row slabs, one per rank / GPU.  Each rank
+  1. holds its slab of the ensemble (+ one read-only halo row above it: the 4-point IDW stencil of
+     IdentityObsOperator.hpp:594-638 reaches one row up),
+  2. applies H to the observations lying in its slab (mdc_hx_idw4),
+  3. exchanges the Y' rows of observations within `radius` of a slab edge with its neighbours
+     (torch.distributed: NCCL over NVLink on GPUs, gloo in the CPU tests) -- the only collective,
+  4. analyses its own columns (mdc_letkf_analyse) with no further communication.
+Observation rows carry their GLOBAL id, and the bucket index orders candidates by (cell, global id)
+on a global cell grid, so every column sees the same rows in the same order whatever the rank count.
+
+The reference has no parallelism of any kind; this module is new plumbing
+around the C ABI, not a port.
+"""
+from __future__ import annotations
+
+import math
+import time
+
+import numpy as np
+
+
+def slab_bounds(gny: int, rank: int, world: int):
+    return (gny * rank) // world, (gny * (rank + 1)) // world
+
+
+def owner_of_row(y, gny: int, world: int):
+    """Rank whose slab contains (clamped) row y -- inverse of slab_bounds."""
+    y = np.clip(np.asarray(y, dtype=np.int64), 0, gny - 1)
+    r = (y * world) // gny
+    # integer slab edges are floor(gny*r/world): fix the rare off-by-one
+    lo = (gny * r) // world
+    hi = (gny * (r + 1)) // world
+    r = np.where(y < lo, r - 1, np.where(y >= hi, r + 1, r))
+    return r
+
+
+def halo_plan(gny: int, world: int, reach: int):
+    """For every ordered pair (src, dst), the row interval [lo, hi) of src's OWN rows whose
+    observations dst needs: rows within `reach` of dst's slab.  Returns {(src, dst): (lo, hi)}."""
+    plan = {}
+    for dst in range(world):
+        d0, d1 = slab_bounds(gny, dst, world)
+        need_lo, need_hi = d0 - reach, d1 + reach   # obs rows y in [need_lo, need_hi)
+        for src in range(world):
+            if src == dst:
+                continue
+            s0, s1 = slab_bounds(gny, src, world)
+            # src also owns out-of-grid obs clamped into its edge slab
+            lo = max(s0 if src > 0 else -(1 << 30), need_lo)
+            hi = min(s1 if src < world - 1 else (1 << 30), need_hi)
+            if lo < hi:
+                plan[(src, dst)] = (int(lo), int(hi))
+    return plan
+
+
+def select_own(obs: dict, gny: int, rank: int, world: int):
+    """Indices (= global ids) of the observations owned by `rank`."""
+    return np.nonzero(owner_of_row(obs["y"], gny, world) == rank)[0]
+
+
+def exchange_rows(dist, rank, world, send: dict, row_doubles: int, device):
+    """send: {dst: tensor [n, row_doubles]} -> returns list of received tensors (by src order).
+    Works with any torch.distributed backend (gloo tensors on cpu, nccl tensors on cuda)."""
+    import torch
+    counts_out = torch.zeros(world, dtype=torch.int64, device=device)
+    for dst, t in send.items():
+        counts_out[dst] = t.shape[0]
+    counts_in = torch.zeros(world, dtype=torch.int64, device=device)
+    # all_to_all_single is not available on gloo; all_gather a [world] vector per rank instead
+    gathered = [torch.zeros(world, dtype=torch.int64, device=device) for _ in range(world)]
+    dist.all_gather(gathered, counts_out)
+    for src in range(world):
+        counts_in[src] = gathered[src][rank]
+    ops, recv = [], {}
+    for src in range(world):
+        n = int(counts_in[src])
+        if src != rank and n > 0:
+            recv[src] = torch.empty((n, row_doubles), dtype=torch.float64, device=device)
+            ops.append(dist.P2POp(dist.irecv, recv[src], src))
+    for dst, t in send.items():
+        if t.shape[0] > 0:
+            ops.append(dist.P2POp(dist.isend, t, dst))
+    if ops:
+        for w in dist.batch_isend_irecv(ops):
+            w.wait()
+    return [recv[s] for s in sorted(recv)]
+
+
+class SlabLetkf:
+    """One rank's share of a column-sharded LETKF (world == 1: the whole domain)."""
+
+    def __init__(self, ctx, gnx, gny, nz, k, rank=0, world=1, radius=8.0):
+        import metada_b200 as mb
+        self.mb, self.ctx = mb, ctx
+        self.gnx, self.gny, self.nz, self.k = gnx, gny, nz, k
+        self.rank, self.world = rank, world
+        self.reach = int(math.floor(radius))
+        self.y0, self.y1 = slab_bounds(gny, rank, world)
+        self.halo_hi = 1 if self.y1 < gny else 0
+        self.ny_loc = (self.y1 - self.y0) + self.halo_hi
+        self.ens = mb.Ensemble(ctx, gnx, self.ny_loc, nz, k)
+        self.ens.set_domain(0, self.y0, gnx, gny, gnx, self.y1 - self.y0)
+        self.obs = None
+        self.plan = halo_plan(gny, world, self.reach)
+        self._own_y = None
+        self.halo_rows_last = 0
+
+    # ---- observations
+    def set_observations(self, obs_all: dict):
+        if self.obs is not None:
+            self.obs.close()
+        own = select_own(obs_all, self.gny, self.rank, self.world) if self.world > 1 else np.arange(len(obs_all["x"]))
+        self._own_y = obs_all["y"][own]
+        self.obs = self.mb.Observations(self.ctx, obs_all["x"][own], obs_all["y"][own], obs_all["z"][own],
+                                        obs_all["value"][own], obs_all["err"][own], obs_all["valid"][own],
+                                        gid=own.astype(np.int64))
+        self.h2d_obs_bytes = int(len(own) * (3 * 4 + 8 + 8 + 8 + 1))
+
+    # ---- analysis
+    def analyse(self, params, dist=None):
+        from . import capi
+        if self.world > 1:
+            import torch
+            import torch.distributed as tdist
+            dist = dist or tdist
+            self.obs.hx(self.ens)
+            rd = self.obs.row_doubles()
+            dev = torch.device("cuda", torch.cuda.current_device())
+            send = {}
+            for (src, dst), (lo, hi) in self.plan.items():
+                if src != self.rank:
+                    continue
+                n = int(np.count_nonzero((self._own_y >= lo) & (self._own_y < hi)))
+                buf = torch.empty((max(n, 1), rd), dtype=torch.float64, device=dev)
+                got = self.obs.pack_rows(lo, hi, buf.data_ptr(), n) if n > 0 else 0
+                assert got == n, (got, n)
+                send[dst] = buf[:n]
+            torch.cuda.synchronize()
+            recv = exchange_rows(dist, self.rank, self.world, send, rd, dev)
+            torch.cuda.synchronize()
+            self.halo_rows_last = 0
+            for t in recv:
+                self.obs.append_rows(t.data_ptr(), t.shape[0])
+                self.halo_rows_last += t.shape[0]
+            self.ctx.sync()
+        return capi.letkf_analyse(self.ens, self.obs, params)
+
+    # ---- end to end with host buffers
+    def e2e_measure(self, params, obs_all, steps=1, dist=None):
+        """Same metric through the C ABI with HOST (pinned) member buffers: every step uploads the
+        rank's slab of all k members, analyses, and downloads the analysed members."""
+        import psutil
+        import torch
+        n_loc = self.nz * self.ny_loc * self.gnx
+        need = n_loc * self.k * 8
+        avail = psutil.virtual_memory().available
+        G = self.gnx * self.gny
+        if need > 0.62 * avail / max(1, self.world if dist is not None else 1):
+            return {"value": None, "unit": "columns/s", "h2d_bytes_per_step": None, "d2h_bytes_per_step": None,
+                    "skipped": f"pinned host buffers need {need/1e9:.1f} GB, {avail/1e9:.1f} GB available"}
+        host = [torch.empty(n_loc, dtype=torch.float64, pin_memory=True) for _ in range(self.k)]
+        ptrs = [t.data_ptr() for t in host]
+        times = []
+        for it in range(steps + 1):           # first pass is the warm-up
+            self.ens.fill_synthetic(1000)
+            self.ens.download_ptrs(0, ptrs)   # background ensemble now lives in HOST memory
+            self.ctx.sync()
+            if dist is not None:
+                dist.barrier()
+            t0 = time.perf_counter()
+            self.ens.upload_ptrs(0, ptrs)
+            self.set_observations(obs_all)
+            self.analyse(params, dist)
+            self.ens.download_ptrs(0, ptrs)   # synchronises
+            mean = self.ens.mean()            # analysis mean read back (LETKF.hpp:116)
+            dt = time.perf_counter() - t0
+            if dist is not None:
+                tt = torch.tensor([dt], dtype=torch.float64, device="cuda")
+                dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+                dt = float(tt[0])
+            if it > 0:
+                times.append(dt)
+            del mean
+        del host
+        tot = float(sum(times))
+        return {"value": G * len(times) / tot, "unit": "columns/s",
+                "h2d_bytes_per_step": int(need + self.h2d_obs_bytes), "d2h_bytes_per_step": int(need + n_loc * 8),
+                "ms_per_step": 1e3 * tot / len(times), "steps": len(times),
+                "note": "pinned host members -> mdc_ens_upload_members -> mdc_letkf_analyse -> "
+                        "mdc_ens_download_members + mdc_ens_mean, host wall clock, max over ranks"}
+
+    def close(self):
+        if self.obs is not None:
+            self.obs.close()
+            self.obs = None
+        self.ens.close()

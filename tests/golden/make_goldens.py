@@ -1,0 +1,127 @@
+"""Generates tests/golden/*.npz by running the reference's own headers (oracle/_ref/ref_driver,
+built by `make -C oracle ref` from /root/reference + the Eigen-API shim) on
+  (1) the reference's tutorial data set (src/backends/simple/tutorial: 36x18 grid, 9 members, 28 obs),
+  (2) a seeded synthetic 2-D case written in the Simple backend's text formats.
+Run in the build container only (needs /root/reference); the .npz files are committed.
+"""
+import json
+import os
+import struct
+import subprocess
+import sys
+import tempfile
+
+import numpy as np
+import yaml
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+from metada_b200 import synthetic as syn  # noqa: E402
+
+REF = "/root/reference/src/backends/simple/tutorial"
+DRIVER = os.path.join(ROOT, "oracle", "_ref", "ref_driver")
+OUT = os.path.dirname(os.path.abspath(__file__))
+
+
+def read_dump(path):
+    b = open(path, "rb").read()
+    k, n, P = struct.unpack_from("<qqq", b, 0)
+    off, vecs = 24, []
+    while off < len(b):
+        (m,) = struct.unpack_from("<q", b, off)
+        off += 8
+        vecs.append(np.frombuffer(b, dtype="<f8", count=m, offset=off).copy())
+        off += 8 * m
+    return k, n, P, vecs
+
+
+def run(mode, cfg_path, tmp):
+    out = os.path.join(tmp, f"{mode}.bin")
+    subprocess.check_call([DRIVER, mode, cfg_path, out], stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    return read_dump(out)
+
+
+def collect(cfg, tmp, nx, ny):
+    cfg_path = os.path.join(tmp, "cfg.json")
+    json.dump(cfg, open(cfg_path, "w"))
+    g = {}
+    k, n, P, v = run("hx", cfg_path, tmp)
+    g["k"], g["nx"], g["ny"], g["P"] = k, nx, ny, P
+    g["HX"] = np.stack(v[:k])                       # [k][P]
+    g["yo"], g["var"] = v[k], v[k + 1]
+    g["ox"], g["oy"], g["oz"] = (v[k + 2 + i].astype(np.int32) for i in range(3))
+    g["counts"] = v[k + 5].astype(np.int32).reshape(ny, nx)
+    g["radius"], g["inflation"] = v[k + 6]
+    g["mean_b"] = v[k + 7].reshape(ny, nx)
+    for mode in ("letkf", "letkf_snapshot", "etkf", "enkf"):
+        _, _, _, v = run(mode, cfg_path, tmp)
+        g[f"Xa_{mode}"] = v[0].reshape(k, 1, ny, nx)
+        if mode.startswith("letkf"):
+            g[f"mean_{mode}"] = v[1].reshape(ny, nx)
+        if mode == "enkf":
+            g["enkf_Z"] = v[1].reshape(P, k)
+            g["enkf_diag"] = v[2]
+    return g
+
+
+def tutorial(tmp):
+    cfg = yaml.safe_load(open(os.path.join(REF, "letkf.yaml")))
+    for m in cfg["ensemble"]["members"]:
+        m["state"]["file"] = os.path.join(REF, os.path.basename(m["state"]["file"]))
+    for t in cfg["observations"]["types"]:
+        for name, tc in t.items():
+            tc["file"] = os.path.join(REF, os.path.basename(tc["file"]))
+    cfg["logger"].update(level="error", console=False)
+    cfg["analysis"].update(output_base_file=os.path.join(tmp, "analysis"), format="txt",
+                           inflation_method="multiplicative")
+    nx, ny = cfg["geometry"]["x_dim"], cfg["geometry"]["y_dim"]
+    g = collect(cfg, tmp, nx, ny)
+    X = np.stack([np.loadtxt(m["state"]["file"]).reshape(1, ny, nx) for m in cfg["ensemble"]["members"]])
+    g["X"] = X
+    g["err_cfg"] = 0.1     # config value; the reference narrows it to float (ConfigValue.hpp:108)
+    return g
+
+
+def synthetic_case(tmp, nx=23, ny=17, k=8, P=70, radius=4.5, inflation=1.1, sigma=0.25, seed=5):
+    X = syn.ensemble(k, nx, ny, 1, seed=1000 + seed)
+    o = syn.observations(P, nx, ny, 1, seed=42 + seed, sigma=sigma)
+    members = []
+    for m in range(k):
+        p = os.path.join(tmp, f"syn_ens_{m}.txt")
+        with open(p, "w") as f:
+            for y in range(ny):
+                f.write(" ".join(repr(float(v)) for v in X[m, 0, y]) + "\n")
+        members.append({"state": {"variables": "simple", "file": p}})
+    op = os.path.join(tmp, "syn_obs.txt")
+    with open(op, "w") as f:
+        f.write("-" * 80 + "\nTime Z   Y   X   ZNU      XLONG_U    XLAT_U     Simple\n" + "-" * 80 + "\n")
+        for i in range(P):
+            f.write(f"0 {int(o['z'][i])} {int(o['y'][i])} {int(o['x'][i])} 0.5 0.0 0.0 {float(o['value'][i])!r}\n")
+    cfg = {"logger": {"app_name": "golden", "level": "error", "color": False, "console": False},
+           "geometry": {"x_dim": nx, "y_dim": ny},
+           "ensemble": {"members": members},
+           "observations": {"types": [{"obs_A": {"if_use": True, "file": op, "coordinate": "grid",
+                                                 "variables": [{"simple": {"if_use": True, "error": sigma, "missing_value": -999.0}}]}}]},
+           "obs_operator": {},
+           "analysis": {"algorithm": "letkf", "inflation": inflation, "localization_radius": radius,
+                        "inflation_method": "multiplicative", "format": "txt",
+                        "output_base_file": os.path.join(tmp, "analysis")}}
+    g = collect(cfg, tmp, nx, ny)
+    g["X"] = X
+    g["err_cfg"] = sigma
+    return g
+
+
+def main():
+    subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle"), "ref"], stdout=subprocess.DEVNULL)
+    with tempfile.TemporaryDirectory() as tmp:
+        np.savez_compressed(os.path.join(OUT, "tutorial_36x18.npz"), **tutorial(tmp))
+    with tempfile.TemporaryDirectory() as tmp:
+        np.savez_compressed(os.path.join(OUT, "synthetic_23x17.npz"), **synthetic_case(tmp))
+    for f in ("tutorial_36x18.npz", "synthetic_23x17.npz"):
+        g = np.load(os.path.join(OUT, f))
+        print(f, {k: (g[k].shape if g[k].ndim else g[k].item()) for k in g.files})
+
+
+if __name__ == "__main__":
+    main()

@@ -48,7 +48,7 @@ int check_global_args(mdc_ens* e, mdc_obs* o, const char* who) {
   if (e->own_nx != e->nx || e->own_ny != e->ny || e->gnx != e->nx || e->gny != e->ny)
     MDC_FAIL(ctx, MDC_ERR_UNSUPPORTED, "%s: the global (non-localised) filters do not shard; use one GPU", who);
   if (o->P <= 0) MDC_FAIL(ctx, MDC_ERR_INVALID, "%s: no observations", who);
-  if (e->k > 128) MDC_FAIL(ctx, MDC_ERR_UNSUPPORTED, "%s: k > 128", who);
+  if (e->k > 128 || e->k < 2) MDC_FAIL(ctx, MDC_ERR_UNSUPPORTED, "%s: needs 2 <= k <= 128 members", who);
   return MDC_OK;
 }
 

@@ -130,7 +130,7 @@ int mdc_ctx_flush_l2(mdc_ctx* ctx) {
 int mdc_ens_create(mdc_ctx* ctx, int nx, int ny, int nz, int k, mdc_ens** out) {
   if (!ctx || !out) return MDC_ERR_INVALID;
   *out = nullptr;
-  if (nx <= 0 || ny <= 0 || nz <= 0 || k <= 1) MDC_FAIL(ctx, MDC_ERR_INVALID, "mdc_ens_create: bad dims %d %d %d k=%d", nx, ny, nz, k);
+  if (nx <= 0 || ny <= 0 || nz <= 0 || k < 1) MDC_FAIL(ctx, MDC_ERR_INVALID, "mdc_ens_create: bad dims %d %d %d k=%d", nx, ny, nz, k);
   MDC_CUDA(ctx, cudaSetDevice(ctx->device));
   mdc_ens* e = new (std::nothrow) mdc_ens();
   if (!e) MDC_FAIL(ctx, MDC_ERR_INVALID, "out of host memory");
@@ -593,6 +593,7 @@ static int letkf_launch(mdc_ens* e, mdc_obs* o, const mdc_letkf_params* p, const
   mdc_ctx* ctx = e->ctx;
   const int k = e->k;
   if (k > 128) MDC_FAIL(ctx, MDC_ERR_UNSUPPORTED, "letkf: k=%d > 128 members not supported", k);
+  if (k < 2) MDC_FAIL(ctx, MDC_ERR_INVALID, "letkf: needs at least 2 members");
   if (p->mode < 0 || p->mode > 2) MDC_FAIL(ctx, MDC_ERR_INVALID, "letkf: bad mode");
   if (!(p->inflation > 0.0)) MDC_FAIL(ctx, MDC_ERR_INVALID, "letkf: inflation must be > 0");
   const size_t smem = lk_smem_bytes(k, p->mode);

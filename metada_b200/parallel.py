@@ -173,10 +173,15 @@ class SlabLetkf:
             t0 = time.perf_counter()
             self.ens.upload_ptrs(0, ptrs)
             self.set_observations(obs_all)
+            self.ctx.sync()
+            t1 = time.perf_counter()
             self.analyse(params, dist)
+            t2 = time.perf_counter()
             self.ens.download_ptrs(0, ptrs)   # synchronises
             mean = self.ens.mean()            # analysis mean read back (LETKF.hpp:116)
             dt = time.perf_counter() - t0
+            phases = {"upload_ms": 1e3 * (t1 - t0), "analyse_ms": 1e3 * (t2 - t1),
+                      "download_ms": 1e3 * (t0 + dt - t2)}
             if dist is not None:
                 tt = torch.tensor([dt], dtype=torch.float64, device="cuda")
                 dist.all_reduce(tt, op=dist.ReduceOp.MAX)
@@ -188,7 +193,7 @@ class SlabLetkf:
         tot = float(sum(times))
         return {"value": G * len(times) / tot, "unit": "columns/s",
                 "h2d_bytes_per_step": int(need + self.h2d_obs_bytes), "d2h_bytes_per_step": int(need + n_loc * 8),
-                "ms_per_step": 1e3 * tot / len(times), "steps": len(times),
+                "ms_per_step": 1e3 * tot / len(times), "steps": len(times), "phases_last_step": phases,
                 "note": "pinned host members -> mdc_ens_upload_members -> mdc_letkf_analyse -> "
                         "mdc_ens_download_members + mdc_ens_mean, host wall clock, max over ranks"}
 

@@ -1,0 +1,152 @@
+"""The C++ host layer: the reference's own adapters/concepts instantiated with CudaBackendTag
+(metada_b200/host), driven like the reference's `letkf/etkf/enkf <config>` applications with the
+reference's config schema and text file formats.  Binaries are prebuilt by __graft_entry__.build()
+in the build container (they need the reference's headers to compile) and travel to the GPU box."""
+import json
+import os
+import struct
+import subprocess
+
+import numpy as np
+import pytest
+
+from tests.common import analysis_errors
+from tests.test_oracle_vs_reference import CASES, load
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+BUILD = os.path.join(ROOT, "metada_b200", "host", "_build")
+
+
+def _need(binary):
+    path = os.path.join(BUILD, binary)
+    if not os.path.exists(path):
+        pytest.fail(f"{path} missing: run __graft_entry__.build() where /root/reference is available")
+    return path
+
+
+def write_case(g, tmp, mode, extra=None):
+    """Simple-backend text formats (SimpleState.hpp:248-263, GridObservation.hpp:401-476) + JSON config."""
+    k, ny, nx = int(g["k"]), int(g["ny"]), int(g["nx"])
+    members = []
+    for m in range(k):
+        p = os.path.join(tmp, f"ens_{m}.txt")
+        with open(p, "w") as f:
+            for y in range(ny):
+                f.write(" ".join(repr(float(v)) for v in g["X"][m, 0, y]) + "\n")
+        members.append({"state": {"variables": "simple", "file": p}})
+    op = os.path.join(tmp, "obs.txt")
+    with open(op, "w") as f:
+        f.write("-" * 80 + "\nTime Z   Y   X   ZNU      XLONG_U    XLAT_U     Simple\n" + "-" * 80 + "\n")
+        for i in range(int(g["P"])):
+            f.write(f"0 {int(g['oz'][i])} {int(g['oy'][i])} {int(g['ox'][i])} 0.5 0.0 0.0 {float(g['yo'][i])!r}\n")
+    analysis = {"algorithm": "letkf", "inflation": float(np.float32(g["inflation"])), "localization_radius": float(g["radius"]),
+                "inflation_method": "multiplicative", "format": "txt", "mode": mode,
+                "output_base_file": os.path.join(tmp, "analysis")}
+    analysis.update(extra or {})
+    cfg = {"logger": {"app_name": "test", "level": "error", "color": False, "console": False},
+           "geometry": {"x_dim": nx, "y_dim": ny},
+           "ensemble": {"members": members},
+           "observations": {"types": [{"obs_A": {"if_use": True, "file": op, "coordinate": "grid",
+                                                 "variables": [{"simple": {"if_use": True, "error": float(g["err_cfg"]), "missing_value": -999.0}}]}}]},
+           "obs_operator": {}, "analysis": analysis}
+    cp = os.path.join(tmp, "cfg.json")
+    json.dump(cfg, open(cp, "w"))
+    return cp
+
+
+def read_dump(path, ny, nx):
+    b = open(path, "rb").read()
+    k, n = struct.unpack_from("<qq", b, 0)
+    return np.frombuffer(b, dtype="<f8", offset=16).reshape(k, 1, ny, nx)
+
+
+def test_driver_without_gpu_fails_loudly_no_cpu_fallback(tmp_path):
+    import shutil
+    if shutil.which("nvidia-smi") and subprocess.run(["nvidia-smi", "-L"], capture_output=True).returncode == 0:
+        pytest.skip("a GPU is present")
+    exe = _need("letkf_cuda")
+    g = load(CASES[1])
+    cfg = write_case(g, str(tmp_path), "ref_compat")
+    r = subprocess.run([exe, cfg], capture_output=True, text=True)
+    assert r.returncode == 1
+    assert "no usable CUDA device" in r.stderr and "no CPU fallback" in r.stderr
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", CASES)
+def test_letkf_driver_matches_reference_snapshot(tmp_path, name):
+    exe = _need("letkf_cuda")
+    g = load(name)
+    cfg = write_case(g, str(tmp_path), "ref_compat")
+    dump = str(tmp_path / "xa.bin")
+    r = subprocess.run([exe, cfg, "--dump", dump], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr + r.stdout
+    Xa = read_dump(dump, int(g["ny"]), int(g["nx"]))
+    em, ep = analysis_errors(Xa, g["Xa_letkf_snapshot"])
+    assert em < 1e-10 and ep < 1e-10, (em, ep)
+    # saveEnsemble(): <base>_mean.txt and <base>_member_<i>.txt in the Simple text format (6 decimals)
+    mean_txt = np.loadtxt(str(tmp_path / "analysis_mean.txt"))
+    assert mean_txt.shape == (int(g["ny"]), int(g["nx"]))
+    assert np.abs(mean_txt - g["mean_letkf_snapshot"]).max() < 1e-6
+    m3 = np.loadtxt(str(tmp_path / "analysis_member_3.txt"))
+    assert np.abs(m3 - g["Xa_letkf_snapshot"][3, 0]).max() < 1e-6
+
+
+@pytest.mark.gpu
+def test_etkf_and_enkf_drivers_match_reference(tmp_path):
+    g = load(CASES[1])
+    d1 = tmp_path / "etkf"; d1.mkdir()
+    cfg = write_case(g, str(d1), "ref_compat")
+    dump = str(d1 / "xa.bin")
+    r = subprocess.run([_need("etkf_cuda"), cfg, "--dump", dump], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr + r.stdout
+    em, ep = analysis_errors(read_dump(dump, int(g["ny"]), int(g["nx"])), g["Xa_etkf"])
+    assert em < 1e-10 and ep < 1e-10, (em, ep)
+    d2 = tmp_path / "enkf"; d2.mkdir()
+    zf = str(d2 / "Z.bin")
+    np.ascontiguousarray(g["enkf_Z"], dtype="<f8").tofile(zf)
+    cfg = write_case(g, str(d2), "ref_compat", {"perturbation_file": zf})
+    dump = str(d2 / "xa.bin")
+    r = subprocess.run([_need("enkf_cuda"), cfg, "--dump", dump], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr + r.stdout
+    em, ep = analysis_errors(read_dump(dump, int(g["ny"]), int(g["nx"])), g["Xa_enkf"])
+    assert em < 1e-10 and ep < 1e-9, (em, ep)
+    assert "EnKF diagnostics" in r.stdout
+
+
+@pytest.mark.gpu
+def test_letkf_driver_canonical_3d(tmp_path):
+    """z_dim > 1 through the drivers: canonical mode against the oracle."""
+    from metada_b200 import synthetic as syn
+    from oracle import orc
+    nx, ny, nz, k, P = 14, 11, 3, 8, 60
+    X = syn.ensemble(k, nx, ny, nz, seed=77)
+    o = syn.observations(P, nx, ny, nz, seed=78, sigma=0.25)
+    tmp = str(tmp_path)
+    members = []
+    for m in range(k):
+        p = os.path.join(tmp, f"ens_{m}.txt")
+        np.savetxt(p, X[m].reshape(nz * ny, nx), fmt="%.17g")
+        members.append({"state": {"variables": "simple", "file": p}})
+    op = os.path.join(tmp, "obs.txt")
+    with open(op, "w") as f:
+        f.write("-" * 80 + "\nTime Z   Y   X   ZNU      XLONG_U    XLAT_U     Simple\n" + "-" * 80 + "\n")
+        for i in range(P):
+            f.write(f"0 {int(o['z'][i])} {int(o['y'][i])} {int(o['x'][i])} 0.5 0.0 0.0 {float(o['value'][i])!r}\n")
+    cfg = {"logger": {"app_name": "t", "level": "error", "color": False, "console": False},
+           "geometry": {"x_dim": nx, "y_dim": ny, "z_dim": nz}, "ensemble": {"members": members},
+           "observations": {"types": [{"obs_A": {"if_use": True, "file": op, "coordinate": "grid",
+                                                 "variables": [{"simple": {"if_use": True, "error": 0.25, "missing_value": -999.0}}]}}]},
+           "obs_operator": {},
+           "analysis": {"inflation": 1.0, "localization_radius": 4.0, "format": "txt", "mode": "canonical",
+                        "output_base_file": os.path.join(tmp, "analysis")}}
+    cp = os.path.join(tmp, "cfg.json")
+    json.dump(cfg, open(cp, "w"))
+    dump = os.path.join(tmp, "xa.bin")
+    r = subprocess.run([_need("letkf_cuda"), cp, "--dump", dump], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr + r.stdout
+    b = open(dump, "rb").read()
+    Xa = np.frombuffer(b, dtype="<f8", offset=16).reshape(k, nz, ny, nx)
+    ref = orc.letkf(X, o["x"], o["y"], o["z"], o["value"], np.full(P, 0.25), radius=4.0, inflation=1.0)
+    em, ep = analysis_errors(Xa, ref["Xa"])
+    assert em < 1e-10 and ep < 1e-10, (em, ep)

@@ -1,0 +1,107 @@
+"""CPU, world_size > 1 over gloo: the column-sharding plumbing (metada_b200/parallel.py) -- slab
+ownership, halo plan, row exchange -- with the oracle standing in for the device kernels."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from metada_b200 import parallel as par
+from metada_b200 import synthetic as syn
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def test_slab_ownership_partitions_every_row():
+    for gny in (7, 24, 1500):
+        for world in (1, 2, 3, 4, 8):
+            if world > gny:
+                continue
+            y = np.arange(-5, gny + 5)
+            own = par.owner_of_row(y, gny, world)
+            assert own.min() == 0 and own.max() == world - 1
+            for r in range(world):
+                y0, y1 = par.slab_bounds(gny, r, world)
+                inside = np.clip(y, 0, gny - 1)
+                assert np.array_equal(own == r, (inside >= y0) & (inside < y1))
+
+
+@pytest.mark.parametrize("gny,world,reach", [(24, 2, 4), (24, 3, 5), (10, 4, 6), (1500, 8, 8)])
+def test_halo_plan_covers_every_needed_row(gny, world, reach):
+    plan = par.halo_plan(gny, world, reach)
+    for dst in range(world):
+        d0, d1 = par.slab_bounds(gny, dst, world)
+        for y in range(-3, gny + 3):
+            src = int(par.owner_of_row(y, gny, world))
+            needed = (d0 - reach <= y < d1 + reach) and src != dst
+            lo, hi = plan.get((src, dst), (0, 0))
+            assert (lo <= y < hi) == needed, (dst, y, src, lo, hi)
+
+
+def _worker(rank, world, port, nx, ny, nz, k, P, radius, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from oracle import orc
+    X = syn.ensemble(k, nx, ny, nz, seed=3)
+    o = syn.observations(P, nx, ny, nz, seed=4, sigma=0.2)
+    o["y"][:3] = [-2, ny + 1, ny - 1]              # out-of-grid obs belong to the edge slabs
+    own = par.select_own(o, ny, rank, world)
+    # the rank's own Y' rows (H on its own observations only)
+    _, _, Yp, d = orc.obs_space(X, o["x"][own], o["y"][own], o["z"][own], o["value"][own])
+    rd = k + 8
+    rows = np.concatenate([Yp, d[:, None], o["value"][own, None], o["err"][own, None], np.ones((len(own), 1)),
+                           o["x"][own, None], o["y"][own, None], o["z"][own, None], own[:, None]], axis=1)
+    plan = par.halo_plan(ny, world, int(np.floor(radius)))
+    send = {}
+    for (src, dst), (lo, hi) in plan.items():
+        if src == rank:
+            m = (o["y"][own] >= lo) & (o["y"][own] < hi)
+            send[dst] = torch.from_numpy(np.ascontiguousarray(rows[m]))
+    recv = par.exchange_rows(dist, rank, world, send, rd, torch.device("cpu"))
+    allrows = np.concatenate([rows] + [t.numpy() for t in recv]) if recv else rows
+    gid = allrows[:, k + 7].astype(np.int64)
+    assert len(np.unique(gid)) == len(gid)         # no observation delivered twice
+    # received rows must be the sender's bits
+    Yp_all = orc.obs_space(X, o["x"], o["y"], o["z"], o["value"])[2]
+    assert np.array_equal(allrows[:, :k], Yp_all[gid])
+    # analyse the rank's own columns with own + halo observations only
+    y0, y1 = par.slab_bounds(ny, rank, world)
+    cols = np.array([y * nx + x for y in range(y0, y1) for x in range(nx)], np.int64)
+    order = np.argsort(gid)
+    loc = orc.letkf(X, allrows[order, k + 4].astype(np.int32), allrows[order, k + 5].astype(np.int32),
+                    allrows[order, k + 6].astype(np.int32), allrows[order, k + 1], allrows[order, k + 2],
+                    radius=radius, cols=cols)
+    out[rank] = loc["Xa"][:, :, y0:y1, :].copy()
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_sharded_analysis_equals_single_process(world):
+    from oracle import orc
+    nx, ny, nz, k, P, radius = 18, 21, 2, 6, 90, 4.0
+    port = _free_port()
+    ctx = mp.get_context("spawn")
+    mgr = ctx.Manager()
+    out = mgr.dict()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, nx, ny, nz, k, P, radius, out)) for r in range(world)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    X = syn.ensemble(k, nx, ny, nz, seed=3)
+    o = syn.observations(P, nx, ny, nz, seed=4, sigma=0.2)
+    o["y"][:3] = [-2, ny + 1, ny - 1]
+    full = orc.letkf(X, o["x"], o["y"], o["z"], o["value"], o["err"], radius=radius)["Xa"]
+    for r in range(world):
+        y0, y1 = par.slab_bounds(ny, r, world)
+        # same observation SETS in the same (global id) order -> bit-identical
+        assert np.array_equal(out[r], full[:, :, y0:y1, :]), r

@@ -113,6 +113,10 @@ int mdc_obs_index_query_lists(mdc_obs* obs, mdc_ens* ens, double radius, const i
 /* ---- LETKF: replaces LETKF<Tag>::Analyse / updateGridPoint (LETKF.hpp:63-119, 152-243) ----- */
 enum { MDC_MODE_REF_COMPAT = 0, MDC_MODE_REF_ETKF = 1, MDC_MODE_CANONICAL = 2 };
 enum { MDC_LOC_CUTOFF = 0, MDC_LOC_GASPARI_COHN = 1 };
+/* AUTO: Newton-Schulz (GEMM-only symmetric square root) for 24 <= k <= 82, else Jacobi.
+ * JACOBI: one-block-per-column one-sided Jacobi eigen-decomposition with warp-shuffle reductions.
+ * Both give the same (unique) symmetric square-root transform to rounding. */
+enum { MDC_SOLVER_AUTO = 0, MDC_SOLVER_JACOBI = 1, MDC_SOLVER_NEWTON_SCHULZ = 2 };
 
 typedef struct {
   double radius;      /* horizontal selection radius (inclusive) = Gaspari-Cohn support       */
@@ -122,8 +126,9 @@ typedef struct {
   int loc;            /* MDC_LOC_* (CANONICAL)                                                */
   int use_R;          /* CANONICAL: 1 -> R = diag(err^2), 0 -> R = I                          */
   int max_sweeps;     /* Jacobi sweep cap (<= 0: 40)                                          */
-  double jacobi_tol;  /* stop when a sweep's max |g_p.g_q|/(|g_p||g_q|) < tol (<= 0: 1e-12)    */
-  int reserved[4];
+  double jacobi_tol;  /* stop when a sweep's max |g_p.g_q|/(|g_p||g_q|) < tol (<= 0: 1e-11)    */
+  int solver;         /* CANONICAL: how A^{-1/2} is formed -- MDC_SOLVER_*                    */
+  int reserved[3];
 } mdc_letkf_params;
 
 typedef struct {
@@ -131,7 +136,7 @@ typedef struct {
   int64_t columns;        /* analysed columns                                                 */
   int64_t sum_local_obs;  /* sum over columns of p_loc                                        */
   int32_t max_local_obs;
-  int32_t max_sweeps;     /* max Jacobi sweeps used by a column                               */
+  int32_t max_sweeps;     /* max Jacobi sweeps (or Newton-Schulz iterations) used by a column */
   int64_t sum_sweeps;
   int32_t numeric_failures;
   int32_t reserved;

@@ -1,0 +1,413 @@
+// letkf_ns.cuh -- CANONICAL column kernel with a GEMM-only symmetric square root.
+//
+// The canonical LETKF needs W = sqrt(k-1) A^{-1/2} and w = A^{-1} g for the SPD matrix
+// A = (k-1)/infl I + C.  The symmetric square root is unique, so any route to A^{-1/2} gives the
+// same transform as the eigen-decomposition W = U sqrt((k-1)/L) U^T (letkf_v2.cuh), to rounding.
+// Here it is the coupled Newton-Schulz iteration (Higham, Functions of Matrices, eq. 6.35)
+//     Y0 = cA, Z0 = I;   T = (3I - Z Y)/2,  Y <- Y T,  Z <- T Z;   Y -> (cA)^{1/2}, Z -> (cA)^{-1/2}
+// with c = 2/(lmin + b), lmin = (k-1)/infl (exact lower bound of the spectrum) and b = ||A||_F
+// (rigorous upper bound), so |1 - c lambda| < 1 for every eigenvalue.  Every iterate is a polynomial
+// in A (symmetric, commuting).  Each product is a register-tiled (TM x TM per thread on a 16 x 16
+// thread grid) k x k x k FP64 GEMM out of shared memory with conflict-free operand reads.  ~9 iterations x 3 products for the C5
+// conditioning, all dense FP64 FMA work with 25 independent accumulators per thread; no
+// rotations, shuffles or rsqrt chains, and the update needs ONE product (X' W) instead of two.
+// Used for k <= 96 (four k x k buffers must fit in shared memory); larger ensembles use the
+// Jacobi kernel.
+#pragma once
+#include "letkf_kernels.cuh"
+
+#define NS_THREADS 256
+#define NS_PCH 32
+#define NS_SELCAP 512
+#define NS_MAX_ITERS 40
+
+__device__ __forceinline__ double block_reduce(double v, bool is_max, double* red /*[9]*/) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int o = 16; o; o >>= 1) {
+    const double t = __shfl_xor_sync(0xffffffffu, v, o);
+    v = is_max ? fmax(v, t) : v + t;
+  }
+  __syncthreads();
+  if (lane == 0) red[warp] = v;
+  __syncthreads();
+  double r = red[0];
+  for (int w = 1; w < NS_THREADS / 32; ++w) r = is_max ? fmax(r, red[w]) : r + red[w];
+  return r;
+}
+
+// acc[a][b] = sum_r P[ty + 16a][r] * Q[r][tx + 16b]  -- the TRUE product P Q.  (Using P^T Q, which
+// is equal for exactly symmetric iterates, lets rounding asymmetry grow like cond(A) per step and
+// the coupled iteration diverges for cond ~ 1e5; with true products it is stable.)  The P operand
+// is a two-address broadcast per warp, the Q operand 16 consecutive doubles: conflict-free.
+template <int TM>
+__device__ __forceinline__ void ns_mm(const double* __restrict__ Pm, const double* __restrict__ Qm,
+                                      int k, int ks, int ty, int tx, double (&acc)[TM][TM]) {
+#pragma unroll
+  for (int a = 0; a < TM; ++a)
+#pragma unroll
+    for (int b = 0; b < TM; ++b) acc[a][b] = 0.0;
+  int ia[TM], ib[TM];
+#pragma unroll
+  for (int a = 0; a < TM; ++a) { ia[a] = min(ty + 16 * a, k - 1); ib[a] = min(tx + 16 * a, k - 1); }
+#pragma unroll 2
+  for (int r = 0; r < k; ++r) {
+    const double* qr = Qm + r * ks;
+    double ya[TM], yb[TM];
+#pragma unroll
+    for (int a = 0; a < TM; ++a) { ya[a] = Pm[ia[a] * ks + r]; yb[a] = qr[ib[a]]; }
+#pragma unroll
+    for (int a = 0; a < TM; ++a)
+#pragma unroll
+      for (int b = 0; b < TM; ++b) acc[a][b] = fma(ya[a], yb[b], acc[a][b]);
+  }
+}
+
+template <int TM>
+__global__ void __launch_bounds__(NS_THREADS) letkf_ns_kernel(ColParams P, int lch) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  constexpr int NT = NS_THREADS;
+  constexpr int TL = 3;
+  const int k = P.k, ks = k | 1, nz = P.nz;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = NT / 32;
+  const size_t msz = (size_t)k * ks;
+  double* Bf[4];
+  Bf[0] = reinterpret_cast<double*>(smem_raw);
+  Bf[1] = Bf[0] + msz; Bf[2] = Bf[1] + msz; Bf[3] = Bf[2] + msz;
+  double* gvec = Bf[3] + msz;
+  double* wa = gvec + k;
+  double* tv = wa + k;
+  double* xm = tv + k;                                         // [lch]
+  double* ml = xm + lch;                                       // [lch]
+  double* red = ml + lch;                                      // [16]
+  double* sel_w = red + 16;                                    // [NS_SELCAP]
+  int* sel_pos = reinterpret_cast<int*>(sel_w + NS_SELCAP);    // [NS_SELCAP]
+  int* warp_cnt = sel_pos + NS_SELCAP;                         // [32]
+  int* s_int = warp_cnt + 32;                                  // [4]
+  // staging areas alias matrix buffers that are idle in that phase
+  double* Ych = Bf[2];                                         // [NS_PCH][k] + dw, phase 1
+  double* dw = Ych + (size_t)NS_PCH * k;
+
+  const double km1 = (double)(k - 1);
+  const bool per_level = P.radius_v > 0.0;
+  const int nxf = per_level ? nz : 1;
+  const int R = (int)floor(P.radius);
+  const long long ncols = P.cols ? P.ncols : (long long)P.own_nx * P.own_ny;
+  const int ty = tid >> 4, tx = tid & 15;
+
+  for (long long ci = blockIdx.x; ci < ncols; ci += gridDim.x) {
+    int lx, ly;
+    if (P.cols) { long long c = P.cols[ci]; lx = (int)(c % P.nx); ly = (int)(c / P.nx); }
+    else { lx = (int)(ci % P.own_nx); ly = (int)(ci / P.own_nx); }
+    const int gx = P.gx0 + lx, gy = P.gy0 + ly;
+    const long long col = (long long)ly * P.nx + lx;
+    double* Xg = P.X + col * nz * k;
+    int col_iters = 0;
+    long long col_npl = 0;
+    bool col_fail = false;
+
+    for (int lt = 0; lt < nxf; ++lt) {
+      // ---------------- 1. selection, gather, register-tiled C += Yw^T Yw, g += Yw^T dw
+      double acc[TM][TM];
+#pragma unroll
+      for (int a = 0; a < TM; ++a)
+#pragma unroll
+        for (int b = 0; b < TM; ++b) acc[a][b] = 0.0;
+      double gacc = 0.0;
+      if (tid == 0) s_int[0] = 0;
+      __syncthreads();
+      int npl = 0;
+      int cy0 = 0, cy1 = -1;
+      if (P.radius >= 0.0) index_cy_range(P.iv, gy, R, cy0, cy1);
+      int cy = cy0, rb = 0, re = 0;
+      bool rows_left = (cy <= cy1);
+      if (rows_left) index_row_range(P.iv, gx, R, cy, rb, re);
+      while (true) {
+        const bool have_batch = rows_left;
+        if (have_batch) {
+          const int a = rb + tid;
+          bool sel = false;
+          double rho = 1.0;
+          if (a < re) {
+            double dist;
+            sel = index_within(gx, gy, P.iv.sx[a], P.iv.sy[a], P.radius, &dist);
+            double dv = 0.0;
+            if (sel && per_level) {
+              dv = fabs((double)(P.iv.sz[a] - lt));
+              sel = dv <= P.radius_v;
+            }
+            if (sel && P.loc == MDC_LOC_GASPARI_COHN) {
+              rho = lk_gaspari_cohn(dist / (0.5 * P.radius));
+              if (per_level) rho *= lk_gaspari_cohn(dv / (0.5 * P.radius_v));
+            }
+          }
+          const unsigned bal = __ballot_sync(0xffffffffu, sel);
+          if (lane == 0) warp_cnt[warp] = __popc(bal);
+          __syncthreads();
+          int off = s_int[0];
+          for (int w = 0; w < warp; ++w) off += warp_cnt[w];
+          if (sel) {
+            const int pos = off + __popc(bal & ((1u << lane) - 1u));
+            sel_pos[pos] = a;
+            sel_w[pos] = rho;
+          }
+          __syncthreads();
+          if (tid == 0) {
+            int tot = 0;
+            for (int w = 0; w < nw; ++w) tot += warp_cnt[w];
+            s_int[0] += tot;
+          }
+          rb += NT;
+          if (rb >= re) {
+            ++cy;
+            rows_left = (cy <= cy1);
+            if (rows_left) index_row_range(P.iv, gx, R, cy, rb, re);
+          }
+          __syncthreads();
+        }
+        const int nsel = s_int[0];
+        if (have_batch && rows_left && nsel <= NS_SELCAP - NT) continue;
+        for (int c0 = 0; c0 < nsel; c0 += NS_PCH) {
+          const int rows = min(NS_PCH, nsel - c0);
+          for (int r = warp; r < rows; r += nw) {
+            const int orow = P.iv.sorted_row[sel_pos[c0 + r]];
+            const double e_ = P.err[orow];
+            const double ivar = P.valid[orow] ? 1.0 / (e_ * e_) : 0.0;
+            const double sq = sqrt(sel_w[c0 + r] * (P.use_R ? ivar : 1.0));
+            const double* src = P.Yp + (long long)orow * k;
+            for (int j = lane; j < k; j += 32) Ych[r * k + j] = sq * src[j];
+            if (lane == 0) dw[r] = sq * P.d[orow];
+          }
+          __syncthreads();
+          for (int r = 0; r < rows; ++r) {
+            double ya[TM], yb[TM];
+#pragma unroll
+            for (int a = 0; a < TM; ++a) {
+              const int ia = ty + 16 * a, ib = tx + 16 * a;
+              ya[a] = ia < k ? Ych[r * k + ia] : 0.0;
+              yb[a] = ib < k ? Ych[r * k + ib] : 0.0;
+            }
+#pragma unroll
+            for (int a = 0; a < TM; ++a)
+#pragma unroll
+              for (int b = 0; b < TM; ++b) acc[a][b] = fma(ya[a], yb[b], acc[a][b]);
+            if (tid < k) gacc = fma(Ych[r * k + tid], dw[r], gacc);
+          }
+          __syncthreads();
+        }
+        npl += nsel;
+        if (tid == 0) s_int[0] = 0;
+        __syncthreads();
+        if (!rows_left) break;
+      }
+      if (lt == 0) col_npl = npl;
+
+      // ---------------- 2. Z = (cA)^{-1/2} by coupled Newton-Schulz
+      double* Ym = Bf[0];
+      double* Zm = Bf[1];
+      double* Tm = Bf[2];
+      double* Sm = Bf[3];
+      double cscale = 1.0;
+      bool ok = true;
+      if (npl > 0) {
+        const double shift = km1 / P.inflation;
+        double fro = 0.0;
+#pragma unroll
+        for (int a = 0; a < TM; ++a)
+#pragma unroll
+          for (int b = 0; b < TM; ++b) {
+            const int ia = ty + 16 * a, ib = tx + 16 * b;
+            if (ia < k && ib < k) {
+              acc[a][b] += (ia == ib ? shift : 0.0);
+              fro = fma(acc[a][b], acc[a][b], fro);
+            }
+          }
+        fro = sqrt(block_reduce(fro, false, red));
+        cscale = 2.0 / (shift + fro);
+        // Y0 = cA; first iteration in closed form (Z0 = I): T = 1.5 I - 0.5 Y0, Z1 = T
+#pragma unroll
+        for (int a = 0; a < TM; ++a)
+#pragma unroll
+          for (int b = 0; b < TM; ++b) {
+            const int ia = ty + 16 * a, ib = tx + 16 * b;
+            if (ia < k && ib < k) {
+              const double y = cscale * acc[a][b];
+              Ym[ia * ks + ib] = y;
+              const double t = (ia == ib ? 1.5 : 0.0) - 0.5 * y;
+              Tm[ia * ks + ib] = t;
+              Zm[ia * ks + ib] = t;
+            }
+          }
+        if (tid < k) gvec[tid] = gacc;
+        __syncthreads();
+        ns_mm<TM>(Ym, Tm, k, ks, ty, tx, acc);          // Y1 = Y0 T
+#pragma unroll
+        for (int a = 0; a < TM; ++a)
+#pragma unroll
+          for (int b = 0; b < TM; ++b) {
+            const int ia = ty + 16 * a, ib = tx + 16 * b;
+            if (ia < k && ib < k) Sm[ia * ks + ib] = acc[a][b];
+          }
+        __syncthreads();
+        { double* t = Ym; Ym = Sm; Sm = t; }              // Y = Y1, S = free
+        int it = 1;
+        bool done = false;
+        for (; it < NS_MAX_ITERS && !done; ++it) {
+          ns_mm<TM>(Zm, Ym, k, ks, ty, tx, acc);        // Z Y
+          double r = 0.0;
+#pragma unroll
+          for (int a = 0; a < TM; ++a)
+#pragma unroll
+            for (int b = 0; b < TM; ++b) {
+              const int ia = ty + 16 * a, ib = tx + 16 * b;
+              if (ia < k && ib < k) {
+                const double e = (ia == ib ? 1.0 : 0.0) - acc[a][b];
+                r = fmax(r, fabs(e));
+                Tm[ia * ks + ib] = (ia == ib ? 1.0 : 0.0) + 0.5 * e;     // (3I - ZY)/2
+              }
+            }
+          r = block_reduce(r, true, red);                 // also publishes T
+          done = r < 1e-7;                                 // error after this update ~ r^2
+          if (!(r < 1.5)) { ok = false; break; }           // cannot happen for SPD input; NaN guard
+          if (!done) {
+            ns_mm<TM>(Ym, Tm, k, ks, ty, tx, acc);      // Y <- Y T
+#pragma unroll
+            for (int a = 0; a < TM; ++a)
+#pragma unroll
+              for (int b = 0; b < TM; ++b) {
+                const int ia = ty + 16 * a, ib = tx + 16 * b;
+                if (ia < k && ib < k) Sm[ia * ks + ib] = acc[a][b];
+              }
+          }
+          ns_mm<TM>(Tm, Zm, k, ks, ty, tx, acc);        // Z <- T Z
+          __syncthreads();                                 // everyone is done reading Y, Z
+          double* Zdst = done ? Ym : Ym;                   // old Y buffer is free once Y T is in S
+#pragma unroll
+          for (int a = 0; a < TM; ++a)
+#pragma unroll
+            for (int b = 0; b < TM; ++b) {
+              const int ia = ty + 16 * a, ib = tx + 16 * b;
+              if (ia < k && ib < k) Zdst[ia * ks + ib] = acc[a][b];
+            }
+          __syncthreads();
+          { double* oldZ = Zm; Zm = Ym; Ym = Sm; Sm = oldZ; }   // Z = new, Y = S, S = old Z
+        }
+        if (!done) ok = false;
+        col_iters = max(col_iters, it);
+        // w = c Z (Z g)
+        if (ok) {
+          for (int a = warp; a < k; a += nw) {
+            double s = 0.0;
+            for (int b = lane; b < k; b += 32) s += Zm[a * ks + b] * gvec[b];
+            s = warp_sum(s);
+            if (lane == 0) tv[a] = s;
+          }
+          __syncthreads();
+          for (int a = warp; a < k; a += nw) {
+            double s = 0.0;
+            for (int b = lane; b < k; b += 32) s += Zm[a * ks + b] * tv[b];
+            s = warp_sum(s);
+            if (lane == 0) wa[a] = cscale * s;
+          }
+          __syncthreads();
+        }
+      }
+      const double sW = sqrt(km1 * cscale);
+      if (!ok) col_fail = true;
+
+      if (P.W_out && P.w_col == col && lt == 0) {
+        for (int e = tid; e < k * k; e += NT) {
+          const int j = e / k, i = e - j * k;
+          double vv;
+          if (npl == 0) vv = (i == j) ? sqrt(P.inflation) : 0.0;
+          else if (!ok) vv = nan("");
+          else vv = wa[j] + sW * Zm[j * ks + i];
+          P.W_out[e] = vv;
+        }
+        __syncthreads();
+      }
+
+      // ---------------- 3. X_a = xbar + X' w + sW X' Z, level chunks of lch (staged in idle buffers)
+      double* Xt = (Zm == Bf[0] || Zm == Bf[1]) ? Bf[2] : Bf[0];
+      double* To = Xt + (size_t)lch * k;   // lch*k*2 <= 2 buffers is checked on the host
+      const int lev_b = per_level ? lt : 0, lev_e = per_level ? lt + 1 : nz;
+      if (ok) {
+        for (int l0 = lev_b; l0 < lev_e; l0 += lch) {
+          const int nl = min(lch, lev_e - l0);
+          for (int e = tid; e < nl * k; e += NT) Xt[e] = Xg[(long long)l0 * k + e];
+          __syncthreads();
+          for (int l = warp; l < nl; l += nw) {
+            double s = 0.0;
+            for (int j = lane; j < k; j += 32) s += Xt[l * k + j];
+            s = warp_sum(s) / (double)k;
+            double m = 0.0;
+            for (int j = lane; j < k; j += 32) {
+              const double xp = Xt[l * k + j] - s;
+              Xt[l * k + j] = xp;
+              if (npl > 0) m = fma(xp, wa[j], m);
+            }
+            m = warp_sum(m);
+            if (lane == 0) { xm[l] = s; ml[l] = s + m; }
+          }
+          __syncthreads();
+          if (npl == 0) {
+            const double f = sqrt(P.inflation);
+            for (int e = tid; e < nl * k; e += NT) To[e] = xm[e / k] + Xt[e] * f;
+          } else {
+            const int nlt = (nl + TL - 1) / TL;
+            for (int lt2 = ty; lt2 < nlt; lt2 += 16) {
+              double o[TL][TM];
+#pragma unroll
+              for (int a = 0; a < TL; ++a)
+#pragma unroll
+                for (int b = 0; b < TM; ++b) o[a][b] = 0.0;
+              for (int j = 0; j < k; ++j) {
+                double xv[TL], zv[TM];
+#pragma unroll
+                for (int a = 0; a < TL; ++a) { const int l = lt2 + nlt * a; xv[a] = l < nl ? Xt[l * k + j] : 0.0; }
+#pragma unroll
+                for (int b = 0; b < TM; ++b) { const int i = tx + 16 * b; zv[b] = i < k ? Zm[j * ks + i] : 0.0; }
+#pragma unroll
+                for (int a = 0; a < TL; ++a)
+#pragma unroll
+                  for (int b = 0; b < TM; ++b) o[a][b] = fma(xv[a], zv[b], o[a][b]);
+              }
+#pragma unroll
+              for (int a = 0; a < TL; ++a)
+#pragma unroll
+                for (int b = 0; b < TM; ++b) {
+                  const int l = lt2 + nlt * a, i = tx + 16 * b;
+                  if (l < nl && i < k) To[l * k + i] = ml[l] + sW * o[a][b];
+                }
+            }
+          }
+          __syncthreads();
+          for (int e = tid; e < nl * k; e += NT) Xg[(long long)l0 * k + e] = To[e];
+          if (P.mean_out) {
+            for (int l = warp; l < nl; l += nw) {
+              double s = 0.0;
+              for (int j = lane; j < k; j += 32) s += To[l * k + j];
+              s = warp_sum(s);
+              if (lane == 0) P.mean_out[col * nz + l0 + l] = s * (1.0 / (double)k);
+            }
+          }
+          __syncthreads();
+        }
+      }
+    }  // lt
+    if (tid == 0) {
+      atomicAdd((unsigned long long*)&P.stats[0], (unsigned long long)col_npl);
+      atomicMax(&P.stats[1], col_npl);
+      atomicAdd((unsigned long long*)&P.stats[2], (unsigned long long)col_iters);
+      atomicMax(&P.stats[3], (long long)col_iters);
+      if (col_fail) atomicAdd((unsigned long long*)&P.stats[4], 1ull);
+      atomicAdd((unsigned long long*)&P.stats[5], 1ull);
+    }
+  }
+}
+
+static size_t ns_smem_bytes(int k, int lch) {
+  const size_t ks = (size_t)(k | 1);
+  const size_t dbl = 4 * (size_t)k * ks + 3 * (size_t)k + 2 * (size_t)lch + 16 + NS_SELCAP;
+  return dbl * 8 + (size_t)NS_SELCAP * 4 + 32 * 4 + 4 * 4 + 16;
+}

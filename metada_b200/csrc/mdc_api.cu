@@ -13,6 +13,7 @@
 #include "hx_kernels.cuh"
 #include "index_kernels.cuh"
 #include "letkf_kernels.cuh"
+#include "letkf_ns.cuh"
 #include "letkf_v2.cuh"
 #include "mdc_internal.cuh"
 
@@ -615,6 +616,29 @@ static int letkf_launch(mdc_ens* e, mdc_obs* o, const mdc_letkf_params* p, const
   cp.W_out = dW; cp.w_col = w_col;
   cp.cols = dcols; cp.ncols = ncols;
   const long long total_cols = dcols ? ncols : (long long)e->own_nx * e->own_ny;
+  if (p->mode == MDC_MODE_CANONICAL && p->solver == MDC_SOLVER_NEWTON_SCHULZ && (k < 24 || k > 82))
+    MDC_FAIL(ctx, MDC_ERR_UNSUPPORTED, "letkf: the Newton-Schulz solver supports 24 <= k <= 82 (k=%d)", k);
+  if (p->mode == MDC_MODE_CANONICAL && p->solver != MDC_SOLVER_JACOBI && k >= 24 && k <= 82 && !getenv("MDC_LETKF_V1")) {
+    // GEMM-only symmetric square root (letkf_ns.cuh): four k x k buffers, one CTA per SM
+    const int lch = std::min(e->nz, std::min(k, 32));
+    const size_t smem3 = ns_smem_bytes(k, lch);
+    if ((int)smem3 <= ctx->max_smem_optin) {
+      auto launch3 = [&](auto kern) -> int {
+        MDC_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3));
+        int occ = 1;
+        MDC_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, NS_THREADS, smem3));
+        if (occ < 1) occ = 1;
+        int grid = (int)std::max<long long>(1, std::min<long long>(total_cols, (long long)ctx->sm_count * occ));
+        kern<<<grid, NS_THREADS, smem3, ctx->stream>>>(cp, lch);
+        MDC_LAUNCH_CHECK(ctx);
+        return MDC_OK;
+      };
+      if (k <= 32) return launch3(letkf_ns_kernel<2>);
+      if (k <= 48) return launch3(letkf_ns_kernel<3>);
+      if (k <= 64) return launch3(letkf_ns_kernel<4>);
+      return launch3(letkf_ns_kernel<5>) ;
+    }
+  }
   if (p->mode == MDC_MODE_CANONICAL && !getenv("MDC_LETKF_V1")) {
     // optimised canonical kernel: level-chunk sized so that two CTAs fit one SM when k allows
     const int lchmax = std::max(4, 2560 / k);

@@ -192,3 +192,31 @@ def test_errors_are_reported_not_swallowed(ctx):
     with pytest.raises(mb.MdcError):
         capi.letkf_analyse(ens, obs, capi.make_params(3.0, -1.0))
     ens.close(); obs.close()
+
+
+@pytest.mark.parametrize("solver", [mb.SOLVER_JACOBI, mb.SOLVER_NEWTON_SCHULZ])
+@pytest.mark.parametrize("k,nz,loc", [(24, 2, 1), (40, 3, 1), (64, 1, 0), (80, 2, 1)])
+def test_canonical_solvers_match_oracle(ctx, solver, k, nz, loc):
+    """Both routes to the symmetric square root (Jacobi eigen-decomposition, Newton-Schulz) against
+    the oracle's eigen-decomposition: the transform is unique, so both must agree to rounding."""
+    X, o = make_case(16, 14, nz, k, 180, seed=100 + k, invalid_frac=0.03)
+    ens, obs = _setup(ctx, X, o)
+    st = capi.letkf_analyse(ens, obs, capi.make_params(5.0, 1.08, mb.MODE_CANONICAL, loc, solver=solver))
+    ref = orc.letkf(X, o["x"], o["y"], o["z"], o["value"], o["err"], o["valid"], radius=5.0, inflation=1.08, loc=loc)
+    em, ep = analysis_errors(ens.download(), ref["Xa"])
+    assert em < TOL and ep < TOL, (solver, k, em, ep)
+    assert st["numeric_failures"] == 0 and st["max_sweeps"] > 0
+    ens.close(); obs.close()
+
+
+def test_newton_schulz_ill_conditioned_and_vertical(ctx):
+    """Tiny obs error (cond(A) ~ 1e5) and per-level transforms through the Newton-Schulz path."""
+    X, o = make_case(12, 12, 4, 32, 150, seed=21, sigma=0.002)
+    o["err"][:] = 0.002
+    ens, obs = _setup(ctx, X, o)
+    p = capi.make_params(4.0, 1.0, mb.MODE_CANONICAL, mb.LOC_GASPARI_COHN, radius_v=2.0, solver=mb.SOLVER_NEWTON_SCHULZ)
+    st = capi.letkf_analyse(ens, obs, p)
+    ref = orc.letkf(X, o["x"], o["y"], o["z"], o["value"], o["err"], radius=4.0, radius_v=2.0)
+    em, ep = analysis_errors(ens.download(), ref["Xa"])
+    assert em < 1e-9 and ep < 1e-9, (em, ep, st)
+    ens.close(); obs.close()

@@ -35,10 +35,11 @@ def main():
     for name, nx, ny, nz, k, P, r in cases:
         ens = mb.Ensemble(ctx, nx, ny, nz, k)
         o = syn.observations(P, nx, ny, nz, seed=42)
-        for mode, mname in ((mb.MODE_CANONICAL, "canonical"), (mb.MODE_REF_ETKF, "ref_etkf"), (mb.MODE_REF_COMPAT, "ref_compat")):
+        for mode, mname, solver in ((mb.MODE_CANONICAL, "canonical-ns", 0), (mb.MODE_CANONICAL, "canonical-jacobi", 1),
+                                    (mb.MODE_REF_ETKF, "ref_etkf", 0), (mb.MODE_REF_COMPAT, "ref_compat", 0)):
             ens.fill_synthetic(1000)
             obs = mb.Observations(ctx, o["x"], o["y"], o["z"], o["value"], o["err"], o["valid"])
-            p = capi.make_params(r, 1.0, mode, mb.LOC_GASPARI_COHN)
+            p = capi.make_params(r, 1.0, mode, mb.LOC_GASPARI_COHN, solver=solver)
             t0 = time.time()
             st = capi.letkf_analyse(ens, obs, p)
             wall = time.time() - t0

@@ -21,6 +21,14 @@
 #define NS_SELCAP 512
 #define NS_MAX_ITERS 40
 
+// Row stride of the k x k buffers: even (16-byte aligned rows for 128-bit loads) with ks/2 odd, so
+// the four consecutive rows a warp reads P[row][r..r+1] from land in four different bank groups.
+__host__ __device__ inline int ns_stride(int k) {
+  int ks = (k + 1) & ~1;
+  if (((ks >> 1) & 1) == 0) ks += 2;
+  return ks;
+}
+
 __device__ __forceinline__ double block_reduce(double v, bool is_max, double* red /*[9]*/) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
@@ -36,31 +44,91 @@ __device__ __forceinline__ double block_reduce(double v, bool is_max, double* re
   return r;
 }
 
-// acc[a][b] = sum_r P[ty + 16a][r] * Q[r][tx + 16b]  -- the TRUE product P Q.  (Using P^T Q, which
-// is equal for exactly symmetric iterates, lets rounding asymmetry grow like cond(A) per step and
-// the coupled iteration diverges for cond ~ 1e5; with true products it is stable.)  The P operand
-// is a two-address broadcast per warp, the Q operand 16 consecutive doubles: conflict-free.
+// GEMM micro-kernel of the iteration: the TRUE product P Q (using P^T Q, equal for exactly
+// symmetric iterates, lets rounding asymmetry grow like cond(A) per step and the coupled iteration
+// diverges for cond ~ 1e5; with true products it is stable).
+// Thread grid 16 (ty) x 16 (tx): thread owns rows ty + 16a (a < TM) and TM columns laid out as
+// TM/2 adjacent PAIRS 32p + 2tx + {0,1} plus, for odd TM, the single column 32 (TM/2) + tx, so the
+// tile is exactly TM x TM (k = 80: 5 x 5, no padding work) and, with an EVEN row stride,
+//   P[row][r..r+1]        is one LDS.128 (two addresses per warp: broadcast),
+//   Q[r][32p + 2tx ..+1]  is one LDS.128 (16 lanes x 16 B contiguous),
+// i.e. per two r-steps TM + 2 (TM/2) 128-bit (+ 2 (TM&1) 64-bit) loads feed 2 TM^2 FMAs.
+template <int TM>
+__device__ __forceinline__ int ns_col(int b, int tx) {
+  return (b < 2 * (TM / 2)) ? 32 * (b >> 1) + 2 * tx + (b & 1) : 32 * (TM / 2) + tx;
+}
+
 template <int TM>
 __device__ __forceinline__ void ns_mm(const double* __restrict__ Pm, const double* __restrict__ Qm,
                                       int k, int ks, int ty, int tx, double (&acc)[TM][TM]) {
+  constexpr int NP = TM / 2;
+  constexpr bool ODD = (TM & 1) != 0;
 #pragma unroll
   for (int a = 0; a < TM; ++a)
 #pragma unroll
     for (int b = 0; b < TM; ++b) acc[a][b] = 0.0;
-  int ia[TM], ib[TM];
+  const double* pa[TM];
 #pragma unroll
-  for (int a = 0; a < TM; ++a) { ia[a] = min(ty + 16 * a, k - 1); ib[a] = min(tx + 16 * a, k - 1); }
+  for (int a = 0; a < TM; ++a) pa[a] = Pm + min(ty + 16 * a, k - 1) * ks;
+  int qoff[NP + 1];
+#pragma unroll
+  for (int p = 0; p < NP; ++p) qoff[p] = min(32 * p + 2 * tx, ks - 2);
+  qoff[NP] = min(32 * NP + tx, ks - 1);
+  const double* q0 = Qm;
+  const int k2 = k & ~1;
 #pragma unroll 2
-  for (int r = 0; r < k; ++r) {
-    const double* qr = Qm + r * ks;
-    double ya[TM], yb[TM];
+  for (int r = 0; r < k2; r += 2) {
+    double2 pv[TM], qv0[NP + 1], qv1[NP + 1];
 #pragma unroll
-    for (int a = 0; a < TM; ++a) { ya[a] = Pm[ia[a] * ks + r]; yb[a] = qr[ib[a]]; }
+    for (int a = 0; a < TM; ++a) pv[a] = *reinterpret_cast<const double2*>(pa[a] + r);
 #pragma unroll
-    for (int a = 0; a < TM; ++a)
+    for (int p = 0; p < NP; ++p) {
+      qv0[p] = *reinterpret_cast<const double2*>(q0 + qoff[p]);
+      qv1[p] = *reinterpret_cast<const double2*>(q0 + ks + qoff[p]);
+    }
+    if (ODD) { qv0[NP].x = q0[qoff[NP]]; qv1[NP].x = q0[ks + qoff[NP]]; }
+    q0 += 2 * ks;
 #pragma unroll
-      for (int b = 0; b < TM; ++b) acc[a][b] = fma(ya[a], yb[b], acc[a][b]);
+    for (int a = 0; a < TM; ++a) {
+#pragma unroll
+      for (int p = 0; p < NP; ++p) {
+        acc[a][2 * p] = fma(pv[a].x, qv0[p].x, acc[a][2 * p]);
+        acc[a][2 * p + 1] = fma(pv[a].x, qv0[p].y, acc[a][2 * p + 1]);
+      }
+      if (ODD) acc[a][TM - 1] = fma(pv[a].x, qv0[NP].x, acc[a][TM - 1]);
+    }
+#pragma unroll
+    for (int a = 0; a < TM; ++a) {
+#pragma unroll
+      for (int p = 0; p < NP; ++p) {
+        acc[a][2 * p] = fma(pv[a].y, qv1[p].x, acc[a][2 * p]);
+        acc[a][2 * p + 1] = fma(pv[a].y, qv1[p].y, acc[a][2 * p + 1]);
+      }
+      if (ODD) acc[a][TM - 1] = fma(pv[a].y, qv1[NP].x, acc[a][TM - 1]);
+    }
   }
+  if (k & 1) {   // odd k: last r
+    const int r = k - 1;
+    const double* qr = Qm + r * ks;
+#pragma unroll
+    for (int a = 0; a < TM; ++a) {
+      const double pvx = pa[a][r];
+#pragma unroll
+      for (int b = 0; b < TM; ++b) acc[a][b] = fma(pvx, qr[min(ns_col<TM>(b, tx), ks - 1)], acc[a][b]);
+    }
+  }
+}
+
+// element-wise epilogue over the micro-kernel's register tile: f(row, col, value&)
+template <int TM, typename F>
+__device__ __forceinline__ void ns_foreach(int k, int ty, int tx, double (&acc)[TM][TM], F&& f) {
+#pragma unroll
+  for (int a = 0; a < TM; ++a)
+#pragma unroll
+    for (int b = 0; b < TM; ++b) {
+      const int i = ty + 16 * a, j = ns_col<TM>(b, tx);
+      if (i < k && j < k) f(i, j, acc[a][b]);
+    }
 }
 
 template <int TM>
@@ -68,7 +136,7 @@ __global__ void __launch_bounds__(NS_THREADS) letkf_ns_kernel(ColParams P, int l
   extern __shared__ __align__(16) unsigned char smem_raw[];
   constexpr int NT = NS_THREADS;
   constexpr int TL = 3;
-  const int k = P.k, ks = k | 1, nz = P.nz;
+  const int k = P.k, ks = ns_stride(k), nz = P.nz;   // even stride, ks/2 odd (see ns_stride)
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = NT / 32;
   const size_t msz = (size_t)k * ks;
   double* Bf[4];
@@ -93,7 +161,7 @@ __global__ void __launch_bounds__(NS_THREADS) letkf_ns_kernel(ColParams P, int l
   const int nxf = per_level ? nz : 1;
   const int R = (int)floor(P.radius);
   const long long ncols = P.cols ? P.ncols : (long long)P.own_nx * P.own_ny;
-  const int ty = tid >> 4, tx = tid & 15;
+  const int ty = tid >> 4, tx = tid & 15;      // 16 x 16 grid: SYRK and the update
 
   for (long long ci = blockIdx.x; ci < ncols; ci += gridDim.x) {
     int lx, ly;
@@ -240,55 +308,31 @@ __global__ void __launch_bounds__(NS_THREADS) letkf_ns_kernel(ColParams P, int l
           }
         if (tid < k) gvec[tid] = gacc;
         __syncthreads();
-        ns_mm<TM>(Ym, Tm, k, ks, ty, tx, acc);          // Y1 = Y0 T
-#pragma unroll
-        for (int a = 0; a < TM; ++a)
-#pragma unroll
-          for (int b = 0; b < TM; ++b) {
-            const int ia = ty + 16 * a, ib = tx + 16 * b;
-            if (ia < k && ib < k) Sm[ia * ks + ib] = acc[a][b];
-          }
+        double nacc[TM][TM];
+        ns_mm<TM>(Ym, Tm, k, ks, ty, tx, nacc);          // Y1 = Y0 T
+        ns_foreach<TM>(k, ty, tx, nacc, [&](int i, int j, double& v) { Sm[i * ks + j] = v; });
         __syncthreads();
         { double* t = Ym; Ym = Sm; Sm = t; }              // Y = Y1, S = free
         int it = 1;
         bool done = false;
         for (; it < NS_MAX_ITERS && !done; ++it) {
-          ns_mm<TM>(Zm, Ym, k, ks, ty, tx, acc);        // Z Y
+          ns_mm<TM>(Zm, Ym, k, ks, ty, tx, nacc);        // Z Y
           double r = 0.0;
-#pragma unroll
-          for (int a = 0; a < TM; ++a)
-#pragma unroll
-            for (int b = 0; b < TM; ++b) {
-              const int ia = ty + 16 * a, ib = tx + 16 * b;
-              if (ia < k && ib < k) {
-                const double e = (ia == ib ? 1.0 : 0.0) - acc[a][b];
-                r = fmax(r, fabs(e));
-                Tm[ia * ks + ib] = (ia == ib ? 1.0 : 0.0) + 0.5 * e;     // (3I - ZY)/2
-              }
-            }
+          ns_foreach<TM>(k, ty, tx, nacc, [&](int i, int j, double& v) {
+            const double e = (i == j ? 1.0 : 0.0) - v;
+            r = fmax(r, fabs(e));
+            Tm[i * ks + j] = (i == j ? 1.0 : 0.0) + 0.5 * e;      // (3I - ZY)/2
+          });
           r = block_reduce(r, true, red);                 // also publishes T
           done = r < 1e-7;                                 // error after this update ~ r^2
           if (!(r < 1.5)) { ok = false; break; }           // cannot happen for SPD input; NaN guard
           if (!done) {
-            ns_mm<TM>(Ym, Tm, k, ks, ty, tx, acc);      // Y <- Y T
-#pragma unroll
-            for (int a = 0; a < TM; ++a)
-#pragma unroll
-              for (int b = 0; b < TM; ++b) {
-                const int ia = ty + 16 * a, ib = tx + 16 * b;
-                if (ia < k && ib < k) Sm[ia * ks + ib] = acc[a][b];
-              }
+            ns_mm<TM>(Ym, Tm, k, ks, ty, tx, nacc);      // Y <- Y T
+            ns_foreach<TM>(k, ty, tx, nacc, [&](int i, int j, double& v) { Sm[i * ks + j] = v; });
           }
-          ns_mm<TM>(Tm, Zm, k, ks, ty, tx, acc);        // Z <- T Z
-          __syncthreads();                                 // everyone is done reading Y, Z
-          double* Zdst = done ? Ym : Ym;                   // old Y buffer is free once Y T is in S
-#pragma unroll
-          for (int a = 0; a < TM; ++a)
-#pragma unroll
-            for (int b = 0; b < TM; ++b) {
-              const int ia = ty + 16 * a, ib = tx + 16 * b;
-              if (ia < k && ib < k) Zdst[ia * ks + ib] = acc[a][b];
-            }
+          ns_mm<TM>(Tm, Zm, k, ks, ty, tx, nacc);        // Z <- T Z
+          __syncthreads();                                 // everyone is done reading Y and Z
+          ns_foreach<TM>(k, ty, tx, nacc, [&](int i, int j, double& v) { Ym[i * ks + j] = v; });
           __syncthreads();
           { double* oldZ = Zm; Zm = Ym; Ym = Sm; Sm = oldZ; }   // Z = new, Y = S, S = old Z
         }
@@ -407,7 +451,7 @@ __global__ void __launch_bounds__(NS_THREADS) letkf_ns_kernel(ColParams P, int l
 }
 
 static size_t ns_smem_bytes(int k, int lch) {
-  const size_t ks = (size_t)(k | 1);
+  const size_t ks = (size_t)ns_stride(k);
   const size_t dbl = 4 * (size_t)k * ks + 3 * (size_t)k + 2 * (size_t)lch + 16 + NS_SELCAP;
   return dbl * 8 + (size_t)NS_SELCAP * 4 + 32 * 4 + 4 * 4 + 16;
 }

@@ -636,7 +636,7 @@ static int letkf_launch(mdc_ens* e, mdc_obs* o, const mdc_letkf_params* p, const
       if (k <= 32) return launch3(letkf_ns_kernel<2>);
       if (k <= 48) return launch3(letkf_ns_kernel<3>);
       if (k <= 64) return launch3(letkf_ns_kernel<4>);
-      return launch3(letkf_ns_kernel<5>) ;
+      return launch3(letkf_ns_kernel<5>);
     }
   }
   if (p->mode == MDC_MODE_CANONICAL && !getenv("MDC_LETKF_V1")) {

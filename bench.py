@@ -114,7 +114,7 @@ def cpu_sample(workload, seconds_hint=12.0, nthreads=0):
     nx, ny, nz, k, P, radius = WORKLOADS[workload]
     threads = nthreads if nthreads > 0 else orc.max_threads()
     # ~30 ms per k=80 column per core; size the tile for ~seconds_hint of work on `threads` cores
-    per_col = 6.0e-8 * k ** 3
+    per_col = 2.0e-8 * k ** 3
     ncol_target = max(64, int(seconds_hint * threads / per_col))
     t = int(min(min(nx, ny), max(8, round(ncol_target ** 0.5))))
     lev = min(nz, 8)            # levels only scale the (cheap) update; keep the tile small in RAM
@@ -190,7 +190,10 @@ def run_ours(args):
     from metada_b200.parallel import SlabLetkf  # row-slab sharding + obs halo exchange
     job = SlabLetkf(ctx, nx, ny, nz, k, rank, world, radius)
     obs_all = syn.observations(P, nx, ny, nz, seed=42, sigma=SIGMA)
-    params = capi.make_params(radius, INFLATION, mb.MODE_CANONICAL, mb.LOC_GASPARI_COHN)
+    solver = {"auto": mb.SOLVER_AUTO, "jacobi": mb.SOLVER_JACOBI, "ns": mb.SOLVER_NEWTON_SCHULZ}[args.solver]
+    params = capi.make_params(radius, INFLATION, mb.MODE_CANONICAL, mb.LOC_GASPARI_COHN, solver=solver)
+    solver_name = {"auto": "Newton-Schulz symmetric square root on FP64 DMMA (k<=80; Jacobi otherwise)" if 24 <= k <= 80 else "Jacobi",
+                   "jacobi": "one-sided block Jacobi eigen-decomposition", "ns": "Newton-Schulz symmetric square root on FP64 DMMA"}[args.solver]
 
     def one_step(timed):
         job.ens.fill_synthetic(1000)
@@ -249,12 +252,13 @@ def run_ours(args):
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": tot_ms / args.steps, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": f"{args.workload}: LETKF {nx}x{ny}x{nz}, {k} members, {P} obs, radius {radius}, "
-                                   "canonical (Gaspari-Cohn R-localisation, symmetric sqrt via Jacobi, X'W), inflation 1.0",
+                                   "canonical (Gaspari-Cohn R-localisation, symmetric square-root transform, X'W), inflation 1.0",
+                       "solver": solver_name,
                        "parallelism": f"row-slab column sharding x{world}, NCCL obs-halo exchange" if world > 1 else "single GPU",
                        "l2": "state (%.1f GB) >> 126 MB L2; background regenerated on device before every step" % (G * nz * k * 8 / 1e9),
-                       "mean_local_obs": pbar, "mean_jacobi_sweeps": sum_sw / ncols},
+                       "mean_local_obs": pbar, "mean_solver_iterations": sum_sw / ncols},
             "roofline": {"bound": "fp64", "achieved": ach_tf, "peak": fp64_peak, "unit": "TFLOP/s", "frac": ach_tf / fp64_peak,
-                         "traffic": None, "kernel": "letkf_column_kernel",
+                         "traffic": None, "kernel": "letkf_ns_kernel" if (24 <= k <= 80 and args.solver != "jacobi") else "letkf_canonical_kernel",
                          "peak_source": "FP64 FMA microbenchmark run in this process (mdc_bench_fp64_fma); "
                                         "MEASURED_PEAKS.json has no FP64 figure",
                          "flops_per_column": F, "bytes_per_column": Bc,
@@ -279,6 +283,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default=os.environ.get("MDC_BENCH_WORKLOAD", "C5"), choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--solver", default="auto", choices=["auto", "jacobi", "ns"])
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -113,7 +113,7 @@ int mdc_obs_index_query_lists(mdc_obs* obs, mdc_ens* ens, double radius, const i
 /* ---- LETKF: replaces LETKF<Tag>::Analyse / updateGridPoint (LETKF.hpp:63-119, 152-243) ----- */
 enum { MDC_MODE_REF_COMPAT = 0, MDC_MODE_REF_ETKF = 1, MDC_MODE_CANONICAL = 2 };
 enum { MDC_LOC_CUTOFF = 0, MDC_LOC_GASPARI_COHN = 1 };
-/* AUTO: Newton-Schulz (GEMM-only symmetric square root) for 24 <= k <= 82, else Jacobi.
+/* AUTO: Newton-Schulz (GEMM-only symmetric square root on FP64 DMMA) for 24 <= k <= 80, else Jacobi.
  * JACOBI: one-block-per-column one-sided Jacobi eigen-decomposition with warp-shuffle reductions.
  * Both give the same (unique) symmetric square-root transform to rounding. */
 enum { MDC_SOLVER_AUTO = 0, MDC_SOLVER_JACOBI = 1, MDC_SOLVER_NEWTON_SCHULZ = 2 };

@@ -7,12 +7,15 @@
 //     Y0 = cA, Z0 = I;   T = (3I - Z Y)/2,  Y <- Y T,  Z <- T Z;   Y -> (cA)^{1/2}, Z -> (cA)^{-1/2}
 // with c = 2/(lmin + b), lmin = (k-1)/infl (exact lower bound of the spectrum) and b = ||A||_F
 // (rigorous upper bound), so |1 - c lambda| < 1 for every eigenvalue.  Every iterate is a polynomial
-// in A (symmetric, commuting).  Each product is a register-tiled (TM x TM per thread on a 16 x 16
-// thread grid) k x k x k FP64 GEMM out of shared memory with conflict-free operand reads.  ~9 iterations x 3 products for the C5
-// conditioning, all dense FP64 FMA work with 25 independent accumulators per thread; no
-// rotations, shuffles or rsqrt chains, and the update needs ONE product (X' W) instead of two.
-// Used for k <= 96 (four k x k buffers must fit in shared memory); larger ensembles use the
-// Jacobi kernel.
+// in A (symmetric, commuting).  ~9 iterations x 3 products for the C5 conditioning, each a real
+// dense k x k x k FP64 contraction out of shared memory -- so they run on the FP64 tensor path
+// (DMMA, mma.sync.m8n8k4.f64): an FMA-pipe version with 5 x 5 register tiles is shared-memory
+// bound on B200 (4 (TM+TN)/(TM TN) = 1.6 wavefront-cycles per FP64-pipe cycle, measured 65 % smem
+// vs 50 % FP64 utilisation), whereas DMMA fragments need ~1.3 eight-byte loads per 256-FMA tile.
+// Products of commuting symmetric matrices are symmetric: only the upper-triangular tiles are
+// computed and mirrored (-45 % MMAs, iterates exactly symmetric).  No rotations, shuffles or rsqrt chains, and the update needs ONE
+// product (X' W) instead of two.  Used for 24 <= k <= 80 (four padded k x k buffers must fit in
+// shared memory); other ensemble sizes use the Jacobi kernel.
 #pragma once
 #include "letkf_kernels.cuh"
 
@@ -21,13 +24,12 @@
 #define NS_SELCAP 512
 #define NS_MAX_ITERS 40
 
-// Row stride of the k x k buffers: even (16-byte aligned rows for 128-bit loads) with ks/2 odd, so
-// the four consecutive rows a warp reads P[row][r..r+1] from land in four different bank groups.
-__host__ __device__ inline int ns_stride(int k) {
-  int ks = (k + 1) & ~1;
-  if (((ks >> 1) & 1) == 0) ks += 2;
-  return ks;
-}
+// Matrices are padded to kp = 8 ceil(k/8) rows/cols (DMMA tiles) with row stride ks == 4 (mod 8)
+// doubles: both fragment patterns -- A: 8 rows x 4 consecutive doubles, B: 4 rows x 8 consecutive
+// doubles -- then touch every bank exactly twice (256 B in the minimum 2 wavefronts), and rows
+// stay 16-byte aligned for the 128-bit accumulator stores.
+__host__ __device__ inline int ns_kp(int k) { return (k + 7) & ~7; }
+__host__ __device__ inline int ns_stride(int k) { return ns_kp(k) + 4; }
 
 __device__ __forceinline__ double block_reduce(double v, bool is_max, double* red /*[9]*/) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -131,14 +133,216 @@ __device__ __forceinline__ void ns_foreach(int k, int ty, int tx, double (&acc)[
     }
 }
 
+// ---- FP64 tensor-core product of two commuting symmetric matrices (result symmetric): only the
+// nt (nt + 1) / 2 upper-triangular 8 x 8 tiles are computed, each warp taking a contiguous chunk of
+// the row-major upper-triangle enumeration (k = 80: 55 tiles, 7 per warp), and every off-diagonal
+// tile is stored twice (as is and transposed).  This keeps the iterates EXACTLY symmetric and
+// removes 45 % of the MMAs.
+template <int NTW>
+struct NsTiles {
+  int ti[NTW], tj[NTW];
+  int n;
+};
+template <int NTW>
+__device__ __forceinline__ NsTiles<NTW> ns_tiles(int kp, int warp) {
+  const int nt = kp >> 3, E = nt * (nt + 1) / 2;
+  const int e0 = (E * warp) / (NS_THREADS / 32), e1 = (E * (warp + 1)) / (NS_THREADS / 32);
+  NsTiles<NTW> w;
+  w.n = e1 - e0;
+  int i = 0, rowstart = 0;              // locate e0: row i starts at rowstart and has nt - i tiles
+  while (e0 >= rowstart + (nt - i)) { rowstart += nt - i; ++i; }
+  int j = i + (e0 - rowstart);
+#pragma unroll
+  for (int n = 0; n < NTW; ++n) {
+    w.ti[n] = i; w.tj[n] = j;
+    if (n + 1 < w.n) { if (++j == nt) { ++i; j = i; } }
+  }
+  return w;
+}
+
+template <int NTW>
+__device__ __forceinline__ void ns_mm_sym(const double* __restrict__ Pm, const double* __restrict__ Qm,
+                                          int kp, int ks, const NsTiles<NTW>& w, int lane,
+                                          double (&acc)[NTW][2]) {
+  const int g = lane >> 2, t = lane & 3;
+#pragma unroll
+  for (int n = 0; n < NTW; ++n) { acc[n][0] = 0.0; acc[n][1] = 0.0; }
+  const double* pa[NTW];
+  const double* qb[NTW];
+#pragma unroll
+  for (int n = 0; n < NTW; ++n) {
+    pa[n] = Pm + ((w.ti[n] * 8 + g) * ks + t);
+    qb[n] = Qm + (t * ks + w.tj[n] * 8 + g);
+  }
+#pragma unroll 2
+  for (int kk = 0; kk < kp; kk += 4) {
+    double a[NTW], b[NTW];
+#pragma unroll
+    for (int n = 0; n < NTW; ++n) {
+      // consecutive tiles of a chunk mostly share their tile row: reuse the A fragment
+      if (n == 0 || w.ti[n] != w.ti[n - 1]) a[n] = pa[n][kk]; else a[n] = a[n - 1];
+      b[n] = qb[n][kk * ks];
+    }
+#pragma unroll
+    for (int n = 0; n < NTW; ++n)
+      if (n < w.n)
+        asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                     : "+d"(acc[n][0]), "+d"(acc[n][1])
+                     : "d"(a[n]), "d"(b[n]));
+  }
+}
+
+// f(row, col, v0, v1, offdiag): accumulator pair at (row, col), (row, col + 1); offdiag tiles must
+// also be written transposed by the caller
+template <int NTW, typename F>
+__device__ __forceinline__ void ns_foreach_sym(const NsTiles<NTW>& w, int lane, double (&acc)[NTW][2], F&& f) {
+  const int g = lane >> 2, t = lane & 3;
+#pragma unroll
+  for (int n = 0; n < NTW; ++n)
+    if (n < w.n) f(w.ti[n] * 8 + g, w.tj[n] * 8 + 2 * t, acc[n][0], acc[n][1], w.ti[n] != w.tj[n]);
+}
+
+__device__ __forceinline__ void ns_store_sym(double* dst, int ks, int i, int j, double v0, double v1, bool offdiag) {
+  *reinterpret_cast<double2*>(dst + i * ks + j) = make_double2(v0, v1);
+  if (offdiag) { dst[j * ks + i] = v0; dst[(j + 1) * ks + i] = v1; }
+}
+
+// ---- FP64 tensor-core product, all tiles (used when cond(A) is large: see ns_iterate).
+// Warp w = (rh, cq): rh = w / 4 picks a half of the tile rows, cq = w % 4 a quarter of the tile
+// columns; the quarters' sizes are listed in opposite order for the two halves so that each SM
+// sub-partition (warps w and w + 4) gets the same number of MMAs (k = 80: 10 x 10 tiles -> warps
+// of 5 x 3 and 5 x 2 tiles, 25 MMAs per k-step per sub-partition).
+struct NsWarpTile { int tr0, ntr, tc0, ntc; };
+__device__ __forceinline__ NsWarpTile ns_warp_tile(int kp, int warp) {
+  const int nt = kp >> 3, rh = warp >> 2, cq = warp & 3;
+  NsWarpTile w;
+  const int h0 = (nt + 1) >> 1;
+  w.tr0 = rh ? h0 : 0;
+  w.ntr = rh ? nt - h0 : h0;
+  const int base = nt >> 2, rem = nt & 3;
+  int start = 0;
+  w.tc0 = 0; w.ntc = 0;
+  for (int i = 0; i < 4; ++i) {
+    const int qi = rh ? 3 - i : i;
+    const int sz = base + (qi < rem ? 1 : 0);
+    if (i == cq) { w.tc0 = start; w.ntc = sz; }
+    start += sz;
+  }
+  return w;
+}
+
+template <int RT, int CT>
+__device__ __forceinline__ void ns_mm_full(const double* __restrict__ Pm, const double* __restrict__ Qm,
+                                           int kp, int ks, const NsWarpTile& w, int lane,
+                                           double (&acc)[RT][CT][2]) {
+  const int g = lane >> 2, t = lane & 3;
+#pragma unroll
+  for (int i = 0; i < RT; ++i)
+#pragma unroll
+    for (int j = 0; j < CT; ++j) { acc[i][j][0] = 0.0; acc[i][j][1] = 0.0; }
+  const double* pa = Pm + ((w.tr0 * 8 + g) * ks + t);
+  const double* qb = Qm + (t * ks + w.tc0 * 8 + g);
+#pragma unroll 2
+  for (int kk = 0; kk < kp; kk += 4) {
+    double a[RT], b[CT];
+#pragma unroll
+    for (int i = 0; i < RT; ++i) a[i] = (i < w.ntr) ? pa[i * 8 * ks + kk] : 0.0;
+#pragma unroll
+    for (int j = 0; j < CT; ++j) b[j] = (j < w.ntc) ? qb[kk * ks + j * 8] : 0.0;
+#pragma unroll
+    for (int i = 0; i < RT; ++i)
+#pragma unroll
+      for (int j = 0; j < CT; ++j)
+        if (i < w.ntr && j < w.ntc)
+          asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                       : "+d"(acc[i][j][0]), "+d"(acc[i][j][1])
+                       : "d"(a[i]), "d"(b[j]));
+  }
+}
+
+template <int RT, int CT, typename F>
+__device__ __forceinline__ void ns_foreach_full(const NsWarpTile& w, int lane, double (&acc)[RT][CT][2], F&& f) {
+  const int g = lane >> 2, t = lane & 3;
+#pragma unroll
+  for (int i = 0; i < RT; ++i)
+#pragma unroll
+    for (int j = 0; j < CT; ++j)
+      if (i < w.ntr && j < w.ntc) f((w.tr0 + i) * 8 + g, (w.tc0 + j) * 8 + 2 * t, acc[i][j][0], acc[i][j][1], false);
+}
+
+// One product C = P Q into registers + visitor; SYM selects the symmetric-tile or the full variant.
+template <int TM, bool SYM>
+struct NsProd {
+  static constexpr int NTW = (TM * (2 * TM + 1) + 7) / 8;
+  static constexpr int RT = (2 * TM + 1) / 2, CT = (2 * TM + 3) / 4;
+  NsTiles<NTW> st;
+  NsWarpTile ft;
+  double sacc[SYM ? NTW : 1][2];
+  double facc[SYM ? 1 : RT][SYM ? 1 : CT][2];
+  __device__ __forceinline__ void init(int kp, int warp) {
+    if (SYM) st = ns_tiles<NTW>(kp, warp); else ft = ns_warp_tile(kp, warp);
+  }
+  __device__ __forceinline__ void mm(const double* Pm, const double* Qm, int kp, int ks, int lane) {
+    if constexpr (SYM) ns_mm_sym<NTW>(Pm, Qm, kp, ks, st, lane, sacc);
+    else ns_mm_full<RT, CT>(Pm, Qm, kp, ks, ft, lane, facc);
+  }
+  template <typename F>
+  __device__ __forceinline__ void foreach(int lane, F&& f) {
+    if constexpr (SYM) ns_foreach_sym<NTW>(st, lane, sacc, f);
+    else ns_foreach_full<RT, CT>(ft, lane, facc, f);
+  }
+};
+
+// Coupled Newton-Schulz from (Y = Y1, Z = T = Z1) already in Bf; returns iterations, sets ok.
+// On exit Zm points at (cA)^{-1/2}.
+template <int TM, bool SYM>
+__device__ __forceinline__ int ns_iterate(double*& Ym, double*& Zm, double*& Tm, double*& Sm, int kp,
+                                          int ks, int warp, int lane, double* red, bool& ok) {
+  NsProd<TM, SYM> pr;
+  pr.init(kp, warp);
+  auto store_to = [&](double* dst) {
+    pr.foreach(lane, [&](int i, int j, double v0, double v1, bool od) { ns_store_sym(dst, ks, i, j, v0, v1, od); });
+  };
+  pr.mm(Ym, Tm, kp, ks, lane);                             // Y1 = Y0 T
+  store_to(Sm);
+  __syncthreads();
+  { double* t = Ym; Ym = Sm; Sm = t; }                      // Y = Y1, S = free
+  int it = 1;
+  bool done = false;
+  for (; it < NS_MAX_ITERS && !done; ++it) {
+    pr.mm(Zm, Ym, kp, ks, lane);                           // Z Y
+    double r = 0.0;
+    pr.foreach(lane, [&](int i, int j, double v0, double v1, bool od) {
+      const double d0 = (i == j ? 1.0 : 0.0), d1 = (i == j + 1 ? 1.0 : 0.0);
+      const double e0 = d0 - v0, e1 = d1 - v1;
+      r = fmax(r, fmax(fabs(e0), fabs(e1)));
+      ns_store_sym(Tm, ks, i, j, d0 + 0.5 * e0, d1 + 0.5 * e1, od);        // (3I - ZY)/2
+    });
+    r = block_reduce(r, true, red);                         // also publishes T
+    done = r < 1e-7;                                         // error after this update ~ r^2
+    if (!(r < 1.5)) { ok = false; break; }                   // cannot happen for SPD input; NaN guard
+    if (!done) {
+      pr.mm(Ym, Tm, kp, ks, lane);                         // Y <- Y T
+      store_to(Sm);
+    }
+    pr.mm(Tm, Zm, kp, ks, lane);                           // Z <- T Z
+    __syncthreads();                                         // everyone is done reading Y and Z
+    store_to(Ym);
+    __syncthreads();
+    { double* oldZ = Zm; Zm = Ym; Ym = Sm; Sm = oldZ; }     // Z = new, Y = S, S = old Z
+  }
+  if (!done) ok = false;
+  return it;
+}
+
 template <int TM>
 __global__ void __launch_bounds__(NS_THREADS) letkf_ns_kernel(ColParams P, int lch) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   constexpr int NT = NS_THREADS;
   constexpr int TL = 3;
-  const int k = P.k, ks = ns_stride(k), nz = P.nz;   // even stride, ks/2 odd (see ns_stride)
+  const int k = P.k, kp = ns_kp(k), ks = ns_stride(k), nz = P.nz;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = NT / 32;
-  const size_t msz = (size_t)k * ks;
+  const size_t msz = (size_t)kp * ks;
   double* Bf[4];
   Bf[0] = reinterpret_cast<double*>(smem_raw);
   Bf[1] = Bf[0] + msz; Bf[2] = Bf[1] + msz; Bf[3] = Bf[2] + msz;
@@ -292,14 +496,15 @@ __global__ void __launch_bounds__(NS_THREADS) letkf_ns_kernel(ColParams P, int l
           }
         fro = sqrt(block_reduce(fro, false, red));
         cscale = 2.0 / (shift + fro);
-        // Y0 = cA; first iteration in closed form (Z0 = I): T = 1.5 I - 0.5 Y0, Z1 = T
+        // Y0 = cA (identity on the zero-padding), first iteration in closed form (Z0 = I):
+        // T = 1.5 I - 0.5 Y0, Z1 = T
 #pragma unroll
         for (int a = 0; a < TM; ++a)
 #pragma unroll
           for (int b = 0; b < TM; ++b) {
             const int ia = ty + 16 * a, ib = tx + 16 * b;
-            if (ia < k && ib < k) {
-              const double y = cscale * acc[a][b];
+            if (ia < kp && ib < kp) {
+              const double y = (ia < k && ib < k) ? cscale * acc[a][b] : (ia == ib ? 1.0 : 0.0);
               Ym[ia * ks + ib] = y;
               const double t = (ia == ib ? 1.5 : 0.0) - 0.5 * y;
               Tm[ia * ks + ib] = t;
@@ -308,35 +513,13 @@ __global__ void __launch_bounds__(NS_THREADS) letkf_ns_kernel(ColParams P, int l
           }
         if (tid < k) gvec[tid] = gacc;
         __syncthreads();
-        double nacc[TM][TM];
-        ns_mm<TM>(Ym, Tm, k, ks, ty, tx, nacc);          // Y1 = Y0 T
-        ns_foreach<TM>(k, ty, tx, nacc, [&](int i, int j, double& v) { Sm[i * ks + j] = v; });
-        __syncthreads();
-        { double* t = Ym; Ym = Sm; Sm = t; }              // Y = Y1, S = free
-        int it = 1;
-        bool done = false;
-        for (; it < NS_MAX_ITERS && !done; ++it) {
-          ns_mm<TM>(Zm, Ym, k, ks, ty, tx, nacc);        // Z Y
-          double r = 0.0;
-          ns_foreach<TM>(k, ty, tx, nacc, [&](int i, int j, double& v) {
-            const double e = (i == j ? 1.0 : 0.0) - v;
-            r = fmax(r, fabs(e));
-            Tm[i * ks + j] = (i == j ? 1.0 : 0.0) + 0.5 * e;      // (3I - ZY)/2
-          });
-          r = block_reduce(r, true, red);                 // also publishes T
-          done = r < 1e-7;                                 // error after this update ~ r^2
-          if (!(r < 1.5)) { ok = false; break; }           // cannot happen for SPD input; NaN guard
-          if (!done) {
-            ns_mm<TM>(Ym, Tm, k, ks, ty, tx, nacc);      // Y <- Y T
-            ns_foreach<TM>(k, ty, tx, nacc, [&](int i, int j, double& v) { Sm[i * ks + j] = v; });
-          }
-          ns_mm<TM>(Tm, Zm, k, ks, ty, tx, nacc);        // Z <- T Z
-          __syncthreads();                                 // everyone is done reading Y and Z
-          ns_foreach<TM>(k, ty, tx, nacc, [&](int i, int j, double& v) { Ym[i * ks + j] = v; });
-          __syncthreads();
-          { double* oldZ = Zm; Zm = Ym; Ym = Sm; Sm = oldZ; }   // Z = new, Y = S, S = old Z
-        }
-        if (!done) ok = false;
+        // Symmetric-tile products are ~2x cheaper but lose commutativity-based stability when
+        // cond(A) is large (error ~1e-13 at cond 1e3, ~5e-8 at 1e4, divergence at 1e5 -- measured);
+        // the rigorous bound (lmin + ||A||_F)/lmin >= cond(A) picks the variant per column.
+        const bool well_conditioned = (shift + fro) < 1.0e3 * shift;
+        int it;
+        if (well_conditioned) it = ns_iterate<TM, true>(Ym, Zm, Tm, Sm, kp, ks, warp, lane, red, ok);
+        else it = ns_iterate<TM, false>(Ym, Zm, Tm, Sm, kp, ks, warp, lane, red, ok);
         col_iters = max(col_iters, it);
         // w = c Z (Z g)
         if (ok) {
@@ -452,6 +635,6 @@ __global__ void __launch_bounds__(NS_THREADS) letkf_ns_kernel(ColParams P, int l
 
 static size_t ns_smem_bytes(int k, int lch) {
   const size_t ks = (size_t)ns_stride(k);
-  const size_t dbl = 4 * (size_t)k * ks + 3 * (size_t)k + 2 * (size_t)lch + 16 + NS_SELCAP;
+  const size_t dbl = 4 * (size_t)ns_kp(k) * ks + 3 * (size_t)k + 2 * (size_t)lch + 16 + NS_SELCAP;
   return dbl * 8 + (size_t)NS_SELCAP * 4 + 32 * 4 + 4 * 4 + 16;
 }

@@ -616,9 +616,9 @@ static int letkf_launch(mdc_ens* e, mdc_obs* o, const mdc_letkf_params* p, const
   cp.W_out = dW; cp.w_col = w_col;
   cp.cols = dcols; cp.ncols = ncols;
   const long long total_cols = dcols ? ncols : (long long)e->own_nx * e->own_ny;
-  if (p->mode == MDC_MODE_CANONICAL && p->solver == MDC_SOLVER_NEWTON_SCHULZ && (k < 24 || k > 82))
-    MDC_FAIL(ctx, MDC_ERR_UNSUPPORTED, "letkf: the Newton-Schulz solver supports 24 <= k <= 82 (k=%d)", k);
-  if (p->mode == MDC_MODE_CANONICAL && p->solver != MDC_SOLVER_JACOBI && k >= 24 && k <= 82 && !getenv("MDC_LETKF_V1")) {
+  if (p->mode == MDC_MODE_CANONICAL && p->solver == MDC_SOLVER_NEWTON_SCHULZ && (k < 24 || k > 80))
+    MDC_FAIL(ctx, MDC_ERR_UNSUPPORTED, "letkf: the Newton-Schulz solver supports 24 <= k <= 80 (k=%d)", k);
+  if (p->mode == MDC_MODE_CANONICAL && p->solver != MDC_SOLVER_JACOBI && k >= 24 && k <= 80 && !getenv("MDC_LETKF_V1")) {
     // GEMM-only symmetric square root (letkf_ns.cuh): four k x k buffers, one CTA per SM
     const int lch = std::min(e->nz, std::min(k, 32));
     const size_t smem3 = ns_smem_bytes(k, lch);

@@ -21,7 +21,7 @@
 
 #define NS_THREADS 256
 #define NS_PCH 32
-#define NS_SELCAP 512
+#define NS_SELCAP 384
 #define NS_MAX_ITERS 40
 
 // Matrices are padded to kp = 8 ceil(k/8) rows/cols (DMMA tiles) with row stride ks == 4 (mod 8)
@@ -174,7 +174,7 @@ __device__ __forceinline__ void ns_mm_sym(const double* __restrict__ Pm, const d
     pa[n] = Pm + ((w.ti[n] * 8 + g) * ks + t);
     qb[n] = Qm + (t * ks + w.tj[n] * 8 + g);
   }
-#pragma unroll 2
+#pragma unroll 4
   for (int kk = 0; kk < kp; kk += 4) {
     double a[NTW], b[NTW];
 #pragma unroll
@@ -335,37 +335,54 @@ __device__ __forceinline__ int ns_iterate(double*& Ym, double*& Zm, double*& Tm,
   return it;
 }
 
+// Rectangular tile chunk of an (ntr x nt) tile grid for the update product X' Z.
+template <int NTA>
+__device__ __forceinline__ NsTiles<NTA> ns_rect_tiles(int ntr, int nt, int warp) {
+  const int E = ntr * nt;
+  const int e0 = (E * warp) / (NS_THREADS / 32), e1 = (E * (warp + 1)) / (NS_THREADS / 32);
+  NsTiles<NTA> w;
+  w.n = e1 - e0;
+#pragma unroll
+  for (int n = 0; n < NTA; ++n) {
+    const int e = min(e0 + n, E - 1);
+    w.ti[n] = e / nt;
+    w.tj[n] = e - w.ti[n] * nt;
+  }
+  return w;
+}
+
 template <int TM>
 __global__ void __launch_bounds__(NS_THREADS) letkf_ns_kernel(ColParams P, int lch) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   constexpr int NT = NS_THREADS;
-  constexpr int TL = 3;
-  const int k = P.k, kp = ns_kp(k), ks = ns_stride(k), nz = P.nz;
+  constexpr int NTW = (TM * (2 * TM + 1) + 7) / 8;     // upper-triangular tiles per warp
+  constexpr int NTA = (4 * 2 * TM + 7) / 8;            // update tiles per warp (lch <= 32 levels)
+  const int k = P.k, kp = ns_kp(k), ks = ns_stride(k), nz = P.nz, nt = kp >> 3;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = NT / 32;
+  const int g = lane >> 2, t = lane & 3;
   const size_t msz = (size_t)kp * ks;
   double* Bf[4];
   Bf[0] = reinterpret_cast<double*>(smem_raw);
   Bf[1] = Bf[0] + msz; Bf[2] = Bf[1] + msz; Bf[3] = Bf[2] + msz;
   double* gvec = Bf[3] + msz;
-  double* wa = gvec + k;
-  double* tv = wa + k;
-  double* xm = tv + k;                                         // [lch]
+  double* wa = gvec + kp;
+  double* tv = wa + kp;
+  double* xm = tv + kp;                                        // [lch]
   double* ml = xm + lch;                                       // [lch]
   double* red = ml + lch;                                      // [16]
-  double* sel_w = red + 16;                                    // [NS_SELCAP]
-  int* sel_pos = reinterpret_cast<int*>(sel_w + NS_SELCAP);    // [NS_SELCAP]
-  int* warp_cnt = sel_pos + NS_SELCAP;                         // [32]
+  double* sel_sq = red + 16;                                   // [NS_SELCAP] sqrt(rho / sigma^2)
+  double* sel_d = sel_sq + NS_SELCAP;                          // [NS_SELCAP] sqrt(rho / sigma^2) * d
+  int* sel_row = reinterpret_cast<int*>(sel_d + NS_SELCAP);    // [NS_SELCAP] obs row
+  int* warp_cnt = sel_row + NS_SELCAP;                         // [32]
   int* s_int = warp_cnt + 32;                                  // [4]
-  // staging areas alias matrix buffers that are idle in that phase
-  double* Ych = Bf[2];                                         // [NS_PCH][k] + dw, phase 1
-  double* dw = Ych + (size_t)NS_PCH * k;
+  double* Ych = Bf[2];       // [NS_PCH][ks] staged weighted rows (phase 1; Bf[2..3] idle then)
 
   const double km1 = (double)(k - 1);
   const bool per_level = P.radius_v > 0.0;
   const int nxf = per_level ? nz : 1;
   const int R = (int)floor(P.radius);
   const long long ncols = P.cols ? P.ncols : (long long)P.own_nx * P.own_ny;
-  const int ty = tid >> 4, tx = tid & 15;      // 16 x 16 grid: SYRK and the update
+  const NsTiles<NTW> st = ns_tiles<NTW>(kp, warp);
 
   for (long long ci = blockIdx.x; ci < ncols; ci += gridDim.x) {
     int lx, ly;
@@ -379,12 +396,10 @@ __global__ void __launch_bounds__(NS_THREADS) letkf_ns_kernel(ColParams P, int l
     bool col_fail = false;
 
     for (int lt = 0; lt < nxf; ++lt) {
-      // ---------------- 1. selection, gather, register-tiled C += Yw^T Yw, g += Yw^T dw
-      double acc[TM][TM];
+      // ---------------- 1. selection, gather, C += Yw^T Yw on the FP64 tensor path, g += Yw^T dw
+      double cacc[NTW][2];
 #pragma unroll
-      for (int a = 0; a < TM; ++a)
-#pragma unroll
-        for (int b = 0; b < TM; ++b) acc[a][b] = 0.0;
+      for (int n = 0; n < NTW; ++n) { cacc[n][0] = 0.0; cacc[n][1] = 0.0; }
       double gacc = 0.0;
       if (tid == 0) s_int[0] = 0;
       __syncthreads();
@@ -399,7 +414,8 @@ __global__ void __launch_bounds__(NS_THREADS) letkf_ns_kernel(ColParams P, int l
         if (have_batch) {
           const int a = rb + tid;
           bool sel = false;
-          double rho = 1.0;
+          double sq = 0.0, sd = 0.0;
+          int orow = 0;
           if (a < re) {
             double dist;
             sel = index_within(gx, gy, P.iv.sx[a], P.iv.sy[a], P.radius, &dist);
@@ -408,9 +424,17 @@ __global__ void __launch_bounds__(NS_THREADS) letkf_ns_kernel(ColParams P, int l
               dv = fabs((double)(P.iv.sz[a] - lt));
               sel = dv <= P.radius_v;
             }
-            if (sel && P.loc == MDC_LOC_GASPARI_COHN) {
-              rho = lk_gaspari_cohn(dist / (0.5 * P.radius));
-              if (per_level) rho *= lk_gaspari_cohn(dv / (0.5 * P.radius_v));
+            if (sel) {
+              double rho = 1.0;
+              if (P.loc == MDC_LOC_GASPARI_COHN) {
+                rho = lk_gaspari_cohn(dist / (0.5 * P.radius));
+                if (per_level) rho *= lk_gaspari_cohn(dv / (0.5 * P.radius_v));
+              }
+              orow = P.iv.sorted_row[a];
+              const double e_ = P.err[orow];
+              const double ivar = P.valid[orow] ? 1.0 / (e_ * e_) : 0.0;
+              sq = sqrt(rho * (P.use_R ? ivar : 1.0));
+              sd = sq * P.d[orow];
             }
           }
           const unsigned bal = __ballot_sync(0xffffffffu, sel);
@@ -420,8 +444,9 @@ __global__ void __launch_bounds__(NS_THREADS) letkf_ns_kernel(ColParams P, int l
           for (int w = 0; w < warp; ++w) off += warp_cnt[w];
           if (sel) {
             const int pos = off + __popc(bal & ((1u << lane) - 1u));
-            sel_pos[pos] = a;
-            sel_w[pos] = rho;
+            sel_row[pos] = orow;
+            sel_sq[pos] = sq;
+            sel_d[pos] = sd;
           }
           __syncthreads();
           if (tid == 0) {
@@ -440,30 +465,53 @@ __global__ void __launch_bounds__(NS_THREADS) letkf_ns_kernel(ColParams P, int l
         const int nsel = s_int[0];
         if (have_batch && rows_left && nsel <= NS_SELCAP - NT) continue;
         for (int c0 = 0; c0 < nsel; c0 += NS_PCH) {
-          const int rows = min(NS_PCH, nsel - c0);
-          for (int r = warp; r < rows; r += nw) {
-            const int orow = P.iv.sorted_row[sel_pos[c0 + r]];
-            const double e_ = P.err[orow];
-            const double ivar = P.valid[orow] ? 1.0 / (e_ * e_) : 0.0;
-            const double sq = sqrt(sel_w[c0 + r] * (P.use_R ? ivar : 1.0));
-            const double* src = P.Yp + (long long)orow * k;
-            for (int j = lane; j < k; j += 32) Ych[r * k + j] = sq * src[j];
-            if (lane == 0) dw[r] = sq * P.d[orow];
-          }
-          __syncthreads();
-          for (int r = 0; r < rows; ++r) {
-            double ya[TM], yb[TM];
+          const int rows = min(NS_PCH, nsel - c0), rows4 = (rows + 3) & ~3;
+          // gather: warp w stages rows w, w + 8, w + 16, w + 24; all loads issued before the stores
+          {
+            double v[NS_PCH / 8][(2 * TM * 8 + 31) / 32];
 #pragma unroll
-            for (int a = 0; a < TM; ++a) {
-              const int ia = ty + 16 * a, ib = tx + 16 * a;
-              ya[a] = ia < k ? Ych[r * k + ia] : 0.0;
-              yb[a] = ib < k ? Ych[r * k + ib] : 0.0;
+            for (int q = 0; q < NS_PCH / 8; ++q) {
+              const int r = warp + 8 * q;
+              const double* src = P.Yp + (long long)sel_row[c0 + min(r, rows - 1)] * k;
+#pragma unroll
+              for (int jj = 0; jj < (2 * TM * 8 + 31) / 32; ++jj) {
+                const int j = lane + 32 * jj;
+                v[q][jj] = (r < rows && j < k) ? src[j] : 0.0;
+              }
             }
 #pragma unroll
-            for (int a = 0; a < TM; ++a)
+            for (int q = 0; q < NS_PCH / 8; ++q) {
+              const int r = warp + 8 * q;
+              if (r < rows4) {
+                const double sq = (r < rows) ? sel_sq[c0 + r] : 0.0;
 #pragma unroll
-              for (int b = 0; b < TM; ++b) acc[a][b] = fma(ya[a], yb[b], acc[a][b]);
-            if (tid < k) gacc = fma(Ych[r * k + tid], dw[r], gacc);
+                for (int jj = 0; jj < (2 * TM * 8 + 31) / 32; ++jj) {
+                  const int j = lane + 32 * jj;
+                  if (j < kp) Ych[r * ks + j] = sq * v[q][jj];
+                }
+              }
+            }
+          }
+          __syncthreads();
+          {
+            const double* ya = Ych + t * ks + g;
+            for (int kk = 0; kk < rows4; kk += 4) {
+              double a[NTW], b[NTW];
+#pragma unroll
+              for (int n = 0; n < NTW; ++n) {
+                if (n == 0 || st.ti[n] != st.ti[n - 1]) a[n] = ya[kk * ks + st.ti[n] * 8]; else a[n] = a[n - 1];
+                b[n] = ya[kk * ks + st.tj[n] * 8];
+              }
+#pragma unroll
+              for (int n = 0; n < NTW; ++n)
+                if (n < st.n)
+                  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                               : "+d"(cacc[n][0]), "+d"(cacc[n][1])
+                               : "d"(a[n]), "d"(b[n]));
+            }
+            if (tid < k) {
+              for (int r = 0; r < rows; ++r) gacc = fma(Ych[r * ks + tid], sel_d[c0 + r], gacc);
+            }
           }
           __syncthreads();
         }
@@ -484,33 +532,26 @@ __global__ void __launch_bounds__(NS_THREADS) letkf_ns_kernel(ColParams P, int l
       if (npl > 0) {
         const double shift = km1 / P.inflation;
         double fro = 0.0;
-#pragma unroll
-        for (int a = 0; a < TM; ++a)
-#pragma unroll
-          for (int b = 0; b < TM; ++b) {
-            const int ia = ty + 16 * a, ib = tx + 16 * b;
-            if (ia < k && ib < k) {
-              acc[a][b] += (ia == ib ? shift : 0.0);
-              fro = fma(acc[a][b], acc[a][b], fro);
-            }
+        ns_foreach_sym<NTW>(st, lane, cacc, [&](int i, int j, double v0, double v1, bool od) {
+          if (i < k) {
+            const double w = od ? 2.0 : 1.0;
+            if (j < k) { const double x = v0 + (i == j ? shift : 0.0); fro = fma(w * x, x, fro); }
+            if (j + 1 < k) { const double x = v1 + (i == j + 1 ? shift : 0.0); fro = fma(w * x, x, fro); }
           }
+        });
         fro = sqrt(block_reduce(fro, false, red));
         cscale = 2.0 / (shift + fro);
-        // Y0 = cA (identity on the zero-padding), first iteration in closed form (Z0 = I):
+        // Y0 = cA (identity on the zero padding); first iteration in closed form (Z0 = I):
         // T = 1.5 I - 0.5 Y0, Z1 = T
-#pragma unroll
-        for (int a = 0; a < TM; ++a)
-#pragma unroll
-          for (int b = 0; b < TM; ++b) {
-            const int ia = ty + 16 * a, ib = tx + 16 * b;
-            if (ia < kp && ib < kp) {
-              const double y = (ia < k && ib < k) ? cscale * acc[a][b] : (ia == ib ? 1.0 : 0.0);
-              Ym[ia * ks + ib] = y;
-              const double t = (ia == ib ? 1.5 : 0.0) - 0.5 * y;
-              Tm[ia * ks + ib] = t;
-              Zm[ia * ks + ib] = t;
-            }
-          }
+        ns_foreach_sym<NTW>(st, lane, cacc, [&](int i, int j, double v0, double v1, bool od) {
+          const double d0 = (i == j ? 1.0 : 0.0), d1 = (i == j + 1 ? 1.0 : 0.0);
+          const double y0 = (i < k && j < k) ? cscale * (v0 + d0 * shift) : d0;
+          const double y1 = (i < k && j + 1 < k) ? cscale * (v1 + d1 * shift) : d1;
+          ns_store_sym(Ym, ks, i, j, y0, y1, od);
+          const double t0 = 1.5 * d0 - 0.5 * y0, t1 = 1.5 * d1 - 0.5 * y1;
+          ns_store_sym(Tm, ks, i, j, t0, t1, od);
+          ns_store_sym(Zm, ks, i, j, t0, t1, od);
+        });
         if (tid < k) gvec[tid] = gacc;
         __syncthreads();
         // Symmetric-tile products are ~2x cheaper but lose commutativity-based stability when
@@ -554,23 +595,28 @@ __global__ void __launch_bounds__(NS_THREADS) letkf_ns_kernel(ColParams P, int l
         __syncthreads();
       }
 
-      // ---------------- 3. X_a = xbar + X' w + sW X' Z, level chunks of lch (staged in idle buffers)
-      double* Xt = (Zm == Bf[0] || Zm == Bf[1]) ? Bf[2] : Bf[0];
-      double* To = Xt + (size_t)lch * k;   // lch*k*2 <= 2 buffers is checked on the host
+      // ---------------- 3. X_a = xbar + X' w + sW X' Z on the tensor path, level chunks of lch,
+      //                     staged in the two matrix buffers that do not hold Z
+      double* Xt = (Zm == Bf[0] || Zm == Bf[1]) ? Bf[2] : Bf[0];      // [lch][ks]
+      double* To = Xt + (size_t)lch * ks;                              // [lch][k]
       const int lev_b = per_level ? lt : 0, lev_e = per_level ? lt + 1 : nz;
       if (ok) {
         for (int l0 = lev_b; l0 < lev_e; l0 += lch) {
           const int nl = min(lch, lev_e - l0);
-          for (int e = tid; e < nl * k; e += NT) Xt[e] = Xg[(long long)l0 * k + e];
+          for (int e = tid; e < nl * k; e += NT) {
+            const int l = e / k, j = e - l * k;
+            Xt[l * ks + j] = Xg[(long long)l0 * k + e];
+          }
+          if (kp > k) for (int e = tid; e < nl * (kp - k); e += NT) Xt[(e / (kp - k)) * ks + k + e % (kp - k)] = 0.0;
           __syncthreads();
           for (int l = warp; l < nl; l += nw) {
             double s = 0.0;
-            for (int j = lane; j < k; j += 32) s += Xt[l * k + j];
+            for (int j = lane; j < k; j += 32) s += Xt[l * ks + j];
             s = warp_sum(s) / (double)k;
             double m = 0.0;
             for (int j = lane; j < k; j += 32) {
-              const double xp = Xt[l * k + j] - s;
-              Xt[l * k + j] = xp;
+              const double xp = Xt[l * ks + j] - s;
+              Xt[l * ks + j] = xp;
               if (npl > 0) m = fma(xp, wa[j], m);
             }
             m = warp_sum(m);
@@ -579,34 +625,39 @@ __global__ void __launch_bounds__(NS_THREADS) letkf_ns_kernel(ColParams P, int l
           __syncthreads();
           if (npl == 0) {
             const double f = sqrt(P.inflation);
-            for (int e = tid; e < nl * k; e += NT) To[e] = xm[e / k] + Xt[e] * f;
+            for (int e = tid; e < nl * k; e += NT) { const int l = e / k; To[e] = xm[l] + Xt[l * ks + (e - l * k)] * f; }
           } else {
-            const int nlt = (nl + TL - 1) / TL;
-            for (int lt2 = ty; lt2 < nlt; lt2 += 16) {
-              double o[TL][TM];
+            const int ntr = (nl + 7) >> 3;
+            const NsTiles<NTA> at = ns_rect_tiles<NTA>(ntr, nt, warp);
+            double uacc[NTA][2];
 #pragma unroll
-              for (int a = 0; a < TL; ++a)
+            for (int n = 0; n < NTA; ++n) { uacc[n][0] = 0.0; uacc[n][1] = 0.0; }
+            const double* xa = Xt + g * ks + t;
+            const double* zb = Zm + t * ks + g;
+#pragma unroll 2
+            for (int kk = 0; kk < kp; kk += 4) {
+              double a[NTA], b[NTA];
 #pragma unroll
-                for (int b = 0; b < TM; ++b) o[a][b] = 0.0;
-              for (int j = 0; j < k; ++j) {
-                double xv[TL], zv[TM];
-#pragma unroll
-                for (int a = 0; a < TL; ++a) { const int l = lt2 + nlt * a; xv[a] = l < nl ? Xt[l * k + j] : 0.0; }
-#pragma unroll
-                for (int b = 0; b < TM; ++b) { const int i = tx + 16 * b; zv[b] = i < k ? Zm[j * ks + i] : 0.0; }
-#pragma unroll
-                for (int a = 0; a < TL; ++a)
-#pragma unroll
-                  for (int b = 0; b < TM; ++b) o[a][b] = fma(xv[a], zv[b], o[a][b]);
+              for (int n = 0; n < NTA; ++n) {
+                if (n == 0 || at.ti[n] != at.ti[n - 1]) a[n] = xa[at.ti[n] * 8 * ks + kk]; else a[n] = a[n - 1];
+                b[n] = zb[kk * ks + at.tj[n] * 8];
               }
 #pragma unroll
-              for (int a = 0; a < TL; ++a)
-#pragma unroll
-                for (int b = 0; b < TM; ++b) {
-                  const int l = lt2 + nlt * a, i = tx + 16 * b;
-                  if (l < nl && i < k) To[l * k + i] = ml[l] + sW * o[a][b];
-                }
+              for (int n = 0; n < NTA; ++n)
+                if (n < at.n)
+                  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                               : "+d"(uacc[n][0]), "+d"(uacc[n][1])
+                               : "d"(a[n]), "d"(b[n]));
             }
+#pragma unroll
+            for (int n = 0; n < NTA; ++n)
+              if (n < at.n) {
+                const int l = at.ti[n] * 8 + g, i = at.tj[n] * 8 + 2 * t;
+                if (l < nl) {
+                  if (i < k) To[l * k + i] = ml[l] + sW * uacc[n][0];
+                  if (i + 1 < k) To[l * k + i + 1] = ml[l] + sW * uacc[n][1];
+                }
+              }
           }
           __syncthreads();
           for (int e = tid; e < nl * k; e += NT) Xg[(long long)l0 * k + e] = To[e];
@@ -635,6 +686,6 @@ __global__ void __launch_bounds__(NS_THREADS) letkf_ns_kernel(ColParams P, int l
 
 static size_t ns_smem_bytes(int k, int lch) {
   const size_t ks = (size_t)ns_stride(k);
-  const size_t dbl = 4 * (size_t)ns_kp(k) * ks + 3 * (size_t)k + 2 * (size_t)lch + 16 + NS_SELCAP;
+  const size_t dbl = 4 * (size_t)ns_kp(k) * ks + 3 * (size_t)ns_kp(k) + 2 * (size_t)lch + 16 + 2 * NS_SELCAP;
   return dbl * 8 + (size_t)NS_SELCAP * 4 + 32 * 4 + 4 * 4 + 16;
 }

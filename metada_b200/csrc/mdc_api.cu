@@ -372,7 +372,10 @@ int mdc_hx_idw4(mdc_ens* e, mdc_obs* o) {
   mdc_ctx* ctx = e->ctx;
   if (o->ctx != ctx) MDC_FAIL(ctx, MDC_ERR_INVALID, "hx: ens/obs belong to different contexts");
   MDC_CUDA(ctx, cudaSetDevice(ctx->device));
-  if (o->P != o->P_own) MDC_FAIL(ctx, MDC_ERR_INVALID, "hx: halo rows already appended; H(x) applies to own obs only");
+  if (o->P != o->P_own) {   // a new cycle: drop the halo rows received for the previous one
+    o->P = o->P_own;
+    o->index_valid = false;
+  }
   if (int rc = obs_reserve(o, o->cap, e->k)) return rc;
   if (o->P == 0) { o->have_hx = true; return MDC_OK; }
   constexpr int W = 8;
@@ -620,7 +623,7 @@ static int letkf_launch(mdc_ens* e, mdc_obs* o, const mdc_letkf_params* p, const
     MDC_FAIL(ctx, MDC_ERR_UNSUPPORTED, "letkf: the Newton-Schulz solver supports 24 <= k <= 80 (k=%d)", k);
   if (p->mode == MDC_MODE_CANONICAL && p->solver != MDC_SOLVER_JACOBI && k >= 24 && k <= 80 && !getenv("MDC_LETKF_V1")) {
     // GEMM-only symmetric square root (letkf_ns.cuh): four k x k buffers, one CTA per SM
-    const int lch = std::min(e->nz, std::min(k, 32));
+    const int lch = std::min(32, (e->nz + 7) & ~7);   // levels per update chunk (multiple of 8)
     const size_t smem3 = ns_smem_bytes(k, lch);
     if ((int)smem3 <= ctx->max_smem_optin) {
       auto launch3 = [&](auto kern) -> int {

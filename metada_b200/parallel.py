@@ -146,6 +146,9 @@ class SlabLetkf:
                 self.obs.append_rows(t.data_ptr(), t.shape[0])
                 self.halo_rows_last += t.shape[0]
             self.ctx.sync()
+        # observations change every assimilation cycle, so the bucket index belongs to the step:
+        # rebuild it even when this object is reused with the same observations (bench.py)
+        self.obs.index_build(max(1, int(math.ceil(params.radius))))
         return capi.letkf_analyse(self.ens, self.obs, params)
 
     # ---- end to end with host buffers

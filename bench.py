@@ -248,6 +248,14 @@ def run_ours(args):
         cols_per_s_kernel = (G / world) / (col_ms * 1e-3)   # columns one GPU's kernel launch processes
         ach_tf = F * cols_per_s_kernel / 1e12
         ach_gb = Bc * cols_per_s_kernel / 1e9
+        traffic, traffic_src = None, None
+        try:   # DRAM bytes per column from the committed ncu capture, scaled to this launch
+            tr = json.load(open(os.path.join(ROOT, "profiles", "r01_ncu_traffic.json")))
+            if tr["kernel"].startswith("letkf_ns") and 24 <= k <= 80 and args.solver != "jacobi" and k == 80 and nz == 60:
+                traffic = tr["dram_bytes_per_column"] * (G / world)
+                traffic_src = tr["source"] + "; per-column figure scaled to this launch's columns"
+        except Exception:  # noqa: BLE001
+            pass
         line = {
             "metric": "LETKF analysed grid-columns/sec", "value": value, "unit": "columns/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": tot_ms / args.steps, "higher_is_better": True,
@@ -259,7 +267,7 @@ def run_ours(args):
                        "l2": "state (%.1f GB) >> 126 MB L2; background regenerated on device before every step" % (G * nz * k * 8 / 1e9),
                        "mean_local_obs": pbar, "mean_solver_iterations": sum_sw / ncols},
             "roofline": {"bound": "fp64", "achieved": ach_tf, "peak": fp64_peak, "unit": "TFLOP/s", "frac": ach_tf / fp64_peak,
-                         "traffic": None, "kernel": "letkf_ns_kernel" if (24 <= k <= 80 and args.solver != "jacobi") else "letkf_canonical_kernel",
+                         "traffic": traffic, "traffic_source": traffic_src, "algorithmic_bytes": Bc * (G / world), "kernel": "letkf_ns_kernel" if (24 <= k <= 80 and args.solver != "jacobi") else "letkf_canonical_kernel",
                          "peak_source": "FP64 FMA microbenchmark run in this process (mdc_bench_fp64_fma); "
                                         "MEASURED_PEAKS.json has no FP64 figure",
                          "flops_per_column": F, "bytes_per_column": Bc,

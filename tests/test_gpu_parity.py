@@ -220,3 +220,32 @@ def test_newton_schulz_ill_conditioned_and_vertical(ctx):
     em, ep = analysis_errors(ens.download(), ref["Xa"])
     assert em < 1e-9 and ep < 1e-9, (em, ep, st)
     ens.close(); obs.close()
+
+
+@pytest.mark.parametrize("k,nz", [(25, 2), (30, 40), (50, 9), (77, 3), (33, 1)])
+def test_newton_schulz_padded_sizes(ctx, k, nz):
+    """k not a multiple of 8 (zero/identity padded DMMA tiles), odd k, and more levels than one
+    update chunk (32)."""
+    X, o = make_case(11, 9, nz, k, 90, seed=300 + k)
+    ens, obs = _setup(ctx, X, o)
+    st = capi.letkf_analyse(ens, obs, capi.make_params(4.0, 1.02, mb.MODE_CANONICAL, mb.LOC_GASPARI_COHN,
+                                                       solver=mb.SOLVER_NEWTON_SCHULZ))
+    ref = orc.letkf(X, o["x"], o["y"], o["z"], o["value"], o["err"], radius=4.0, inflation=1.02)
+    em, ep = analysis_errors(ens.download(), ref["Xa"])
+    assert em < TOL and ep < TOL, (k, nz, em, ep)
+    assert st["numeric_failures"] == 0
+    ens.close(); obs.close()
+
+
+def test_empty_observation_set_inflates_everything(ctx):
+    X, _ = make_case(9, 7, 2, 24, 3, seed=31)
+    ens = mb.Ensemble(ctx, 9, 7, 2, 24)
+    ens.upload(X)
+    obs = mb.Observations(ctx, np.zeros(0, np.int32), np.zeros(0, np.int32), np.zeros(0, np.int32),
+                          np.zeros(0), np.zeros(0))
+    for mode in (mb.MODE_CANONICAL, mb.MODE_REF_COMPAT):
+        ens.upload(X)
+        capi.letkf_analyse(ens, obs, capi.make_params(3.0, 1.21, mode))
+        m = X.mean(0)
+        assert rel_err(ens.download(), m + (X - m) * 1.1) < 1e-14
+    ens.close(); obs.close()

@@ -51,6 +51,9 @@ int64_t mdc_ctx_launch_count(const mdc_ctx* ctx);
 int mdc_ctx_sm_count(const mdc_ctx* ctx);
 /* writes > L2-size bytes to evict the L2 between timed iterations */
 int mdc_ctx_flush_l2(mdc_ctx* ctx);
+/* plain device buffers (halo staging between observation stores on one device) */
+int mdc_dev_malloc(mdc_ctx* ctx, int64_t bytes, void** out);
+int mdc_dev_free(mdc_ctx* ctx, void* p);
 
 /* ---- ensemble store: replaces framework/adapters/Ensemble.hpp:42-194 (vector<State>) ------
  * Device layout: X[col][lev][member], col = y*nx + x  (one contiguous nz*k block per column).
@@ -61,11 +64,21 @@ int mdc_ctx_flush_l2(mdc_ctx* ctx);
 int mdc_ens_create(mdc_ctx* ctx, int nx, int ny, int nz, int k, mdc_ens** out);
 int mdc_ens_destroy(mdc_ens* ens);
 int mdc_ens_set_domain(mdc_ens* ens, int gx0, int gy0, int gnx, int gny, int own_nx, int own_ny);
+/* reuse one allocation for slabs of different heights: ny <= the ny given to mdc_ens_create */
+int mdc_ens_set_rows(mdc_ens* ens, int ny);
 int mdc_ens_upload_member(mdc_ens* ens, int m, const double* host);
 int mdc_ens_download_member(mdc_ens* ens, int m, double* host);
 /* batched variants (coalesced transposes): members m0..m0+count-1, one host pointer each */
 int mdc_ens_upload_members(mdc_ens* ens, int m0, int count, const double* const* hosts);
 int mdc_ens_download_members(mdc_ens* ens, int m0, int count, double* const* hosts);
+/* Row-slab variants for streaming a large host ensemble through the device in pieces: hosts[m]
+ * points at the FULL member array [lev][host_ny][nx]; upload reads its rows host_y0 .. host_y0+ny-1
+ * (ny = this store's local rows), download writes local rows 0 .. nrows-1 to host rows host_y0 ..
+ * (nrows < ny leaves a read-only halo row untouched).  One strided copy per member and batch. */
+int mdc_ens_upload_members_rows(mdc_ens* ens, int m0, int count, const double* const* hosts,
+                                int host_ny, int host_y0);
+int mdc_ens_download_members_rows(mdc_ens* ens, int m0, int count, double* const* hosts,
+                                  int host_ny, int host_y0, int nrows);
 /* seeded synthetic ensemble generated on the device (bit-identical to
  * metada_b200.synthetic.member on the host); coordinates are global. */
 int mdc_ens_fill_synthetic(mdc_ens* ens, uint64_t seed);
@@ -84,6 +97,10 @@ int64_t mdc_ens_bytes(const mdc_ens* ens);
 int mdc_obs_create(mdc_ctx* ctx, int64_t P, const int32_t* x, const int32_t* y, const int32_t* z,
                    const double* value, const double* err, const uint8_t* valid,
                    const int64_t* gid, mdc_obs** out);
+/* replace the contents of an existing store (buffers are reused / grown; halo rows, H(x) results
+ * and the index are dropped) */
+int mdc_obs_assign(mdc_obs* obs, int64_t P, const int32_t* x, const int32_t* y, const int32_t* z,
+                   const double* value, const double* err, const uint8_t* valid, const int64_t* gid);
 int mdc_obs_destroy(mdc_obs* obs);
 int64_t mdc_obs_size(const mdc_obs* obs);       /* own + halo rows */
 

@@ -13,3 +13,4 @@ from .capi import (  # noqa: F401
     lib_path, load_library, build_library, exported_symbols,
 )
 from . import synthetic  # noqa: F401
+from .pipeline import StreamedLetkf  # noqa: F401

@@ -109,12 +109,18 @@ def load_library() -> C.CDLL:
         "mdc_ens_download_member": (C.c_int, [vp, C.c_int, vp]),
         "mdc_ens_upload_members": (C.c_int, [vp, C.c_int, C.c_int, C.POINTER(vp)]),
         "mdc_ens_download_members": (C.c_int, [vp, C.c_int, C.c_int, C.POINTER(vp)]),
+        "mdc_ens_upload_members_rows": (C.c_int, [vp, C.c_int, C.c_int, C.POINTER(vp), C.c_int, C.c_int]),
+        "mdc_ens_download_members_rows": (C.c_int, [vp, C.c_int, C.c_int, C.POINTER(vp), C.c_int, C.c_int, C.c_int]),
+        "mdc_dev_malloc": (C.c_int, [vp, i64, C.POINTER(vp)]),
+        "mdc_dev_free": (C.c_int, [vp, vp]),
         "mdc_ens_fill_synthetic": (C.c_int, [vp, C.c_uint64]),
         "mdc_ens_mean": (C.c_int, [vp, vp]),
         "mdc_ens_checksum": (C.c_int, [vp, pd, pd]),
         "mdc_ens_devptr": (vp, [vp]),
         "mdc_ens_bytes": (i64, [vp]),
         "mdc_obs_create": (C.c_int, [vp, i64, vp, vp, vp, vp, vp, vp, vp, C.POINTER(vp)]),
+        "mdc_obs_assign": (C.c_int, [vp, i64, vp, vp, vp, vp, vp, vp, vp]),
+        "mdc_ens_set_rows": (C.c_int, [vp, C.c_int]),
         "mdc_obs_destroy": (C.c_int, [vp]),
         "mdc_obs_size": (i64, [vp]),
         "mdc_hx_idw4": (C.c_int, [vp, vp]),
@@ -198,6 +204,14 @@ class Context:
         self.check(self.L.mdc_bench_hbm_copy(self.h, C.byref(v)))
         return v.value
 
+    def dev_malloc(self, nbytes: int) -> int:
+        p = C.c_void_p()
+        self.check(self.L.mdc_dev_malloc(self.h, nbytes, C.byref(p)))
+        return int(p.value or 0)
+
+    def dev_free(self, ptr: int):
+        self.check(self.L.mdc_dev_free(self.h, C.c_void_p(ptr)))
+
     def close(self):
         if self.h:
             self.L.mdc_ctx_destroy(self.h)
@@ -216,6 +230,10 @@ class Ensemble:
     def set_domain(self, gx0, gy0, gnx, gny, own_nx, own_ny):
         self.ctx.check(self.ctx.L.mdc_ens_set_domain(self.h, gx0, gy0, gnx, gny, own_nx, own_ny))
 
+    def set_rows(self, ny: int):
+        self.ctx.check(self.ctx.L.mdc_ens_set_rows(self.h, ny))
+        self.ny = ny
+
     def upload(self, X: np.ndarray):
         """X: [k, nz, ny, nx] float64 (any host memory)."""
         X = np.ascontiguousarray(X, dtype=np.float64)
@@ -230,6 +248,14 @@ class Ensemble:
     def download_ptrs(self, m0: int, ptrs):
         arr = (C.c_void_p * len(ptrs))(*ptrs)
         self.ctx.check(self.ctx.L.mdc_ens_download_members(self.h, m0, len(ptrs), arr))
+
+    def upload_rows(self, ptrs, host_ny: int, host_y0: int, m0: int = 0):
+        arr = (C.c_void_p * len(ptrs))(*ptrs)
+        self.ctx.check(self.ctx.L.mdc_ens_upload_members_rows(self.h, m0, len(ptrs), arr, host_ny, host_y0))
+
+    def download_rows(self, ptrs, host_ny: int, host_y0: int, nrows: int, m0: int = 0):
+        arr = (C.c_void_p * len(ptrs))(*ptrs)
+        self.ctx.check(self.ctx.L.mdc_ens_download_members_rows(self.h, m0, len(ptrs), arr, host_ny, host_y0, nrows))
 
     def download(self) -> np.ndarray:
         out = np.empty((self.k, self.nz, self.ny, self.nx))
@@ -287,6 +313,17 @@ class Observations:
         ctx.check(ctx.L.mdc_obs_create(ctx.h, len(x), _ptr(x), _ptr(y), _ptr(z), _ptr(value),
                                        _ptr(err), _ptr(valid), _ptr(gid), C.byref(h)))
         self.h = h
+
+    def assign(self, x, y, z, value, err, valid=None, gid=None):
+        x = np.ascontiguousarray(x, dtype=np.int32)
+        y = np.ascontiguousarray(y, dtype=np.int32)
+        z = np.ascontiguousarray(z, dtype=np.int32) if z is not None else None
+        value = np.ascontiguousarray(value, dtype=np.float64)
+        err = np.ascontiguousarray(err, dtype=np.float64)
+        valid = np.ascontiguousarray(valid, dtype=np.uint8) if valid is not None else None
+        gid = np.ascontiguousarray(gid, dtype=np.int64) if gid is not None else None
+        self.ctx.check(self.ctx.L.mdc_obs_assign(self.h, len(x), _ptr(x), _ptr(y), _ptr(z), _ptr(value),
+                                                 _ptr(err), _ptr(valid), _ptr(gid)))
 
     def size(self) -> int:
         return int(self.ctx.L.mdc_obs_size(self.h))

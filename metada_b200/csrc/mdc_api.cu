@@ -127,6 +127,18 @@ int mdc_ctx_flush_l2(mdc_ctx* ctx) {
   return MDC_OK;
 }
 
+int mdc_dev_malloc(mdc_ctx* ctx, int64_t bytes, void** out) {
+  if (!out || bytes < 0) return MDC_ERR_INVALID;
+  MDC_CUDA(ctx, cudaSetDevice(ctx->device));
+  MDC_CUDA(ctx, cudaMalloc(out, (size_t)std::max<int64_t>(bytes, 8)));
+  return MDC_OK;
+}
+int mdc_dev_free(mdc_ctx* ctx, void* p) {
+  MDC_CUDA(ctx, cudaSetDevice(ctx->device));
+  MDC_CUDA(ctx, cudaFree(p));
+  return MDC_OK;
+}
+
 // ------------------------------------------------------------------------------ ensemble
 int mdc_ens_create(mdc_ctx* ctx, int nx, int ny, int nz, int k, mdc_ens** out) {
   if (!ctx || !out) return MDC_ERR_INVALID;
@@ -136,7 +148,7 @@ int mdc_ens_create(mdc_ctx* ctx, int nx, int ny, int nz, int k, mdc_ens** out) {
   mdc_ens* e = new (std::nothrow) mdc_ens();
   if (!e) MDC_FAIL(ctx, MDC_ERR_INVALID, "out of host memory");
   e->ctx = ctx;
-  e->nx = nx; e->ny = ny; e->nz = nz; e->k = k;
+  e->nx = nx; e->ny = ny; e->nz = nz; e->k = k; e->ny_cap = ny;
   e->gx0 = 0; e->gy0 = 0; e->gnx = nx; e->gny = ny; e->own_nx = nx; e->own_ny = ny;
   size_t total = (size_t)nx * ny * nz * k;
   cudaError_t ce = cudaMalloc((void**)&e->X, total * sizeof(double));
@@ -165,6 +177,16 @@ int mdc_ens_set_domain(mdc_ens* e, int gx0, int gy0, int gnx, int gny, int own_n
       own_nx <= 0 || own_ny <= 0 || own_nx > e->nx || own_ny > e->ny)
     MDC_FAIL(ctx, MDC_ERR_INVALID, "mdc_ens_set_domain: inconsistent domain");
   e->gx0 = gx0; e->gy0 = gy0; e->gnx = gnx; e->gny = gny; e->own_nx = own_nx; e->own_ny = own_ny;
+  return MDC_OK;
+}
+
+int mdc_ens_set_rows(mdc_ens* e, int ny) {
+  mdc_ctx* ctx = e->ctx;
+  if (ny <= 0 || ny > e->ny_cap) MDC_FAIL(ctx, MDC_ERR_INVALID, "set_rows: %d rows requested, %d allocated", ny, e->ny_cap);
+  if (ny != e->ny) {
+    e->ny = ny;
+    e->gx0 = 0; e->gy0 = 0; e->gnx = e->nx; e->gny = ny; e->own_nx = e->nx; e->own_ny = ny;
+  }
   return MDC_OK;
 }
 
@@ -215,6 +237,49 @@ int mdc_ens_download_members(mdc_ens* e, int m0, int count, double* const* hosts
   return MDC_OK;
 }
 
+int mdc_ens_upload_members_rows(mdc_ens* e, int m0, int count, const double* const* hosts,
+                                int host_ny, int host_y0) {
+  mdc_ctx* ctx = e->ctx;
+  if (m0 < 0 || count <= 0 || m0 + count > e->k) MDC_FAIL(ctx, MDC_ERR_INVALID, "upload_rows: member range out of range");
+  if (host_y0 < 0 || host_y0 + e->ny > host_ny) MDC_FAIL(ctx, MDC_ERR_INVALID, "upload_rows: rows [%d,%d) outside the host array (%d rows)", host_y0, host_y0 + e->ny, host_ny);
+  MDC_CUDA(ctx, cudaSetDevice(ctx->device));
+  const int64_t G = (int64_t)e->nx * e->ny, n = G * e->nz;
+  const size_t width = (size_t)e->ny * e->nx * sizeof(double), spitch = (size_t)host_ny * e->nx * sizeof(double);
+  for (int mb = 0; mb < count; mb += kMemberBatch) {
+    const int cb = std::min(kMemberBatch, count - mb);
+    if (int rc = ensure_stage(e, (size_t)n * cb)) return rc;
+    for (int c = 0; c < cb; ++c)
+      MDC_CUDA(ctx, cudaMemcpy2DAsync(e->stage + (int64_t)c * n, width, hosts[mb + c] + (int64_t)host_y0 * e->nx, spitch, width,
+                                      (size_t)e->nz, cudaMemcpyHostToDevice, ctx->stream));
+    ens_scatter_members_kernel<<<mdc_div_up(n, 256), 256, 0, ctx->stream>>>(e->X, e->stage, 0, n, G, e->nz, e->k, m0 + mb, cb);
+    MDC_LAUNCH_CHECK(ctx);
+  }
+  return MDC_OK;
+}
+
+int mdc_ens_download_members_rows(mdc_ens* e, int m0, int count, double* const* hosts, int host_ny,
+                                  int host_y0, int nrows) {
+  mdc_ctx* ctx = e->ctx;
+  if (m0 < 0 || count <= 0 || m0 + count > e->k) MDC_FAIL(ctx, MDC_ERR_INVALID, "download_rows: member range out of range");
+  if (nrows <= 0 || nrows > e->ny || host_y0 < 0 || host_y0 + nrows > host_ny) MDC_FAIL(ctx, MDC_ERR_INVALID, "download_rows: bad row range");
+  MDC_CUDA(ctx, cudaSetDevice(ctx->device));
+  const int64_t G = (int64_t)e->nx * e->ny, n = G * e->nz;
+  const size_t spitch = (size_t)e->ny * e->nx * sizeof(double), dpitch = (size_t)host_ny * e->nx * sizeof(double);
+  const size_t width = (size_t)nrows * e->nx * sizeof(double);
+  for (int mb = 0; mb < count; mb += kMemberBatch) {
+    const int cb = std::min(kMemberBatch, count - mb);
+    if (int rc = ensure_stage(e, (size_t)n * cb)) return rc;
+    ens_gather_members_kernel<<<mdc_div_up(n, 256), 256, 0, ctx->stream>>>(e->X, e->stage, 0, n, G, e->nz, e->k, m0 + mb, cb);
+    MDC_LAUNCH_CHECK(ctx);
+    for (int c = 0; c < cb; ++c)
+      MDC_CUDA(ctx, cudaMemcpy2DAsync(hosts[mb + c] + (int64_t)host_y0 * e->nx, dpitch, e->stage + (int64_t)c * n, spitch, width,
+                                      (size_t)e->nz, cudaMemcpyDeviceToHost, ctx->stream));
+    // the next batch reuses the staging buffer: same stream, so ordered after these copies
+  }
+  MDC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return MDC_OK;
+}
+
 int mdc_ens_download_member(mdc_ens* e, int m, double* host) {
   double* h[1] = {host};
   return mdc_ens_download_members(e, m, 1, h);
@@ -233,7 +298,7 @@ int mdc_ens_fill_synthetic(mdc_ens* e, uint64_t seed) {
 static int ens_mean_device(mdc_ens* e) {
   mdc_ctx* ctx = e->ctx;
   const int64_t npts = (int64_t)e->nx * e->ny * e->nz;
-  if (!e->mean) MDC_CUDA(ctx, cudaMalloc((void**)&e->mean, npts * sizeof(double)));
+  if (!e->mean) MDC_CUDA(ctx, cudaMalloc((void**)&e->mean, (size_t)e->nx * e->ny_cap * e->nz * sizeof(double)));
   constexpr int W = 4;
   size_t smem = (size_t)W * 32 * (e->k | 1) * sizeof(double);
   MDC_CUDA(ctx, cudaFuncSetAttribute(ens_mean_kernel<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -290,7 +355,7 @@ static void obs_free_arrays(mdc_obs* o) {
 static int obs_reserve(mdc_obs* o, int64_t cap, int k) {
   mdc_ctx* ctx = o->ctx;
   if (cap <= o->cap && (k == o->k || k == 0)) return MDC_OK;
-  const int64_t ncap = std::max(cap, o->cap);
+  const int64_t ncap = (cap > o->cap) ? std::max(cap, o->cap + o->cap / 2) : o->cap;   // geometric growth
   const int nk = k ? k : o->k;
   mdc_obs n = *o;
   auto mv = [&](auto** dst, auto* src, size_t elems_new, size_t elems_old) -> int {
@@ -350,6 +415,37 @@ int mdc_obs_create(mdc_ctx* ctx, int64_t P, const int32_t* x, const int32_t* y, 
     MDC_CUDA(ctx, cudaStreamSynchronize(s));  // temporaries above go out of scope
   }
   *out = o;
+  return MDC_OK;
+}
+
+int mdc_obs_assign(mdc_obs* o, int64_t P, const int32_t* x, const int32_t* y, const int32_t* z,
+                   const double* value, const double* err, const uint8_t* valid, const int64_t* gid) {
+  mdc_ctx* ctx = o->ctx;
+  if (P < 0 || P > INT32_MAX / 2) MDC_FAIL(ctx, MDC_ERR_INVALID, "mdc_obs_assign: bad P");
+  if (P > 0 && (!x || !y || !value || !err)) MDC_FAIL(ctx, MDC_ERR_INVALID, "mdc_obs_assign: null arrays");
+  MDC_CUDA(ctx, cudaSetDevice(ctx->device));
+  o->P = 0;                      // nothing to preserve when growing
+  if (int rc = obs_reserve(o, std::max<int64_t>(P, 1), o->k)) return rc;
+  o->P = o->P_own = P;
+  o->have_hx = false;
+  o->index_valid = false;
+  if (P > 0) {
+    std::vector<int32_t> zz;
+    if (!z) { zz.assign((size_t)P, 0); z = zz.data(); }
+    std::vector<uint8_t> vv;
+    if (!valid) { vv.assign((size_t)P, 1); valid = vv.data(); }
+    std::vector<int64_t> gg;
+    if (!gid) { gg.resize((size_t)P); for (int64_t i = 0; i < P; ++i) gg[(size_t)i] = i; gid = gg.data(); }
+    cudaStream_t s = ctx->stream;
+    MDC_CUDA(ctx, cudaMemcpyAsync(o->x, x, P * 4, cudaMemcpyHostToDevice, s));
+    MDC_CUDA(ctx, cudaMemcpyAsync(o->y, y, P * 4, cudaMemcpyHostToDevice, s));
+    MDC_CUDA(ctx, cudaMemcpyAsync(o->z, z, P * 4, cudaMemcpyHostToDevice, s));
+    MDC_CUDA(ctx, cudaMemcpyAsync(o->gid, gid, P * 8, cudaMemcpyHostToDevice, s));
+    MDC_CUDA(ctx, cudaMemcpyAsync(o->val, value, P * 8, cudaMemcpyHostToDevice, s));
+    MDC_CUDA(ctx, cudaMemcpyAsync(o->err, err, P * 8, cudaMemcpyHostToDevice, s));
+    MDC_CUDA(ctx, cudaMemcpyAsync(o->valid, valid, P, cudaMemcpyHostToDevice, s));
+    MDC_CUDA(ctx, cudaStreamSynchronize(s));  // temporaries above go out of scope
+  }
   return MDC_OK;
 }
 
@@ -503,8 +599,11 @@ int mdc_obs_index_build(mdc_obs* o, int cell) {
     MDC_CUDA(ctx, cudaMemcpyAsync(bbox, ctx->d_flags + 4, sizeof(bbox), cudaMemcpyDeviceToHost, s));
     MDC_CUDA(ctx, cudaStreamSynchronize(s));
   }
-  o->xmin = bbox[0]; o->ymin = bbox[1];
-  const int64_t ncx = ((int64_t)bbox[2] - bbox[0]) / cell + 1, ncy = ((int64_t)bbox[3] - bbox[1]) / cell + 1;
+  // cell boundaries sit at global multiples of `cell` (not at this store's bounding box), so a
+  // column sees its candidates in the same (cell, global id) order on every rank / slab
+  auto floor_to = [cell](int v) { int q = v / cell; if (v % cell != 0 && v < 0) --q; return q * cell; };
+  o->xmin = floor_to(bbox[0]); o->ymin = floor_to(bbox[1]);
+  const int64_t ncx = ((int64_t)bbox[2] - o->xmin) / cell + 1, ncy = ((int64_t)bbox[3] - o->ymin) / cell + 1;
   if (ncx * ncy > (1ll << 28)) MDC_FAIL(ctx, MDC_ERR_INVALID, "index_build: %lld x %lld cells is too many; use a larger cell", (long long)ncx, (long long)ncy);
   o->ncx = (int)ncx; o->ncy = (int)ncy;
   const size_t ncell = (size_t)(ncx * ncy);
@@ -605,7 +704,7 @@ static int letkf_launch(mdc_ens* e, mdc_obs* o, const mdc_letkf_params* p, const
     MDC_FAIL(ctx, MDC_ERR_UNSUPPORTED, "letkf: k=%d mode=%d needs %zu B shared memory > %d available", k, p->mode, smem, ctx->max_smem_optin);
   ColParams cp;
   cp.X = e->X;
-  if (!e->mean) MDC_CUDA(ctx, cudaMalloc((void**)&e->mean, (size_t)e->nx * e->ny * e->nz * sizeof(double)));
+  if (!e->mean) MDC_CUDA(ctx, cudaMalloc((void**)&e->mean, (size_t)e->nx * e->ny_cap * e->nz * sizeof(double)));
   cp.mean_out = e->mean;
   cp.nx = e->nx; cp.ny = e->ny; cp.nz = e->nz; cp.k = k; cp.own_nx = e->own_nx; cp.own_ny = e->own_ny;
   cp.gx0 = e->gx0; cp.gy0 = e->gy0;

@@ -25,6 +25,7 @@ struct mdc_ctx {
 struct mdc_ens {
   mdc_ctx* ctx = nullptr;
   int nx = 0, ny = 0, nz = 0, k = 0;           // local grid (incl. halo)
+  int ny_cap = 0;                              // rows allocated (mdc_ens_set_rows)
   int gx0 = 0, gy0 = 0, gnx = 0, gny = 0;      // placement in the global grid
   int own_nx = 0, own_ny = 0;                  // analysed columns: x < own_nx, y < own_ny
   double* X = nullptr;                         // [col][lev][member]

@@ -249,3 +249,22 @@ def test_empty_observation_set_inflates_everything(ctx):
         m = X.mean(0)
         assert rel_err(ens.download(), m + (X - m) * 1.1) < 1e-14
     ens.close(); obs.close()
+
+
+@pytest.mark.parametrize("slab_rows,workers", [(8, 3), (5, 2), (64, 4)])
+def test_streamed_host_pipeline_is_bit_identical_to_one_shot(ctx, slab_rows, workers):
+    """Row slabs streamed through the device (upload || analyse || download on separate streams,
+    obs halo between slabs) give exactly the one-shot result, in place in the host members."""
+    nx, ny, nz, k, P, radius = 21, 37, 3, 24, 400, 4.0
+    X, o = make_case(nx, ny, nz, k, P, seed=41, out_of_grid=6)
+    ens, obs = _setup(ctx, X, o)
+    params = capi.make_params(radius, 1.05, mb.MODE_CANONICAL, mb.LOC_GASPARI_COHN)
+    st1 = capi.letkf_analyse(ens, obs, params)
+    one_shot = ens.download()
+    ens.close(); obs.close()
+    host = X.copy()
+    sl = mb.StreamedLetkf(0, nx, ny, nz, k, radius, slab_rows=slab_rows, workers=workers)
+    st2 = sl.analyse([host[m].ctypes.data for m in range(k)], o, params)
+    sl.close()
+    assert np.array_equal(host, one_shot)
+    assert st2["columns"] == nx * ny and st2["sum_local_obs"] == st1["sum_local_obs"]

@@ -243,6 +243,7 @@ def run_ours(args):
     if rank == 0:
         pk = peaks()
         fp64_peak = ctx.bench_fp64_fma()
+        dmma_peak = ctx.bench_fp64_dmma()
         F = flops_per_column(k, pbar, nz)
         Bc = bytes_per_column(k, nz, P, G)
         cols_per_s_kernel = (G / world) / (col_ms * 1e-3)   # columns one GPU's kernel launch processes
@@ -270,6 +271,8 @@ def run_ours(args):
                          "traffic": traffic, "traffic_source": traffic_src, "algorithmic_bytes": Bc * (G / world), "kernel": "letkf_ns_kernel" if (24 <= k <= 80 and args.solver != "jacobi") else "letkf_canonical_kernel",
                          "peak_source": "FP64 FMA microbenchmark run in this process (mdc_bench_fp64_fma); "
                                         "MEASURED_PEAKS.json has no FP64 figure",
+                         "pipe": "FP64 tensor path (DMMA mma.sync.m8n8k4.f64) for the Newton-Schulz products, SYRK and update",
+                         "fp64_dmma_peak": dmma_peak, "frac_of_dmma_peak": ach_tf / dmma_peak,
                          "flops_per_column": F, "bytes_per_column": Bc,
                          "hbm": {"achieved": ach_gb, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": ach_gb / pk["hbm_gbs"], "peak_source": pk["source"]}},
             "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,

@@ -145,7 +145,9 @@ typedef struct {
   int max_sweeps;     /* Jacobi sweep cap (<= 0: 40)                                          */
   double jacobi_tol;  /* stop when a sweep's max |g_p.g_q|/(|g_p||g_q|) < tol (<= 0: 1e-11)    */
   int solver;         /* CANONICAL: how A^{-1/2} is formed -- MDC_SOLVER_*                    */
-  int reserved[3];
+  int sm_reserve;     /* SMs the persistent column kernel leaves free for concurrent streams
+                         (member transposes of a streamed pipeline); 0 = use every SM          */
+  int reserved[2];
 } mdc_letkf_params;
 
 typedef struct {

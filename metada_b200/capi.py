@@ -33,7 +33,7 @@ class MdcError(RuntimeError):
 class LetkfParams(C.Structure):
     _fields_ = [("radius", C.c_double), ("radius_v", C.c_double), ("inflation", C.c_double),
                 ("mode", C.c_int), ("loc", C.c_int), ("use_R", C.c_int), ("max_sweeps", C.c_int),
-                ("jacobi_tol", C.c_double), ("solver", C.c_int), ("reserved", C.c_int * 3)]
+                ("jacobi_tol", C.c_double), ("solver", C.c_int), ("sm_reserve", C.c_int), ("reserved", C.c_int * 2)]
 
 
 class LetkfStats(C.Structure):
@@ -384,11 +384,12 @@ SOLVER_AUTO, SOLVER_JACOBI, SOLVER_NEWTON_SCHULZ = 0, 1, 2
 
 
 def make_params(radius, inflation=1.0, mode=MODE_CANONICAL, loc=LOC_GASPARI_COHN, use_R=1,
-                radius_v=0.0, max_sweeps=0, jacobi_tol=0.0, solver=SOLVER_AUTO) -> LetkfParams:
+                radius_v=0.0, max_sweeps=0, jacobi_tol=0.0, solver=SOLVER_AUTO, sm_reserve=0) -> LetkfParams:
     p = LetkfParams()
     p.radius, p.radius_v, p.inflation = radius, radius_v, inflation
     p.mode, p.loc, p.use_R, p.max_sweeps, p.jacobi_tol = mode, loc, use_R, max_sweeps, jacobi_tol
     p.solver = solver
+    p.sm_reserve = sm_reserve
     return p
 
 

@@ -718,6 +718,7 @@ static int letkf_launch(mdc_ens* e, mdc_obs* o, const mdc_letkf_params* p, const
   cp.W_out = dW; cp.w_col = w_col;
   cp.cols = dcols; cp.ncols = ncols;
   const long long total_cols = dcols ? ncols : (long long)e->own_nx * e->own_ny;
+  const int sms = std::max(1, ctx->sm_count - std::max(0, std::min(p->sm_reserve, ctx->sm_count / 2)));
   if (p->mode == MDC_MODE_CANONICAL && p->solver == MDC_SOLVER_NEWTON_SCHULZ && (k < 24 || k > 80))
     MDC_FAIL(ctx, MDC_ERR_UNSUPPORTED, "letkf: the Newton-Schulz solver supports 24 <= k <= 80 (k=%d)", k);
   if (p->mode == MDC_MODE_CANONICAL && p->solver != MDC_SOLVER_JACOBI && k >= 24 && k <= 80 && !getenv("MDC_LETKF_V1")) {
@@ -730,7 +731,7 @@ static int letkf_launch(mdc_ens* e, mdc_obs* o, const mdc_letkf_params* p, const
         int occ = 1;
         MDC_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, NS_THREADS, smem3));
         if (occ < 1) occ = 1;
-        int grid = (int)std::max<long long>(1, std::min<long long>(total_cols, (long long)ctx->sm_count * occ));
+        int grid = (int)std::max<long long>(1, std::min<long long>(total_cols, (long long)sms * occ));
         kern<<<grid, NS_THREADS, smem3, ctx->stream>>>(cp, lch);
         MDC_LAUNCH_CHECK(ctx);
         return MDC_OK;
@@ -754,7 +755,7 @@ static int letkf_launch(mdc_ens* e, mdc_obs* o, const mdc_letkf_params* p, const
       int occ = 1;
       MDC_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, nt, smem2));
       if (occ < 1) occ = 1;
-      int grid = (int)std::max<long long>(1, std::min<long long>(total_cols, (long long)ctx->sm_count * occ));
+      int grid = (int)std::max<long long>(1, std::min<long long>(total_cols, (long long)sms * occ));
       kern<<<grid, nt, smem2, ctx->stream>>>(cp, lch);
       MDC_LAUNCH_CHECK(ctx);
       return MDC_OK;
@@ -773,7 +774,7 @@ static int letkf_launch(mdc_ens* e, mdc_obs* o, const mdc_letkf_params* p, const
     int occ = 1;
     MDC_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, LK_THREADS, smem));
     if (occ < 1) occ = 1;
-    int grid = (int)std::max<long long>(1, std::min<long long>(total_cols, (long long)ctx->sm_count * occ));
+    int grid = (int)std::max<long long>(1, std::min<long long>(total_cols, (long long)sms * occ));
     kern<<<grid, LK_THREADS, smem, ctx->stream>>>(cp);
     MDC_LAUNCH_CHECK(ctx);
     return MDC_OK;

@@ -208,7 +208,7 @@ class SlabLetkf:
         from .pipeline import StreamedLetkf
         G = self.gnx * self.gny
         sl = StreamedLetkf(self.ctx.device, self.gnx, self.gny, self.nz, self.k, params.radius,
-                           slab_rows=32, workers=4)
+                           slab_rows=32, slots=4)
         times = []
         for it in range(steps + 1):           # first pass is the warm-up
             self.ens.fill_synthetic(1000)
@@ -227,7 +227,7 @@ class SlabLetkf:
         return {"value": G * len(times) / tot, "unit": "columns/s",
                 "h2d_bytes_per_step": int(need + obs_bytes + halo_rows_bytes), "d2h_bytes_per_step": int(need),
                 "ms_per_step": 1e3 * tot / len(times), "steps": len(times), "slabs": sl.nslab, "columns_checked": st["columns"],
-                "note": "pinned host members streamed in %d row slabs on 4 streams: mdc_ens_upload_members_rows -> "
+                "note": "pinned host members streamed in %d row slabs through a 3-stage pipeline (4 slots/streams): mdc_ens_upload_members_rows -> "
                         "mdc_hx_idw4 -> obs-halo pack/append between slabs -> mdc_letkf_analyse -> "
                         "mdc_ens_download_members_rows (in place); host wall clock" % sl.nslab}
 

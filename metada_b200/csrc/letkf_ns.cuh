@@ -46,92 +46,11 @@ __device__ __forceinline__ double block_reduce(double v, bool is_max, double* re
   return r;
 }
 
-// GEMM micro-kernel of the iteration: the TRUE product P Q (using P^T Q, equal for exactly
-// symmetric iterates, lets rounding asymmetry grow like cond(A) per step and the coupled iteration
-// diverges for cond ~ 1e5; with true products it is stable).
-// Thread grid 16 (ty) x 16 (tx): thread owns rows ty + 16a (a < TM) and TM columns laid out as
-// TM/2 adjacent PAIRS 32p + 2tx + {0,1} plus, for odd TM, the single column 32 (TM/2) + tx, so the
-// tile is exactly TM x TM (k = 80: 5 x 5, no padding work) and, with an EVEN row stride,
-//   P[row][r..r+1]        is one LDS.128 (two addresses per warp: broadcast),
-//   Q[r][32p + 2tx ..+1]  is one LDS.128 (16 lanes x 16 B contiguous),
-// i.e. per two r-steps TM + 2 (TM/2) 128-bit (+ 2 (TM&1) 64-bit) loads feed 2 TM^2 FMAs.
-template <int TM>
-__device__ __forceinline__ int ns_col(int b, int tx) {
-  return (b < 2 * (TM / 2)) ? 32 * (b >> 1) + 2 * tx + (b & 1) : 32 * (TM / 2) + tx;
-}
-
-template <int TM>
-__device__ __forceinline__ void ns_mm(const double* __restrict__ Pm, const double* __restrict__ Qm,
-                                      int k, int ks, int ty, int tx, double (&acc)[TM][TM]) {
-  constexpr int NP = TM / 2;
-  constexpr bool ODD = (TM & 1) != 0;
-#pragma unroll
-  for (int a = 0; a < TM; ++a)
-#pragma unroll
-    for (int b = 0; b < TM; ++b) acc[a][b] = 0.0;
-  const double* pa[TM];
-#pragma unroll
-  for (int a = 0; a < TM; ++a) pa[a] = Pm + min(ty + 16 * a, k - 1) * ks;
-  int qoff[NP + 1];
-#pragma unroll
-  for (int p = 0; p < NP; ++p) qoff[p] = min(32 * p + 2 * tx, ks - 2);
-  qoff[NP] = min(32 * NP + tx, ks - 1);
-  const double* q0 = Qm;
-  const int k2 = k & ~1;
-#pragma unroll 2
-  for (int r = 0; r < k2; r += 2) {
-    double2 pv[TM], qv0[NP + 1], qv1[NP + 1];
-#pragma unroll
-    for (int a = 0; a < TM; ++a) pv[a] = *reinterpret_cast<const double2*>(pa[a] + r);
-#pragma unroll
-    for (int p = 0; p < NP; ++p) {
-      qv0[p] = *reinterpret_cast<const double2*>(q0 + qoff[p]);
-      qv1[p] = *reinterpret_cast<const double2*>(q0 + ks + qoff[p]);
-    }
-    if (ODD) { qv0[NP].x = q0[qoff[NP]]; qv1[NP].x = q0[ks + qoff[NP]]; }
-    q0 += 2 * ks;
-#pragma unroll
-    for (int a = 0; a < TM; ++a) {
-#pragma unroll
-      for (int p = 0; p < NP; ++p) {
-        acc[a][2 * p] = fma(pv[a].x, qv0[p].x, acc[a][2 * p]);
-        acc[a][2 * p + 1] = fma(pv[a].x, qv0[p].y, acc[a][2 * p + 1]);
-      }
-      if (ODD) acc[a][TM - 1] = fma(pv[a].x, qv0[NP].x, acc[a][TM - 1]);
-    }
-#pragma unroll
-    for (int a = 0; a < TM; ++a) {
-#pragma unroll
-      for (int p = 0; p < NP; ++p) {
-        acc[a][2 * p] = fma(pv[a].y, qv1[p].x, acc[a][2 * p]);
-        acc[a][2 * p + 1] = fma(pv[a].y, qv1[p].y, acc[a][2 * p + 1]);
-      }
-      if (ODD) acc[a][TM - 1] = fma(pv[a].y, qv1[NP].x, acc[a][TM - 1]);
-    }
-  }
-  if (k & 1) {   // odd k: last r
-    const int r = k - 1;
-    const double* qr = Qm + r * ks;
-#pragma unroll
-    for (int a = 0; a < TM; ++a) {
-      const double pvx = pa[a][r];
-#pragma unroll
-      for (int b = 0; b < TM; ++b) acc[a][b] = fma(pvx, qr[min(ns_col<TM>(b, tx), ks - 1)], acc[a][b]);
-    }
-  }
-}
-
-// element-wise epilogue over the micro-kernel's register tile: f(row, col, value&)
-template <int TM, typename F>
-__device__ __forceinline__ void ns_foreach(int k, int ty, int tx, double (&acc)[TM][TM], F&& f) {
-#pragma unroll
-  for (int a = 0; a < TM; ++a)
-#pragma unroll
-    for (int b = 0; b < TM; ++b) {
-      const int i = ty + 16 * a, j = ns_col<TM>(b, tx);
-      if (i < k && j < k) f(i, j, acc[a][b]);
-    }
-}
+// (An FMA-pipe micro-kernel with exact TM x TM register tiles and 128-bit shared loads preceded the
+// DMMA products below; it measured shared-memory bound -- 65 % smem wavefronts vs 50 % FP64 pipe,
+// profiles/r01_ncu_column_kernel.json entry b -- and was removed.  The products must be TRUE
+// products P Q: P^T Q, equal for exactly symmetric iterates, lets rounding asymmetry grow like
+// cond(A) per step and the coupled iteration diverges for cond ~ 1e5.)
 
 // ---- FP64 tensor-core product of two commuting symmetric matrices (result symmetric): only the
 // nt (nt + 1) / 2 upper-triangular 8 x 8 tiles are computed, each warp taking a contiguous chunk of

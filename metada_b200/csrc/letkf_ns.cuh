@@ -19,9 +19,10 @@
 #pragma once
 #include "letkf_kernels.cuh"
 
-#define NS_THREADS 256
+#define NS_THREADS 256   /* 512 (16 warps, 128 regs) measured 10 % slower: C5q 69.8 vs 63.0 ms */
+#define NS_WARPS (NS_THREADS / 32)
 #define NS_PCH 32
-#define NS_SELCAP 384
+#define NS_SELCAP 512
 #define NS_MAX_ITERS 40
 
 // Matrices are padded to kp = 8 ceil(k/8) rows/cols (DMMA tiles) with row stride ks == 4 (mod 8)
@@ -31,7 +32,7 @@
 __host__ __device__ inline int ns_kp(int k) { return (k + 7) & ~7; }
 __host__ __device__ inline int ns_stride(int k) { return ns_kp(k) + 4; }
 
-__device__ __forceinline__ double block_reduce(double v, bool is_max, double* red /*[9]*/) {
+__device__ __forceinline__ double block_reduce(double v, bool is_max, double* red /*[NS_WARPS]*/) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
   for (int o = 16; o; o >>= 1) {
@@ -79,6 +80,16 @@ __device__ __forceinline__ NsTiles<NTW> ns_tiles(int kp, int warp) {
   return w;
 }
 
+__device__ __forceinline__ double lds_f64(unsigned addr) {
+  double v;
+  asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr));
+  return v;
+}
+
+// Both operands are EXACTLY symmetric here (mirrored stores), so the B fragment Q[kk+t][8 tj + g]
+// is read as Q[8 tj + g][kk+t]: the same 8-rows-x-4-consecutive-doubles pattern as the A fragment,
+// and every load address is a per-tile 32-bit shared base plus the running k offset -- no address
+// arithmetic inside the unrolled loop.
 template <int NTW>
 __device__ __forceinline__ void ns_mm_sym(const double* __restrict__ Pm, const double* __restrict__ Qm,
                                           int kp, int ks, const NsTiles<NTW>& w, int lane,
@@ -86,21 +97,24 @@ __device__ __forceinline__ void ns_mm_sym(const double* __restrict__ Pm, const d
   const int g = lane >> 2, t = lane & 3;
 #pragma unroll
   for (int n = 0; n < NTW; ++n) { acc[n][0] = 0.0; acc[n][1] = 0.0; }
-  const double* pa[NTW];
-  const double* qb[NTW];
+  const unsigned pbase = (unsigned)__cvta_generic_to_shared(Pm) + (unsigned)((g * ks + t) * 8);
+  const unsigned qbase = (unsigned)__cvta_generic_to_shared(Qm) + (unsigned)((g * ks + t) * 8);
+  unsigned pa[NTW], qb[NTW];
+  bool fresh[NTW];
 #pragma unroll
   for (int n = 0; n < NTW; ++n) {
-    pa[n] = Pm + ((w.ti[n] * 8 + g) * ks + t);
-    qb[n] = Qm + (t * ks + w.tj[n] * 8 + g);
+    pa[n] = pbase + (unsigned)(w.ti[n] * 8 * ks * 8);
+    qb[n] = qbase + (unsigned)(w.tj[n] * 8 * ks * 8);
+    fresh[n] = (n == 0) || (w.ti[n] != w.ti[n - 1]);   // consecutive tiles mostly share their tile row
   }
 #pragma unroll 4
   for (int kk = 0; kk < kp; kk += 4) {
+    const unsigned ko = (unsigned)(kk * 8);
     double a[NTW], b[NTW];
 #pragma unroll
     for (int n = 0; n < NTW; ++n) {
-      // consecutive tiles of a chunk mostly share their tile row: reuse the A fragment
-      if (n == 0 || w.ti[n] != w.ti[n - 1]) a[n] = pa[n][kk]; else a[n] = a[n - 1];
-      b[n] = qb[n][kk * ks];
+      if (fresh[n]) a[n] = lds_f64(pa[n] + ko); else a[n] = a[n - 1];
+      b[n] = lds_f64(qb[n] + ko);
     }
 #pragma unroll
     for (int n = 0; n < NTW; ++n)
@@ -133,16 +147,18 @@ __device__ __forceinline__ void ns_store_sym(double* dst, int ks, int i, int j, 
 // of 5 x 3 and 5 x 2 tiles, 25 MMAs per k-step per sub-partition).
 struct NsWarpTile { int tr0, ntr, tc0, ntc; };
 __device__ __forceinline__ NsWarpTile ns_warp_tile(int kp, int warp) {
-  const int nt = kp >> 3, rh = warp >> 2, cq = warp & 3;
+  // NS_WARPS / 4 row groups x 4 column quarters; odd row groups list the quarter sizes in reverse
+  // order, so the four warps of one SM sub-partition (w, w+4, w+8, ...) carry equal MMA counts
+  constexpr int RG = NS_WARPS / 4;
+  const int nt = kp >> 3, rg = warp >> 2, cq = warp & 3;
   NsWarpTile w;
-  const int h0 = (nt + 1) >> 1;
-  w.tr0 = rh ? h0 : 0;
-  w.ntr = rh ? nt - h0 : h0;
+  w.tr0 = (nt * rg) / RG;
+  w.ntr = (nt * (rg + 1)) / RG - w.tr0;
   const int base = nt >> 2, rem = nt & 3;
   int start = 0;
   w.tc0 = 0; w.ntc = 0;
   for (int i = 0; i < 4; ++i) {
-    const int qi = rh ? 3 - i : i;
+    const int qi = (rg & 1) ? 3 - i : i;
     const int sz = base + (qi < rem ? 1 : 0);
     if (i == cq) { w.tc0 = start; w.ntc = sz; }
     start += sz;
@@ -192,8 +208,8 @@ __device__ __forceinline__ void ns_foreach_full(const NsWarpTile& w, int lane, d
 // One product C = P Q into registers + visitor; SYM selects the symmetric-tile or the full variant.
 template <int TM, bool SYM>
 struct NsProd {
-  static constexpr int NTW = (TM * (2 * TM + 1) + 7) / 8;
-  static constexpr int RT = (2 * TM + 1) / 2, CT = (2 * TM + 3) / 4;
+  static constexpr int NTW = (TM * (2 * TM + 1) + NS_WARPS - 1) / NS_WARPS;
+  static constexpr int RT = (2 * TM + NS_WARPS / 4 - 1) / (NS_WARPS / 4), CT = (2 * TM + 3) / 4;
   NsTiles<NTW> st;
   NsWarpTile ft;
   double sacc[SYM ? NTW : 1][2];
@@ -274,8 +290,8 @@ template <int TM>
 __global__ void __launch_bounds__(NS_THREADS) letkf_ns_kernel(ColParams P, int lch) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   constexpr int NT = NS_THREADS;
-  constexpr int NTW = (TM * (2 * TM + 1) + 7) / 8;     // upper-triangular tiles per warp
-  constexpr int NTA = (4 * 2 * TM + 7) / 8;            // update tiles per warp (lch <= 32 levels)
+  constexpr int NTW = (TM * (2 * TM + 1) + NS_WARPS - 1) / NS_WARPS;   // upper-triangular tiles per warp
+  constexpr int NTA = (4 * 2 * TM + NS_WARPS - 1) / NS_WARPS;          // update tiles per warp (lch <= 32 levels)
   const int k = P.k, kp = ns_kp(k), ks = ns_stride(k), nz = P.nz, nt = kp >> 3;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = NT / 32;
   const int g = lane >> 2, t = lane & 3;
@@ -385,12 +401,12 @@ __global__ void __launch_bounds__(NS_THREADS) letkf_ns_kernel(ColParams P, int l
         if (have_batch && rows_left && nsel <= NS_SELCAP - NT) continue;
         for (int c0 = 0; c0 < nsel; c0 += NS_PCH) {
           const int rows = min(NS_PCH, nsel - c0), rows4 = (rows + 3) & ~3;
-          // gather: warp w stages rows w, w + 8, w + 16, w + 24; all loads issued before the stores
+          // gather: warp w stages rows w, w + NS_WARPS, ...; all loads issued before the stores
           {
-            double v[NS_PCH / 8][(2 * TM * 8 + 31) / 32];
+            double v[NS_PCH / NS_WARPS][(2 * TM * 8 + 31) / 32];
 #pragma unroll
-            for (int q = 0; q < NS_PCH / 8; ++q) {
-              const int r = warp + 8 * q;
+            for (int q = 0; q < NS_PCH / NS_WARPS; ++q) {
+              const int r = warp + NS_WARPS * q;
               const double* src = P.Yp + (long long)sel_row[c0 + min(r, rows - 1)] * k;
 #pragma unroll
               for (int jj = 0; jj < (2 * TM * 8 + 31) / 32; ++jj) {
@@ -399,8 +415,8 @@ __global__ void __launch_bounds__(NS_THREADS) letkf_ns_kernel(ColParams P, int l
               }
             }
 #pragma unroll
-            for (int q = 0; q < NS_PCH / 8; ++q) {
-              const int r = warp + 8 * q;
+            for (int q = 0; q < NS_PCH / NS_WARPS; ++q) {
+              const int r = warp + NS_WARPS * q;
               if (r < rows4) {
                 const double sq = (r < rows) ? sel_sq[c0 + r] : 0.0;
 #pragma unroll

@@ -135,9 +135,10 @@ int mdc_enkf_analyse(mdc_ens* e, mdc_obs* o, double inflation, const double* Z, 
     cudaMemcpyAsync(dmm, init, sizeof(init), cudaMemcpyHostToDevice, s);
     enkf_gain_factor_kernel<<<grid_for(ctx, P * k, 256, 8), 256, 0, s>>>(o->Yp, dAinv, o->err, o->valid, P, k, dM);
     ctx->launches++;
-    size_t smem = (size_t)2 * 64 * ks * sizeof(double);
+    const int gkc = std::min((k + 3) & ~3, GM_KC), gks = ((gkc + 7) & ~7) + 4;
+    size_t smem = (size_t)(GM_TP + GM_TO) * gks * sizeof(double);
     cudaFuncSetAttribute(enkf_gain_minmax_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    dim3 grid((unsigned)((npts + 63) / 64), (unsigned)((P + 63) / 64));
+    dim3 grid((unsigned)((npts + GM_TP - 1) / GM_TP), (unsigned)((P + GM_TO - 1) / GM_TO));
     enkf_gain_minmax_kernel<<<grid, GK_THREADS, smem, s>>>(e->X, e->mean, dM, npts, P, k, std::sqrt(inflation), dmm);
     ctx->launches++;
     double hmm[2];

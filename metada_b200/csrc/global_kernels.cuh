@@ -273,55 +273,78 @@ __device__ __forceinline__ void atomic_min_double(double* addr, double v) {
   } while (assumed != old);
 }
 
-// max/min over K[pt][o] = scale * sum_j (X[pt][j] - mean[pt]) M[o][j]: 64 x 64 output tile per CTA,
-// 4 x 4 register tile per thread, K is never written (EnKF.hpp:199-203).
+// max/min over K[pt][o] = scale * sum_j (X[pt][j] - mean[pt]) M[o][j]  (EnKF.hpp:199-203): a dense
+// n x P x k FP64 contraction (4e10 FMA at C2) whose result is never written -- FP64 tensor path.
+// CTA tile 128 points x 128 obs; both operands staged in shared memory as [row][kp] with stride
+// == 4 (mod 8) (conflict-free DMMA fragments: A[m][kk] = Xp[m][kk], B[kk][n] = M[n][kk], both the
+// 8-rows-x-4-doubles pattern); 8 warps = 2 (points) x 4 (obs), each 64 x 32 = 8 x 4 DMMA tiles:
+// 12 fragment loads per 32 MMAs.  Max/min reduced in registers, one atomic pair per warp.
+#define GM_TP 128
+#define GM_TO 128
+#define GM_KC 64
 __global__ void __launch_bounds__(GK_THREADS)
 enkf_gain_minmax_kernel(const double* __restrict__ X, const double* __restrict__ mean,
                         const double* __restrict__ Mo, int64_t npoints, int64_t P, int k,
                         double scale, double* __restrict__ mm /*[0]=max [1]=min*/) {
   extern __shared__ double sm[];
-  const int ks = k | 1;
-  double* Xs = sm;                       // [64][ks]
-  double* Ms = Xs + (size_t)64 * ks;     // [64][ks]
-  const int tid = threadIdx.x;
-  const int64_t pt0 = (int64_t)blockIdx.x * 64, ob0 = (int64_t)blockIdx.y * 64;
-  for (int e = tid; e < 64 * k; e += GK_THREADS) {
-    const int r = e / k, j = e - r * k;
-    Xs[r * ks + j] = (pt0 + r < npoints) ? (X[(pt0 + r) * k + j] - mean[pt0 + r]) * scale : 0.0;
-    Ms[r * ks + j] = (ob0 + r < P) ? Mo[(ob0 + r) * k + j] : 0.0;
-  }
-  __syncthreads();
-  const int tp = (tid >> 4) * 4, to = (tid & 15) * 4;
-  double o[4][4];
+  const int kp = (k + 3) & ~3;
+  const int kc = min(kp, GM_KC), ks = ((kc + 7) & ~7) + 4;     // members staged GM_KC at a time
+  double* Xs = sm;                           // [GM_TP][ks]
+  double* Ms = Xs + (size_t)GM_TP * ks;      // [GM_TO][ks]
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int g = lane >> 2, t = lane & 3;
+  const int64_t pt0 = (int64_t)blockIdx.x * GM_TP, ob0 = (int64_t)blockIdx.y * GM_TO;
+  const int wp = warp >> 2, wo = warp & 3;       // warp tile: points [64 wp, +64), obs [32 wo, +32)
+  double acc[8][4][2];
 #pragma unroll
-  for (int a = 0; a < 4; ++a)
+  for (int i = 0; i < 8; ++i)
 #pragma unroll
-    for (int b = 0; b < 4; ++b) o[a][b] = 0.0;
-  for (int j = 0; j < k; ++j) {
-    double xv[4], mv[4];
+    for (int j = 0; j < 4; ++j) { acc[i][j][0] = 0.0; acc[i][j][1] = 0.0; }
+  const double* xa = Xs + (64 * wp + g) * ks + t;
+  const double* mb = Ms + (32 * wo + g) * ks + t;
+  for (int k0 = 0; k0 < kp; k0 += kc) {
+    const int kn = min(kc, kp - k0);
+    __syncthreads();
+    for (int e = tid; e < GM_TP * kn; e += GK_THREADS) {
+      const int r = e / kn, j = e - r * kn;
+      Xs[r * ks + j] = (pt0 + r < npoints && k0 + j < k) ? (X[(pt0 + r) * k + k0 + j] - mean[pt0 + r]) * scale : 0.0;
+    }
+    for (int e = tid; e < GM_TO * kn; e += GK_THREADS) {
+      const int r = e / kn, j = e - r * kn;
+      Ms[r * ks + j] = (ob0 + r < P && k0 + j < k) ? Mo[(ob0 + r) * k + k0 + j] : 0.0;
+    }
+    __syncthreads();
+    for (int kk = 0; kk < kn; kk += 4) {
+      double a[8], b[4];
 #pragma unroll
-    for (int a = 0; a < 4; ++a) xv[a] = Xs[(tp + a) * ks + j];
+      for (int i = 0; i < 8; ++i) a[i] = xa[i * 8 * ks + kk];
 #pragma unroll
-    for (int b = 0; b < 4; ++b) mv[b] = Ms[(to + b) * ks + j];
+      for (int j = 0; j < 4; ++j) b[j] = mb[j * 8 * ks + kk];
 #pragma unroll
-    for (int a = 0; a < 4; ++a)
+      for (int i = 0; i < 8; ++i)
 #pragma unroll
-      for (int b = 0; b < 4; ++b) o[a][b] += xv[a] * mv[b];
+        for (int j = 0; j < 4; ++j)
+          asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                       : "+d"(acc[i][j][0]), "+d"(acc[i][j][1])
+                       : "d"(a[i]), "d"(b[j]));
+    }
   }
   double vmax = -INFINITY, vmin = INFINITY;
 #pragma unroll
-  for (int a = 0; a < 4; ++a)
+  for (int i = 0; i < 8; ++i)
 #pragma unroll
-    for (int b = 0; b < 4; ++b)
-      if (pt0 + tp + a < npoints && ob0 + to + b < P) {
-        vmax = fmax(vmax, o[a][b]);
-        vmin = fmin(vmin, o[a][b]);
+    for (int j = 0; j < 4; ++j) {
+      const int64_t pt = pt0 + 64 * wp + 8 * i + g, ob = ob0 + 32 * wo + 8 * j + 2 * t;
+      if (pt < npoints) {
+        if (ob < P) { vmax = fmax(vmax, acc[i][j][0]); vmin = fmin(vmin, acc[i][j][0]); }
+        if (ob + 1 < P) { vmax = fmax(vmax, acc[i][j][1]); vmin = fmin(vmin, acc[i][j][1]); }
       }
+    }
   for (int off = 16; off; off >>= 1) {
     vmax = fmax(vmax, __shfl_xor_sync(0xffffffffu, vmax, off));
     vmin = fmin(vmin, __shfl_xor_sync(0xffffffffu, vmin, off));
   }
-  if ((tid & 31) == 0) {
+  if (lane == 0) {
     atomic_max_double(mm + 0, vmax);
     atomic_min_double(mm + 1, vmin);
   }

@@ -228,21 +228,61 @@ struct NsProd {
   }
 };
 
-// Coupled Newton-Schulz from (Y = Y1, Z = T = Z1) already in Bf; returns iterations, sets ok.
-// On exit Zm points at (cA)^{-1/2}.
+// Starting point of the iteration: Z0 = q(A) with q the degree-2 Chebyshev interpolant of x^{-1/2}
+// on [lo, hi] >= spectrum(A), rescaled so that p(x) = q(x)^2 x -- the spectrum of Z0 Y0 = Z0^2 A --
+// is centred on 1 (sampled at 64 points; the iteration only needs |1 - p| < 1, and the exact
+// centring only affects the iteration count).  Costs two products (A^2, A Z0) and saves four to five
+// iterations of three against the textbook start Z0 = I, Y0 = 2A/(lo + hi).
+struct NsStart { double a0, a1, a2; };
+__device__ __forceinline__ NsStart ns_chebyshev_start(double lo, double hi) {
+  hi = fmax(hi, lo * (1.0 + 1e-6));
+  const double t0 = 0.86602540378443865;                   // cos(pi/6); nodes t0, 0, -t0
+  const double hw = 0.5 * (hi - lo), mid = 0.5 * (hi + lo);
+  const double f0 = rsqrt(mid + hw * t0), f1 = rsqrt(mid), f2 = rsqrt(mid - hw * t0);
+  const double c0 = (f0 + f1 + f2) / 3.0;
+  const double c1 = (2.0 / 3.0) * t0 * (f0 - f2);
+  const double c2 = (2.0 / 3.0) * (0.5 * f0 - f1 + 0.5 * f2);      // T2(t0) = 1/2, T2(0) = -1
+  const double m = 1.0 / hw, n = -mid / hw;                         // u = m x + n
+  NsStart q;
+  q.a0 = c0 + c1 * n + c2 * (2.0 * n * n - 1.0);
+  q.a1 = c1 * m + 4.0 * c2 * m * n;
+  q.a2 = 2.0 * c2 * m * m;
+  double pmin = 1e300, pmax = 0.0;
+  for (int i = 0; i < 64; ++i) {
+    const double x = lo + (hi - lo) * ((double)i * (1.0 / 63.0));
+    const double qx = fma(fma(q.a2, x, q.a1), x, q.a0);
+    const double p = qx * qx * x;
+    pmin = fmin(pmin, p); pmax = fmax(pmax, p);
+  }
+  const double s = sqrt(2.0 / (pmin + pmax));
+  q.a0 *= s; q.a1 *= s; q.a2 *= s;
+  return q;
+}
+
+// Coupled Newton-Schulz  T = (3I - ZY)/2, Y <- YT, Z <- TZ  from a commuting start
+// (Z0 = q(A), Y0 = A Z0, A in Tm; see ns_chebyshev_start).  Returns the iterations used, sets ok.
+// On exit Zm points at A^{-1/2}.
 template <int TM, bool SYM>
 __device__ __forceinline__ int ns_iterate(double*& Ym, double*& Zm, double*& Tm, double*& Sm, int kp,
-                                          int ks, int warp, int lane, double* red, bool& ok) {
+                                          int ks, int warp, int lane, double* red, const NsStart& q,
+                                          bool& ok) {
   NsProd<TM, SYM> pr;
   pr.init(kp, warp);
   auto store_to = [&](double* dst) {
     pr.foreach(lane, [&](int i, int j, double v0, double v1, bool od) { ns_store_sym(dst, ks, i, j, v0, v1, od); });
   };
-  pr.mm(Ym, Tm, kp, ks, lane);                             // Y1 = Y0 T
+  pr.mm(Tm, Tm, kp, ks, lane);                             // A^2
   store_to(Sm);
   __syncthreads();
-  { double* t = Ym; Ym = Sm; Sm = t; }                      // Y = Y1, S = free
-  int it = 1;
+  for (int e = warp * 32 + lane; e < kp * kp; e += NS_THREADS) {   // Z0 = q(A), exactly symmetric
+    const int i = e / kp, j = e - i * kp;
+    Zm[i * ks + j] = fma(q.a2, Sm[i * ks + j], fma(q.a1, Tm[i * ks + j], i == j ? q.a0 : 0.0));
+  }
+  __syncthreads();
+  pr.mm(Tm, Zm, kp, ks, lane);                             // Y0 = A Z0
+  store_to(Ym);
+  __syncthreads();
+  int it = 0;
   bool done = false;
   for (; it < NS_MAX_ITERS && !done; ++it) {
     pr.mm(Zm, Ym, kp, ks, lane);                           // Z Y
@@ -457,47 +497,43 @@ __global__ void __launch_bounds__(NS_THREADS) letkf_ns_kernel(ColParams P, int l
       }
       if (lt == 0) col_npl = npl;
 
-      // ---------------- 2. Z = (cA)^{-1/2} by coupled Newton-Schulz
-      double* Ym = Bf[0];
+      // ---------------- 2. Z = A^{-1/2}, A = shift I + C, by coupled Newton-Schulz
+      double* Tm = Bf[0];       // A, then T
       double* Zm = Bf[1];
-      double* Tm = Bf[2];
+      double* Ym = Bf[2];
       double* Sm = Bf[3];
-      double cscale = 1.0;
       bool ok = true;
       if (npl > 0) {
+        // spectrum(A) lies in [shift, shift + ||C||_F]: C is PSD, and its smallest eigenvalue is
+        // exactly 0 (Y' 1 = 0)
         const double shift = km1 / P.inflation;
         double fro = 0.0;
         ns_foreach_sym<NTW>(st, lane, cacc, [&](int i, int j, double v0, double v1, bool od) {
           if (i < k) {
             const double w = od ? 2.0 : 1.0;
-            if (j < k) { const double x = v0 + (i == j ? shift : 0.0); fro = fma(w * x, x, fro); }
-            if (j + 1 < k) { const double x = v1 + (i == j + 1 ? shift : 0.0); fro = fma(w * x, x, fro); }
+            if (j < k) fro = fma(w * v0, v0, fro);
+            if (j + 1 < k) fro = fma(w * v1, v1, fro);
           }
         });
         fro = sqrt(block_reduce(fro, false, red));
-        cscale = 2.0 / (shift + fro);
-        // Y0 = cA (identity on the zero padding); first iteration in closed form (Z0 = I):
-        // T = 1.5 I - 0.5 Y0, Z1 = T
         ns_foreach_sym<NTW>(st, lane, cacc, [&](int i, int j, double v0, double v1, bool od) {
-          const double d0 = (i == j ? 1.0 : 0.0), d1 = (i == j + 1 ? 1.0 : 0.0);
-          const double y0 = (i < k && j < k) ? cscale * (v0 + d0 * shift) : d0;
-          const double y1 = (i < k && j + 1 < k) ? cscale * (v1 + d1 * shift) : d1;
-          ns_store_sym(Ym, ks, i, j, y0, y1, od);
-          const double t0 = 1.5 * d0 - 0.5 * y0, t1 = 1.5 * d1 - 0.5 * y1;
-          ns_store_sym(Tm, ks, i, j, t0, t1, od);
-          ns_store_sym(Zm, ks, i, j, t0, t1, od);
+          const double d0 = (i == j ? shift : 0.0), d1 = (i == j + 1 ? shift : 0.0);
+          const double y0 = (i < k && j < k) ? v0 + d0 : d0;           // shift I on the zero padding
+          const double y1 = (i < k && j + 1 < k) ? v1 + d1 : d1;
+          ns_store_sym(Tm, ks, i, j, y0, y1, od);
         });
         if (tid < k) gvec[tid] = gacc;
         __syncthreads();
+        const NsStart q0 = ns_chebyshev_start(shift, shift + fro);
         // Symmetric-tile products are ~2x cheaper but lose commutativity-based stability when
         // cond(A) is large (error ~1e-13 at cond 1e3, ~5e-8 at 1e4, divergence at 1e5 -- measured);
-        // the rigorous bound (lmin + ||A||_F)/lmin >= cond(A) picks the variant per column.
+        // the rigorous bound (shift + ||C||_F)/shift >= cond(A) picks the variant per column.
         const bool well_conditioned = (shift + fro) < 1.0e3 * shift;
         int it;
-        if (well_conditioned) it = ns_iterate<TM, true>(Ym, Zm, Tm, Sm, kp, ks, warp, lane, red, ok);
-        else it = ns_iterate<TM, false>(Ym, Zm, Tm, Sm, kp, ks, warp, lane, red, ok);
+        if (well_conditioned) it = ns_iterate<TM, true>(Ym, Zm, Tm, Sm, kp, ks, warp, lane, red, q0, ok);
+        else it = ns_iterate<TM, false>(Ym, Zm, Tm, Sm, kp, ks, warp, lane, red, q0, ok);
         col_iters = max(col_iters, it);
-        // w = c Z (Z g)
+        // w = Z (Z g)
         if (ok) {
           for (int a = warp; a < k; a += nw) {
             double s = 0.0;
@@ -510,12 +546,12 @@ __global__ void __launch_bounds__(NS_THREADS) letkf_ns_kernel(ColParams P, int l
             double s = 0.0;
             for (int b = lane; b < k; b += 32) s += Zm[a * ks + b] * tv[b];
             s = warp_sum(s);
-            if (lane == 0) wa[a] = cscale * s;
+            if (lane == 0) wa[a] = s;
           }
           __syncthreads();
         }
       }
-      const double sW = sqrt(km1 * cscale);
+      const double sW = sqrt(km1);
       if (!ok) col_fail = true;
 
       if (P.W_out && P.w_col == col && lt == 0) {

@@ -130,10 +130,13 @@ int mdc_obs_index_query_lists(mdc_obs* obs, mdc_ens* ens, double radius, const i
 /* ---- LETKF: replaces LETKF<Tag>::Analyse / updateGridPoint (LETKF.hpp:63-119, 152-243) ----- */
 enum { MDC_MODE_REF_COMPAT = 0, MDC_MODE_REF_ETKF = 1, MDC_MODE_CANONICAL = 2 };
 enum { MDC_LOC_CUTOFF = 0, MDC_LOC_GASPARI_COHN = 1 };
-/* AUTO: Newton-Schulz (GEMM-only symmetric square root on FP64 DMMA) for 24 <= k <= 80, else Jacobi.
+/* AUTO: Newton-Schulz (GEMM-only symmetric square root on FP64 DMMA) for 24 <= k <= 128, else Jacobi.
  * JACOBI: one-block-per-column one-sided Jacobi eigen-decomposition with warp-shuffle reductions.
- * Both give the same (unique) symmetric square-root transform to rounding. */
-enum { MDC_SOLVER_AUTO = 0, MDC_SOLVER_JACOBI = 1, MDC_SOLVER_NEWTON_SCHULZ = 2 };
+ * NEWTON_SCHULZ: packed symmetric tiles (two columns per SM for k <= 80); transforms whose
+ *   conditioning bound exceeds 256 are redone by NEWTON_SCHULZ_FULL (k <= 80) or JACOBI (k > 80).
+ * NEWTON_SCHULZ_FULL: every product computed in full, any conditioning, 24 <= k <= 80.
+ * All give the same (unique) symmetric square-root transform to rounding. */
+enum { MDC_SOLVER_AUTO = 0, MDC_SOLVER_JACOBI = 1, MDC_SOLVER_NEWTON_SCHULZ = 2, MDC_SOLVER_NEWTON_SCHULZ_FULL = 3 };
 
 typedef struct {
   double radius;      /* horizontal selection radius (inclusive) = Gaspari-Cohn support       */
@@ -158,7 +161,7 @@ typedef struct {
   int32_t max_sweeps;     /* max Jacobi sweeps (or Newton-Schulz iterations) used by a column */
   int64_t sum_sweeps;
   int32_t numeric_failures;
-  int32_t reserved;
+  int32_t redo_transforms; /* transforms the packed Newton-Schulz kernel handed to its fallback */
 } mdc_letkf_stats;
 
 int mdc_letkf_analyse(mdc_ens* ens, mdc_obs* obs, const mdc_letkf_params* params,

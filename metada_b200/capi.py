@@ -23,7 +23,7 @@ LOC_CUTOFF, LOC_GASPARI_COHN = 0, 1
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-shared", "-Xcompiler", "-fPIC", "-cudart", "shared",
-              "-Xlinker", "-rpath=/usr/local/cuda/lib64"]
+              "-Xlinker", "-rpath=/usr/local/cuda/lib64", "-split-compile", "0"]
 
 
 class MdcError(RuntimeError):
@@ -40,7 +40,7 @@ class LetkfStats(C.Structure):
     _fields_ = [("ms_hx", C.c_float), ("ms_index", C.c_float), ("ms_columns", C.c_float),
                 ("ms_total", C.c_float), ("columns", C.c_int64), ("sum_local_obs", C.c_int64),
                 ("max_local_obs", C.c_int32), ("max_sweeps", C.c_int32), ("sum_sweeps", C.c_int64),
-                ("numeric_failures", C.c_int32), ("reserved", C.c_int32)]
+                ("numeric_failures", C.c_int32), ("redo_transforms", C.c_int32)]
 
     def asdict(self):
         return {n: getattr(self, n) for n, _ in self._fields_ if n != "reserved"}
@@ -380,7 +380,7 @@ class Observations:
             self.h = None
 
 
-SOLVER_AUTO, SOLVER_JACOBI, SOLVER_NEWTON_SCHULZ = 0, 1, 2
+SOLVER_AUTO, SOLVER_JACOBI, SOLVER_NEWTON_SCHULZ, SOLVER_NEWTON_SCHULZ_FULL = 0, 1, 2, 3
 
 
 def make_params(radius, inflation=1.0, mode=MODE_CANONICAL, loc=LOC_GASPARI_COHN, use_R=1,

@@ -39,6 +39,12 @@ struct ColParams {
   long long w_col;
   const long long* cols;  // optional explicit (local linear) column list
   long long ncols;
+  // redo list: (local linear column) * nxf + transform index, nxf = nz with per-level transforms,
+  // else 1.  The packed Newton-Schulz kernel appends the transforms it must not handle; a kernel
+  // launched with redo_consume = 1 processes exactly that list (and leaves stats [0], [1], [5] alone).
+  long long* redo_items;
+  unsigned* redo_count;
+  int redo_consume;
 };
 
 __device__ __forceinline__ double lk_gaspari_cohn(double z) {

@@ -1,21 +1,24 @@
-// letkf_ns.cuh -- CANONICAL column kernel with a GEMM-only symmetric square root.
+// letkf_ns.cuh -- CANONICAL column kernel with a GEMM-only symmetric square root, full products.
 //
 // The canonical LETKF needs W = sqrt(k-1) A^{-1/2} and w = A^{-1} g for the SPD matrix
 // A = (k-1)/infl I + C.  The symmetric square root is unique, so any route to A^{-1/2} gives the
 // same transform as the eigen-decomposition W = U sqrt((k-1)/L) U^T (letkf_v2.cuh), to rounding.
 // Here it is the coupled Newton-Schulz iteration (Higham, Functions of Matrices, eq. 6.35)
-//     Y0 = cA, Z0 = I;   T = (3I - Z Y)/2,  Y <- Y T,  Z <- T Z;   Y -> (cA)^{1/2}, Z -> (cA)^{-1/2}
-// with c = 2/(lmin + b), lmin = (k-1)/infl (exact lower bound of the spectrum) and b = ||A||_F
-// (rigorous upper bound), so |1 - c lambda| < 1 for every eigenvalue.  Every iterate is a polynomial
-// in A (symmetric, commuting).  ~9 iterations x 3 products for the C5 conditioning, each a real
-// dense k x k x k FP64 contraction out of shared memory -- so they run on the FP64 tensor path
-// (DMMA, mma.sync.m8n8k4.f64): an FMA-pipe version with 5 x 5 register tiles is shared-memory
+//     T = (3I - Z Y)/2,  Y <- Y T,  Z <- T Z;   Y -> A^{1/2}, Z -> A^{-1/2}
+// started from Z0 = q(A), Y0 = A Z0 with q a Chebyshev approximation of x^{-1/2} on the spectral
+// interval [lmin, lmin + ||C||_F], lmin = (k-1)/infl the exact lower end (ns_chebyshev_start).
+// Every iterate is a polynomial in A; ~7 iterations x 3 products for the C5 conditioning, each a
+// real dense k x k x k FP64 contraction out of shared memory -- so they run on the FP64 tensor
+// path (DMMA, mma.sync.m8n8k4.f64): an FMA-pipe version with 5 x 5 register tiles is shared-memory
 // bound on B200 (4 (TM+TN)/(TM TN) = 1.6 wavefront-cycles per FP64-pipe cycle, measured 65 % smem
 // vs 50 % FP64 utilisation), whereas DMMA fragments need ~1.3 eight-byte loads per 256-FMA tile.
-// Products of commuting symmetric matrices are symmetric: only the upper-triangular tiles are
-// computed and mirrored (-45 % MMAs, iterates exactly symmetric).  No rotations, shuffles or rsqrt chains, and the update needs ONE
-// product (X' W) instead of two.  Used for 24 <= k <= 80 (four padded k x k buffers must fit in
-// shared memory); other ensemble sizes use the Jacobi kernel.
+// No rotations, shuffles or rsqrt chains, and the update needs ONE product (X' W) instead of two.
+//
+// This kernel computes every product in full (all tiles, true products P Q), which is stable for any
+// conditioning: the identities Z f(YZ) = f(ZY) Z hold structurally, commutativity is not assumed.
+// It needs four padded k x k buffers (one CTA per SM, 24 <= k <= 80) and is the fallback of the
+// packed symmetric kernel (letkf_nsp.cuh), which is ~2x cheaper per product and runs two columns
+// per SM but is only accurate while cond(A) is moderate (NS_SYM_COND_MAX).
 #pragma once
 #include "letkf_kernels.cuh"
 
@@ -24,6 +27,12 @@
 #define NS_PCH 32
 #define NS_SELCAP 512
 #define NS_MAX_ITERS 40
+// Symmetric-tile products (upper triangle computed, lower implied) assume the iterates commute;
+// rounding breaks that and the defect grows with cond(A).  Error of W against the eigen-decomposition
+// (numpy emulation of both variants on the test columns, tools notes in DESIGN.md):
+//   bound < 100: 1e-14 | 100-200: 1e-13 | 200-300: 5e-13 | 300-500: 3e-12 | 700-1000: 3e-10 | 1e4: 5e-8
+// with bound = (lmin + ||C||_F) / lmin >= cond(A); full products stay at 1e-14 .. 1e-13 throughout.
+#define NS_SYM_COND_MAX 256.0
 
 // Matrices are padded to kp = 8 ceil(k/8) rows/cols (DMMA tiles) with row stride ks == 4 (mod 8)
 // doubles: both fragment patterns -- A: 8 rows x 4 consecutive doubles, B: 4 rows x 8 consecutive
@@ -53,11 +62,9 @@ __device__ __forceinline__ double block_reduce(double v, bool is_max, double* re
 // products P Q: P^T Q, equal for exactly symmetric iterates, lets rounding asymmetry grow like
 // cond(A) per step and the coupled iteration diverges for cond ~ 1e5.)
 
-// ---- FP64 tensor-core product of two commuting symmetric matrices (result symmetric): only the
-// nt (nt + 1) / 2 upper-triangular 8 x 8 tiles are computed, each warp taking a contiguous chunk of
-// the row-major upper-triangle enumeration (k = 80: 55 tiles, 7 per warp), and every off-diagonal
-// tile is stored twice (as is and transposed).  This keeps the iterates EXACTLY symmetric and
-// removes 45 % of the MMAs.
+// ---- upper-triangular tile bookkeeping for the SYRK accumulation of C (phase 1): each warp takes a
+// contiguous chunk of the row-major upper-triangle enumeration (k = 80: 55 tiles, 7 per warp), and
+// A is written out mirrored.
 template <int NTW>
 struct NsTiles {
   int ti[NTW], tj[NTW];
@@ -84,45 +91,6 @@ __device__ __forceinline__ double lds_f64(unsigned addr) {
   double v;
   asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr));
   return v;
-}
-
-// Both operands are EXACTLY symmetric here (mirrored stores), so the B fragment Q[kk+t][8 tj + g]
-// is read as Q[8 tj + g][kk+t]: the same 8-rows-x-4-consecutive-doubles pattern as the A fragment,
-// and every load address is a per-tile 32-bit shared base plus the running k offset -- no address
-// arithmetic inside the unrolled loop.
-template <int NTW>
-__device__ __forceinline__ void ns_mm_sym(const double* __restrict__ Pm, const double* __restrict__ Qm,
-                                          int kp, int ks, const NsTiles<NTW>& w, int lane,
-                                          double (&acc)[NTW][2]) {
-  const int g = lane >> 2, t = lane & 3;
-#pragma unroll
-  for (int n = 0; n < NTW; ++n) { acc[n][0] = 0.0; acc[n][1] = 0.0; }
-  const unsigned pbase = (unsigned)__cvta_generic_to_shared(Pm) + (unsigned)((g * ks + t) * 8);
-  const unsigned qbase = (unsigned)__cvta_generic_to_shared(Qm) + (unsigned)((g * ks + t) * 8);
-  unsigned pa[NTW], qb[NTW];
-  bool fresh[NTW];
-#pragma unroll
-  for (int n = 0; n < NTW; ++n) {
-    pa[n] = pbase + (unsigned)(w.ti[n] * 8 * ks * 8);
-    qb[n] = qbase + (unsigned)(w.tj[n] * 8 * ks * 8);
-    fresh[n] = (n == 0) || (w.ti[n] != w.ti[n - 1]);   // consecutive tiles mostly share their tile row
-  }
-#pragma unroll 4
-  for (int kk = 0; kk < kp; kk += 4) {
-    const unsigned ko = (unsigned)(kk * 8);
-    double a[NTW], b[NTW];
-#pragma unroll
-    for (int n = 0; n < NTW; ++n) {
-      if (fresh[n]) a[n] = lds_f64(pa[n] + ko); else a[n] = a[n - 1];
-      b[n] = lds_f64(qb[n] + ko);
-    }
-#pragma unroll
-    for (int n = 0; n < NTW; ++n)
-      if (n < w.n)
-        asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
-                     : "+d"(acc[n][0]), "+d"(acc[n][1])
-                     : "d"(a[n]), "d"(b[n]));
-  }
 }
 
 // f(row, col, v0, v1, offdiag): accumulator pair at (row, col), (row, col + 1); offdiag tiles must
@@ -205,27 +173,18 @@ __device__ __forceinline__ void ns_foreach_full(const NsWarpTile& w, int lane, d
       if (i < w.ntr && j < w.ntc) f((w.tr0 + i) * 8 + g, (w.tc0 + j) * 8 + 2 * t, acc[i][j][0], acc[i][j][1], false);
 }
 
-// One product C = P Q into registers + visitor; SYM selects the symmetric-tile or the full variant.
-template <int TM, bool SYM>
+// One full product C = P Q into registers + visitor.
+template <int TM>
 struct NsProd {
-  static constexpr int NTW = (TM * (2 * TM + 1) + NS_WARPS - 1) / NS_WARPS;
   static constexpr int RT = (2 * TM + NS_WARPS / 4 - 1) / (NS_WARPS / 4), CT = (2 * TM + 3) / 4;
-  NsTiles<NTW> st;
   NsWarpTile ft;
-  double sacc[SYM ? NTW : 1][2];
-  double facc[SYM ? 1 : RT][SYM ? 1 : CT][2];
-  __device__ __forceinline__ void init(int kp, int warp) {
-    if (SYM) st = ns_tiles<NTW>(kp, warp); else ft = ns_warp_tile(kp, warp);
-  }
+  double facc[RT][CT][2];
+  __device__ __forceinline__ void init(int kp, int warp) { ft = ns_warp_tile(kp, warp); }
   __device__ __forceinline__ void mm(const double* Pm, const double* Qm, int kp, int ks, int lane) {
-    if constexpr (SYM) ns_mm_sym<NTW>(Pm, Qm, kp, ks, st, lane, sacc);
-    else ns_mm_full<RT, CT>(Pm, Qm, kp, ks, ft, lane, facc);
+    ns_mm_full<RT, CT>(Pm, Qm, kp, ks, ft, lane, facc);
   }
   template <typename F>
-  __device__ __forceinline__ void foreach(int lane, F&& f) {
-    if constexpr (SYM) ns_foreach_sym<NTW>(st, lane, sacc, f);
-    else ns_foreach_full<RT, CT>(ft, lane, facc, f);
-  }
+  __device__ __forceinline__ void foreach(int lane, F&& f) { ns_foreach_full<RT, CT>(ft, lane, facc, f); }
 };
 
 // Starting point of the iteration: Z0 = q(A) with q the degree-2 Chebyshev interpolant of x^{-1/2}
@@ -262,11 +221,11 @@ __device__ __forceinline__ NsStart ns_chebyshev_start(double lo, double hi) {
 // Coupled Newton-Schulz  T = (3I - ZY)/2, Y <- YT, Z <- TZ  from a commuting start
 // (Z0 = q(A), Y0 = A Z0, A in Tm; see ns_chebyshev_start).  Returns the iterations used, sets ok.
 // On exit Zm points at A^{-1/2}.
-template <int TM, bool SYM>
+template <int TM>
 __device__ __forceinline__ int ns_iterate(double*& Ym, double*& Zm, double*& Tm, double*& Sm, int kp,
                                           int ks, int warp, int lane, double* red, const NsStart& q,
                                           bool& ok) {
-  NsProd<TM, SYM> pr;
+  NsProd<TM> pr;
   pr.init(kp, warp);
   auto store_to = [&](double* dst) {
     pr.foreach(lane, [&](int i, int j, double v0, double v1, bool od) { ns_store_sym(dst, ks, i, j, v0, v1, od); });
@@ -356,12 +315,17 @@ __global__ void __launch_bounds__(NS_THREADS) letkf_ns_kernel(ColParams P, int l
   const bool per_level = P.radius_v > 0.0;
   const int nxf = per_level ? nz : 1;
   const int R = (int)floor(P.radius);
-  const long long ncols = P.cols ? P.ncols : (long long)P.own_nx * P.own_ny;
+  const bool redo = P.redo_consume != 0;
+  const long long ncols = redo ? (long long)*P.redo_count : (P.cols ? P.ncols : (long long)P.own_nx * P.own_ny);
   const NsTiles<NTW> st = ns_tiles<NTW>(kp, warp);
 
   for (long long ci = blockIdx.x; ci < ncols; ci += gridDim.x) {
-    int lx, ly;
-    if (P.cols) { long long c = P.cols[ci]; lx = (int)(c % P.nx); ly = (int)(c / P.nx); }
+    int lx, ly, lt_b = 0, lt_e = nxf;
+    if (redo) {
+      const long long item = P.redo_items[ci], c = item / nxf;
+      lt_b = (int)(item - c * nxf); lt_e = lt_b + 1;
+      lx = (int)(c % P.nx); ly = (int)(c / P.nx);
+    } else if (P.cols) { long long c = P.cols[ci]; lx = (int)(c % P.nx); ly = (int)(c / P.nx); }
     else { lx = (int)(ci % P.own_nx); ly = (int)(ci / P.own_nx); }
     const int gx = P.gx0 + lx, gy = P.gy0 + ly;
     const long long col = (long long)ly * P.nx + lx;
@@ -370,7 +334,7 @@ __global__ void __launch_bounds__(NS_THREADS) letkf_ns_kernel(ColParams P, int l
     long long col_npl = 0;
     bool col_fail = false;
 
-    for (int lt = 0; lt < nxf; ++lt) {
+    for (int lt = lt_b; lt < lt_e; ++lt) {
       // ---------------- 1. selection, gather, C += Yw^T Yw on the FP64 tensor path, g += Yw^T dw
       double cacc[NTW][2];
 #pragma unroll
@@ -495,7 +459,7 @@ __global__ void __launch_bounds__(NS_THREADS) letkf_ns_kernel(ColParams P, int l
         __syncthreads();
         if (!rows_left) break;
       }
-      if (lt == 0) col_npl = npl;
+      if (lt == lt_b) col_npl = npl;
 
       // ---------------- 2. Z = A^{-1/2}, A = shift I + C, by coupled Newton-Schulz
       double* Tm = Bf[0];       // A, then T
@@ -525,13 +489,7 @@ __global__ void __launch_bounds__(NS_THREADS) letkf_ns_kernel(ColParams P, int l
         if (tid < k) gvec[tid] = gacc;
         __syncthreads();
         const NsStart q0 = ns_chebyshev_start(shift, shift + fro);
-        // Symmetric-tile products are ~2x cheaper but lose commutativity-based stability when
-        // cond(A) is large (error ~1e-13 at cond 1e3, ~5e-8 at 1e4, divergence at 1e5 -- measured);
-        // the rigorous bound (shift + ||C||_F)/shift >= cond(A) picks the variant per column.
-        const bool well_conditioned = (shift + fro) < 1.0e3 * shift;
-        int it;
-        if (well_conditioned) it = ns_iterate<TM, true>(Ym, Zm, Tm, Sm, kp, ks, warp, lane, red, q0, ok);
-        else it = ns_iterate<TM, false>(Ym, Zm, Tm, Sm, kp, ks, warp, lane, red, q0, ok);
+        const int it = ns_iterate<TM>(Ym, Zm, Tm, Sm, kp, ks, warp, lane, red, q0, ok);
         col_iters = max(col_iters, it);
         // w = Z (Z g)
         if (ok) {
@@ -645,12 +603,15 @@ __global__ void __launch_bounds__(NS_THREADS) letkf_ns_kernel(ColParams P, int l
       }
     }  // lt
     if (tid == 0) {
-      atomicAdd((unsigned long long*)&P.stats[0], (unsigned long long)col_npl);
-      atomicMax(&P.stats[1], col_npl);
+      if (!redo) {
+        atomicAdd((unsigned long long*)&P.stats[0], (unsigned long long)col_npl);
+        atomicMax(&P.stats[1], col_npl);
+        atomicAdd((unsigned long long*)&P.stats[5], 1ull);
+      }
+      else atomicAdd((unsigned long long*)&P.stats[6], 1ull);
       atomicAdd((unsigned long long*)&P.stats[2], (unsigned long long)col_iters);
       atomicMax(&P.stats[3], (long long)col_iters);
       if (col_fail) atomicAdd((unsigned long long*)&P.stats[4], 1ull);
-      atomicAdd((unsigned long long*)&P.stats[5], 1ull);
     }
   }
 }

@@ -1,0 +1,665 @@
+// letkf_nsp.cuh -- CANONICAL column kernel, Newton-Schulz square root on PACKED symmetric tiles.
+//
+// Same mathematics as letkf_ns.cuh (coupled Newton-Schulz from a Chebyshev start, every product on
+// the FP64 tensor path), different storage: every iterate is a symmetric polynomial in A, so only
+// the nt (nt + 1) / 2 upper-triangular 8 x 8 tiles are kept, each tile a dense 512-byte block.
+//   * k = 80: 55 tiles = 28 KB per matrix instead of 54 KB, and the iteration needs three matrices
+//     (Z, Y, T; the products Y T and T Z are both held in accumulator registers across the barrier
+//     and written back in place) instead of four  ->  ~96 KB per CTA, TWO CTAs per SM: one column's
+//     selection / gather / update phases and barrier bubbles hide under the other's products.
+//   * k = 128: 136 tiles = 70 KB per matrix, three of them fit one SM (the padded square layout
+//     does not), so C4-sized ensembles get the tensor path too (16 warps, one CTA per SM).
+// A fragment of the logical matrix S[8 I + g][8 K + 4 h + t] is read from tile (I, K) when I <= K
+// and, by symmetry, transposed from tile (K, I) otherwise; the column index inside a tile is XORed
+// with 4 on rows 2, 3, 6, 7, which makes the straight read (8 rows x 4 doubles), the transposed read
+// (4 rows x 8 doubles) and the 16-byte accumulator stores all bank-conflict free without padding.
+// Off-diagonal tiles are stored once (no mirrored store).
+//
+// Forcing symmetry is only stable while cond(A) is moderate (letkf_ns.cuh); a column (or level, with
+// per-level transforms) whose rigorous bound (shift + ||C||_F) / shift exceeds NS_SYM_COND_MAX is appended to a
+// redo list, which a second launch of the full-product kernel (k <= 80) or the Jacobi kernel
+// (k > 80) consumes.
+#pragma once
+#include <type_traits>
+#include <utility>
+
+#include "letkf_ns.cuh"
+
+__host__ __device__ inline int nsp_ntiles(int k) { const int nt = (k + 7) >> 3; return nt * (nt + 1) / 2; }
+__device__ __forceinline__ int nsp_row_start(int I, int nt) { return (I * (2 * nt - I + 1)) >> 1; }
+
+// offset (in doubles) of S[i][j] inside a packed matrix; reads the upper copy
+__device__ __forceinline__ int nsp_elem(int i, int j, int nt) {
+  if (i > j) { const int s = i; i = j; j = s; }
+  const int I = i >> 3, J = j >> 3, r = i & 7, c = j & 7;
+  return ((nsp_row_start(I, nt) + J - I) << 6) + r * 8 + (c ^ ((r & 2) << 1));
+}
+
+struct NspLane { unsigned offd, offt, offc, dh; };   // byte offsets inside a tile (k-half h = 0)
+__device__ __forceinline__ NspLane nsp_lane(int lane) {
+  const int g = lane >> 2, t = lane & 3;
+  NspLane L;
+  L.offd = (unsigned)((g * 8 + (t ^ ((g & 2) << 1))) * 8);          // element (g, t); h = 1: ^ 32 = + dh
+  L.dh = (g & 2) ? 0xffffffe0u : 32u;
+  L.offt = (unsigned)((t * 8 + (g ^ ((t & 2) << 1))) * 8);          // element (t, g); h = 1: + 256
+  L.offc = (unsigned)((g * 8 + ((2 * t) ^ ((g & 2) << 1))) * 8);    // accumulator pair (g, 2t), (g, 2t+1)
+  return L;
+}
+// Fragment element S[8 I + g][8 K + 4 h + t] lives at  tile(I, K) * 512 + lane part, with
+//   K <  I: tile (K, I) read transposed, lane part offt + 256 h, next tile (K -> K + 1) + (nt - K - 1)
+//   K >= I: tile (I, K) read straight,   lane part offd + dh h,  next tile + 1
+// and tile(I, 0) = I in both cases, so a running tile offset needs one select + add per K step.
+struct NspWalk {
+  unsigned tile;   // byte offset of the current tile
+  int I;
+  __device__ __forceinline__ void start(int I_) { I = I_; tile = (unsigned)I_ << 9; }
+  __device__ __forceinline__ unsigned addr(unsigned base, int K, int h, const NspLane& L) const {
+    const bool tr = K < I;
+    return base + tile + (tr ? L.offt : L.offd) + (h ? (tr ? 256u : L.dh) : 0u);
+  }
+  __device__ __forceinline__ void next(int K, int nt) { tile += (K < I) ? ((unsigned)(nt - K - 1) << 9) : 512u; }
+};
+
+template <int NTH>
+__device__ __forceinline__ double nsp_block_reduce(double v, bool is_max, double* red /*[NTH/32]*/) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int o = 16; o; o >>= 1) {
+    const double t = __shfl_xor_sync(0xffffffffu, v, o);
+    v = is_max ? fmax(v, t) : v + t;
+  }
+  __syncthreads();
+  if (lane == 0) red[warp] = v;
+  __syncthreads();
+  double r = red[0];
+#pragma unroll
+  for (int w = 1; w < NTH / 32; ++w) r = is_max ? fmax(r, red[w]) : r + red[w];
+  return r;
+}
+
+// upper-triangular tiles of this warp: contiguous chunk of the row-major enumeration, plus the byte
+// offset of each tile's accumulator pair in packed storage
+template <int NTW>
+struct NspTiles {
+  int ti[NTW], tj[NTW];
+  int n;
+};
+__device__ __forceinline__ unsigned nsp_cbase(int ti, int tj, int nt, const NspLane& L) {
+  return (((unsigned)(nsp_row_start(ti, nt) + tj - ti)) << 9) + L.offc;
+}
+template <int NTW, int NTH>
+__device__ __forceinline__ NspTiles<NTW> nsp_tiles(int nt, int warp) {
+  const int E = nt * (nt + 1) / 2;
+  const int e0 = (E * warp) / (NTH / 32), e1 = (E * (warp + 1)) / (NTH / 32);
+  NspTiles<NTW> w;
+  w.n = e1 - e0;
+  int i = 0, rowstart = 0;
+  while (e0 >= rowstart + (nt - i)) { rowstart += nt - i; ++i; }
+  int j = i + (e0 - rowstart);
+#pragma unroll
+  for (int n = 0; n < NTW; ++n) {
+    w.ti[n] = i; w.tj[n] = j;
+    if (n + 1 < w.n) { if (++j == nt) { ++i; j = i; } }
+  }
+  return w;
+}
+
+__device__ __forceinline__ void sts_f64x2(unsigned addr, double v0, double v1) {
+  asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(addr), "d"(v0), "d"(v1) : "memory");
+}
+
+#define NSP_DMMA(acc, a, b)                                                                      \
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" \
+               : "+d"((acc)[0]), "+d"((acc)[1])                                                 \
+               : "d"(a), "d"(b))
+
+// ---- The Newton-Schulz products proper: ONE code site per kernel (the iteration is a small state
+// machine around it), specialised per warp at compile time.  The tile count NT and the warp index W
+// fix the warp's tile list, hence every fragment address: each load is  base register + immediate
+// (six base registers: straight h = 0 / h = 1 and transposed, for P and for Q), no address
+// arithmetic, no predicates, A fragments shared between the tiles of one tile row at compile time.
+// (Double-buffering the fragments in registers spills under the 128-register cap of two CTAs per SM.)
+// (A rolled generic version with a running tile walk per operand -- NspWalk, still used by the update
+// product -- measured ~17 instructions per DMMA and no faster than the padded one-CTA kernel.)
+template <int B, int E, typename F>
+__device__ __forceinline__ void nsp_static_for(F&& f) {
+  if constexpr (B < E) {
+    f(std::integral_constant<int, B>{});
+    nsp_static_for<B + 1, E>(f);
+  }
+}
+__host__ __device__ constexpr int nsp_tile_i(int nt, int e) { int i = 0, rs = 0; while (e >= rs + (nt - i)) { rs += nt - i; ++i; } return i; }
+__host__ __device__ constexpr int nsp_tile_j(int nt, int e) { int i = 0, rs = 0; while (e >= rs + (nt - i)) { rs += nt - i; ++i; } return i + (e - rs); }
+__host__ __device__ constexpr int nsp_rs(int I, int nt) { return (I * (2 * nt - I + 1)) / 2; }
+
+template <int IMM>
+__device__ __forceinline__ double lds_f64_imm(unsigned addr) {
+  double v;
+  asm volatile("ld.shared.f64 %0, [%1+%2];" : "=d"(v) : "r"(addr), "n"(IMM));
+  return v;
+}
+// fragment element S[8 I + g][8 K + 4 h + t]: d = base + straight lane offset of this k-half,
+// tr = base + transposed lane offset of this k-half
+template <int NT, int I, int K>
+__device__ __forceinline__ double nsp_frag_fixed(unsigned d, unsigned tr) {
+  if constexpr (I <= K) return lds_f64_imm<(nsp_rs(I, NT) + K - I) * 512>(d);
+  else return lds_f64_imm<(nsp_rs(K, NT) + I - K) * 512>(tr);
+}
+
+// The k-half loop (h) stays rolled: the body is then half as long, and the eight warp variants of
+// NT = 10 together (20 KB) stay inside the 32 KB L1.5 instruction cache; fully unrolled (41 KB) the
+// same code measured no faster than the generic walk.
+template <int NT, int NW, int NTW, int W>
+__device__ __forceinline__ void nsp_mm_warp(unsigned pd0, unsigned pd1, unsigned pt, unsigned qd0, unsigned qd1,
+                                            unsigned qt, double (&acc)[NTW][2]) {
+  constexpr int E = NT * (NT + 1) / 2, e0 = (E * W) / NW, e1 = (E * (W + 1)) / NW, N = e1 - e0;
+#pragma unroll 1
+  for (int h = 0; h < 2; ++h) {
+    const unsigned pd = h ? pd1 : pd0, ptr = pt + (h << 8), qd = h ? qd1 : qd0, qtr = qt + (h << 8);
+    nsp_static_for<0, NT>([&](auto K_c) {
+      constexpr int K = decltype(K_c)::value;
+      double a[NTW], b[NTW];
+      nsp_static_for<0, N>([&](auto n_c) {
+        constexpr int n = decltype(n_c)::value;
+        constexpr int ti = nsp_tile_i(NT, e0 + n), tj = nsp_tile_j(NT, e0 + n);
+        if constexpr (n > 0 && ti == nsp_tile_i(NT, e0 + (n > 0 ? n - 1 : 0))) a[n] = a[n - 1];
+        else a[n] = nsp_frag_fixed<NT, ti, K>(pd, ptr);
+        b[n] = nsp_frag_fixed<NT, tj, K>(qd, qtr);
+      });
+      nsp_static_for<0, N>([&](auto n_c) {
+        constexpr int n = decltype(n_c)::value;
+        NSP_DMMA(acc[n], a[n], b[n]);
+      });
+    });
+  }
+}
+
+template <int NT, int NW, int NTW, int... Ws>
+__device__ __forceinline__ void nsp_mm_dispatch(std::integer_sequence<int, Ws...>, int warp, unsigned pd0,
+                                                unsigned pd1, unsigned pt, unsigned qd0, unsigned qd1,
+                                                unsigned qt, double (&acc)[NTW][2]) {
+  ((warp == Ws ? (nsp_mm_warp<NT, NW, NTW, Ws>(pd0, pd1, pt, qd0, qd1, qt, acc), 0) : 0), ...);
+}
+// Generic product for the larger tile counts (their specialised bodies would not fit the
+// instruction cache): a running tile walk per operand, ~17 instructions per DMMA.  Warps with one
+// tile fewer than NTW repeat their last tile (never stored) so that no MMA is predicated.
+template <int NTW>
+__device__ __forceinline__ void nsp_mm_walk(unsigned pbase, unsigned qbase, int nt, const NspTiles<NTW>& w,
+                                            const NspLane& L, double (&acc)[NTW][2]) {
+  NspWalk pw[NTW], qw[NTW];
+#pragma unroll
+  for (int n = 0; n < NTW; ++n) { pw[n].start(w.ti[n]); qw[n].start(w.tj[n]); }
+#pragma unroll 1
+  for (int K = 0; K < nt; ++K) {
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      double a[NTW], b[NTW];
+#pragma unroll
+      for (int n = 0; n < NTW; ++n) {
+        if (n == 0 || w.ti[n] != w.ti[n - 1]) a[n] = lds_f64(pw[n].addr(pbase, K, h, L));
+        else a[n] = a[n - 1];
+        b[n] = lds_f64(qw[n].addr(qbase, K, h, L));
+      }
+#pragma unroll
+      for (int n = 0; n < NTW; ++n) NSP_DMMA(acc[n], a[n], b[n]);
+    }
+#pragma unroll
+    for (int n = 0; n < NTW; ++n) { pw[n].next(K, nt); qw[n].next(K, nt); }
+  }
+}
+
+#define NSP_FIXED_MAX_NT 10
+template <int NT, int NW, int NTW>
+__device__ __forceinline__ void nsp_mm_any(unsigned pbase, unsigned qbase, int warp, const NspTiles<NTW>& w,
+                                           const NspLane& L, double (&acc)[NTW][2]) {
+#pragma unroll
+  for (int n = 0; n < NTW; ++n) { acc[n][0] = 0.0; acc[n][1] = 0.0; }
+  if constexpr (NT <= NSP_FIXED_MAX_NT) {
+    const unsigned pd0 = pbase + L.offd, qd0 = qbase + L.offd;
+    nsp_mm_dispatch<NT, NW, NTW>(std::make_integer_sequence<int, NW>{}, warp, pd0, pd0 + L.dh, pbase + L.offt,
+                                 qd0, qd0 + L.dh, qbase + L.offt, acc);
+  } else {
+    nsp_mm_walk<NTW>(pbase, qbase, NT, w, L, acc);
+  }
+}
+
+template <int NTW>
+__device__ __forceinline__ void nsp_store(unsigned dbase, int nt, const NspTiles<NTW>& w, const NspLane& L,
+                                          double (&acc)[NTW][2]) {
+#pragma unroll
+  for (int n = 0; n < NTW; ++n)
+    if (n < w.n) sts_f64x2(dbase + nsp_cbase(w.ti[n], w.tj[n], nt, L), acc[n][0], acc[n][1]);
+}
+
+template <int NTA, int NTH>
+__device__ __forceinline__ NsTiles<NTA> nsp_rect_tiles(int ntr, int nt, int warp) {
+  const int E = ntr * nt;
+  const int e0 = (E * warp) / (NTH / 32), e1 = (E * (warp + 1)) / (NTH / 32);
+  NsTiles<NTA> w;
+  w.n = e1 - e0;
+#pragma unroll
+  for (int n = 0; n < NTA; ++n) {
+    const int e = min(e0 + n, E - 1);
+    w.ti[n] = e / nt;
+    w.tj[n] = e - w.ti[n] * nt;
+  }
+  return w;
+}
+
+template <int NT, int NTH, int MINB>
+__global__ void __launch_bounds__(NTH, MINB) letkf_nsp_kernel(ColParams P, int lch) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  constexpr int NW = NTH / 32;
+  constexpr int NTW = (NT * (NT + 1) / 2 + NW - 1) / NW;       // upper-triangular tiles per warp
+  constexpr int NTA = (4 * NT + NW - 1) / NW;                  // update tiles per warp (lch <= 32 levels)
+  constexpr int PCH = (NS_PCH > NW) ? NS_PCH : NW;             // staged observation rows per chunk
+  constexpr int nt = NT, kp = 8 * NT, ks = kp + 4, msz = NT * (NT + 1) / 2 * 64;   // host: NT == ceil(k / 8)
+  const int k = P.k, nz = P.nz;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int g = lane >> 2, t = lane & 3;
+  double* Zp = reinterpret_cast<double*>(smem_raw);
+  double* Yp = Zp + msz;
+  double* Tp = Yp + msz;
+  double* gvec = Tp + msz;
+  double* wa = gvec + kp;
+  double* tv = wa + kp;
+  double* xm = tv + kp;                                        // [lch]
+  double* ml = xm + lch;                                       // [lch]
+  double* red = ml + lch;                                      // [16]
+  double* sel_sq = red + 16;                                   // [NS_SELCAP] sqrt(rho / sigma^2)
+  double* sel_d = sel_sq + NS_SELCAP;                          // [NS_SELCAP] sqrt(rho / sigma^2) * d
+  int* sel_row = reinterpret_cast<int*>(sel_d + NS_SELCAP);    // [NS_SELCAP] obs row
+  int* warp_cnt = sel_row + NS_SELCAP;                         // [32]
+  int* s_int = warp_cnt + 32;                                  // [4]
+  double* Ych = Zp;          // [PCH][ks] staged weighted rows (phase 1: no matrix is live)
+  const unsigned zs = (unsigned)__cvta_generic_to_shared(Zp);
+  const unsigned ys = (unsigned)__cvta_generic_to_shared(Yp);
+  const unsigned ts = (unsigned)__cvta_generic_to_shared(Tp);
+
+  const double km1 = (double)(k - 1);
+  const double sW = sqrt(km1);
+  const bool per_level = P.radius_v > 0.0;
+  const int nxf = per_level ? nz : 1;
+  const int R = (int)floor(P.radius);
+  const long long ncols = P.cols ? P.ncols : (long long)P.own_nx * P.own_ny;
+  const NspLane L = nsp_lane(lane);
+  const NspTiles<NTW> st = nsp_tiles<NTW, NTH>(nt, warp);
+
+  for (long long ci = blockIdx.x; ci < ncols; ci += gridDim.x) {
+    int lx, ly;
+    if (P.cols) { long long c = P.cols[ci]; lx = (int)(c % P.nx); ly = (int)(c / P.nx); }
+    else { lx = (int)(ci % P.own_nx); ly = (int)(ci / P.own_nx); }
+    const int gx = P.gx0 + lx, gy = P.gy0 + ly;
+    const long long col = (long long)ly * P.nx + lx;
+    double* Xg = P.X + col * nz * k;
+    int col_iters = 0;
+    long long col_npl = 0;
+    bool col_fail = false;
+
+    for (int lt = 0; lt < nxf; ++lt) {
+      // ---------------- 1. selection, gather, C += Yw^T Yw on the FP64 tensor path, g += Yw^T dw
+      double cacc[NTW][2];
+#pragma unroll
+      for (int n = 0; n < NTW; ++n) { cacc[n][0] = 0.0; cacc[n][1] = 0.0; }
+      double gacc = 0.0;
+      if (tid == 0) s_int[0] = 0;
+      __syncthreads();
+      int npl = 0;
+      int cy0 = 0, cy1 = -1;
+      if (P.radius >= 0.0) index_cy_range(P.iv, gy, R, cy0, cy1);
+      int cy = cy0, rb = 0, re = 0;
+      bool rows_left = (cy <= cy1);
+      if (rows_left) index_row_range(P.iv, gx, R, cy, rb, re);
+      while (true) {
+        const bool have_batch = rows_left;
+        if (have_batch) {
+          const int a = rb + tid;
+          bool sel = false;
+          double sq = 0.0, sd = 0.0;
+          int orow = 0;
+          if (a < re) {
+            double dist;
+            sel = index_within(gx, gy, P.iv.sx[a], P.iv.sy[a], P.radius, &dist);
+            double dv = 0.0;
+            if (sel && per_level) {
+              dv = fabs((double)(P.iv.sz[a] - lt));
+              sel = dv <= P.radius_v;
+            }
+            if (sel) {
+              double rho = 1.0;
+              if (P.loc == MDC_LOC_GASPARI_COHN) {
+                rho = lk_gaspari_cohn(dist / (0.5 * P.radius));
+                if (per_level) rho *= lk_gaspari_cohn(dv / (0.5 * P.radius_v));
+              }
+              orow = P.iv.sorted_row[a];
+              const double e_ = P.err[orow];
+              const double ivar = P.valid[orow] ? 1.0 / (e_ * e_) : 0.0;
+              sq = sqrt(rho * (P.use_R ? ivar : 1.0));
+              sd = sq * P.d[orow];
+            }
+          }
+          const unsigned bal = __ballot_sync(0xffffffffu, sel);
+          if (lane == 0) warp_cnt[warp] = __popc(bal);
+          __syncthreads();
+          int off = s_int[0];
+          for (int w = 0; w < warp; ++w) off += warp_cnt[w];
+          if (sel) {
+            const int pos = off + __popc(bal & ((1u << lane) - 1u));
+            sel_row[pos] = orow;
+            sel_sq[pos] = sq;
+            sel_d[pos] = sd;
+          }
+          __syncthreads();
+          if (tid == 0) {
+            int tot = 0;
+            for (int w = 0; w < NW; ++w) tot += warp_cnt[w];
+            s_int[0] += tot;
+          }
+          rb += NTH;
+          if (rb >= re) {
+            ++cy;
+            rows_left = (cy <= cy1);
+            if (rows_left) index_row_range(P.iv, gx, R, cy, rb, re);
+          }
+          __syncthreads();
+        }
+        const int nsel = s_int[0];
+        if (have_batch && rows_left && nsel <= NS_SELCAP - NTH) continue;
+        for (int c0 = 0; c0 < nsel; c0 += PCH) {
+          const int rows = min(PCH, nsel - c0), rows4 = (rows + 3) & ~3;
+          // gather: warp w stages rows w, w + NW, ...; all loads issued before the stores
+          {
+            double v[PCH / NW][(NT * 8 + 31) / 32];
+#pragma unroll
+            for (int q = 0; q < PCH / NW; ++q) {
+              const int r = warp + NW * q;
+              const double* src = P.Yp + (long long)sel_row[c0 + min(r, rows - 1)] * k;
+#pragma unroll
+              for (int jj = 0; jj < (NT * 8 + 31) / 32; ++jj) {
+                const int j = lane + 32 * jj;
+                v[q][jj] = (r < rows && j < k) ? src[j] : 0.0;
+              }
+            }
+#pragma unroll
+            for (int q = 0; q < PCH / NW; ++q) {
+              const int r = warp + NW * q;
+              if (r < rows4) {
+                const double sq = (r < rows) ? sel_sq[c0 + r] : 0.0;
+#pragma unroll
+                for (int jj = 0; jj < (NT * 8 + 31) / 32; ++jj) {
+                  const int j = lane + 32 * jj;
+                  if (j < kp) Ych[r * ks + j] = sq * v[q][jj];
+                }
+              }
+            }
+          }
+          __syncthreads();
+          {
+            const double* ya = Ych + t * ks + g;
+            for (int kk = 0; kk < rows4; kk += 4) {
+              double a[NTW], b[NTW];
+#pragma unroll
+              for (int n = 0; n < NTW; ++n) {
+                if (n == 0 || st.ti[n] != st.ti[n - 1]) a[n] = ya[kk * ks + st.ti[n] * 8]; else a[n] = a[n - 1];
+                b[n] = ya[kk * ks + st.tj[n] * 8];
+              }
+#pragma unroll
+              for (int n = 0; n < NTW; ++n) NSP_DMMA(cacc[n], a[n], b[n]);
+            }
+            if (tid < k) {
+              for (int r = 0; r < rows; ++r) gacc = fma(Ych[r * ks + tid], sel_d[c0 + r], gacc);
+            }
+          }
+          __syncthreads();
+        }
+        npl += nsel;
+        if (tid == 0) s_int[0] = 0;
+        __syncthreads();
+        if (!rows_left) break;
+      }
+      if (lt == 0) col_npl = npl;
+
+      // ---------------- 2. Z = A^{-1/2}, A = shift I + C, by coupled Newton-Schulz
+      bool ok = true;
+      if (npl > 0) {
+        // spectrum(A) lies in [shift, shift + ||C||_F]: C is PSD with smallest eigenvalue 0 (Y' 1 = 0)
+        const double shift = km1 / P.inflation;
+        double fro = 0.0;
+#pragma unroll
+        for (int n = 0; n < NTW; ++n)
+          if (n < st.n) {
+            const int i = st.ti[n] * 8 + g, j = st.tj[n] * 8 + 2 * t;
+            const double w = (st.ti[n] != st.tj[n]) ? 2.0 : 1.0;
+            if (i < k && j < k) fro = fma(w * cacc[n][0], cacc[n][0], fro);
+            if (i < k && j + 1 < k) fro = fma(w * cacc[n][1], cacc[n][1], fro);
+          }
+        fro = sqrt(nsp_block_reduce<NTH>(fro, false, red));
+        if (!((shift + fro) < NS_SYM_COND_MAX * shift)) {
+          // symmetric tiles are not stable at this conditioning: hand over to the full-product kernel
+          if (tid == 0) {
+            const unsigned slot = atomicAdd(P.redo_count, 1u);
+            P.redo_items[slot] = col * nxf + lt;
+          }
+          continue;
+        }
+        // A -> T (shift I on the zero padding)
+#pragma unroll
+        for (int n = 0; n < NTW; ++n)
+          if (n < st.n) {
+            const int i = st.ti[n] * 8 + g, j = st.tj[n] * 8 + 2 * t;
+            const double d0 = (i == j ? shift : 0.0), d1 = (i == j + 1 ? shift : 0.0);
+            const double y0 = (i < k && j < k) ? cacc[n][0] + d0 : d0;
+            const double y1 = (i < k && j + 1 < k) ? cacc[n][1] + d1 : d1;
+            sts_f64x2(ts + nsp_cbase(st.ti[n], st.tj[n], nt, L), y0, y1);
+          }
+        if (tid < k) gvec[tid] = gacc;
+        __syncthreads();
+        // The iteration as a state machine around the single product site:
+        //   A2: Y <- A A, spectral bound, Z0 = q(A)      Y0: Y <- A Z0
+        //   ZY: T <- (3I - Z Y)/2, residual              YT: keep Y T in registers
+        //   TZ: Z <- T Z and Y <- (kept) Y T, both written in place after one barrier
+        enum { OP_A2, OP_Y0, OP_ZY, OP_YT, OP_TZ };
+        double acc[NTW][2], accY[NTW][2];
+        int op = OP_A2, it = 0;
+        bool done = false;
+#pragma unroll 1
+        while (true) {
+          const unsigned pb = (op == OP_ZY) ? zs : (op == OP_YT) ? ys : ts;
+          const unsigned qb = (op == OP_A2) ? ts : (op == OP_ZY) ? ys : (op == OP_YT) ? ts : zs;
+          nsp_mm_any<NT, NW, NTW>(pb, qb, warp, st, L, acc);
+          if (op == OP_A2) {
+            nsp_store<NTW>(ys, nt, st, L, acc);
+            // tighter upper end of the spectrum from the product just made: lmax(C)^2 <= ||C^2||_F
+            // (Schatten-4 norm of C; C^2 = A^2 - 2 shift A + shift^2 I), typically 2-3x below ||C||_F
+            double f4 = 0.0;
+#pragma unroll
+            for (int n = 0; n < NTW; ++n)
+              if (n < st.n) {
+                const int i = st.ti[n] * 8 + g, j = st.tj[n] * 8 + 2 * t;
+                const double2 a = *reinterpret_cast<const double2*>(
+                    reinterpret_cast<const unsigned char*>(Tp) + nsp_cbase(st.ti[n], st.tj[n], nt, L));
+                const double w = (st.ti[n] != st.tj[n]) ? 2.0 : 1.0;
+                const double c0 = acc[n][0] - 2.0 * shift * a.x + (i == j ? shift * shift : 0.0);
+                const double c1 = acc[n][1] - 2.0 * shift * a.y + (i == j + 1 ? shift * shift : 0.0);
+                if (i < k && j < k) f4 = fma(w * c0, c0, f4);
+                if (i < k && j + 1 < k) f4 = fma(w * c1, c1, f4);
+              }
+            f4 = nsp_block_reduce<NTH>(f4, false, red);            // (its barriers also publish A^2)
+            const double hi = shift + fro;
+            const NsStart q0 = ns_chebyshev_start(shift, fmin(hi, shift + sqrt(sqrt(f4) + 1e-13 * hi * hi)));
+            for (int e = tid; e < msz; e += NTH) Zp[e] = fma(q0.a2, Yp[e], q0.a1 * Tp[e]);
+            __syncthreads();
+            if (tid < kp) Zp[nsp_elem(tid, tid, nt)] += q0.a0;      // Z0 = q(A)
+            __syncthreads();
+            op = OP_Y0;
+          } else if (op == OP_Y0) {
+            nsp_store<NTW>(ys, nt, st, L, acc);                     // (A^2 no longer read: barrier above)
+            __syncthreads();
+            op = OP_ZY;
+          } else if (op == OP_ZY) {
+            double r = 0.0;
+#pragma unroll
+            for (int n = 0; n < NTW; ++n)
+              if (n < st.n) {
+                const int i = st.ti[n] * 8 + g, j = st.tj[n] * 8 + 2 * t;
+                const double d0 = (i == j ? 1.0 : 0.0), d1 = (i == j + 1 ? 1.0 : 0.0);
+                const double e0 = d0 - acc[n][0], e1 = d1 - acc[n][1];
+                r = fmax(r, fmax(fabs(e0), fabs(e1)));
+                sts_f64x2(ts + nsp_cbase(st.ti[n], st.tj[n], nt, L), d0 + 0.5 * e0, d1 + 0.5 * e1);   // T = (3I - ZY)/2
+              }
+            r = nsp_block_reduce<NTH>(r, true, red);                // also publishes T
+            done = r < 1e-7;                                         // error after this update ~ r^2
+            if (!(r < 1.5)) { ok = false; break; }                   // cannot happen for SPD input; NaN guard
+            op = done ? OP_TZ : OP_YT;
+          } else if (op == OP_YT) {
+#pragma unroll
+            for (int n = 0; n < NTW; ++n) { accY[n][0] = acc[n][0]; accY[n][1] = acc[n][1]; }
+            op = OP_TZ;
+          } else {
+            __syncthreads();                                         // everyone is done reading Y and Z
+            if (!done) nsp_store<NTW>(ys, nt, st, L, accY);
+            nsp_store<NTW>(zs, nt, st, L, acc);
+            __syncthreads();
+            ++it;
+            if (done || it >= NS_MAX_ITERS) break;
+            op = OP_ZY;
+          }
+        }
+        if (!done) ok = false;
+        col_iters = max(col_iters, it);
+        // w = Z (Z g)
+        if (ok) {
+          for (int a = warp; a < k; a += NW) {
+            double s = 0.0;
+            for (int b = lane; b < k; b += 32) s += Zp[nsp_elem(a, b, nt)] * gvec[b];
+            s = warp_sum(s);
+            if (lane == 0) tv[a] = s;
+          }
+          __syncthreads();
+          for (int a = warp; a < k; a += NW) {
+            double s = 0.0;
+            for (int b = lane; b < k; b += 32) s += Zp[nsp_elem(a, b, nt)] * tv[b];
+            s = warp_sum(s);
+            if (lane == 0) wa[a] = s;
+          }
+          __syncthreads();
+        }
+      }
+      if (!ok) col_fail = true;
+
+      if (P.W_out && P.w_col == col && lt == 0) {
+        for (int e = tid; e < k * k; e += NTH) {
+          const int j = e / k, i = e - j * k;
+          double vv;
+          if (npl == 0) vv = (i == j) ? sqrt(P.inflation) : 0.0;
+          else if (!ok) vv = nan("");
+          else vv = wa[j] + sW * Zp[nsp_elem(j, i, nt)];
+          P.W_out[e] = vv;
+        }
+        __syncthreads();
+      }
+
+      // ---------------- 3. X_a = xbar + X' w + sW X' Z on the tensor path, level chunks of lch,
+      //                     staged in the Y and T buffers
+      double* Xt = Yp;                                                 // [lch][ks]
+      double* To = Xt + (size_t)lch * ks;                              // [lch][k]
+      const int lev_b = per_level ? lt : 0, lev_e = per_level ? lt + 1 : nz;
+      if (ok) {
+        for (int l0 = lev_b; l0 < lev_e; l0 += lch) {
+          const int nl = min(lch, lev_e - l0);
+          for (int e = tid; e < nl * k; e += NTH) {
+            const int l = e / k, j = e - l * k;
+            Xt[l * ks + j] = Xg[(long long)l0 * k + e];
+          }
+          if (kp > k) for (int e = tid; e < nl * (kp - k); e += NTH) Xt[(e / (kp - k)) * ks + k + e % (kp - k)] = 0.0;
+          __syncthreads();
+          for (int l = warp; l < nl; l += NW) {
+            double s = 0.0;
+            for (int j = lane; j < k; j += 32) s += Xt[l * ks + j];
+            s = warp_sum(s) / (double)k;
+            double m = 0.0;
+            for (int j = lane; j < k; j += 32) {
+              const double xp = Xt[l * ks + j] - s;
+              Xt[l * ks + j] = xp;
+              if (npl > 0) m = fma(xp, wa[j], m);
+            }
+            m = warp_sum(m);
+            if (lane == 0) { xm[l] = s; ml[l] = s + m; }
+          }
+          __syncthreads();
+          if (npl == 0) {
+            const double f = sqrt(P.inflation);
+            for (int e = tid; e < nl * k; e += NTH) { const int l = e / k; To[e] = xm[l] + Xt[l * ks + (e - l * k)] * f; }
+          } else {
+            const int ntr = (nl + 7) >> 3;
+            const NsTiles<NTA> at = nsp_rect_tiles<NTA, NTH>(ntr, nt, warp);
+            double uacc[NTA][2];
+#pragma unroll
+            for (int n = 0; n < NTA; ++n) { uacc[n][0] = 0.0; uacc[n][1] = 0.0; }
+            const double* xa = Xt + g * ks + t;
+            NspWalk zw[NTA];
+#pragma unroll
+            for (int n = 0; n < NTA; ++n) zw[n].start(at.tj[n]);
+#pragma unroll 1
+            for (int K = 0; K < nt; ++K) {
+#pragma unroll
+              for (int h = 0; h < 2; ++h) {
+                double a[NTA], b[NTA];
+#pragma unroll
+                for (int n = 0; n < NTA; ++n) {
+                  if (n == 0 || at.ti[n] != at.ti[n - 1]) a[n] = xa[at.ti[n] * 8 * ks + K * 8 + h * 4]; else a[n] = a[n - 1];
+                  b[n] = lds_f64(zw[n].addr(zs, K, h, L));
+                }
+#pragma unroll
+                for (int n = 0; n < NTA; ++n) NSP_DMMA(uacc[n], a[n], b[n]);
+              }
+#pragma unroll
+              for (int n = 0; n < NTA; ++n) zw[n].next(K, nt);
+            }
+#pragma unroll
+            for (int n = 0; n < NTA; ++n)
+              if (n < at.n) {
+                const int l = at.ti[n] * 8 + g, i = at.tj[n] * 8 + 2 * t;
+                if (l < nl) {
+                  if (i < k) To[l * k + i] = ml[l] + sW * uacc[n][0];
+                  if (i + 1 < k) To[l * k + i + 1] = ml[l] + sW * uacc[n][1];
+                }
+              }
+          }
+          __syncthreads();
+          for (int e = tid; e < nl * k; e += NTH) Xg[(long long)l0 * k + e] = To[e];
+          if (P.mean_out) {
+            for (int l = warp; l < nl; l += NW) {
+              double s = 0.0;
+              for (int j = lane; j < k; j += 32) s += To[l * k + j];
+              s = warp_sum(s);
+              if (lane == 0) P.mean_out[col * nz + l0 + l] = s * (1.0 / (double)k);
+            }
+          }
+          __syncthreads();
+        }
+      }
+    }  // lt
+    if (tid == 0) {
+      atomicAdd((unsigned long long*)&P.stats[0], (unsigned long long)col_npl);
+      atomicMax(&P.stats[1], col_npl);
+      atomicAdd((unsigned long long*)&P.stats[2], (unsigned long long)col_iters);
+      atomicMax(&P.stats[3], (long long)col_iters);
+      if (col_fail) atomicAdd((unsigned long long*)&P.stats[4], 1ull);
+      atomicAdd((unsigned long long*)&P.stats[5], 1ull);
+    }
+  }
+}
+
+// largest level chunk (multiple of 8, <= 32) whose staging fits in the two free matrix buffers
+static int nsp_level_chunk(int k, int nz) {
+  const int fit = (2 * nsp_ntiles(k) * 64) / (ns_stride(k) + k);
+  return std::max(8, std::min(std::min(32, (nz + 7) & ~7), fit & ~7));
+}
+static size_t nsp_smem_bytes(int k, int lch, int nth) {
+  const int pch = std::max(NS_PCH, nth / 32);
+  size_t mats = 3 * (size_t)nsp_ntiles(k) * 64;
+  mats = std::max(mats, (size_t)pch * ns_stride(k));                       // phase-1 staging aliases them
+  const size_t dbl = mats + 3 * (size_t)ns_kp(k) + 2 * (size_t)lch + 16 + 2 * NS_SELCAP;
+  return dbl * 8 + (size_t)NS_SELCAP * 4 + 32 * 4 + 4 * 4 + 16;
+}

@@ -209,12 +209,17 @@ __global__ void __launch_bounds__(NT, MINB) letkf_canonical_kernel(ColParams P, 
   const bool per_level = P.radius_v > 0.0;
   const int nxf = per_level ? nz : 1;
   const int R = (int)floor(P.radius);
-  const long long ncols = P.cols ? P.ncols : (long long)P.own_nx * P.own_ny;
+  const bool redo = P.redo_consume != 0;
+  const long long ncols = redo ? (long long)*P.redo_count : (P.cols ? P.ncols : (long long)P.own_nx * P.own_ny);
   const int ty = tid >> 4, tx = tid & 15;   // SYRK thread grid
 
   for (long long ci = blockIdx.x; ci < ncols; ci += gridDim.x) {
-    int lx, ly;
-    if (P.cols) { long long c = P.cols[ci]; lx = (int)(c % P.nx); ly = (int)(c / P.nx); }
+    int lx, ly, lt_b = 0, lt_e = nxf;
+    if (redo) {
+      const long long item = P.redo_items[ci], c = item / nxf;
+      lt_b = (int)(item - c * nxf); lt_e = lt_b + 1;
+      lx = (int)(c % P.nx); ly = (int)(c / P.nx);
+    } else if (P.cols) { long long c = P.cols[ci]; lx = (int)(c % P.nx); ly = (int)(c / P.nx); }
     else { lx = (int)(ci % P.own_nx); ly = (int)(ci / P.own_nx); }
     const int gx = P.gx0 + lx, gy = P.gy0 + ly;
     const long long col = (long long)ly * P.nx + lx;
@@ -222,7 +227,7 @@ __global__ void __launch_bounds__(NT, MINB) letkf_canonical_kernel(ColParams P, 
     int col_sweeps = 0;
     long long col_npl = 0;
 
-    for (int lt = 0; lt < nxf; ++lt) {
+    for (int lt = lt_b; lt < lt_e; ++lt) {
       // ---------------- 1. selection, gather, register-tiled C += Yw^T Yw, g += Yw^T dw
       double acc[TMY][TM];
 #pragma unroll
@@ -464,11 +469,14 @@ __global__ void __launch_bounds__(NT, MINB) letkf_canonical_kernel(ColParams P, 
       }
     }  // lt
     if (tid == 0) {
-      atomicAdd((unsigned long long*)&P.stats[0], (unsigned long long)col_npl);
-      atomicMax(&P.stats[1], col_npl);
+      if (!redo) {
+        atomicAdd((unsigned long long*)&P.stats[0], (unsigned long long)col_npl);
+        atomicMax(&P.stats[1], col_npl);
+        atomicAdd((unsigned long long*)&P.stats[5], 1ull);
+      }
+      else atomicAdd((unsigned long long*)&P.stats[6], 1ull);
       atomicAdd((unsigned long long*)&P.stats[2], (unsigned long long)col_sweeps);
       atomicMax(&P.stats[3], (long long)col_sweeps);
-      atomicAdd((unsigned long long*)&P.stats[5], 1ull);
     }
   }
 }

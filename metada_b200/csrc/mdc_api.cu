@@ -14,6 +14,7 @@
 #include "index_kernels.cuh"
 #include "letkf_kernels.cuh"
 #include "letkf_ns.cuh"
+#include "letkf_nsp.cuh"
 #include "letkf_v2.cuh"
 #include "mdc_internal.cuh"
 
@@ -86,6 +87,7 @@ int mdc_ctx_destroy(mdc_ctx* ctx) {
   cudaStreamSynchronize(ctx->stream);
   if (ctx->flush_buf) cudaFree(ctx->flush_buf);
   cudaFree(ctx->d_flags);
+  if (ctx->redo_items) cudaFree(ctx->redo_items);
   cudaFree(ctx->d_stats);
   cudaEventDestroy(ctx->ev0);
   cudaEventDestroy(ctx->ev1);
@@ -719,31 +721,31 @@ static int letkf_launch(mdc_ens* e, mdc_obs* o, const mdc_letkf_params* p, const
   cp.cols = dcols; cp.ncols = ncols;
   const long long total_cols = dcols ? ncols : (long long)e->own_nx * e->own_ny;
   const int sms = std::max(1, ctx->sm_count - std::max(0, std::min(p->sm_reserve, ctx->sm_count / 2)));
-  if (p->mode == MDC_MODE_CANONICAL && p->solver == MDC_SOLVER_NEWTON_SCHULZ && (k < 24 || k > 80))
-    MDC_FAIL(ctx, MDC_ERR_UNSUPPORTED, "letkf: the Newton-Schulz solver supports 24 <= k <= 80 (k=%d)", k);
-  if (p->mode == MDC_MODE_CANONICAL && p->solver != MDC_SOLVER_JACOBI && k >= 24 && k <= 80 && !getenv("MDC_LETKF_V1")) {
-    // GEMM-only symmetric square root (letkf_ns.cuh): four k x k buffers, one CTA per SM
+  cp.redo_items = nullptr; cp.redo_count = nullptr; cp.redo_consume = 0;
+  if (p->mode == MDC_MODE_CANONICAL && p->solver == MDC_SOLVER_NEWTON_SCHULZ && (k < 24 || k > 128))
+    MDC_FAIL(ctx, MDC_ERR_UNSUPPORTED, "letkf: the Newton-Schulz solver supports 24 <= k <= 128 (k=%d)", k);
+  if (p->mode == MDC_MODE_CANONICAL && p->solver == MDC_SOLVER_NEWTON_SCHULZ_FULL && (k < 24 || k > 80))
+    MDC_FAIL(ctx, MDC_ERR_UNSUPPORTED, "letkf: the full-product Newton-Schulz solver supports 24 <= k <= 80 (k=%d)", k);
+  // full-product Newton-Schulz (letkf_ns.cuh): four padded k x k buffers, one CTA per SM
+  auto launch_ns_full = [&](const ColParams& cq, long long work) -> int {
     const int lch = std::min(32, (e->nz + 7) & ~7);   // levels per update chunk (multiple of 8)
     const size_t smem3 = ns_smem_bytes(k, lch);
-    if ((int)smem3 <= ctx->max_smem_optin) {
-      auto launch3 = [&](auto kern) -> int {
-        MDC_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3));
-        int occ = 1;
-        MDC_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, NS_THREADS, smem3));
-        if (occ < 1) occ = 1;
-        int grid = (int)std::max<long long>(1, std::min<long long>(total_cols, (long long)sms * occ));
-        kern<<<grid, NS_THREADS, smem3, ctx->stream>>>(cp, lch);
-        MDC_LAUNCH_CHECK(ctx);
-        return MDC_OK;
-      };
-      if (k <= 32) return launch3(letkf_ns_kernel<2>);
-      if (k <= 48) return launch3(letkf_ns_kernel<3>);
-      if (k <= 64) return launch3(letkf_ns_kernel<4>);
-      return launch3(letkf_ns_kernel<5>);
-    }
-  }
-  if (p->mode == MDC_MODE_CANONICAL && !getenv("MDC_LETKF_V1")) {
-    // optimised canonical kernel: level-chunk sized so that two CTAs fit one SM when k allows
+    if ((int)smem3 > ctx->max_smem_optin)
+      MDC_FAIL(ctx, MDC_ERR_UNSUPPORTED, "letkf: k=%d needs %zu B shared memory > %d available", k, smem3, ctx->max_smem_optin);
+    auto launch3 = [&](auto kern) -> int {
+      MDC_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3));
+      int grid = (int)std::max<long long>(1, std::min<long long>(work, (long long)sms));
+      kern<<<grid, NS_THREADS, smem3, ctx->stream>>>(cq, lch);
+      MDC_LAUNCH_CHECK(ctx);
+      return MDC_OK;
+    };
+    if (k <= 32) return launch3(letkf_ns_kernel<2>);
+    if (k <= 48) return launch3(letkf_ns_kernel<3>);
+    if (k <= 64) return launch3(letkf_ns_kernel<4>);
+    return launch3(letkf_ns_kernel<5>);
+  };
+  // blocked Jacobi eigensolver (letkf_v2.cuh): level-chunk sized so that two CTAs fit one SM when k allows
+  auto launch_jacobi = [&](const ColParams& cq, long long work) -> int {
     const int lchmax = std::max(4, 2560 / k);
     const int nchunk = (e->nz + lchmax - 1) / lchmax;
     const int lch = (e->nz + nchunk - 1) / nchunk;
@@ -755,8 +757,8 @@ static int letkf_launch(mdc_ens* e, mdc_obs* o, const mdc_letkf_params* p, const
       int occ = 1;
       MDC_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, nt, smem2));
       if (occ < 1) occ = 1;
-      int grid = (int)std::max<long long>(1, std::min<long long>(total_cols, (long long)sms * occ));
-      kern<<<grid, nt, smem2, ctx->stream>>>(cp, lch);
+      int grid = (int)std::max<long long>(1, std::min<long long>(work, (long long)sms * occ));
+      kern<<<grid, nt, smem2, ctx->stream>>>(cq, lch);
       MDC_LAUNCH_CHECK(ctx);
       return MDC_OK;
     };
@@ -767,7 +769,61 @@ static int letkf_launch(mdc_ens* e, mdc_obs* o, const mdc_letkf_params* p, const
     if (k <= 64) return launch2(letkf_canonical_kernel<64, 4, 8, 8, 4, 16>, 64);
     if (k <= 80) return launch2(letkf_canonical_kernel<160, 2, 16, 5, 5, 8>, 160);
     return launch2(letkf_canonical_kernel<256, 1, 16, 8, 8, 8>, 256);
+  };
+  const bool v1 = getenv("MDC_LETKF_V1") != nullptr;
+  if (p->mode == MDC_MODE_CANONICAL && p->solver == MDC_SOLVER_NEWTON_SCHULZ_FULL && !v1)
+    return launch_ns_full(cp, total_cols);
+  if (p->mode == MDC_MODE_CANONICAL && p->solver != MDC_SOLVER_JACOBI && k >= 24 && k <= 128 && !v1) {
+    // packed symmetric Newton-Schulz (letkf_nsp.cuh), then its redo list through the full-product
+    // kernel (k <= 80) or the Jacobi kernel
+    const int nxf = p->radius_v > 0.0 ? e->nz : 1;
+    const size_t need = (size_t)total_cols * nxf;
+    if (ctx->redo_cap < need) {
+      if (ctx->redo_items) cudaFree(ctx->redo_items);
+      ctx->redo_items = nullptr; ctx->redo_cap = 0;
+      MDC_CUDA(ctx, cudaMalloc((void**)&ctx->redo_items, need * sizeof(long long)));
+      ctx->redo_cap = need;
+    }
+    cp.redo_items = ctx->redo_items;
+    cp.redo_count = reinterpret_cast<unsigned*>(ctx->d_flags + 12);
+    MDC_CUDA(ctx, cudaMemsetAsync(cp.redo_count, 0, sizeof(unsigned), ctx->stream));
+    const int lch = nsp_level_chunk(k, e->nz);
+    auto launchp = [&](auto kern, int nth) -> int {
+      const size_t smemp = nsp_smem_bytes(k, lch, nth);
+      if ((int)smemp > ctx->max_smem_optin)
+        MDC_FAIL(ctx, MDC_ERR_UNSUPPORTED, "letkf: k=%d needs %zu B shared memory > %d available", k, smemp, ctx->max_smem_optin);
+      MDC_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemp));
+      int occ = 1;
+      MDC_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, nth, smemp));
+      if (occ < 1) occ = 1;
+      int grid = (int)std::max<long long>(1, std::min<long long>(total_cols, (long long)sms * occ));
+      kern<<<grid, nth, smemp, ctx->stream>>>(cp, lch);
+      MDC_LAUNCH_CHECK(ctx);
+      return MDC_OK;
+    };
+    int rc;
+    switch ((k + 7) >> 3) {   // tile rows: the kernel is specialised on the exact count
+      case 3: rc = launchp(letkf_nsp_kernel<3, 256, 2>, 256); break;
+      case 4: rc = launchp(letkf_nsp_kernel<4, 256, 2>, 256); break;
+      case 5: rc = launchp(letkf_nsp_kernel<5, 256, 2>, 256); break;
+      case 6: rc = launchp(letkf_nsp_kernel<6, 256, 2>, 256); break;
+      case 7: rc = launchp(letkf_nsp_kernel<7, 256, 2>, 256); break;
+      case 8: rc = launchp(letkf_nsp_kernel<8, 256, 2>, 256); break;
+      case 9: rc = launchp(letkf_nsp_kernel<9, 256, 2>, 256); break;
+      case 10: rc = launchp(letkf_nsp_kernel<10, 256, 2>, 256); break;
+      case 11: rc = launchp(letkf_nsp_kernel<11, 512, 1>, 512); break;
+      case 12: rc = launchp(letkf_nsp_kernel<12, 512, 1>, 512); break;
+      case 13: rc = launchp(letkf_nsp_kernel<13, 512, 1>, 512); break;
+      case 14: rc = launchp(letkf_nsp_kernel<14, 512, 1>, 512); break;
+      case 15: rc = launchp(letkf_nsp_kernel<15, 512, 1>, 512); break;
+      default: rc = launchp(letkf_nsp_kernel<16, 512, 1>, 512); break;
+    }
+    if (rc) return rc;
+    ColParams cq = cp;
+    cq.redo_consume = 1;
+    return k <= 80 ? launch_ns_full(cq, (long long)need) : launch_jacobi(cq, (long long)need);
   }
+  if (p->mode == MDC_MODE_CANONICAL && !v1) return launch_jacobi(cp, total_cols);
   const int nr = (k + 31) / 32;
   auto launch = [&](auto kern) -> int {
     MDC_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -822,6 +878,7 @@ int mdc_letkf_analyse(mdc_ens* e, mdc_obs* o, const mdc_letkf_params* p, mdc_let
     st->sum_sweeps = h[2];
     st->max_sweeps = (int32_t)h[3];
     st->numeric_failures = (int32_t)h[4];
+    st->redo_transforms = (int32_t)h[6];
   }
   if (h[4]) MDC_FAIL(ctx, MDC_ERR_NUMERIC, "letkf: %lld column transforms failed (non-SPD matrix); those columns were left unchanged", h[4]);
   return MDC_OK;

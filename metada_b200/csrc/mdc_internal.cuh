@@ -20,6 +20,8 @@ struct mdc_ctx {
   size_t flush_bytes = 0;
   int* d_flags = nullptr;      // [16] device scratch for error flags / counters
   long long* d_stats = nullptr;  // [16]
+  long long* redo_items = nullptr;  // transforms handed from the packed Newton-Schulz kernel to its fallback
+  size_t redo_cap = 0;
 };
 
 struct mdc_ens {

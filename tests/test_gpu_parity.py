@@ -194,7 +194,7 @@ def test_errors_are_reported_not_swallowed(ctx):
     ens.close(); obs.close()
 
 
-@pytest.mark.parametrize("solver", [mb.SOLVER_JACOBI, mb.SOLVER_NEWTON_SCHULZ])
+@pytest.mark.parametrize("solver", [mb.SOLVER_JACOBI, mb.SOLVER_NEWTON_SCHULZ, mb.SOLVER_NEWTON_SCHULZ_FULL])
 @pytest.mark.parametrize("k,nz,loc", [(24, 2, 1), (40, 3, 1), (64, 1, 0), (80, 2, 1)])
 def test_canonical_solvers_match_oracle(ctx, solver, k, nz, loc):
     """Both routes to the symmetric square root (Jacobi eigen-decomposition, Newton-Schulz) against
@@ -209,20 +209,44 @@ def test_canonical_solvers_match_oracle(ctx, solver, k, nz, loc):
     ens.close(); obs.close()
 
 
-def test_newton_schulz_ill_conditioned_and_vertical(ctx):
-    """Tiny obs error (cond(A) ~ 1e5) and per-level transforms through the Newton-Schulz path."""
+@pytest.mark.parametrize("solver", [mb.SOLVER_NEWTON_SCHULZ, mb.SOLVER_NEWTON_SCHULZ_FULL])
+def test_newton_schulz_ill_conditioned_and_vertical(ctx, solver):
+    """Tiny obs error (cond(A) ~ 1e5) and per-level transforms through the Newton-Schulz path (the
+    packed kernel hands every such transform to the full-product kernel)."""
     X, o = make_case(12, 12, 4, 32, 150, seed=21, sigma=0.002)
     o["err"][:] = 0.002
     ens, obs = _setup(ctx, X, o)
-    p = capi.make_params(4.0, 1.0, mb.MODE_CANONICAL, mb.LOC_GASPARI_COHN, radius_v=2.0, solver=mb.SOLVER_NEWTON_SCHULZ)
+    p = capi.make_params(4.0, 1.0, mb.MODE_CANONICAL, mb.LOC_GASPARI_COHN, radius_v=2.0, solver=solver)
     st = capi.letkf_analyse(ens, obs, p)
     ref = orc.letkf(X, o["x"], o["y"], o["z"], o["value"], o["err"], radius=4.0, radius_v=2.0)
     em, ep = analysis_errors(ens.download(), ref["Xa"])
     assert em < 1e-9 and ep < 1e-9, (em, ep, st)
+    assert st["columns"] == 144 and st["numeric_failures"] == 0
+    assert st["redo_transforms"] == (144 * 4 if solver == mb.SOLVER_NEWTON_SCHULZ else 0), st
     ens.close(); obs.close()
 
 
-@pytest.mark.parametrize("k,nz", [(25, 2), (30, 40), (50, 9), (77, 3), (33, 1)])
+@pytest.mark.parametrize("k,radius_v", [(48, 0.0), (40, 1.5), (104, 0.0)])
+def test_newton_schulz_mixed_conditioning(ctx, k, radius_v):
+    """Accurate observations in one corner only: some transforms stay on the packed symmetric
+    kernel, the others go through its redo list (full-product kernel for k <= 80, Jacobi above)."""
+    nx, ny, nz = 14, 13, 3
+    X, o = make_case(nx, ny, nz, k, 160, seed=77 + k)
+    corner = (o["x"] < 6) & (o["y"] < 6)
+    o["err"][corner] = 0.01
+    ens, obs = _setup(ctx, X, o)
+    p = capi.make_params(3.0, 1.0, mb.MODE_CANONICAL, mb.LOC_GASPARI_COHN, radius_v=radius_v,
+                         solver=mb.SOLVER_NEWTON_SCHULZ)
+    st = capi.letkf_analyse(ens, obs, p)
+    ref = orc.letkf(X, o["x"], o["y"], o["z"], o["value"], o["err"], radius=3.0, radius_v=radius_v)
+    em, ep = analysis_errors(ens.download(), ref["Xa"])
+    assert em < 1e-9 and ep < 1e-9, (em, ep, st)
+    assert st["columns"] == nx * ny and st["numeric_failures"] == 0
+    assert 0 < st["redo_transforms"] < nx * ny * (nz if radius_v > 0 else 1), st
+    ens.close(); obs.close()
+
+
+@pytest.mark.parametrize("k,nz", [(25, 2), (30, 40), (50, 9), (77, 3), (33, 1), (90, 2), (101, 5), (128, 33)])
 def test_newton_schulz_padded_sizes(ctx, k, nz):
     """k not a multiple of 8 (zero/identity padded DMMA tiles), odd k, and more levels than one
     update chunk (32)."""

@@ -206,12 +206,19 @@ __device__ __forceinline__ NsStart ns_chebyshev_start(double lo, double hi) {
   q.a0 = c0 + c1 * n + c2 * (2.0 * n * n - 1.0);
   q.a1 = c1 * m + 4.0 * c2 * m * n;
   q.a2 = 2.0 * c2 * m * m;
+  // 64 sample points, two per lane (every warp computes the same values; call with all lanes active)
   double pmin = 1e300, pmax = 0.0;
-  for (int i = 0; i < 64; ++i) {
-    const double x = lo + (hi - lo) * ((double)i * (1.0 / 63.0));
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const double x = lo + (hi - lo) * ((double)((threadIdx.x & 31) + 32 * i) * (1.0 / 63.0));
     const double qx = fma(fma(q.a2, x, q.a1), x, q.a0);
     const double p = qx * qx * x;
     pmin = fmin(pmin, p); pmax = fmax(pmax, p);
+  }
+#pragma unroll
+  for (int o = 16; o; o >>= 1) {
+    pmin = fmin(pmin, __shfl_xor_sync(0xffffffffu, pmin, o));
+    pmax = fmax(pmax, __shfl_xor_sync(0xffffffffu, pmax, o));
   }
   const double s = sqrt(2.0 / (pmin + pmax));
   q.a0 *= s; q.a1 *= s; q.a2 *= s;

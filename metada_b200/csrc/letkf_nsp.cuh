@@ -4,8 +4,8 @@
 // the FP64 tensor path), different storage: every iterate is a symmetric polynomial in A, so only
 // the nt (nt + 1) / 2 upper-triangular 8 x 8 tiles are kept, each tile a dense 512-byte block.
 //   * k = 80: 55 tiles = 28 KB per matrix instead of 54 KB, and the iteration needs three matrices
-//     (Z, Y, T; the products Y T and T Z are both held in accumulator registers across the barrier
-//     and written back in place) instead of four  ->  ~96 KB per CTA, TWO CTAs per SM: one column's
+//     (Z, Y, T; each product is held in the accumulator registers across a barrier and written
+//     back in place) instead of four  ->  ~96 KB per CTA, TWO CTAs per SM: one column's
 //     selection / gather / update phases and barrier bubbles hide under the other's products.
 //   * k = 128: 136 tiles = 70 KB per matrix, three of them fit one SM (the padded square layout
 //     does not), so C4-sized ensembles get the tensor path too (16 warps, one CTA per SM).
@@ -209,6 +209,7 @@ __device__ __forceinline__ void nsp_mm_walk(unsigned pbase, unsigned qbase, int 
 }
 
 #define NSP_FIXED_MAX_NT 10
+#define NSP_LCH_MAX 32   /* levels per update chunk */
 template <int NT, int NW, int NTW>
 __device__ __forceinline__ void nsp_mm_any(unsigned pbase, unsigned qbase, int warp, const NspTiles<NTW>& w,
                                            const NspLane& L, double (&acc)[NTW][2]) {
@@ -246,6 +247,97 @@ __device__ __forceinline__ NsTiles<NTA> nsp_rect_tiles(int ntr, int nt, int warp
   return w;
 }
 
+// Z <- A^{-1/2} for the A held in the T buffer.  Deliberately NOT inlined: the column loop around it
+// keeps ~60 registers of state alive, and under the 128-register cap ptxas then serialises every
+// fragment load behind the MMA that frees its register; as a separate function the products get
+// the whole budget (the caller's state is saved once per column).  Returns the iterations used,
+// -1 if the iteration did not converge.
+template <int NT, int NTH>
+__device__ __noinline__ int nsp_inverse_sqrt(double* Zp, double shift, double fro, int k) {
+  constexpr int NW = NTH / 32, NTW = (NT * (NT + 1) / 2 + NW - 1) / NW, nt = NT, kp = 8 * NT;
+  constexpr int msz = NT * (NT + 1) / 2 * 64;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t = lane & 3;
+  double* Yp = Zp + msz;
+  double* Tp = Yp + msz;
+  double* red = Tp + msz + 3 * kp + 2 * NSP_LCH_MAX;
+  const unsigned zs = (unsigned)__cvta_generic_to_shared(Zp), ys = zs + msz * 8, ts = ys + msz * 8;
+  const NspLane L = nsp_lane(lane);
+  const NspTiles<NTW> st = nsp_tiles<NTW, NTH>(nt, warp);
+  bool ok = true;
+    // The iteration as a state machine around the single product site:
+    //   A2: Y <- A A, spectral bound, Z0 = q(A)      Y0: Y <- A Z0
+    //   ZY: T <- (3I - Z Y)/2, residual              YT: Y <- Y T     TZ: Z <- T Z
+    // Y and Z are overwritten in place after a barrier (the product is held in the accumulator
+    // registers meanwhile), so three matrices suffice.
+    enum { OP_A2, OP_Y0, OP_ZY, OP_YT, OP_TZ };
+    double acc[NTW][2];
+    int op = OP_A2, it = 0;
+    bool done = false;
+#pragma unroll 1
+    while (true) {
+      const unsigned pb = (op == OP_ZY) ? zs : (op == OP_YT) ? ys : ts;
+      const unsigned qb = (op == OP_A2) ? ts : (op == OP_ZY) ? ys : (op == OP_YT) ? ts : zs;
+      nsp_mm_any<NT, NW, NTW>(pb, qb, warp, st, L, acc);
+      if (op == OP_A2) {
+        nsp_store<NTW>(ys, nt, st, L, acc);
+        // tighter upper end of the spectrum from the product just made: lmax(C)^2 <= ||C^2||_F
+        // (Schatten-4 norm of C; C^2 = A^2 - 2 shift A + shift^2 I), typically 2-3x below ||C||_F
+        double f4 = 0.0;
+#pragma unroll
+        for (int n = 0; n < NTW; ++n)
+          if (n < st.n) {
+            const int i = st.ti[n] * 8 + g, j = st.tj[n] * 8 + 2 * t;
+            const double2 a = *reinterpret_cast<const double2*>(
+                reinterpret_cast<const unsigned char*>(Tp) + nsp_cbase(st.ti[n], st.tj[n], nt, L));
+            const double w = (st.ti[n] != st.tj[n]) ? 2.0 : 1.0;
+            const double c0 = acc[n][0] - 2.0 * shift * a.x + (i == j ? shift * shift : 0.0);
+            const double c1 = acc[n][1] - 2.0 * shift * a.y + (i == j + 1 ? shift * shift : 0.0);
+            if (i < k && j < k) f4 = fma(w * c0, c0, f4);
+            if (i < k && j + 1 < k) f4 = fma(w * c1, c1, f4);
+          }
+        f4 = nsp_block_reduce<NTH>(f4, false, red);            // (its barriers also publish A^2)
+        const double hi = shift + fro;
+        const NsStart q0 = ns_chebyshev_start(shift, fmin(hi, shift + sqrt(sqrt(f4) + 1e-13 * hi * hi)));
+        for (int e = tid; e < msz; e += NTH) Zp[e] = fma(q0.a2, Yp[e], q0.a1 * Tp[e]);
+        __syncthreads();
+        if (tid < kp) Zp[nsp_elem(tid, tid, nt)] += q0.a0;      // Z0 = q(A)
+        __syncthreads();
+        op = OP_Y0;
+      } else if (op == OP_Y0) {
+        nsp_store<NTW>(ys, nt, st, L, acc);                     // (A^2 no longer read: barrier above)
+        __syncthreads();
+        op = OP_ZY;
+      } else if (op == OP_ZY) {
+        double r = 0.0;
+#pragma unroll
+        for (int n = 0; n < NTW; ++n)
+          if (n < st.n) {
+            const int i = st.ti[n] * 8 + g, j = st.tj[n] * 8 + 2 * t;
+            const double d0 = (i == j ? 1.0 : 0.0), d1 = (i == j + 1 ? 1.0 : 0.0);
+            const double e0 = d0 - acc[n][0], e1 = d1 - acc[n][1];
+            r = fmax(r, fmax(fabs(e0), fabs(e1)));
+            sts_f64x2(ts + nsp_cbase(st.ti[n], st.tj[n], nt, L), d0 + 0.5 * e0, d1 + 0.5 * e1);   // T = (3I - ZY)/2
+          }
+        r = nsp_block_reduce<NTH>(r, true, red);                // also publishes T
+        done = r < 1e-7;                                         // error after this update ~ r^2
+        if (!(r < 1.5)) { ok = false; break; }                   // cannot happen for SPD input; NaN guard
+        op = done ? OP_TZ : OP_YT;
+      } else if (op == OP_YT) {
+        __syncthreads();                                         // everyone is done reading Y
+        nsp_store<NTW>(ys, nt, st, L, acc);                     // in place; T Z does not read Y
+        op = OP_TZ;
+      } else {
+        __syncthreads();                                         // everyone is done reading Z
+        nsp_store<NTW>(zs, nt, st, L, acc);
+        __syncthreads();
+        ++it;
+        if (done || it >= NS_MAX_ITERS) break;
+        op = OP_ZY;
+      }
+    }
+  return (ok && done) ? it : -1;
+}
+
 template <int NT, int NTH, int MINB>
 __global__ void __launch_bounds__(NTH, MINB) letkf_nsp_kernel(ColParams P, int lch) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -263,9 +355,9 @@ __global__ void __launch_bounds__(NTH, MINB) letkf_nsp_kernel(ColParams P, int l
   double* gvec = Tp + msz;
   double* wa = gvec + kp;
   double* tv = wa + kp;
-  double* xm = tv + kp;                                        // [lch]
-  double* ml = xm + lch;                                       // [lch]
-  double* red = ml + lch;                                      // [16]
+  double* xm = tv + kp;                                        // [NSP_LCH_MAX]
+  double* ml = xm + NSP_LCH_MAX;                               // [NSP_LCH_MAX]
+  double* red = ml + NSP_LCH_MAX;                              // [16]
   double* sel_sq = red + 16;                                   // [NS_SELCAP] sqrt(rho / sigma^2)
   double* sel_d = sel_sq + NS_SELCAP;                          // [NS_SELCAP] sqrt(rho / sigma^2) * d
   int* sel_row = reinterpret_cast<int*>(sel_d + NS_SELCAP);    // [NS_SELCAP] obs row
@@ -295,6 +387,8 @@ __global__ void __launch_bounds__(NTH, MINB) letkf_nsp_kernel(ColParams P, int l
     int col_iters = 0;
     long long col_npl = 0;
     bool col_fail = false;
+    // the column's state is first touched in phase 3: start pulling it towards L2 now
+    for (int e = tid * 16; e < nz * k; e += NTH * 16) asm volatile("prefetch.global.L2 [%0];" ::"l"(Xg + e));
 
     for (int lt = 0; lt < nxf; ++lt) {
       // ---------------- 1. selection, gather, C += Yw^T Yw on the FP64 tensor path, g += Yw^T dw
@@ -454,95 +548,33 @@ __global__ void __launch_bounds__(NTH, MINB) letkf_nsp_kernel(ColParams P, int l
           }
         if (tid < k) gvec[tid] = gacc;
         __syncthreads();
-        // The iteration as a state machine around the single product site:
-        //   A2: Y <- A A, spectral bound, Z0 = q(A)      Y0: Y <- A Z0
-        //   ZY: T <- (3I - Z Y)/2, residual              YT: keep Y T in registers
-        //   TZ: Z <- T Z and Y <- (kept) Y T, both written in place after one barrier
-        enum { OP_A2, OP_Y0, OP_ZY, OP_YT, OP_TZ };
-        double acc[NTW][2], accY[NTW][2];
-        int op = OP_A2, it = 0;
-        bool done = false;
-#pragma unroll 1
-        while (true) {
-          const unsigned pb = (op == OP_ZY) ? zs : (op == OP_YT) ? ys : ts;
-          const unsigned qb = (op == OP_A2) ? ts : (op == OP_ZY) ? ys : (op == OP_YT) ? ts : zs;
-          nsp_mm_any<NT, NW, NTW>(pb, qb, warp, st, L, acc);
-          if (op == OP_A2) {
-            nsp_store<NTW>(ys, nt, st, L, acc);
-            // tighter upper end of the spectrum from the product just made: lmax(C)^2 <= ||C^2||_F
-            // (Schatten-4 norm of C; C^2 = A^2 - 2 shift A + shift^2 I), typically 2-3x below ||C||_F
-            double f4 = 0.0;
-#pragma unroll
-            for (int n = 0; n < NTW; ++n)
-              if (n < st.n) {
-                const int i = st.ti[n] * 8 + g, j = st.tj[n] * 8 + 2 * t;
-                const double2 a = *reinterpret_cast<const double2*>(
-                    reinterpret_cast<const unsigned char*>(Tp) + nsp_cbase(st.ti[n], st.tj[n], nt, L));
-                const double w = (st.ti[n] != st.tj[n]) ? 2.0 : 1.0;
-                const double c0 = acc[n][0] - 2.0 * shift * a.x + (i == j ? shift * shift : 0.0);
-                const double c1 = acc[n][1] - 2.0 * shift * a.y + (i == j + 1 ? shift * shift : 0.0);
-                if (i < k && j < k) f4 = fma(w * c0, c0, f4);
-                if (i < k && j + 1 < k) f4 = fma(w * c1, c1, f4);
-              }
-            f4 = nsp_block_reduce<NTH>(f4, false, red);            // (its barriers also publish A^2)
-            const double hi = shift + fro;
-            const NsStart q0 = ns_chebyshev_start(shift, fmin(hi, shift + sqrt(sqrt(f4) + 1e-13 * hi * hi)));
-            for (int e = tid; e < msz; e += NTH) Zp[e] = fma(q0.a2, Yp[e], q0.a1 * Tp[e]);
-            __syncthreads();
-            if (tid < kp) Zp[nsp_elem(tid, tid, nt)] += q0.a0;      // Z0 = q(A)
-            __syncthreads();
-            op = OP_Y0;
-          } else if (op == OP_Y0) {
-            nsp_store<NTW>(ys, nt, st, L, acc);                     // (A^2 no longer read: barrier above)
-            __syncthreads();
-            op = OP_ZY;
-          } else if (op == OP_ZY) {
-            double r = 0.0;
-#pragma unroll
-            for (int n = 0; n < NTW; ++n)
-              if (n < st.n) {
-                const int i = st.ti[n] * 8 + g, j = st.tj[n] * 8 + 2 * t;
-                const double d0 = (i == j ? 1.0 : 0.0), d1 = (i == j + 1 ? 1.0 : 0.0);
-                const double e0 = d0 - acc[n][0], e1 = d1 - acc[n][1];
-                r = fmax(r, fmax(fabs(e0), fabs(e1)));
-                sts_f64x2(ts + nsp_cbase(st.ti[n], st.tj[n], nt, L), d0 + 0.5 * e0, d1 + 0.5 * e1);   // T = (3I - ZY)/2
-              }
-            r = nsp_block_reduce<NTH>(r, true, red);                // also publishes T
-            done = r < 1e-7;                                         // error after this update ~ r^2
-            if (!(r < 1.5)) { ok = false; break; }                   // cannot happen for SPD input; NaN guard
-            op = done ? OP_TZ : OP_YT;
-          } else if (op == OP_YT) {
-#pragma unroll
-            for (int n = 0; n < NTW; ++n) { accY[n][0] = acc[n][0]; accY[n][1] = acc[n][1]; }
-            op = OP_TZ;
-          } else {
-            __syncthreads();                                         // everyone is done reading Y and Z
-            if (!done) nsp_store<NTW>(ys, nt, st, L, accY);
-            nsp_store<NTW>(zs, nt, st, L, acc);
-            __syncthreads();
-            ++it;
-            if (done || it >= NS_MAX_ITERS) break;
-            op = OP_ZY;
-          }
-        }
-        if (!done) ok = false;
+        const int it = nsp_inverse_sqrt<NT, NTH>(Zp, shift, fro, k);
+        if (it < 0) ok = false;
         col_iters = max(col_iters, it);
-        // w = Z (Z g)
+        // w = Z (Z g): warp per tile row, lanes read Z in the fragment pattern (row g, columns t, 4 + t
+        // of every tile) and reduce over t
         if (ok) {
-          for (int a = warp; a < k; a += NW) {
-            double s = 0.0;
-            for (int b = lane; b < k; b += 32) s += Zp[nsp_elem(a, b, nt)] * gvec[b];
-            s = warp_sum(s);
-            if (lane == 0) tv[a] = s;
+          for (int pass = 0; pass < 2; ++pass) {
+            const double* vin = pass ? tv : gvec;
+            double* vout = pass ? wa : tv;
+            for (int I = warp; I < nt; I += NW) {
+              NspWalk zw;
+              zw.start(I);
+              double s = 0.0;
+#pragma unroll 1
+              for (int K = 0; K < nt; ++K) {
+                const double z0 = lds_f64(zw.addr(zs, K, 0, L)), z1 = lds_f64(zw.addr(zs, K, 1, L));
+                const int c = K * 8 + t;
+                s = fma(z0, c < k ? vin[c] : 0.0, s);
+                s = fma(z1, c + 4 < k ? vin[c + 4] : 0.0, s);
+                zw.next(K, nt);
+              }
+              s += __shfl_xor_sync(0xffffffffu, s, 1);
+              s += __shfl_xor_sync(0xffffffffu, s, 2);
+              if (t == 0 && I * 8 + g < k) vout[I * 8 + g] = s;
+            }
+            __syncthreads();
           }
-          __syncthreads();
-          for (int a = warp; a < k; a += NW) {
-            double s = 0.0;
-            for (int b = lane; b < k; b += 32) s += Zp[nsp_elem(a, b, nt)] * tv[b];
-            s = warp_sum(s);
-            if (lane == 0) wa[a] = s;
-          }
-          __syncthreads();
         }
       }
       if (!ok) col_fail = true;
@@ -660,6 +692,6 @@ static size_t nsp_smem_bytes(int k, int lch, int nth) {
   const int pch = std::max(NS_PCH, nth / 32);
   size_t mats = 3 * (size_t)nsp_ntiles(k) * 64;
   mats = std::max(mats, (size_t)pch * ns_stride(k));                       // phase-1 staging aliases them
-  const size_t dbl = mats + 3 * (size_t)ns_kp(k) + 2 * (size_t)lch + 16 + 2 * NS_SELCAP;
+  const size_t dbl = mats + 3 * (size_t)ns_kp(k) + 2 * NSP_LCH_MAX + 16 + 2 * NS_SELCAP;
   return dbl * 8 + (size_t)NS_SELCAP * 4 + 32 * 4 + 4 * 4 + 16;
 }

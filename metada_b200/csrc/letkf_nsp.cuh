@@ -132,30 +132,34 @@ __host__ __device__ constexpr int nsp_tile_i(int nt, int e) { int i = 0, rs = 0;
 __host__ __device__ constexpr int nsp_tile_j(int nt, int e) { int i = 0, rs = 0; while (e >= rs + (nt - i)) { rs += nt - i; ++i; } return i + (e - rs); }
 __host__ __device__ constexpr int nsp_rs(int I, int nt) { return (I * (2 * nt - I + 1)) / 2; }
 
-template <int IMM>
-__device__ __forceinline__ double lds_f64_imm(unsigned addr) {
-  double v;
-  asm volatile("ld.shared.f64 %0, [%1+%2];" : "=d"(v) : "r"(addr), "n"(IMM));
-  return v;
+// The operands are read with plain loads through pointers derived from the dynamic shared array
+// (provably shared, so they compile to LDS with immediate offsets): with inline-asm loads ptxas
+// funnels every B fragment through one register and serialises load -> MMA -> load.
+__device__ __forceinline__ unsigned char* nsp_smem() {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  return smem_raw;
 }
-// fragment element S[8 I + g][8 K + 4 h + t]: d = base + straight lane offset of this k-half,
-// tr = base + transposed lane offset of this k-half
+// fragment element S[8 I + g][8 K + 4 h + t]: d = matrix + straight lane offset of this k-half,
+// tr = matrix + transposed lane offset of this k-half
 template <int NT, int I, int K>
-__device__ __forceinline__ double nsp_frag_fixed(unsigned d, unsigned tr) {
-  if constexpr (I <= K) return lds_f64_imm<(nsp_rs(I, NT) + K - I) * 512>(d);
-  else return lds_f64_imm<(nsp_rs(K, NT) + I - K) * 512>(tr);
+__device__ __forceinline__ double nsp_frag_fixed(const double* d, const double* tr) {
+  if constexpr (I <= K) return d[(nsp_rs(I, NT) + K - I) * 64];
+  else return tr[(nsp_rs(K, NT) + I - K) * 64];
 }
 
 // The k-half loop (h) stays rolled: the body is then half as long, and the eight warp variants of
 // NT = 10 together (20 KB) stay inside the 32 KB L1.5 instruction cache; fully unrolled (41 KB) the
 // same code measured no faster than the generic walk.
 template <int NT, int NW, int NTW, int W>
-__device__ __forceinline__ void nsp_mm_warp(unsigned pd0, unsigned pd1, unsigned pt, unsigned qd0, unsigned qd1,
-                                            unsigned qt, double (&acc)[NTW][2]) {
+__device__ __forceinline__ void nsp_mm_warp(unsigned pbase, unsigned qbase, const NspLane& L, double (&acc)[NTW][2]) {
   constexpr int E = NT * (NT + 1) / 2, e0 = (E * W) / NW, e1 = (E * (W + 1)) / NW, N = e1 - e0;
+  const unsigned char* sm = nsp_smem();
 #pragma unroll 1
   for (int h = 0; h < 2; ++h) {
-    const unsigned pd = h ? pd1 : pd0, ptr = pt + (h << 8), qd = h ? qd1 : qd0, qtr = qt + (h << 8);
+    const double* pd = reinterpret_cast<const double*>(sm + pbase + L.offd + (h ? L.dh : 0u));
+    const double* ptr = reinterpret_cast<const double*>(sm + pbase + L.offt + (h << 8));
+    const double* qd = reinterpret_cast<const double*>(sm + qbase + L.offd + (h ? L.dh : 0u));
+    const double* qtr = reinterpret_cast<const double*>(sm + qbase + L.offt + (h << 8));
     nsp_static_for<0, NT>([&](auto K_c) {
       constexpr int K = decltype(K_c)::value;
       double a[NTW], b[NTW];
@@ -175,11 +179,11 @@ __device__ __forceinline__ void nsp_mm_warp(unsigned pd0, unsigned pd1, unsigned
 }
 
 template <int NT, int NW, int NTW, int... Ws>
-__device__ __forceinline__ void nsp_mm_dispatch(std::integer_sequence<int, Ws...>, int warp, unsigned pd0,
-                                                unsigned pd1, unsigned pt, unsigned qd0, unsigned qd1,
-                                                unsigned qt, double (&acc)[NTW][2]) {
-  ((warp == Ws ? (nsp_mm_warp<NT, NW, NTW, Ws>(pd0, pd1, pt, qd0, qd1, qt, acc), 0) : 0), ...);
+__device__ __forceinline__ void nsp_mm_dispatch(std::integer_sequence<int, Ws...>, int warp, unsigned pbase,
+                                                unsigned qbase, const NspLane& L, double (&acc)[NTW][2]) {
+  ((warp == Ws ? (nsp_mm_warp<NT, NW, NTW, Ws>(pbase, qbase, L, acc), 0) : 0), ...);
 }
+
 // Generic product for the larger tile counts (their specialised bodies would not fit the
 // instruction cache): a running tile walk per operand, ~17 instructions per DMMA.  Warps with one
 // tile fewer than NTW repeat their last tile (never stored) so that no MMA is predicated.
@@ -216,9 +220,9 @@ __device__ __forceinline__ void nsp_mm_any(unsigned pbase, unsigned qbase, int w
 #pragma unroll
   for (int n = 0; n < NTW; ++n) { acc[n][0] = 0.0; acc[n][1] = 0.0; }
   if constexpr (NT <= NSP_FIXED_MAX_NT) {
-    const unsigned pd0 = pbase + L.offd, qd0 = qbase + L.offd;
-    nsp_mm_dispatch<NT, NW, NTW>(std::make_integer_sequence<int, NW>{}, warp, pd0, pd0 + L.dh, pbase + L.offt,
-                                 qd0, qd0 + L.dh, qbase + L.offt, acc);
+    // byte offsets from the start of dynamic shared memory
+    const unsigned s0 = (unsigned)__cvta_generic_to_shared(nsp_smem());
+    nsp_mm_dispatch<NT, NW, NTW>(std::make_integer_sequence<int, NW>{}, warp, pbase - s0, qbase - s0, L, acc);
   } else {
     nsp_mm_walk<NTW>(pbase, qbase, NT, w, L, acc);
   }

@@ -192,8 +192,9 @@ def run_ours(args):
     obs_all = syn.observations(P, nx, ny, nz, seed=42, sigma=SIGMA)
     solver = {"auto": mb.SOLVER_AUTO, "jacobi": mb.SOLVER_JACOBI, "ns": mb.SOLVER_NEWTON_SCHULZ}[args.solver]
     params = capi.make_params(radius, INFLATION, mb.MODE_CANONICAL, mb.LOC_GASPARI_COHN, solver=solver)
-    solver_name = {"auto": "Newton-Schulz symmetric square root on FP64 DMMA (k<=80; Jacobi otherwise)" if 24 <= k <= 80 else "Jacobi",
-                   "jacobi": "one-sided block Jacobi eigen-decomposition", "ns": "Newton-Schulz symmetric square root on FP64 DMMA"}[args.solver]
+    ns_name = "Newton-Schulz symmetric square root on FP64 DMMA, packed symmetric tiles (24<=k<=128; Jacobi otherwise)"
+    solver_name = {"auto": ns_name if 24 <= k <= 128 else "one-sided block Jacobi eigen-decomposition",
+                   "jacobi": "one-sided block Jacobi eigen-decomposition", "ns": ns_name}[args.solver]
 
     job.set_observations(obs_all)     # device SoA + H/Y' buffers are allocated once and reused
 
@@ -268,7 +269,7 @@ def run_ours(args):
                        "l2": "state (%.1f GB) >> 126 MB L2; background regenerated on device before every step" % (G * nz * k * 8 / 1e9),
                        "mean_local_obs": pbar, "mean_solver_iterations": sum_sw / ncols},
             "roofline": {"bound": "fp64", "achieved": ach_tf, "peak": fp64_peak, "unit": "TFLOP/s", "frac": ach_tf / fp64_peak,
-                         "traffic": traffic, "traffic_source": traffic_src, "algorithmic_bytes": Bc * (G / world), "kernel": "letkf_ns_kernel" if (24 <= k <= 80 and args.solver != "jacobi") else "letkf_canonical_kernel",
+                         "traffic": traffic, "traffic_source": traffic_src, "algorithmic_bytes": Bc * (G / world), "kernel": "letkf_nsp_kernel" if (24 <= k <= 128 and args.solver != "jacobi") else "letkf_canonical_kernel",
                          "peak_source": "FP64 FMA microbenchmark run in this process (mdc_bench_fp64_fma); "
                                         "MEASURED_PEAKS.json has no FP64 figure",
                          "pipe": "FP64 tensor path (DMMA mma.sync.m8n8k4.f64) for the Newton-Schulz products, SYRK and update",

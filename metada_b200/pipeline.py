@@ -34,14 +34,20 @@ from . import capi
 
 
 class StreamedLetkf:
-    def __init__(self, device, gnx, gny, nz, k, radius, slab_rows=32, slots=4, sm_reserve=4, workers=None):
+    def __init__(self, device, gnx, gny, nz, k, radius, slab_rows=32, slots=4, sm_reserve=4, workers=None,
+                 row_range=None):
+        """row_range = (Y0, Y1): analyse only the global rows [Y0, Y1) (one rank's share of a
+        column-sharded job, parallel.py); default: the whole grid."""
         self.gnx, self.gny, self.nz, self.k = gnx, gny, nz, k
         self.reach = int(math.floor(radius))
-        self.nslab = max(1, (gny + slab_rows - 1) // slab_rows)
+        self.Y0, self.Y1 = (0, gny) if row_range is None else row_range
+        rows = self.Y1 - self.Y0
+        self.nslab = max(1, (rows + slab_rows - 1) // slab_rows)
         self.nslots = max(3, slots if workers is None else workers) if self.nslab > 1 else 1
         self.sm_reserve = sm_reserve
         self.ctxs = [capi.Context(device) for _ in range(self.nslots)]
-        self.bounds = [((gny * s) // self.nslab, (gny * (s + 1)) // self.nslab) for s in range(self.nslab)]
+        self.bounds = [(self.Y0 + (rows * s) // self.nslab, self.Y0 + (rows * (s + 1)) // self.nslab)
+                       for s in range(self.nslab)]
         self._ens = [None] * self.nslots
         self._obs = [None] * self.nslots
         self._pool = None
@@ -59,11 +65,15 @@ class StreamedLetkf:
             c.close()
         self.ctxs = []
 
-    def analyse(self, member_ptrs, obs, params):
-        """member_ptrs: k host pointers (pinned for full PCIe speed) to [nz][gny][gnx] float64 arrays,
-        updated IN PLACE.  obs: dict of global observation arrays.  Returns summed stats."""
+    def analyse(self, member_ptrs, obs, params, host_row0=0, host_ny=None, ext_top=(), ext_bottom=()):
+        """member_ptrs: k host pointers (pinned for full PCIe speed) to [nz][host_ny][gnx] float64
+        arrays whose first row is global row host_row0 (default: the whole grid), updated IN PLACE.
+        obs: dict of global observation arrays.  ext_top / ext_bottom: (device pointer, rows) of packed
+        observation rows received from the ranks above / below this row range; they are appended to
+        the slabs within reach of that edge.  Returns summed stats."""
         import metada_b200 as mb
         S, R, K = self.nslab, self.reach, self.nslots
+        host_ny = self.gny if host_ny is None else host_ny
         prm = copy.copy(params)
         if S > 1:
             prm.sm_reserve = self.sm_reserve
@@ -116,7 +126,7 @@ class StreamedLetkf:
                     ens = self._ens[w]
                     ens.set_rows((y1 - y0) + (1 if y1 < self.gny else 0))
                     ens.set_domain(0, y0, self.gnx, self.gny, self.gnx, y1 - y0)
-                    ens.upload_rows(member_ptrs, self.gny, y0)
+                    ens.upload_rows(member_ptrs, host_ny, y0 - host_row0)
                     self.ctxs[w].sync()
                     self.trace.append(("up", s, w, t0 - t_base, time.perf_counter() - t_base))
                     q_up.put((s, w))
@@ -165,6 +175,12 @@ class StreamedLetkf:
                         if 0 <= src < S and s in halo_buf[src]:
                             p, n = halo_buf[src][s]
                             ob.append_rows(p, n)
+                    if self.bounds[s][0] - R < self.Y0:        # rows from other ranks: supersets are harmless
+                        for p, n in ext_top:
+                            ob.append_rows(p, n)
+                    if self.bounds[s][1] + R > self.Y1:
+                        for p, n in ext_bottom:
+                            ob.append_rows(p, n)
                     stats[s] = capi.letkf_analyse(self._ens[w], ob, prm)
                     self.trace.append(("an", s, w, t0 - t_base, time.perf_counter() - t_base))
                     q_down.put((s, w))
@@ -181,7 +197,7 @@ class StreamedLetkf:
                     s, w = item
                     t0 = time.perf_counter()
                     y0, y1 = self.bounds[s]
-                    self._ens[w].download_rows(member_ptrs, self.gny, y0, y1 - y0)
+                    self._ens[w].download_rows(member_ptrs, host_ny, y0 - host_row0, y1 - y0)
                     self.trace.append(("dn", s, w, t0 - t_base, time.perf_counter() - t_base))
                     free_slots.put(w)
             except BaseException as e:  # noqa: BLE001

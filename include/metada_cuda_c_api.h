@@ -129,7 +129,14 @@ int mdc_obs_index_query_lists(mdc_obs* obs, mdc_ens* ens, double radius, const i
 
 /* ---- LETKF: replaces LETKF<Tag>::Analyse / updateGridPoint (LETKF.hpp:63-119, 152-243) ----- */
 enum { MDC_MODE_REF_COMPAT = 0, MDC_MODE_REF_ETKF = 1, MDC_MODE_CANONICAL = 2 };
-enum { MDC_LOC_CUTOFF = 0, MDC_LOC_GASPARI_COHN = 1 };
+/* R-localisation weight rho(d) of an observation at distance d (CANONICAL mode; the selection cutoff d <= radius
+ * always applies).  GASPARI_COHN: Gaspari & Cohn 1999 eq. 4.10 with support = radius.  The other three are the
+ * reference's localisation functions (LWEnKF.hpp:597-635) of d / L, L = loc_scale (<= 0: L = radius):
+ * GAUSSIAN exp(-(d/L)^2 / 2), EXPONENTIAL exp(-d/L), REF_GASPARI_COHN the reference's own two-piece polynomial
+ * (LWEnKF.hpp:624-635) -- NOT the Gaspari-Cohn taper (it is 4 at d = 0 and discontinuous at d = L); kept only so
+ * that the reference's choice can be reproduced. */
+enum { MDC_LOC_CUTOFF = 0, MDC_LOC_GASPARI_COHN = 1, MDC_LOC_GAUSSIAN = 2, MDC_LOC_EXPONENTIAL = 3,
+       MDC_LOC_REF_GASPARI_COHN = 4 };
 /* AUTO: Newton-Schulz (GEMM-only symmetric square root on FP64 DMMA) for 24 <= k <= 128, else Jacobi.
  * JACOBI: one-block-per-column one-sided Jacobi eigen-decomposition with warp-shuffle reductions.
  * NEWTON_SCHULZ: packed symmetric tiles (two columns per SM for k <= 80); transforms whose
@@ -150,7 +157,8 @@ typedef struct {
   int solver;         /* CANONICAL: how A^{-1/2} is formed -- MDC_SOLVER_*                    */
   int sm_reserve;     /* SMs the persistent column kernel leaves free for concurrent streams
                          (member transposes of a streamed pipeline); 0 = use every SM          */
-  int reserved[2];
+  double loc_scale;   /* length scale L of MDC_LOC_GAUSSIAN / EXPONENTIAL / REF_GASPARI_COHN; <= 0: radius.
+                         The vertical scale is radius_v * L / radius.                          */
 } mdc_letkf_params;
 
 typedef struct {

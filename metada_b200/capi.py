@@ -19,7 +19,7 @@ _SRC = os.path.join(_HERE, "csrc", "mdc_api.cu")
 _HEADER = os.path.join(_ROOT, "include", "metada_cuda_c_api.h")
 
 MODE_REF_COMPAT, MODE_REF_ETKF, MODE_CANONICAL = 0, 1, 2
-LOC_CUTOFF, LOC_GASPARI_COHN = 0, 1
+LOC_CUTOFF, LOC_GASPARI_COHN, LOC_GAUSSIAN, LOC_EXPONENTIAL, LOC_REF_GASPARI_COHN = 0, 1, 2, 3, 4
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-shared", "-Xcompiler", "-fPIC", "-cudart", "shared",
@@ -33,7 +33,7 @@ class MdcError(RuntimeError):
 class LetkfParams(C.Structure):
     _fields_ = [("radius", C.c_double), ("radius_v", C.c_double), ("inflation", C.c_double),
                 ("mode", C.c_int), ("loc", C.c_int), ("use_R", C.c_int), ("max_sweeps", C.c_int),
-                ("jacobi_tol", C.c_double), ("solver", C.c_int), ("sm_reserve", C.c_int), ("reserved", C.c_int * 2)]
+                ("jacobi_tol", C.c_double), ("solver", C.c_int), ("sm_reserve", C.c_int), ("loc_scale", C.c_double)]
 
 
 class LetkfStats(C.Structure):
@@ -43,7 +43,7 @@ class LetkfStats(C.Structure):
                 ("numeric_failures", C.c_int32), ("redo_transforms", C.c_int32)]
 
     def asdict(self):
-        return {n: getattr(self, n) for n, _ in self._fields_ if n != "reserved"}
+        return {n: getattr(self, n) for n, _ in self._fields_}
 
 
 class EnkfDiag(C.Structure):
@@ -384,12 +384,14 @@ SOLVER_AUTO, SOLVER_JACOBI, SOLVER_NEWTON_SCHULZ, SOLVER_NEWTON_SCHULZ_FULL = 0,
 
 
 def make_params(radius, inflation=1.0, mode=MODE_CANONICAL, loc=LOC_GASPARI_COHN, use_R=1,
-                radius_v=0.0, max_sweeps=0, jacobi_tol=0.0, solver=SOLVER_AUTO, sm_reserve=0) -> LetkfParams:
+                radius_v=0.0, max_sweeps=0, jacobi_tol=0.0, solver=SOLVER_AUTO, sm_reserve=0,
+                loc_scale=0.0) -> LetkfParams:
     p = LetkfParams()
     p.radius, p.radius_v, p.inflation = radius, radius_v, inflation
     p.mode, p.loc, p.use_R, p.max_sweeps, p.jacobi_tol = mode, loc, use_R, max_sweeps, jacobi_tol
     p.solver = solver
     p.sm_reserve = sm_reserve
+    p.loc_scale = loc_scale
     return p
 
 

@@ -32,6 +32,7 @@ struct ColParams {
   const double* err;
   const uint8_t* valid;
   double radius, radius_v, inflation;
+  double loc_scale, loc_scale_v;   // length scales of the exp-type localisation functions
   int mode, loc, use_R, max_sweeps;
   double jtol;
   long long* stats;  // [0] sum p_loc [1] max p_loc [2] sum sweeps [3] max sweeps [4] failures [5] columns
@@ -52,6 +53,22 @@ __device__ __forceinline__ double lk_gaspari_cohn(double z) {
   if (z >= 2.0) return 0.0;
   if (z <= 1.0) return (((-0.25 * z + 0.5) * z + 0.625) * z - 5.0 / 3.0) * z * z + 1.0;
   return ((((z / 12.0 - 0.5) * z + 0.625) * z + 5.0 / 3.0) * z - 5.0) * z + 4.0 - 2.0 / (3.0 * z);
+}
+
+// The reference's localisation functions (LWEnKF.hpp:597-635) next to the Gaspari-Cohn taper
+__device__ __forceinline__ double lk_loc_weight(int loc, double dist, double support, double scale) {
+  switch (loc) {
+    case MDC_LOC_GASPARI_COHN: return lk_gaspari_cohn(dist / (0.5 * support));
+    case MDC_LOC_GAUSSIAN: { const double r = dist / scale; return exp(-0.5 * r * r); }          // :601-602
+    case MDC_LOC_EXPONENTIAL: return exp(-(dist / scale));                                         // :604-605
+    case MDC_LOC_REF_GASPARI_COHN: {                                                               // :624-635
+      const double r = dist / scale;
+      if (r >= 2.0) return 0.0;
+      if (r >= 1.0) { const double z = r - 1.0; return ((-0.25 * z + 0.5) * z + 0.625) * z + 0.125; }
+      return (((-0.25 * r + 0.5) * r + 0.625) * r - 5.0) * r + 4.0;
+    }
+    default: return 1.0;
+  }
 }
 
 __device__ __forceinline__ double warp_sum(double v) {
@@ -237,9 +254,9 @@ __global__ void __launch_bounds__(LK_THREADS) letkf_column_kernel(ColParams P) {
               dv = fabs((double)(P.iv.sz[a] - lt));
               sel = dv <= P.radius_v;
             }
-            if (sel && P.mode == MDC_MODE_CANONICAL && P.loc == MDC_LOC_GASPARI_COHN) {
-              rho = lk_gaspari_cohn(dist / (0.5 * P.radius));
-              if (per_level) rho *= lk_gaspari_cohn(dv / (0.5 * P.radius_v));
+            if (sel && P.mode == MDC_MODE_CANONICAL && P.loc != MDC_LOC_CUTOFF) {
+              rho = lk_loc_weight(P.loc, dist, P.radius, P.loc_scale);
+              if (per_level) rho *= lk_loc_weight(P.loc, dv, P.radius_v, P.loc_scale_v);
             }
           }
           unsigned bal = __ballot_sync(0xffffffffu, sel);

@@ -372,9 +372,9 @@ __global__ void __launch_bounds__(NS_THREADS) letkf_ns_kernel(ColParams P, int l
             }
             if (sel) {
               double rho = 1.0;
-              if (P.loc == MDC_LOC_GASPARI_COHN) {
-                rho = lk_gaspari_cohn(dist / (0.5 * P.radius));
-                if (per_level) rho *= lk_gaspari_cohn(dv / (0.5 * P.radius_v));
+              if (P.loc != MDC_LOC_CUTOFF) {
+                rho = lk_loc_weight(P.loc, dist, P.radius, P.loc_scale);
+                if (per_level) rho *= lk_loc_weight(P.loc, dv, P.radius_v, P.loc_scale_v);
               }
               orow = P.iv.sorted_row[a];
               const double e_ = P.err[orow];

@@ -257,9 +257,9 @@ __global__ void __launch_bounds__(NT, MINB) letkf_canonical_kernel(ColParams P, 
               dv = fabs((double)(P.iv.sz[a] - lt));
               sel = dv <= P.radius_v;
             }
-            if (sel && P.loc == MDC_LOC_GASPARI_COHN) {
-              rho = lk_gaspari_cohn(dist / (0.5 * P.radius));
-              if (per_level) rho *= lk_gaspari_cohn(dv / (0.5 * P.radius_v));
+            if (sel && P.loc != MDC_LOC_CUTOFF) {
+              rho = lk_loc_weight(P.loc, dist, P.radius, P.loc_scale);
+              if (per_level) rho *= lk_loc_weight(P.loc, dv, P.radius_v, P.loc_scale_v);
             }
           }
           const unsigned bal = __ballot_sync(0xffffffffu, sel);

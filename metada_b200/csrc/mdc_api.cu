@@ -700,6 +700,7 @@ static int letkf_launch(mdc_ens* e, mdc_obs* o, const mdc_letkf_params* p, const
   if (k > 128) MDC_FAIL(ctx, MDC_ERR_UNSUPPORTED, "letkf: k=%d > 128 members not supported", k);
   if (k < 2) MDC_FAIL(ctx, MDC_ERR_INVALID, "letkf: needs at least 2 members");
   if (p->mode < 0 || p->mode > 2) MDC_FAIL(ctx, MDC_ERR_INVALID, "letkf: bad mode");
+  if (p->loc < 0 || p->loc > MDC_LOC_REF_GASPARI_COHN) MDC_FAIL(ctx, MDC_ERR_INVALID, "letkf: bad localisation function");
   if (!(p->inflation > 0.0)) MDC_FAIL(ctx, MDC_ERR_INVALID, "letkf: inflation must be > 0");
   const size_t smem = lk_smem_bytes(k, p->mode);
   if ((int)smem > ctx->max_smem_optin)
@@ -714,6 +715,8 @@ static int letkf_launch(mdc_ens* e, mdc_obs* o, const mdc_letkf_params* p, const
   cp.Yp = o->Yp; cp.d = o->d; cp.err = o->err; cp.valid = o->valid;
   cp.radius = p->radius; cp.radius_v = p->radius_v; cp.inflation = p->inflation;
   cp.mode = p->mode; cp.loc = p->loc; cp.use_R = p->use_R;
+  cp.loc_scale = p->loc_scale > 0.0 ? p->loc_scale : p->radius;
+  cp.loc_scale_v = p->radius_v > 0.0 && p->radius > 0.0 ? p->radius_v * (cp.loc_scale / p->radius) : 1.0;
   cp.max_sweeps = p->max_sweeps > 0 ? p->max_sweeps : 40;
   cp.jtol = p->jacobi_tol > 0.0 ? p->jacobi_tol : 1e-11;
   cp.stats = ctx->d_stats;

@@ -6,7 +6,9 @@
 // (inflation, localization_radius, output_base_file, format -- all via asFloat/asString, so reals
 // arrive float-narrowed exactly as in LETKF.hpp:52-55) plus the optional
 //   mode: "ref_compat" (default; the arithmetic of LETKF.hpp:209-238) | "ref_etkf" | "canonical"
-//   localization_function: "cutoff" | "gaspari_cohn" (canonical only; default gaspari_cohn)
+//   localization_function: "cutoff" | "gaspari_cohn" | "gaussian" | "exponential" | "ref_gaspari_cohn"
+//                          (canonical only; default gaspari_cohn; the last three are LWEnKF.hpp:597-635)
+//   localization_scale:    length scale of the last three (default: localization_radius)
 //   vertical_radius: levels (canonical only; default 0 = none)
 #include <string>
 
@@ -41,9 +43,18 @@ class LETKF {
     try { mode = config.Get("mode").asString(); } catch (...) {}
     try { loc = config.Get("localization_function").asString(); } catch (...) {}
     try { params_.radius_v = config.Get("vertical_radius").asFloat(); } catch (...) {}
+    try { params_.loc_scale = config.Get("localization_scale").asFloat(); } catch (...) {}
     if (mode == "ref_compat") params_.mode = MDC_MODE_REF_COMPAT;
     else if (mode == "ref_etkf") params_.mode = MDC_MODE_REF_ETKF;
-    else if (mode == "canonical") { params_.mode = MDC_MODE_CANONICAL; params_.loc = (loc == "cutoff") ? MDC_LOC_CUTOFF : MDC_LOC_GASPARI_COHN; }
+    else if (mode == "canonical") {
+      params_.mode = MDC_MODE_CANONICAL;
+      if (loc == "cutoff") params_.loc = MDC_LOC_CUTOFF;
+      else if (loc == "gaspari_cohn") params_.loc = MDC_LOC_GASPARI_COHN;
+      else if (loc == "gaussian") params_.loc = MDC_LOC_GAUSSIAN;
+      else if (loc == "exponential") params_.loc = MDC_LOC_EXPONENTIAL;
+      else if (loc == "ref_gaspari_cohn") params_.loc = MDC_LOC_REF_GASPARI_COHN;
+      else throw std::invalid_argument("LETKF: unknown localization_function '" + loc + "'");
+    }
     else throw std::invalid_argument("LETKF: unknown mode '" + mode + "'");
     logger_.Info() << "LETKF constructed with radius " << localization_radius_ << " (device path, mode " << mode << ")";
   }

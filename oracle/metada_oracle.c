@@ -162,6 +162,23 @@ double orc_gaspari_cohn(double z) {
   return ((((z / 12.0 - 0.5) * z + 0.625) * z + 5.0 / 3.0) * z - 5.0) * z + 4.0 - 2.0 / (3.0 * z);
 }
 
+/* LWEnKF.hpp:597-621 (switch over LocalizationFunction) and :624-635 (the reference's own
+ * "Gaspari-Cohn" polynomial, which is not the Gaspari-Cohn taper: 4 at r = 0, jump at r = 1). */
+double orc_loc_weight(int loc, double dist, double support, double scale) {
+  switch (loc) {
+    case ORC_LOC_GASPARI_COHN: return orc_gaspari_cohn(dist / (0.5 * support));
+    case ORC_LOC_GAUSSIAN: { double r = dist / scale; return exp(-0.5 * r * r); }   /* :601-602 */
+    case ORC_LOC_EXPONENTIAL: return exp(-(dist / scale));                           /* :604-605 */
+    case ORC_LOC_REF_GASPARI_COHN: {                                                 /* :624-635 */
+      double r = dist / scale;
+      if (r >= 2.0) return 0.0;
+      if (r >= 1.0) { double z = r - 1.0; return ((-0.25 * z + 0.5) * z + 0.625) * z + 0.125; }
+      return (((-0.25 * r + 0.5) * r + 0.625) * r - 5.0) * r + 4.0;
+    }
+    default: return 1.0;
+  }
+}
+
 /* ------------------------------------------------------------------ dense kit (row-major) */
 
 /* Partial-pivot LU inverse: what Eigen's MatrixXd::inverse() does for dynamic sizes. */
@@ -439,6 +456,7 @@ static int letkf_snapshot(const orc_letkf_params* p, double* X, const int32_t* o
   int rc_all = 0;
   int nthreads = p->nthreads;
 #ifdef _OPENMP
+  const double loc_scale = p->loc_scale > 0.0 ? p->loc_scale : p->radius;
   if (nthreads <= 0) nthreads = omp_get_max_threads();
 #pragma omp parallel num_threads(nthreads)
 #endif
@@ -474,11 +492,11 @@ static int letkf_snapshot(const orc_letkf_params* p, double* X, const int32_t* o
           if (per_level) {
             double dv = fabs((double)(oz[i] - lt));
             if (!(dv <= p->radius_v)) continue;
-            if (p->mode == ORC_MODE_CANONICAL && p->loc == ORC_LOC_GASPARI_COHN)
-              rho *= orc_gaspari_cohn(dv / (0.5 * p->radius_v));
+            if (p->mode == ORC_MODE_CANONICAL && p->loc != ORC_LOC_CUTOFF)
+              rho *= orc_loc_weight(p->loc, dv, p->radius_v, p->radius_v * (loc_scale / p->radius));
           }
-          if (p->mode == ORC_MODE_CANONICAL && p->loc == ORC_LOC_GASPARI_COHN)
-            rho *= orc_gaspari_cohn(orc_distance_grid(gx, gy, ox[i], oy[i]) / (0.5 * p->radius));
+          if (p->mode == ORC_MODE_CANONICAL && p->loc != ORC_LOC_CUTOFF)
+            rho *= orc_loc_weight(p->loc, orc_distance_grid(gx, gy, ox[i], oy[i]), p->radius, loc_scale);
           idl[pl] = i;
           double var = oerr[i] * oerr[i]; /* GridObservation.hpp:239-252 */
           if (valid && !valid[i]) var = INFINITY;

@@ -28,7 +28,8 @@ extern "C" {
 #endif
 
 enum { ORC_MODE_REF_COMPAT = 0, ORC_MODE_REF_ETKF = 1, ORC_MODE_CANONICAL = 2 };
-enum { ORC_LOC_CUTOFF = 0, ORC_LOC_GASPARI_COHN = 1 };
+enum { ORC_LOC_CUTOFF = 0, ORC_LOC_GASPARI_COHN = 1, ORC_LOC_GAUSSIAN = 2, ORC_LOC_EXPONENTIAL = 3,
+       ORC_LOC_REF_GASPARI_COHN = 4 };
 enum { ORC_SEM_SNAPSHOT = 0, ORC_SEM_AS_WRITTEN = 1 };
 
 typedef struct {
@@ -42,7 +43,13 @@ typedef struct {
   int use_R;              /* CANONICAL: 1 = R = diag(err^2), 0 = R = I                */
   int semantics;          /* ORC_SEM_*                                                */
   int nthreads;           /* OpenMP threads for SNAPSHOT (<=0: all)                   */
+  double loc_scale;       /* length scale of the exp-type functions; <= 0: radius     */
 } orc_letkf_params;
+
+/* LWEnKF::computeLocalizationFunction (LWEnKF.hpp:597-621) and its computeGaspariCohnFunction
+ * (:624-635) for loc = GAUSSIAN / EXPONENTIAL / REF_GASPARI_COHN with normalised distance
+ * dist / scale; loc = GASPARI_COHN is the Gaspari-Cohn 1999 taper with support `support`. */
+double orc_loc_weight(int loc, double dist, double support, double scale);
 
 /* Location::distance_to for two GRID locations (Location.hpp:204-211). */
 double orc_distance_grid(int i1, int j1, int i2, int j2);

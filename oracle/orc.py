@@ -19,7 +19,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB_PATH = os.path.join(_HERE, "libmetada_oracle.so")
 
 MODE_REF_COMPAT, MODE_REF_ETKF, MODE_CANONICAL = 0, 1, 2
-LOC_CUTOFF, LOC_GASPARI_COHN = 0, 1
+LOC_CUTOFF, LOC_GASPARI_COHN, LOC_GAUSSIAN, LOC_EXPONENTIAL, LOC_REF_GASPARI_COHN = 0, 1, 2, 3, 4
 SEM_SNAPSHOT, SEM_AS_WRITTEN = 0, 1
 
 
@@ -29,7 +29,7 @@ class LetkfParams(C.Structure):
         ("P", C.c_int64),
         ("radius", C.c_double), ("radius_v", C.c_double), ("inflation", C.c_double),
         ("mode", C.c_int), ("loc", C.c_int), ("use_R", C.c_int), ("semantics", C.c_int),
-        ("nthreads", C.c_int),
+        ("nthreads", C.c_int), ("loc_scale", C.c_double),
     ]
 
 
@@ -59,6 +59,8 @@ def lib() -> C.CDLL:
         _lib.orc_distance_grid.argtypes = [C.c_int] * 4
         _lib.orc_gaspari_cohn.restype = C.c_double
         _lib.orc_gaspari_cohn.argtypes = [C.c_double]
+        _lib.orc_loc_weight.restype = C.c_double
+        _lib.orc_loc_weight.argtypes = [C.c_int, C.c_double, C.c_double, C.c_double]
         _lib.orc_select_local.restype = C.c_int64
         _lib.orc_max_threads.restype = C.c_int
     return _lib
@@ -82,6 +84,10 @@ def max_threads() -> int:
 
 def gaspari_cohn(z: float) -> float:
     return lib().orc_gaspari_cohn(float(z))
+
+
+def loc_weight(loc: int, dist: float, support: float, scale: float) -> float:
+    return lib().orc_loc_weight(int(loc), float(dist), float(support), float(scale))
 
 
 def select_local(gx, gy, ox, oy, radius):
@@ -143,7 +149,7 @@ def obs_space(X, ox, oy, oz, oval, valid=None):
 
 def letkf(X, ox, oy, oz, oval, oerr, valid=None, *, radius, inflation=1.0, mode=MODE_CANONICAL,
           loc=LOC_GASPARI_COHN, use_R=1, radius_v=0.0, semantics=SEM_SNAPSHOT, nthreads=0,
-          cols=None, want_W=False):
+          cols=None, want_W=False, loc_scale=0.0):
     """Returns dict(Xa, counts[, W]).  X is not modified."""
     Xa = _f64(X).copy()
     k, nz, ny, nx = Xa.shape
@@ -152,7 +158,7 @@ def letkf(X, ox, oy, oz, oval, oerr, valid=None, *, radius, inflation=1.0, mode=
     P = len(ox)
     v = np.ascontiguousarray(valid, dtype=np.uint8) if valid is not None else None
     prm = LetkfParams(nx, ny, nz, k, P, radius, radius_v, inflation, mode, loc, use_R, semantics,
-                      nthreads)
+                      nthreads, loc_scale)
     counts = np.full(nx * ny, -1, dtype=np.int32)
     cs = np.ascontiguousarray(cols, dtype=np.int64) if cols is not None else None
     ncols = len(cs) if cs is not None else nx * ny

@@ -120,6 +120,24 @@ def test_letkf_vertical_localisation(ctx):
     ens.close(); obs.close()
 
 
+@pytest.mark.parametrize("loc,scale", [(mb.LOC_GAUSSIAN, 0.0), (mb.LOC_GAUSSIAN, 2.2), (mb.LOC_EXPONENTIAL, 1.5),
+                                       (mb.LOC_REF_GASPARI_COHN, 0.0)])
+@pytest.mark.parametrize("k,radius_v,solver", [(12, 0.0, mb.SOLVER_AUTO), (32, 2.0, mb.SOLVER_AUTO), (40, 0.0, mb.SOLVER_JACOBI)])
+def test_letkf_reference_localisation_functions(ctx, loc, scale, k, radius_v, solver):
+    """The reference's localisation functions (LWEnKF.hpp:597-635) as R-localisation weights, in every
+    canonical column kernel, horizontal and per-level."""
+    X, o = make_case(15, 13, 4, k, 140, seed=60 + k)
+    ens, obs = _setup(ctx, X, o)
+    p = capi.make_params(4.0, 1.03, mb.MODE_CANONICAL, loc, radius_v=radius_v, solver=solver, loc_scale=scale)
+    st = capi.letkf_analyse(ens, obs, p)
+    ref = orc.letkf(X, o["x"], o["y"], o["z"], o["value"], o["err"], o["valid"], radius=4.0, inflation=1.03,
+                    loc=loc, radius_v=radius_v, loc_scale=scale)
+    em, ep = analysis_errors(ens.download(), ref["Xa"])
+    assert em < TOL and ep < TOL, (loc, scale, k, em, ep)
+    assert st["numeric_failures"] == 0
+    ens.close(); obs.close()
+
+
 def test_letkf_no_obs_in_reach_only_inflates(ctx):
     # LETKF.hpp:167-190: empty local set -> mean kept, perturbations * sqrt(inflation)
     X, o = make_case(16, 16, 2, 8, 3, seed=5)

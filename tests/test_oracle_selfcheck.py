@@ -136,3 +136,45 @@ def test_etkf_and_enkf_vs_numpy():
     assert abs(diag["condition_number"] / (sv[0] / sv[-1]) - 1) < 1e-9
     assert abs(diag["innovation_norm"] - np.linalg.norm(d)) < 1e-12
     assert abs(diag["background_spread"] - np.sqrt((Xp ** 2).sum() / Xp.size)) < 1e-13
+
+
+def test_localisation_functions_match_closed_forms():
+    """orc_loc_weight restates LWEnKF::computeLocalizationFunction (LWEnKF.hpp:597-635): Gaussian,
+    exponential, and the reference's own two-piece 'Gaspari-Cohn' polynomial (which is NOT the
+    Gaspari-Cohn taper: 4 at zero distance)."""
+    L = 3.5
+    for d in (0.0, 0.3, 1.0, 3.5, 5.0, 6.999, 7.0, 9.0):
+        r = d / L
+        assert orc.loc_weight(orc.LOC_GAUSSIAN, d, 7.0, L) == pytest.approx(np.exp(-0.5 * r * r), rel=1e-15)
+        assert orc.loc_weight(orc.LOC_EXPONENTIAL, d, 7.0, L) == pytest.approx(np.exp(-r), rel=1e-15)
+        if r >= 2.0:
+            want = 0.0
+        elif r >= 1.0:
+            z = r - 1.0
+            want = ((-0.25 * z + 0.5) * z + 0.625) * z + 0.125
+        else:
+            want = (((-0.25 * r + 0.5) * r + 0.625) * r - 5.0) * r + 4.0
+        assert orc.loc_weight(orc.LOC_REF_GASPARI_COHN, d, 7.0, L) == want
+        assert orc.loc_weight(orc.LOC_GASPARI_COHN, d, 7.0, L) == orc.gaspari_cohn(d / 3.5)
+        assert orc.loc_weight(orc.LOC_CUTOFF, d, 7.0, L) == 1.0
+    assert orc.loc_weight(orc.LOC_REF_GASPARI_COHN, 0.0, 1.0, 1.0) == 4.0     # the flagged defect
+
+
+@pytest.mark.parametrize("loc", [orc.LOC_GAUSSIAN, orc.LOC_EXPONENTIAL])
+def test_letkf_exp_type_localisation_against_numpy(loc):
+    """One column of the canonical LETKF with Gaussian / exponential R-localisation, dense numpy."""
+    from tests.common import make_case
+    nx, ny, k, radius, L = 9, 8, 7, 3.0, 1.7
+    X, o = make_case(nx, ny, 1, k, 40, seed=5)
+    gx, gy = 4, 3
+    ref = orc.letkf(X, o["x"], o["y"], o["z"], o["value"], o["err"], radius=radius, loc=loc, loc_scale=L,
+                    cols=[gy * nx + gx], want_W=True)
+    Y, ybar, Yp, d = orc.obs_space(X, o["x"], o["y"], o["z"], o["value"])
+    sel = orc.select_local(gx, gy, o["x"], o["y"], radius)
+    dist = np.sqrt((o["x"][sel] - gx) ** 2.0 + (o["y"][sel] - gy) ** 2.0)
+    rho = np.exp(-0.5 * (dist / L) ** 2) if loc == orc.LOC_GAUSSIAN else np.exp(-dist / L)
+    w = rho / o["err"][sel] ** 2
+    A = (Yp[sel] * w[:, None]).T @ Yp[sel] + (k - 1) * np.eye(k)
+    lam, V = np.linalg.eigh(A)
+    W = ((V / lam) @ (V.T @ ((Yp[sel] * w[:, None]).T @ d[sel])))[:, None] + np.sqrt(k - 1) * (V / np.sqrt(lam)) @ V.T
+    assert np.abs(ref["W"][0] - W).max() < 1e-12 * np.abs(W).max()

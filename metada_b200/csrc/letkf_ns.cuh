@@ -462,7 +462,7 @@ __global__ void __launch_bounds__(NS_THREADS) letkf_ns_kernel(ColParams P, int l
           __syncthreads();
         }
         npl += nsel;
-        if (tid == 0) s_int[0] = 0;
+        if (tid == 0 && nsel) s_int[0] = 0;      // (nsel == 0: already 0, and no barrier since it was read)
         __syncthreads();
         if (!rows_left) break;
       }

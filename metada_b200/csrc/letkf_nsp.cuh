@@ -273,14 +273,24 @@ __device__ __noinline__ int nsp_inverse_sqrt(double* Zp, double shift, double fr
     //   ZY: T <- (3I - Z Y)/2, residual              YT: Y <- Y T     TZ: Z <- T Z
     // Y and Z are overwritten in place after a barrier (the product is held in the accumulator
     // registers meanwhile), so three matrices suffice.
-    enum { OP_A2, OP_Y0, OP_ZY, OP_YT, OP_TZ };
+    // Finish.  With E = I - Z Y the exact answer is Z (I - E)^{-1/2} = Z (I + E/2 + 3/8 E^2 + 5/16 E^3 + ...);
+    // Newton-Schulz applies the first-order factor each iteration.  Once the residual r = ||E||_F
+    // (>= the spectral norm; max|E_ij| underestimates it by up to 35x on these matrices) is small the
+    // series is applied ONCE to the order that suffices, by Horner's rule on B = E/2
+    // (W <- c1 I + c2 B, then m times W <- I + B W, then Z <- W Z); truncation errors are rigorous:
+    //   r < 3e-7: I + B                       1 product  (3/8 r^2   < 4e-14)
+    //   r < 5e-5: I + B + 1.5 B^2             2 products (5/16 r^3  < 4e-14)
+    //   r < 6e-4: I + B + 1.5 B^2 + 2.5 B^3   3 products (35/128 r^4 < 4e-14)
+    // instead of one more full iteration (3 products) plus the first-order finish (2).
+    //   HB: W <- I + B W (W in the Y buffer, dead by then)      FZ: Z <- W Z
+    enum { OP_A2, OP_Y0, OP_ZY, OP_YT, OP_TZ, OP_HB, OP_FZ };
     double acc[NTW][2];
-    int op = OP_A2, it = 0;
+    int op = OP_A2, it = 0, horner = 0;
     bool done = false;
 #pragma unroll 1
     while (true) {
-      const unsigned pb = (op == OP_ZY) ? zs : (op == OP_YT) ? ys : ts;
-      const unsigned qb = (op == OP_A2) ? ts : (op == OP_ZY) ? ys : (op == OP_YT) ? ts : zs;
+      const unsigned pb = (op == OP_ZY) ? zs : (op == OP_YT || op == OP_FZ) ? ys : ts;
+      const unsigned qb = (op == OP_A2 || op == OP_YT) ? ts : (op == OP_ZY || op == OP_HB) ? ys : zs;
       nsp_mm_any<NT, NW, NTW>(pb, qb, warp, st, L, acc);
       if (op == OP_A2) {
         nsp_store<NTW>(ys, nt, st, L, acc);
@@ -312,20 +322,49 @@ __device__ __noinline__ int nsp_inverse_sqrt(double* Zp, double shift, double fr
         __syncthreads();
         op = OP_ZY;
       } else if (op == OP_ZY) {
-        double r = 0.0;
+        double r = 0.0;                                          // ||E||_F >= ||E||_2, E = I - Z Y
 #pragma unroll
         for (int n = 0; n < NTW; ++n)
           if (n < st.n) {
             const int i = st.ti[n] * 8 + g, j = st.tj[n] * 8 + 2 * t;
             const double d0 = (i == j ? 1.0 : 0.0), d1 = (i == j + 1 ? 1.0 : 0.0);
             const double e0 = d0 - acc[n][0], e1 = d1 - acc[n][1];
-            r = fmax(r, fmax(fabs(e0), fabs(e1)));
+            const double w = (st.ti[n] != st.tj[n]) ? 2.0 : 1.0;
+            r = fma(w * e0, e0, fma(w * e1, e1, r));
             sts_f64x2(ts + nsp_cbase(st.ti[n], st.tj[n], nt, L), d0 + 0.5 * e0, d1 + 0.5 * e1);   // T = (3I - ZY)/2
           }
-        r = nsp_block_reduce<NTH>(r, true, red);                // also publishes T
-        done = r < 1e-7;                                         // error after this update ~ r^2
-        if (!(r < 1.5)) { ok = false; break; }                   // cannot happen for SPD input; NaN guard
-        op = done ? OP_TZ : OP_YT;
+        r = sqrt(nsp_block_reduce<NTH>(r, false, red));         // also publishes T
+        if (!(r < 1e6)) { ok = false; break; }                   // NaN guard (divergence runs into the cap)
+        done = r < 6e-4;
+        if (r < 3e-7) {
+          op = OP_TZ;                                            // first-order finish: Z <- T Z
+        } else if (done) {
+          // B = T - I in place, W0 = c1 I + c2 B into the Y buffer (Y is dead from here on)
+          const double c1 = (r < 5e-5) ? 1.0 : 1.5, c2 = (r < 5e-5) ? 1.5 : 2.5;
+          horner = (r < 5e-5) ? 1 : 2;
+          if (tid < kp) Tp[nsp_elem(tid, tid, nt)] -= 1.0;
+          __syncthreads();
+          for (int e = tid; e < msz; e += NTH) Yp[e] = c2 * Tp[e];
+          __syncthreads();
+          if (tid < kp) Yp[nsp_elem(tid, tid, nt)] += c1;
+          __syncthreads();
+          op = OP_HB;
+        } else {
+          op = OP_YT;
+        }
+      } else if (op == OP_HB || op == OP_FZ) {
+        const unsigned dst = (op == OP_HB) ? ys : zs;
+        __syncthreads();                                         // everyone is done reading W (or Z)
+#pragma unroll
+        for (int n = 0; n < NTW; ++n)
+          if (n < st.n) {
+            const int i = st.ti[n] * 8 + g, j = st.tj[n] * 8 + 2 * t;
+            const double d0 = (op == OP_HB && i == j) ? 1.0 : 0.0, d1 = (op == OP_HB && i == j + 1) ? 1.0 : 0.0;
+            sts_f64x2(dst + nsp_cbase(st.ti[n], st.tj[n], nt, L), acc[n][0] + d0, acc[n][1] + d1);
+          }
+        __syncthreads();
+        if (op == OP_FZ) { ++it; break; }
+        if (--horner == 0) op = OP_FZ;
       } else if (op == OP_YT) {
         __syncthreads();                                         // everyone is done reading Y
         nsp_store<NTW>(ys, nt, st, L, acc);                     // in place; T Z does not read Y
@@ -511,7 +550,7 @@ __global__ void __launch_bounds__(NTH, MINB) letkf_nsp_kernel(ColParams P, int l
           __syncthreads();
         }
         npl += nsel;
-        if (tid == 0) s_int[0] = 0;
+        if (tid == 0 && nsel) s_int[0] = 0;      // (nsel == 0: already 0, and no barrier since it was read)
         __syncthreads();
         if (!rows_left) break;
       }

@@ -315,7 +315,7 @@ __global__ void __launch_bounds__(NT, MINB) letkf_canonical_kernel(ColParams P, 
           __syncthreads();
         }
         npl += nsel;
-        if (tid == 0) s_int[0] = 0;
+        if (tid == 0 && nsel) s_int[0] = 0;      // (nsel == 0: already 0, and no barrier since it was read)
         __syncthreads();
         if (!rows_left) break;
       }

@@ -387,7 +387,7 @@ __global__ void __launch_bounds__(NTH, MINB) letkf_nsp_kernel(ColParams P, int l
   constexpr int NW = NTH / 32;
   constexpr int NTW = (NT * (NT + 1) / 2 + NW - 1) / NW;       // upper-triangular tiles per warp
   constexpr int NTA = (4 * NT + NW - 1) / NW;                  // update tiles per warp (lch <= 32 levels)
-  constexpr int PCH = (NS_PCH > NW) ? NS_PCH : NW;             // staged observation rows per chunk
+  constexpr int PCH = ((NS_PCH + NW - 1) / NW) * NW;           // staged observation rows per chunk (whole rows per warp)
   constexpr int nt = NT, kp = 8 * NT, ks = kp + 4, msz = NT * (NT + 1) / 2 * 64;   // host: NT == ceil(k / 8)
   const int k = P.k, nz = P.nz;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -732,7 +732,7 @@ static int nsp_level_chunk(int k, int nz) {
   return std::max(8, std::min(std::min(32, (nz + 7) & ~7), fit & ~7));
 }
 static size_t nsp_smem_bytes(int k, int lch, int nth) {
-  const int pch = std::max(NS_PCH, nth / 32);
+  const int pch = ((NS_PCH + nth / 32 - 1) / (nth / 32)) * (nth / 32);
   size_t mats = 3 * (size_t)nsp_ntiles(k) * 64;
   mats = std::max(mats, (size_t)pch * ns_stride(k));                       // phase-1 staging aliases them
   const size_t dbl = mats + 3 * (size_t)ns_kp(k) + 2 * NSP_LCH_MAX + 16 + 2 * NS_SELCAP;

@@ -191,6 +191,17 @@ typedef struct {
 int mdc_enkf_analyse(mdc_ens* ens, mdc_obs* obs, double inflation, const double* Z, uint64_t seed,
                      int want_gain_stats, mdc_enkf_diag* diag);
 
+/* ---- verification metrics against a truth state -------------------------------------------------
+ * Replaces framework/algorithms/Metrics.hpp:74-290 (Metrics<T>::CalculateAll): ensemble mean and
+ * spread (unbiased standard deviation) per state point, RMSE / bias / correlation of the mean
+ * against the truth, CRPS (empirical-CDF form, :232-254) and the average spread.  `truth` is a
+ * one-member ensemble on the same grid (mdc_ens_create(..., k = 1) + mdc_ens_upload_member).
+ * host_spread: optional [nz][ny][nx] output of the spread field (member-major host order). */
+typedef struct {
+  double rmse, bias, correlation, crps, avg_spread;
+} mdc_metrics;
+int mdc_ens_metrics(mdc_ens* ens, mdc_ens* truth, mdc_metrics* out, double* host_spread);
+
 /* ---- microbenchmarks used for the roofline denominators (profiles/) ------------------------ */
 int mdc_bench_fp64_fma(mdc_ctx* ctx, double* tflops);
 int mdc_bench_fp64_dmma(mdc_ctx* ctx, double* tflops);

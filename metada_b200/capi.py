@@ -46,6 +46,14 @@ class LetkfStats(C.Structure):
         return {n: getattr(self, n) for n, _ in self._fields_}
 
 
+class Metrics(C.Structure):
+    """mdc_metrics (Metrics.hpp:15-23 MetricValues scalars)."""
+    _fields_ = [(n, C.c_double) for n in ("rmse", "bias", "correlation", "crps", "avg_spread")]
+
+    def asdict(self):
+        return {n: getattr(self, n) for n, _ in self._fields_}
+
+
 class EnkfDiag(C.Structure):
     _fields_ = [(n, C.c_double) for n in (
         "innovation_norm", "background_spread", "analysis_spread",
@@ -116,6 +124,7 @@ def load_library() -> C.CDLL:
         "mdc_ens_fill_synthetic": (C.c_int, [vp, C.c_uint64]),
         "mdc_ens_mean": (C.c_int, [vp, vp]),
         "mdc_ens_checksum": (C.c_int, [vp, pd, pd]),
+        "mdc_ens_metrics": (C.c_int, [vp, vp, C.POINTER(Metrics), vp]),
         "mdc_ens_devptr": (vp, [vp]),
         "mdc_ens_bytes": (i64, [vp]),
         "mdc_obs_create": (C.c_int, [vp, i64, vp, vp, vp, vp, vp, vp, vp, C.POINTER(vp)]),
@@ -284,6 +293,21 @@ class Ensemble:
         s, s2 = C.c_double(), C.c_double()
         self.ctx.check(self.ctx.L.mdc_ens_checksum(self.h, C.byref(s), C.byref(s2)))
         return s.value, s2.value
+
+    def metrics(self, truth: np.ndarray, want_spread: bool = False) -> dict:
+        """Verification metrics of this ensemble against truth [nz, ny, nx] (Metrics.hpp:74-103)."""
+        t = Ensemble(self.ctx, self.nx, self.ny, self.nz, 1)
+        try:
+            t.upload_member(0, np.ascontiguousarray(truth, dtype=np.float64).reshape(self.nz, self.ny, self.nx))
+            m = Metrics()
+            sp = np.empty((self.nz, self.ny, self.nx)) if want_spread else None
+            self.ctx.check(self.ctx.L.mdc_ens_metrics(self.h, t.h, C.byref(m), _ptr(sp) if sp is not None else None))
+        finally:
+            t.close()
+        out = m.asdict()
+        if want_spread:
+            out["spread"] = sp
+        return out
 
     def devptr(self) -> int:
         return int(self.ctx.L.mdc_ens_devptr(self.h))

@@ -16,6 +16,7 @@
 #include "letkf_ns.cuh"
 #include "letkf_nsp.cuh"
 #include "letkf_v2.cuh"
+#include "metrics_kernels.cuh"
 #include "mdc_internal.cuh"
 
 namespace {
@@ -908,6 +909,38 @@ int mdc_letkf_column_transform(mdc_ens* e, mdc_obs* o, const mdc_letkf_params* p
   }
   cudaFree(dW); cudaFree(dcol);
   return rc;
+}
+
+// ------------------------------------------------------------------------------ verification metrics
+int mdc_ens_metrics(mdc_ens* e, mdc_ens* truth, mdc_metrics* out, double* host_spread) {
+  mdc_ctx* ctx = e->ctx;
+  if (truth->ctx != ctx) MDC_FAIL(ctx, MDC_ERR_INVALID, "metrics: ensemble and truth belong to different contexts");
+  if (truth->k != 1 || truth->nx != e->nx || truth->ny != e->ny || truth->nz != e->nz)
+    MDC_FAIL(ctx, MDC_ERR_INVALID, "metrics: truth must be a one-member ensemble on the same %dx%dx%d grid", e->nx, e->ny, e->nz);
+  if (e->k < 2 || e->k > 128) MDC_FAIL(ctx, MDC_ERR_UNSUPPORTED, "metrics: needs 2 <= k <= 128 members (k=%d)", e->k);
+  MDC_CUDA(ctx, cudaSetDevice(ctx->device));
+  const int64_t G = (int64_t)e->nx * e->ny, npoints = G * e->nz;
+  const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((npoints + 7) / 8, (int64_t)ctx->sm_count * 8));
+  double *partial = nullptr, *res = nullptr, *spread = nullptr, *spread_h = nullptr;
+  if (dev_alloc(ctx, &partial, (size_t)grid * MT_NSUM) || dev_alloc(ctx, &res, 8)) return MDC_ERR_CUDA;
+  if (host_spread && (dev_alloc(ctx, &spread, (size_t)npoints) || dev_alloc(ctx, &spread_h, (size_t)npoints))) return MDC_ERR_CUDA;
+  metrics_points_kernel<<<grid, 256, 0, ctx->stream>>>(e->X, truth->X, npoints, e->k, spread, partial);
+  MDC_LAUNCH_CHECK(ctx);
+  metrics_final_kernel<<<1, 32, 0, ctx->stream>>>(partial, grid, (double)npoints, res);
+  MDC_LAUNCH_CHECK(ctx);
+  double h[5];
+  MDC_CUDA(ctx, cudaMemcpyAsync(h, res, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
+  if (host_spread) {
+    mean_to_host_order_kernel<<<mdc_div_up(npoints, 256), 256, 0, ctx->stream>>>(spread, spread_h, G, e->nz);
+    MDC_LAUNCH_CHECK(ctx);
+    MDC_CUDA(ctx, cudaMemcpyAsync(host_spread, spread_h, (size_t)npoints * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  }
+  MDC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  out->rmse = h[0]; out->bias = h[1]; out->correlation = h[2]; out->crps = h[3]; out->avg_spread = h[4];
+  cudaFree(partial); cudaFree(res);
+  if (spread) cudaFree(spread);
+  if (spread_h) cudaFree(spread_h);
+  return MDC_OK;
 }
 
 // ------------------------------------------------------------------------------ microbenchmarks

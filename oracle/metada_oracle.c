@@ -179,6 +179,50 @@ double orc_loc_weight(int loc, double dist, double support, double scale) {
   }
 }
 
+/* Metrics.hpp, loop for loop: mean :108-121, spread :137-150, bias :166-173, correlation :189-210,
+ * CRPS :232-254, RMSE :265-273, average spread :286-292. */
+void orc_metrics(const double* X, const double* truth, int64_t n, int k, double* mean_out,
+                 double* spread_out, double out[5]) {
+  double* mean = (double*)calloc((size_t)n, sizeof(double));
+  double* spread = (double*)calloc((size_t)n, sizeof(double));
+  for (int m = 0; m < k; ++m)
+    for (int64_t i = 0; i < n; ++i) mean[i] += X[(int64_t)m * n + i];
+  for (int64_t i = 0; i < n; ++i) mean[i] /= (double)k;      /* val /= ens_size (size_t -> double) */
+  for (int m = 0; m < k; ++m)
+    for (int64_t i = 0; i < n; ++i) {
+      double diff = X[(int64_t)m * n + i] - mean[i];
+      spread[i] += diff * diff;
+    }
+  for (int64_t i = 0; i < n; ++i) spread[i] = sqrt(spread[i] / (double)(k - 1));
+  double rmse = 0.0, bias = 0.0;
+  for (int64_t i = 0; i < n; ++i) { double diff = mean[i] - truth[i]; rmse += diff * diff; }
+  for (int64_t i = 0; i < n; ++i) bias += mean[i] - truth[i];
+  double sx = 0.0, sy = 0.0, sxy = 0.0, sx2 = 0.0, sy2 = 0.0;
+  for (int64_t i = 0; i < n; ++i) {
+    sx += mean[i]; sy += truth[i]; sxy += mean[i] * truth[i];
+    sx2 += mean[i] * mean[i]; sy2 += truth[i] * truth[i];
+  }
+  double nn = (double)n;
+  double crps = 0.0;
+  for (int64_t i = 0; i < n; ++i) {
+    double sum_diff = 0.0, sum_truth_diff = 0.0;
+    for (int j = 0; j < k; ++j)
+      for (int l = 0; l < k; ++l) sum_diff += fabs(X[(int64_t)j * n + i] - X[(int64_t)l * n + i]);
+    for (int j = 0; j < k; ++j) sum_truth_diff += fabs(X[(int64_t)j * n + i] - truth[i]);
+    crps += sum_truth_diff / (double)k - sum_diff / (2.0 * (double)k * (double)k);
+  }
+  double avg = 0.0;
+  for (int64_t i = 0; i < n; ++i) avg += spread[i];
+  out[0] = sqrt(rmse / nn);
+  out[1] = bias / nn;
+  out[2] = (nn * sxy - sx * sy) / sqrt((nn * sx2 - sx * sx) * (nn * sy2 - sy * sy));
+  out[3] = crps / nn;
+  out[4] = avg / nn;
+  if (mean_out) memcpy(mean_out, mean, sizeof(double) * (size_t)n);
+  if (spread_out) memcpy(spread_out, spread, sizeof(double) * (size_t)n);
+  free(mean); free(spread);
+}
+
 /* ------------------------------------------------------------------ dense kit (row-major) */
 
 /* Partial-pivot LU inverse: what Eigen's MatrixXd::inverse() does for dynamic sizes. */

@@ -51,6 +51,11 @@ typedef struct {
  * dist / scale; loc = GASPARI_COHN is the Gaspari-Cohn 1999 taper with support `support`. */
 double orc_loc_weight(int loc, double dist, double support, double scale);
 
+/* Metrics<double>::CalculateAll (framework/algorithms/Metrics.hpp:74-103): X is [k][n] (member
+ * major), truth [n]; mean/spread [n] may be NULL.  out = {rmse, bias, correlation, crps, avg_spread}. */
+void orc_metrics(const double* X, const double* truth, int64_t n, int k, double* mean, double* spread,
+                 double out[5]);
+
 /* Location::distance_to for two GRID locations (Location.hpp:204-211). */
 double orc_distance_grid(int i1, int j1, int i2, int j2);
 

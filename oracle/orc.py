@@ -59,6 +59,7 @@ def lib() -> C.CDLL:
         _lib.orc_distance_grid.argtypes = [C.c_int] * 4
         _lib.orc_gaspari_cohn.restype = C.c_double
         _lib.orc_gaspari_cohn.argtypes = [C.c_double]
+        _lib.orc_metrics.restype = None
         _lib.orc_loc_weight.restype = C.c_double
         _lib.orc_loc_weight.argtypes = [C.c_int, C.c_double, C.c_double, C.c_double]
         _lib.orc_select_local.restype = C.c_int64
@@ -207,6 +208,20 @@ def enkf(X, ox, oy, oz, oval, oerr, Z, valid=None, *, inflation=1.0, want_gain_s
     if rc:
         raise RuntimeError(f"orc_enkf failed rc={rc}")
     return Xa, {n: getattr(diag, n) for n, _ in EnkfDiag._fields_}
+
+
+def metrics(X, truth):
+    """Metrics<double>::CalculateAll (Metrics.hpp:74-103).  X: [k, ...state], truth: [...state]."""
+    X = _f64(X)
+    k = X.shape[0]
+    Xf = np.ascontiguousarray(X.reshape(k, -1))
+    t = _f64(truth).reshape(-1)
+    n = Xf.shape[1]
+    mean, spread, out = np.empty(n), np.empty(n), np.empty(5)
+    lib().orc_metrics(_p(Xf, C.c_double), _p(t, C.c_double), C.c_int64(n), C.c_int(k), _p(mean, C.c_double),
+                      _p(spread, C.c_double), _p(out, C.c_double))
+    return {"mean": mean.reshape(X.shape[1:]), "spread": spread.reshape(X.shape[1:]), "rmse": out[0], "bias": out[1],
+            "correlation": out[2], "crps": out[3], "avg_spread": out[4]}
 
 
 def jacobi_eigh(A):

@@ -112,13 +112,32 @@ def synthetic_case(tmp, nx=23, ny=17, k=8, P=70, radius=4.5, inflation=1.1, sigm
     return g
 
 
+def metrics_case(tmp):
+    """The reference's Metrics.hpp (oracle/_ref/ref_metrics) on a seeded ensemble + truth."""
+    k, nx, ny, nz = 7, 11, 6, 3
+    X = syn.ensemble(k, nx, ny, nz, seed=4242)                       # [k][nz][ny][nx]
+    truth = syn.ensemble(3, nx, ny, nz, seed=99).mean(0)             # an independent smooth field
+    n = nx * ny * nz
+    inp, out = os.path.join(tmp, "m_in.bin"), os.path.join(tmp, "m_out.bin")
+    with open(inp, "wb") as f:
+        f.write(struct.pack("<qq", k, n))
+        f.write(np.ascontiguousarray(X.reshape(k, n)).tobytes())
+        f.write(np.ascontiguousarray(truth.reshape(n)).tobytes())
+    subprocess.check_call([os.path.join(ROOT, "oracle", "_ref", "ref_metrics"), inp, out])
+    b = np.frombuffer(open(out, "rb").read(), dtype="<f8")
+    return {"X": X, "truth": truth.reshape(nz, ny, nx), "scalars": b[:5].copy(),
+            "mean": b[5:5 + n].reshape(nz, ny, nx).copy(), "spread": b[5 + n:5 + 2 * n].reshape(nz, ny, nx).copy()}
+
+
 def main():
     subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle"), "ref"], stdout=subprocess.DEVNULL)
+    with tempfile.TemporaryDirectory() as tmp:
+        np.savez_compressed(os.path.join(OUT, "metrics_7x11x6x3.npz"), **metrics_case(tmp))
     with tempfile.TemporaryDirectory() as tmp:
         np.savez_compressed(os.path.join(OUT, "tutorial_36x18.npz"), **tutorial(tmp))
     with tempfile.TemporaryDirectory() as tmp:
         np.savez_compressed(os.path.join(OUT, "synthetic_23x17.npz"), **synthetic_case(tmp))
-    for f in ("tutorial_36x18.npz", "synthetic_23x17.npz"):
+    for f in ("tutorial_36x18.npz", "synthetic_23x17.npz", "metrics_7x11x6x3.npz"):
         g = np.load(os.path.join(OUT, f))
         print(f, {k: (g[k].shape if g[k].ndim else g[k].item()) for k in g.files})
 

@@ -314,6 +314,22 @@ def test_sharded_streamed_pipeline_is_bit_identical_to_one_shot(ctx, world, slab
     assert np.array_equal(out, one_shot)
 
 
+@pytest.mark.parametrize("k,nx,ny,nz", [(7, 11, 6, 3), (40, 33, 9, 2), (128, 10, 7, 1), (2, 5, 4, 1)])
+def test_verification_metrics_match_oracle(ctx, k, nx, ny, nz):
+    """mdc_ens_metrics (Metrics.hpp:74-290: RMSE, bias, correlation, CRPS, spread) against the oracle's
+    loop-for-loop restatement; tree vs sequential summation -> 1e-12."""
+    X = syn.ensemble(k, nx, ny, nz, seed=500 + k)
+    truth = syn.ensemble(3, nx, ny, nz, seed=77).mean(0)
+    ens = mb.Ensemble(ctx, nx, ny, nz, k)
+    ens.upload(X)
+    got = ens.metrics(truth, want_spread=True)
+    ref = orc.metrics(X, truth)
+    for name in ("rmse", "bias", "correlation", "crps", "avg_spread"):
+        assert abs(got[name] - ref[name]) <= 1e-12 * max(1.0, abs(ref[name])), (name, got[name], ref[name])
+    assert rel_err(got["spread"], ref["spread"]) < 1e-13
+    ens.close()
+
+
 def test_empty_observation_set_inflates_everything(ctx):
     X, _ = make_case(9, 7, 2, 24, 3, seed=31)
     ens = mb.Ensemble(ctx, 9, 7, 2, 24)

@@ -88,3 +88,18 @@ def test_enkf_matches_reference_with_its_own_draws(name):
                     "min_kalman_gain", "condition_number"), g["enkf_diag"]))
     for key, v in ref.items():
         assert abs(diag[key] - v) <= 1e-8 * abs(v), (key, diag[key], v)
+
+
+def test_metrics_match_reference_header_bit_exactly():
+    """orc_metrics against the reference's own Metrics.hpp (tests/golden/metrics_7x11x6x3.npz, made by
+    oracle/_ref/ref_metrics): same loops, same order, no contraction -> identical bits."""
+    g = np.load(os.path.join(G, "metrics_7x11x6x3.npz"))
+    m = orc.metrics(g["X"], g["truth"])
+    assert np.array_equal(m["mean"], g["mean"])
+    assert np.array_equal(m["spread"], g["spread"])
+    got = np.array([m["rmse"], m["bias"], m["correlation"], m["crps"], m["avg_spread"]])
+    assert np.array_equal(got, g["scalars"]), (got, g["scalars"])
+    # sanity against closed forms
+    X, t = g["X"], g["truth"]
+    assert abs(m["rmse"] - np.sqrt(((X.mean(0) - t) ** 2).mean())) < 1e-14
+    assert abs(m["avg_spread"] - X.std(0, ddof=1).mean()) < 1e-14

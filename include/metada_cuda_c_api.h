@@ -170,6 +170,7 @@ typedef struct {
   int64_t sum_sweeps;
   int32_t numeric_failures;
   int32_t redo_transforms; /* transforms the packed Newton-Schulz kernel handed to its fallback */
+  int64_t small_transforms; /* transforms done in observation space (p_loc <= 24 and 2 p_loc <= k)  */
 } mdc_letkf_stats;
 
 int mdc_letkf_analyse(mdc_ens* ens, mdc_obs* obs, const mdc_letkf_params* params,

@@ -40,7 +40,8 @@ class LetkfStats(C.Structure):
     _fields_ = [("ms_hx", C.c_float), ("ms_index", C.c_float), ("ms_columns", C.c_float),
                 ("ms_total", C.c_float), ("columns", C.c_int64), ("sum_local_obs", C.c_int64),
                 ("max_local_obs", C.c_int32), ("max_sweeps", C.c_int32), ("sum_sweeps", C.c_int64),
-                ("numeric_failures", C.c_int32), ("redo_transforms", C.c_int32)]
+                ("numeric_failures", C.c_int32), ("redo_transforms", C.c_int32),
+                ("small_transforms", C.c_int64)]
 
     def asdict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}

@@ -46,6 +46,10 @@ struct ColParams {
   long long* redo_items;
   unsigned* redo_count;
   int redo_consume;
+  // transforms with few local observations, handed to the observation-space kernel (letkf_smallp.cuh);
+  // same item encoding
+  long long* small_items;
+  unsigned* small_count;
 };
 
 __device__ __forceinline__ double lk_gaspari_cohn(double z) {
@@ -55,20 +59,24 @@ __device__ __forceinline__ double lk_gaspari_cohn(double z) {
   return ((((z / 12.0 - 0.5) * z + 0.625) * z + 5.0 / 3.0) * z - 5.0) * z + 4.0 - 2.0 / (3.0 * z);
 }
 
-// The reference's localisation functions (LWEnKF.hpp:597-635) next to the Gaspari-Cohn taper
-__device__ __forceinline__ double lk_loc_weight(int loc, double dist, double support, double scale) {
+// The reference's localisation functions (LWEnKF.hpp:597-635).  Not inlined: two double-precision
+// exp expansions in the selection loop cost the column kernels ~300 bytes of spills under their
+// register cap (C5 probe 35 -> 40 ms), for functions that are evaluated once per selected observation.
+__device__ __noinline__ double lk_loc_reference(int loc, double r) {
   switch (loc) {
-    case MDC_LOC_GASPARI_COHN: return lk_gaspari_cohn(dist / (0.5 * support));
-    case MDC_LOC_GAUSSIAN: { const double r = dist / scale; return exp(-0.5 * r * r); }          // :601-602
-    case MDC_LOC_EXPONENTIAL: return exp(-(dist / scale));                                         // :604-605
-    case MDC_LOC_REF_GASPARI_COHN: {                                                               // :624-635
-      const double r = dist / scale;
+    case MDC_LOC_GAUSSIAN: return exp(-0.5 * r * r);                                               // :601-602
+    case MDC_LOC_EXPONENTIAL: return exp(-r);                                                      // :604-605
+    case MDC_LOC_REF_GASPARI_COHN:                                                                 // :624-635
       if (r >= 2.0) return 0.0;
       if (r >= 1.0) { const double z = r - 1.0; return ((-0.25 * z + 0.5) * z + 0.625) * z + 0.125; }
       return (((-0.25 * r + 0.5) * r + 0.625) * r - 5.0) * r + 4.0;
-    }
     default: return 1.0;
   }
+}
+// rho(dist): Gaspari-Cohn taper with the given support, or a reference function of dist / scale
+__device__ __forceinline__ double lk_loc_weight(int loc, double dist, double support, double scale) {
+  if (loc == MDC_LOC_GASPARI_COHN) return lk_gaspari_cohn(dist / (0.5 * support));
+  return lk_loc_reference(loc, dist / scale);
 }
 
 __device__ __forceinline__ double warp_sum(double v) {

@@ -24,6 +24,7 @@
 #include <utility>
 
 #include "letkf_ns.cuh"
+#include "letkf_smallp.cuh"
 
 __host__ __device__ inline int nsp_ntiles(int k) { const int nt = (k + 7) >> 3; return nt * (nt + 1) / 2; }
 __device__ __forceinline__ int nsp_row_start(int I, int nt) { return (I * (2 * nt - I + 1)) >> 1; }
@@ -442,6 +443,7 @@ __global__ void __launch_bounds__(NTH, MINB) letkf_nsp_kernel(ColParams P, int l
       if (tid == 0) s_int[0] = 0;
       __syncthreads();
       int npl = 0;
+      bool deferred = false;
       int cy0 = 0, cy1 = -1;
       if (P.radius >= 0.0) index_cy_range(P.iv, gy, R, cy0, cy1);
       int cy = cy0, rb = 0, re = 0;
@@ -501,7 +503,19 @@ __global__ void __launch_bounds__(NTH, MINB) letkf_nsp_kernel(ColParams P, int l
           __syncthreads();
         }
         const int nsel = s_int[0];
-        if (have_batch && rows_left && nsel <= NS_SELCAP - NTH) continue;
+        if (have_batch && rows_left && nsel + min(NTH, re - rb) <= NS_SELCAP) continue;   // the next batch still fits
+        if (P.small_items && !rows_left && npl == 0 && nsel > 0 && nsel <= SP_PMAX && 2 * nsel <= k &&
+            !(P.W_out && P.w_col == col)) {
+          // few local observations: the observation-space kernel does this transform (letkf_smallp.cuh)
+          __syncthreads();                                       // everyone has read the count
+          if (tid == 0) {
+            const unsigned slot = atomicAdd(P.small_count, 1u);
+            P.small_items[slot] = col * nxf + lt;
+          }
+          npl = nsel;
+          deferred = true;
+          break;
+        }
         for (int c0 = 0; c0 < nsel; c0 += PCH) {
           const int rows = min(PCH, nsel - c0), rows4 = (rows + 3) & ~3;
           // gather: warp w stages rows w, w + NW, ...; all loads issued before the stores
@@ -555,6 +569,7 @@ __global__ void __launch_bounds__(NTH, MINB) letkf_nsp_kernel(ColParams P, int l
         if (!rows_left) break;
       }
       if (lt == 0) col_npl = npl;
+      if (deferred) continue;
 
       // ---------------- 2. Z = A^{-1/2}, A = shift I + C, by coupled Newton-Schulz
       bool ok = true;

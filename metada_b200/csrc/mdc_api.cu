@@ -726,6 +726,7 @@ static int letkf_launch(mdc_ens* e, mdc_obs* o, const mdc_letkf_params* p, const
   const long long total_cols = dcols ? ncols : (long long)e->own_nx * e->own_ny;
   const int sms = std::max(1, ctx->sm_count - std::max(0, std::min(p->sm_reserve, ctx->sm_count / 2)));
   cp.redo_items = nullptr; cp.redo_count = nullptr; cp.redo_consume = 0;
+  cp.small_items = nullptr; cp.small_count = nullptr;
   if (p->mode == MDC_MODE_CANONICAL && p->solver == MDC_SOLVER_NEWTON_SCHULZ && (k < 24 || k > 128))
     MDC_FAIL(ctx, MDC_ERR_UNSUPPORTED, "letkf: the Newton-Schulz solver supports 24 <= k <= 128 (k=%d)", k);
   if (p->mode == MDC_MODE_CANONICAL && p->solver == MDC_SOLVER_NEWTON_SCHULZ_FULL && (k < 24 || k > 80))
@@ -782,15 +783,19 @@ static int letkf_launch(mdc_ens* e, mdc_obs* o, const mdc_letkf_params* p, const
     // kernel (k <= 80) or the Jacobi kernel
     const int nxf = p->radius_v > 0.0 ? e->nz : 1;
     const size_t need = (size_t)total_cols * nxf;
-    if (ctx->redo_cap < need) {
+    if (ctx->redo_cap < need) {      // two lists: redo (ill-conditioned) and small (few local observations)
       if (ctx->redo_items) cudaFree(ctx->redo_items);
       ctx->redo_items = nullptr; ctx->redo_cap = 0;
-      MDC_CUDA(ctx, cudaMalloc((void**)&ctx->redo_items, need * sizeof(long long)));
+      MDC_CUDA(ctx, cudaMalloc((void**)&ctx->redo_items, 2 * need * sizeof(long long)));
       ctx->redo_cap = need;
     }
     cp.redo_items = ctx->redo_items;
     cp.redo_count = reinterpret_cast<unsigned*>(ctx->d_flags + 12);
-    MDC_CUDA(ctx, cudaMemsetAsync(cp.redo_count, 0, sizeof(unsigned), ctx->stream));
+    if (!getenv("MDC_LETKF_NO_SMALLP")) {
+      cp.small_items = ctx->redo_items + ctx->redo_cap;
+      cp.small_count = reinterpret_cast<unsigned*>(ctx->d_flags + 13);
+    }
+    MDC_CUDA(ctx, cudaMemsetAsync(ctx->d_flags + 12, 0, 2 * sizeof(unsigned), ctx->stream));
     const int lch = nsp_level_chunk(k, e->nz);
     auto launchp = [&](auto kern, int nth) -> int {
       const size_t smemp = nsp_smem_bytes(k, lch, nth);
@@ -823,6 +828,14 @@ static int letkf_launch(mdc_ens* e, mdc_obs* o, const mdc_letkf_params* p, const
       default: rc = launchp(letkf_nsp_kernel<16, 512, 1>, 512); break;
     }
     if (rc) return rc;
+    if (cp.small_items) {
+      const size_t smems = smallp_smem_bytes();
+      MDC_CUDA(ctx, cudaFuncSetAttribute(letkf_smallp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smems));
+      int occ = 1;
+      MDC_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, letkf_smallp_kernel, SP_WARPS * 32, smems));
+      letkf_smallp_kernel<<<sms * std::max(1, occ), SP_WARPS * 32, smems, ctx->stream>>>(cp);
+      MDC_LAUNCH_CHECK(ctx);
+    }
     ColParams cq = cp;
     cq.redo_consume = 1;
     return k <= 80 ? launch_ns_full(cq, (long long)need) : launch_jacobi(cq, (long long)need);
@@ -883,6 +896,7 @@ int mdc_letkf_analyse(mdc_ens* e, mdc_obs* o, const mdc_letkf_params* p, mdc_let
     st->max_sweeps = (int32_t)h[3];
     st->numeric_failures = (int32_t)h[4];
     st->redo_transforms = (int32_t)h[6];
+    st->small_transforms = h[7];
   }
   if (h[4]) MDC_FAIL(ctx, MDC_ERR_NUMERIC, "letkf: %lld column transforms failed (non-SPD matrix); those columns were left unchanged", h[4]);
   return MDC_OK;

@@ -240,7 +240,8 @@ def test_newton_schulz_ill_conditioned_and_vertical(ctx, solver):
     em, ep = analysis_errors(ens.download(), ref["Xa"])
     assert em < 1e-9 and ep < 1e-9, (em, ep, st)
     assert st["columns"] == 144 and st["numeric_failures"] == 0
-    assert st["redo_transforms"] == (144 * 4 if solver == mb.SOLVER_NEWTON_SCHULZ else 0), st
+    # (transforms with few local observations go to the observation-space kernel instead)
+    assert st["redo_transforms"] + st["small_transforms"] == (144 * 4 if solver == mb.SOLVER_NEWTON_SCHULZ else 0), st
     ens.close(); obs.close()
 
 
@@ -328,6 +329,26 @@ def test_verification_metrics_match_oracle(ctx, k, nx, ny, nz):
         assert abs(got[name] - ref[name]) <= 1e-12 * max(1.0, abs(ref[name])), (name, got[name], ref[name])
     assert rel_err(got["spread"], ref["spread"]) < 1e-13
     ens.close()
+
+
+@pytest.mark.parametrize("k,nz,radius_v,P,loc", [(128, 6, 2.0, 260, mb.LOC_GASPARI_COHN), (48, 5, 0.0, 25, mb.LOC_GASPARI_COHN),
+                                                 (32, 3, 1.0, 120, mb.LOC_GAUSSIAN), (80, 2, 0.0, 60, mb.LOC_CUTOFF)])
+def test_observation_space_transform_for_few_local_obs(ctx, k, nz, radius_v, P, loc):
+    """Transforms with p_loc <= 24 and 2 p_loc <= k are done in observation space (letkf_smallp.cuh:
+    p x p Jacobi, one warp per transform); the rest of the same analysis stays on the k-space kernel.
+    Same unique symmetric square-root transform -> oracle parity at the usual bar."""
+    nx, ny = 17, 15
+    X, o = make_case(nx, ny, nz, k, P, seed=900 + k, invalid_frac=0.04)
+    ens, obs = _setup(ctx, X, o)
+    p = capi.make_params(3.0, 1.04, mb.MODE_CANONICAL, loc, radius_v=radius_v)
+    st = capi.letkf_analyse(ens, obs, p)
+    ref = orc.letkf(X, o["x"], o["y"], o["z"], o["value"], o["err"], o["valid"], radius=3.0, inflation=1.04,
+                    loc=loc, radius_v=radius_v)
+    em, ep = analysis_errors(ens.download(), ref["Xa"])
+    assert em < TOL and ep < TOL, (k, em, ep, st)
+    assert st["small_transforms"] > 0 and st["numeric_failures"] == 0 and st["columns"] == nx * ny, st
+    assert rel_err(ens.mean(), ens.download().sum(0) / k) < 1e-14
+    ens.close(); obs.close()
 
 
 def test_empty_observation_set_inflates_everything(ctx):

@@ -31,7 +31,7 @@ letkf_case("C1 ref_compat (LETKF.hpp arithmetic)", 100, 100, 1, 20, 1000, 10.0, 
 letkf_case("C3 400x400x50 k=40 P=1e5 r=7 canonical (packed NS on DMMA)", 400, 400, 50, 40, 100000, 7.0)
 letkf_case("C3 canonical (Jacobi)", 400, 400, 50, 40, 100000, 7.0, solver=1)
 letkf_case("C3 ref_etkf", 400, 400, 50, 40, 100000, 7.0, mode=mb.MODE_REF_ETKF)
-letkf_case("C4-tile 96x96x60 k=128 P=4608 r_h=8 r_v=5 canonical (packed NS on DMMA, per-level transforms)", 96, 96, 60, 128, 4608, 8.0, rv=5.0, reps=1)
+letkf_case("C4-tile 96x96x60 k=128 P=4608 r_h=8 r_v=5 canonical (observation-space kernel for p_loc <= 24, packed NS on DMMA otherwise; per-level transforms)", 96, 96, 60, 128, 4608, 8.0, rv=5.0, reps=1)
 letkf_case("C4-tile same, horizontal localisation only", 96, 96, 60, 128, 4608, 8.0, reps=2)
 
 # C2: global stochastic EnKF, n = 1e5 (400 x 250), 40 members, 1e4 distinct obs, supplied draws

@@ -14,8 +14,26 @@ def test_library_builds_and_exports_all_header_symbols():
     assert not missing, missing
 
 
-def test_struct_layouts_match_header_sizes():
-    # mdc_letkf_params: 3 doubles + 4 ints + double + 4 ints; mdc_letkf_stats: 4 floats + ...
-    assert ctypes.sizeof(mb.LetkfParams) == 3 * 8 + 4 * 4 + 8 + 4 * 4
-    assert ctypes.sizeof(mb.LetkfStats) == 4 * 4 + 2 * 8 + 2 * 4 + 8 + 2 * 4
-    assert ctypes.sizeof(mb.EnkfDiag) == 6 * 8
+def test_struct_layouts_match_header_sizes(tmp_path):
+    """ctypes mirrors against the real header: a C program prints sizeof / offsetof of every struct."""
+    import os
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = tmp_path / "sz.c"
+    src.write_text('''#include <stdio.h>
+#include <stddef.h>
+#include "metada_cuda_c_api.h"
+int main(void) {
+  printf("%zu %zu %zu %zu %zu %zu %zu %zu\\n", sizeof(mdc_letkf_params), sizeof(mdc_letkf_stats), sizeof(mdc_enkf_diag),
+         sizeof(mdc_metrics), offsetof(mdc_letkf_params, loc_scale), offsetof(mdc_letkf_params, solver),
+         offsetof(mdc_letkf_stats, small_transforms), offsetof(mdc_letkf_stats, sum_sweeps));
+  return 0;
+}
+''')
+    exe = tmp_path / "sz"
+    subprocess.check_call(["gcc", "-I", os.path.join(root, "include"), str(src), "-o", str(exe)])
+    got = [int(v) for v in subprocess.check_output([str(exe)], text=True).split()]
+    want = [ctypes.sizeof(mb.LetkfParams), ctypes.sizeof(mb.LetkfStats), ctypes.sizeof(mb.EnkfDiag), ctypes.sizeof(mb.Metrics),
+            mb.LetkfParams.loc_scale.offset, mb.LetkfParams.solver.offset, mb.LetkfStats.small_transforms.offset,
+            mb.LetkfStats.sum_sweeps.offset]
+    assert got == want, (got, want)

@@ -23,7 +23,8 @@ LOC_CUTOFF, LOC_GASPARI_COHN, LOC_GAUSSIAN, LOC_EXPONENTIAL, LOC_REF_GASPARI_COH
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-shared", "-Xcompiler", "-fPIC", "-cudart", "shared",
-              "-Xlinker", "-rpath=/usr/local/cuda/lib64", "-split-compile", "0"]
+              "-Xlinker", "-rpath=/usr/local/cuda/lib64"]   # (no -split-compile: parallel ptxas made the column
+# kernels' register allocation, hence their spills and speed, vary from build to build)
 
 
 class MdcError(RuntimeError):

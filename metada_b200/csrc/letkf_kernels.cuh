@@ -50,6 +50,11 @@ struct ColParams {
   // same item encoding
   long long* small_items;
   unsigned* small_count;
+  // per-level analyses: transforms the classifying first pass (letkf_smallp_classify_kernel) left for
+  // the packed k-space kernel; with work_consume = 1 that kernel processes exactly this list
+  long long* work_items;
+  unsigned* work_count;
+  int work_consume;
 };
 
 __device__ __forceinline__ double lk_gaspari_cohn(double z) {

@@ -382,7 +382,9 @@ __device__ __noinline__ int nsp_inverse_sqrt(double* Zp, double shift, double fr
   return (ok && done) ? it : -1;
 }
 
-template <int NT, int NTH, int MINB>
+// WORK = true: consume the classifying pass's work list (per-level analyses); a separate instantiation
+// because the two extra live values of the list mode push the default kernel into spilling.
+template <int NT, int NTH, int MINB, bool WORK>
 __global__ void __launch_bounds__(NTH, MINB) letkf_nsp_kernel(ColParams P, int lch) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   constexpr int NW = NTH / 32;
@@ -417,13 +419,18 @@ __global__ void __launch_bounds__(NTH, MINB) letkf_nsp_kernel(ColParams P, int l
   const bool per_level = P.radius_v > 0.0;
   const int nxf = per_level ? nz : 1;
   const int R = (int)floor(P.radius);
-  const long long ncols = P.cols ? P.ncols : (long long)P.own_nx * P.own_ny;
+  constexpr bool work = WORK;
+  const long long ncols = work ? (long long)*P.work_count : (P.cols ? P.ncols : (long long)P.own_nx * P.own_ny);
   const NspLane L = nsp_lane(lane);
   const NspTiles<NTW> st = nsp_tiles<NTW, NTH>(nt, warp);
 
   for (long long ci = blockIdx.x; ci < ncols; ci += gridDim.x) {
-    int lx, ly;
-    if (P.cols) { long long c = P.cols[ci]; lx = (int)(c % P.nx); ly = (int)(c / P.nx); }
+    int lx, ly, lt_b = 0;
+    if constexpr (work) {
+      const long long item = P.work_items[ci], c = item / nxf;
+      lt_b = (int)(item - c * nxf);
+      lx = (int)(c % P.nx); ly = (int)(c / P.nx);
+    } else if (P.cols) { long long c = P.cols[ci]; lx = (int)(c % P.nx); ly = (int)(c / P.nx); }
     else { lx = (int)(ci % P.own_nx); ly = (int)(ci / P.own_nx); }
     const int gx = P.gx0 + lx, gy = P.gy0 + ly;
     const long long col = (long long)ly * P.nx + lx;
@@ -434,7 +441,8 @@ __global__ void __launch_bounds__(NTH, MINB) letkf_nsp_kernel(ColParams P, int l
     // the column's state is first touched in phase 3: start pulling it towards L2 now
     for (int e = tid * 16; e < nz * k; e += NTH * 16) asm volatile("prefetch.global.L2 [%0];" ::"l"(Xg + e));
 
-    for (int lt = 0; lt < nxf; ++lt) {
+    const int lt_e = work ? lt_b + 1 : nxf;
+    for (int lt = lt_b; lt < lt_e; ++lt) {
       // ---------------- 1. selection, gather, C += Yw^T Yw on the FP64 tensor path, g += Yw^T dw
       double cacc[NTW][2];
 #pragma unroll
@@ -504,6 +512,7 @@ __global__ void __launch_bounds__(NTH, MINB) letkf_nsp_kernel(ColParams P, int l
         }
         const int nsel = s_int[0];
         if (have_batch && rows_left && nsel + min(NTH, re - rb) <= NS_SELCAP) continue;   // the next batch still fits
+#ifndef NSP_NO_DEFER
         if (P.small_items && !rows_left && npl == 0 && nsel > 0 && nsel <= SP_PMAX && 2 * nsel <= k &&
             !(P.W_out && P.w_col == col)) {
           // few local observations: the observation-space kernel does this transform (letkf_smallp.cuh)
@@ -516,6 +525,7 @@ __global__ void __launch_bounds__(NTH, MINB) letkf_nsp_kernel(ColParams P, int l
           deferred = true;
           break;
         }
+#endif
         for (int c0 = 0; c0 < nsel; c0 += PCH) {
           const int rows = min(PCH, nsel - c0), rows4 = (rows + 3) & ~3;
           // gather: warp w stages rows w, w + NW, ...; all loads issued before the stores
@@ -568,7 +578,7 @@ __global__ void __launch_bounds__(NTH, MINB) letkf_nsp_kernel(ColParams P, int l
         __syncthreads();
         if (!rows_left) break;
       }
-      if (lt == 0) col_npl = npl;
+      if (lt == lt_b) col_npl = npl;
       if (deferred) continue;
 
       // ---------------- 2. Z = A^{-1/2}, A = shift I + C, by coupled Newton-Schulz
@@ -731,12 +741,14 @@ __global__ void __launch_bounds__(NTH, MINB) letkf_nsp_kernel(ColParams P, int l
       }
     }  // lt
     if (tid == 0) {
-      atomicAdd((unsigned long long*)&P.stats[0], (unsigned long long)col_npl);
-      atomicMax(&P.stats[1], col_npl);
+      if (!work) {                       // (work mode: the classifying pass counted the columns)
+        atomicAdd((unsigned long long*)&P.stats[0], (unsigned long long)col_npl);
+        atomicMax(&P.stats[1], col_npl);
+        atomicAdd((unsigned long long*)&P.stats[5], 1ull);
+      }
       atomicAdd((unsigned long long*)&P.stats[2], (unsigned long long)col_iters);
       atomicMax(&P.stats[3], (long long)col_iters);
       if (col_fail) atomicAdd((unsigned long long*)&P.stats[4], 1ull);
-      atomicAdd((unsigned long long*)&P.stats[5], 1ull);
     }
   }
 }

@@ -10,8 +10,8 @@
 // and a level's update is  q = M x'^T,  xa_j = xbar + q.u + sqrt(k-1) (s^{-1/2} x'_j + (Phi q)^T M[:, j]):
 // O(p^2 k + p^3) for the transform and O(p k) per level instead of ~20 k^3-products -- three orders
 // of magnitude less arithmetic for the C4 shape with per-level localisation (p ~ 9, k = 128), where
-// the k x k route spends 280 us of a whole SM per transform.  The p x p eigenproblem is a cyclic
-// two-sided Jacobi in the warp's shared-memory tile; M is never staged: its rows (1 KB, contiguous)
+// the k x k route spends 280 us of a whole SM per transform.  The p x p eigenproblem is a two-sided
+// Jacobi with parallel (round-robin) ordering in the warp's shared-memory tile; M is never staged: its rows (1 KB, contiguous)
 // are re-read through L1/L2.  Same transform as the k-space kernels to rounding (the symmetric
 // square root is unique); the packed Newton-Schulz kernel hands over the transforms that qualify
 // (ColParams.small_items), this kernel consumes the list.
@@ -27,215 +27,306 @@ struct SpWarpSmem {
   double S[SP_PMAX][SP_PS];
   double V[SP_PMAX][SP_PS];
   double wgt[SP_PMAX], dw[SP_PMAX], u[SP_PMAX], phi[SP_PMAX], q[SP_PMAX], r[SP_PMAX];
+  double pc[SP_PMAX / 2], ps[SP_PMAX / 2];     // rotations of one Jacobi round
+  int pa[SP_PMAX / 2], pb[SP_PMAX / 2];
   int row[SP_PMAX];
   int pad[8];
 };
 
-__global__ void __launch_bounds__(SP_WARPS * 32) letkf_smallp_kernel(ColParams P) {
-  extern __shared__ __align__(16) unsigned char sp_smem_raw[];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  SpWarpSmem& W = reinterpret_cast<SpWarpSmem*>(sp_smem_raw)[warp];
+// One transform (col, lt) by the calling warp.  Returns 0: done in observation space (sweeps_out =
+// Jacobi sweeps), 1: no observation in reach, perturbations inflated, 2: too many local observations
+// for this route (nothing written).  p_out = number of local observations.
+__device__ __forceinline__ int sp_transform(const ColParams& P, SpWarpSmem& W, long long col, int lt, int lane,
+                                            int& p_out, int& sweeps_out) {
   const int k = P.k, nz = P.nz, nr = (k + 31) >> 5;
   const bool per_level = P.radius_v > 0.0;
-  const int nxf = per_level ? nz : 1;
   const int R = (int)floor(P.radius);
   const double km1 = (double)(k - 1), s = km1 / P.inflation, sW = sqrt(km1), rs = 1.0 / sqrt(s);
-  const long long nitems = (long long)*P.small_count;
-
-  for (long long it = (long long)blockIdx.x * SP_WARPS + warp; it < nitems; it += (long long)gridDim.x * SP_WARPS) {
-    const long long item = P.small_items[it], col = item / nxf;
-    const int lt = (int)(item - col * nxf);
-    const int lx = (int)(col % P.nx), ly = (int)(col / P.nx);
-    const int gx = P.gx0 + lx, gy = P.gy0 + ly;
-    double* Xg = P.X + col * nz * k;
+  const int lx = (int)(col % P.nx), ly = (int)(col / P.nx);
+  const int gx = P.gx0 + lx, gy = P.gy0 + ly;
+  double* Xg = P.X + col * nz * k;
 
     // ---- selection (same predicate and weights as the other column kernels)
-    int p = 0;
-    bool overflow = false;
-    int cy0 = 0, cy1 = -1;
-    index_cy_range(P.iv, gy, R, cy0, cy1);
-    for (int cy = cy0; cy <= cy1; ++cy) {
-      int rb, re;
-      index_row_range(P.iv, gx, R, cy, rb, re);
-      for (int a0 = rb; a0 < re; a0 += 32) {
-        const int a = a0 + lane;
-        bool sel = false;
-        double sq = 0.0, sd = 0.0;
-        int orow = 0;
-        if (a < re) {
-          double dist;
-          sel = index_within(gx, gy, P.iv.sx[a], P.iv.sy[a], P.radius, &dist);
-          double dv = 0.0;
-          if (sel && per_level) {
-            dv = fabs((double)(P.iv.sz[a] - lt));
-            sel = dv <= P.radius_v;
+  int p = 0;
+  bool overflow = false;
+  int cy0 = 0, cy1 = -1;
+  index_cy_range(P.iv, gy, R, cy0, cy1);
+  for (int cy = cy0; cy <= cy1; ++cy) {
+    int rb, re;
+    index_row_range(P.iv, gx, R, cy, rb, re);
+    for (int a0 = rb; a0 < re; a0 += 32) {
+      const int a = a0 + lane;
+      bool sel = false;
+      double sq = 0.0, sd = 0.0;
+      int orow = 0;
+      if (a < re) {
+        double dist;
+        sel = index_within(gx, gy, P.iv.sx[a], P.iv.sy[a], P.radius, &dist);
+        double dv = 0.0;
+        if (sel && per_level) {
+          dv = fabs((double)(P.iv.sz[a] - lt));
+          sel = dv <= P.radius_v;
+        }
+        if (sel) {
+          double rho = 1.0;
+          if (P.loc != MDC_LOC_CUTOFF) {
+            rho = lk_loc_weight(P.loc, dist, P.radius, P.loc_scale);
+            if (per_level) rho *= lk_loc_weight(P.loc, dv, P.radius_v, P.loc_scale_v);
           }
-          if (sel) {
-            double rho = 1.0;
-            if (P.loc != MDC_LOC_CUTOFF) {
-              rho = lk_loc_weight(P.loc, dist, P.radius, P.loc_scale);
-              if (per_level) rho *= lk_loc_weight(P.loc, dv, P.radius_v, P.loc_scale_v);
-            }
-            orow = P.iv.sorted_row[a];
-            const double e_ = P.err[orow];
-            const double ivar = P.valid[orow] ? 1.0 / (e_ * e_) : 0.0;
-            sq = sqrt(rho * (P.use_R ? ivar : 1.0));
-            sd = sq * P.d[orow];
+          orow = P.iv.sorted_row[a];
+          const double e_ = P.err[orow];
+          const double ivar = P.valid[orow] ? 1.0 / (e_ * e_) : 0.0;
+          sq = sqrt(rho * (P.use_R ? ivar : 1.0));
+          sd = sq * P.d[orow];
+        }
+      }
+      const unsigned bal = __ballot_sync(0xffffffffu, sel);
+      const int pos = p + __popc(bal & ((1u << lane) - 1u));
+      if (sel && pos < SP_PMAX) { W.row[pos] = orow; W.wgt[pos] = sq; W.dw[pos] = sd; }
+      p += __popc(bal);
+      if (p > SP_PMAX) overflow = true;
+    }
+  }
+  __syncwarp();
+  p_out = p;
+  if (p == 0) {                 // no observation in reach: inflate the perturbations (LETKF.hpp:167-190)
+    const double f = sqrt(P.inflation);
+    const int lb = per_level ? lt : 0, le = per_level ? lt + 1 : nz;
+    for (int l = lb; l < le; ++l) {
+      double* x = Xg + (long long)l * k;
+      double xv[SP_MAXR], sum = 0.0;
+#pragma unroll
+      for (int r = 0; r < SP_MAXR; ++r) { xv[r] = (r < nr && lane + 32 * r < k) ? x[lane + 32 * r] : 0.0; sum += xv[r]; }
+      const double xbar = warp_sum(sum) / (double)k;
+      double msum = 0.0;
+#pragma unroll
+      for (int r = 0; r < SP_MAXR; ++r)
+        if (r < nr && lane + 32 * r < k) { const double v = xbar + (xv[r] - xbar) * f; x[lane + 32 * r] = v; msum += v; }
+      if (P.mean_out) { msum = warp_sum(msum); if (lane == 0) P.mean_out[col * nz + l] = msum * (1.0 / (double)k); }
+    }
+    return 1;
+  }
+  if (overflow || 2 * p > k) return 2;    // not for this kernel
+
+  // ---- S = M M^T (upper triangle, mirrored), rows re-read from L1/L2
+  for (int a = 0; a < p; ++a) {
+    const double* ya = P.Yp + (long long)W.row[a] * k;
+    double va[SP_MAXR];
+#pragma unroll
+    for (int r = 0; r < SP_MAXR; ++r) va[r] = (r < nr && lane + 32 * r < k) ? ya[lane + 32 * r] : 0.0;
+    for (int b = a; b < p; ++b) {
+      const double* yb = P.Yp + (long long)W.row[b] * k;
+      double acc = 0.0;
+#pragma unroll
+      for (int r = 0; r < SP_MAXR; ++r)
+        if (r < nr && lane + 32 * r < k) acc = fma(va[r], yb[lane + 32 * r], acc);
+      acc = warp_sum(acc);
+      if (lane == 0) { const double v = acc * W.wgt[a] * W.wgt[b]; W.S[a][b] = v; W.S[b][a] = v; }
+    }
+  }
+  for (int e = lane; e < p * p; e += 32) W.V[e / p][e % p] = (e / p == e % p) ? 1.0 : 0.0;
+  __syncwarp();
+
+  // ---- two-sided Jacobi on S (p x p), eigenvectors in the columns of V.  Parallel ordering: a round
+  // rotates p/2 DISJOINT index pairs at once (round-robin tournament, p - 1 rounds per sweep); lane l
+  // computes the rotation of pair l, then every lane applies all of them to its row (S J, V J) and to
+  // its column (J^T S).  The scalar sqrt/div chain of a rotation is the latency that matters here, and
+  // this way it is paid p - 1 times per sweep instead of p (p - 1) / 2.
+  const int n = (p + 1) & ~1, half = n >> 1;
+  int sweeps = 0;
+  for (; sweeps < 30; ++sweeps) {
+    double off = 0.0, dia = 0.0;
+    for (int e = lane; e < p * p; e += 32) {
+      const int i = e / p, j = e - i * p;
+      const double v = W.S[i][j];
+      if (i == j) dia = fma(v, v, dia); else off = fma(v, v, off);
+    }
+    off = warp_sum(off); dia = warp_sum(dia);
+    if (!(off > 1e-26 * dia) || off == 0.0) break;      // off-diagonal mass below 1e-13 of the diagonal
+    for (int r = 0; r < n - 1; ++r) {
+      if (lane < half) {
+        int a = (lane == 0) ? n - 1 : (r + lane) % (n - 1);
+        int b = (r - lane + (n - 1)) % (n - 1);
+        if (a > b) { const int t_ = a; a = b; b = t_; }
+        double c = 1.0, sn = 0.0;
+        if (b < p) {                                           // (index p is the padding of an odd p)
+          const double apq = W.S[a][b];
+          if (fabs(apq) > 1e-300) {
+            const double theta = (W.S[b][b] - W.S[a][a]) / (2.0 * apq);
+            const double t = (theta >= 0.0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
+            c = 1.0 / sqrt(t * t + 1.0); sn = t * c;
           }
         }
-        const unsigned bal = __ballot_sync(0xffffffffu, sel);
-        const int pos = p + __popc(bal & ((1u << lane) - 1u));
-        if (sel && pos < SP_PMAX) { W.row[pos] = orow; W.wgt[pos] = sq; W.dw[pos] = sd; }
-        p += __popc(bal);
-        if (p > SP_PMAX) overflow = true;
+        W.pa[lane] = a; W.pb[lane] = b; W.pc[lane] = c; W.ps[lane] = sn;
       }
-    }
-    __syncwarp();
-    if (overflow || p == 0) {     // cannot happen: the producer kernel counted 0 < p <= SP_PMAX
-      if (lane == 0) atomicAdd((unsigned long long*)&P.stats[4], 1ull);
-      continue;
-    }
-
-    // ---- S = M M^T (upper triangle, mirrored), rows re-read from L1/L2
-    for (int a = 0; a < p; ++a) {
-      const double* ya = P.Yp + (long long)W.row[a] * k;
-      double va[SP_MAXR];
-#pragma unroll
-      for (int r = 0; r < SP_MAXR; ++r) va[r] = (r < nr && lane + 32 * r < k) ? ya[lane + 32 * r] : 0.0;
-      for (int b = a; b < p; ++b) {
-        const double* yb = P.Yp + (long long)W.row[b] * k;
-        double acc = 0.0;
-#pragma unroll
-        for (int r = 0; r < SP_MAXR; ++r)
-          if (r < nr && lane + 32 * r < k) acc = fma(va[r], yb[lane + 32 * r], acc);
-        acc = warp_sum(acc);
-        if (lane == 0) { const double v = acc * W.wgt[a] * W.wgt[b]; W.S[a][b] = v; W.S[b][a] = v; }
-      }
-    }
-    for (int e = lane; e < p * p; e += 32) W.V[e / p][e % p] = (e / p == e % p) ? 1.0 : 0.0;
-    __syncwarp();
-
-    // ---- cyclic two-sided Jacobi on S (p x p), eigenvectors in the columns of V
-    int sweeps = 0;
-    for (; sweeps < 30; ++sweeps) {
-      double off = 0.0, dia = 0.0;
-      for (int e = lane; e < p * p; e += 32) {
-        const int i = e / p, j = e - i * p;
-        const double v = W.S[i][j];
-        if (i == j) dia = fma(v, v, dia); else off = fma(v, v, off);
-      }
-      off = warp_sum(off); dia = warp_sum(dia);
-      if (!(off > 1e-26 * dia) || off == 0.0) break;      // off-diagonal mass below 1e-13 of the diagonal
-      for (int a = 0; a < p - 1; ++a)
-        for (int b = a + 1; b < p; ++b) {
-          const double apq = W.S[a][b];
-          if (fabs(apq) < 1e-300) continue;                       // warp-uniform
-          const double app = W.S[a][a], aqq = W.S[b][b];
-          const double theta = (aqq - app) / (2.0 * apq);
-          const double t = (theta >= 0.0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
-          const double c = 1.0 / sqrt(t * t + 1.0), sn = t * c;
-          __syncwarp();
-          if (lane < p) {                                         // S <- S J (columns a, b), V <- V J
+      __syncwarp();
+      if (lane < p)                                            // S <- S J, V <- V J: row `lane`
+        for (int l = 0; l < half; ++l) {
+          const double sn = W.ps[l];
+          if (sn != 0.0) {
+            const int a = W.pa[l], b = W.pb[l];
+            const double c = W.pc[l];
             const double sa = W.S[lane][a], sb = W.S[lane][b];
             W.S[lane][a] = c * sa - sn * sb; W.S[lane][b] = sn * sa + c * sb;
             const double v0 = W.V[lane][a], v1 = W.V[lane][b];
             W.V[lane][a] = c * v0 - sn * v1; W.V[lane][b] = sn * v0 + c * v1;
           }
-          __syncwarp();
-          if (lane < p) {                                         // S <- J^T S (rows a, b)
+        }
+      __syncwarp();
+      if (lane < p)                                            // S <- J^T S: column `lane`
+        for (int l = 0; l < half; ++l) {
+          const double sn = W.ps[l];
+          if (sn != 0.0) {
+            const int a = W.pa[l], b = W.pb[l];
+            const double c = W.pc[l];
             const double sa = W.S[a][lane], sb = W.S[b][lane];
             W.S[a][lane] = c * sa - sn * sb; W.S[b][lane] = sn * sa + c * sb;
           }
-          __syncwarp();
         }
+      __syncwarp();
     }
+  }
 
-    // ---- phi_i, u = V diag(1/a) V^T dw
-    if (lane < p) {
-      const double l = fmax(W.S[lane][lane], 0.0), a = s + l, ra = sqrt(a), r0 = sqrt(s);
-      W.phi[lane] = -1.0 / (ra * r0 * (ra + r0));
-      double tv = 0.0;
-      for (int b = 0; b < p; ++b) tv = fma(W.V[b][lane], W.dw[b], tv);   // (V^T dw)_lane
-      W.q[lane] = tv / a;
-    }
-    __syncwarp();
-    if (lane < p) {
-      double uv = 0.0;
-      for (int b = 0; b < p; ++b) uv = fma(W.V[lane][b], W.q[b], uv);
-      W.u[lane] = uv;
-    }
-    __syncwarp();
+  // ---- phi_i, u = V diag(1/a) V^T dw
+  if (lane < p) {
+    const double l = fmax(W.S[lane][lane], 0.0), a = s + l, ra = sqrt(a), r0 = sqrt(s);
+    W.phi[lane] = -1.0 / (ra * r0 * (ra + r0));
+    double tv = 0.0;
+    for (int b = 0; b < p; ++b) tv = fma(W.V[b][lane], W.dw[b], tv);   // (V^T dw)_lane
+    W.q[lane] = tv / a;
+  }
+  __syncwarp();
+  if (lane < p) {
+    double uv = 0.0;
+    for (int b = 0; b < p; ++b) uv = fma(W.V[lane][b], W.q[b], uv);
+    W.u[lane] = uv;
+  }
+  __syncwarp();
 
-    // ---- levels
-    const int lev_b = per_level ? lt : 0, lev_e = per_level ? lt + 1 : nz;
-    for (int l = lev_b; l < lev_e; ++l) {
-      double* x = Xg + (long long)l * k;
-      double xv[SP_MAXR];
-      double sum = 0.0;
+  // ---- levels
+  const int lev_b = per_level ? lt : 0, lev_e = per_level ? lt + 1 : nz;
+  for (int l = lev_b; l < lev_e; ++l) {
+    double* x = Xg + (long long)l * k;
+    double xv[SP_MAXR];
+    double sum = 0.0;
 #pragma unroll
-      for (int r = 0; r < SP_MAXR; ++r) {
-        xv[r] = (r < nr && lane + 32 * r < k) ? x[lane + 32 * r] : 0.0;
-        sum += xv[r];
-      }
-      const double xbar = warp_sum(sum) / (double)k;
+    for (int r = 0; r < SP_MAXR; ++r) {
+      xv[r] = (r < nr && lane + 32 * r < k) ? x[lane + 32 * r] : 0.0;
+      sum += xv[r];
+    }
+    const double xbar = warp_sum(sum) / (double)k;
 #pragma unroll
-      for (int r = 0; r < SP_MAXR; ++r) xv[r] = (r < nr && lane + 32 * r < k) ? xv[r] - xbar : 0.0;
-      // q = M x'^T
-      for (int a = 0; a < p; ++a) {
-        const double* ya = P.Yp + (long long)W.row[a] * k;
-        double acc = 0.0;
-#pragma unroll
-        for (int r = 0; r < SP_MAXR; ++r)
-          if (r < nr && lane + 32 * r < k) acc = fma(ya[lane + 32 * r], xv[r], acc);
-        acc = warp_sum(acc);
-        if (lane == 0) W.q[a] = acc * W.wgt[a];
-      }
-      __syncwarp();
-      // c = q . u ;  r = Phi q = V diag(phi) V^T q, scaled by the row weights for the last product
-      double cpart = (lane < p) ? W.q[lane] * W.u[lane] : 0.0;
-      const double cq = warp_sum(cpart);
-      double tq = 0.0;
-      if (lane < p) {
-        for (int b = 0; b < p; ++b) tq = fma(W.V[b][lane], W.q[b], tq);
-        tq *= W.phi[lane];
-      }
-      __syncwarp();
-      if (lane < p) W.S[0][lane] = tq;            // S is dead: reuse its first row as scratch
-      __syncwarp();
-      if (lane < p) {
-        double rv = 0.0;
-        for (int b = 0; b < p; ++b) rv = fma(W.V[lane][b], W.S[0][b], rv);
-        W.r[lane] = rv * W.wgt[lane];
-      }
-      __syncwarp();
-      double out[SP_MAXR], msum = 0.0;
-#pragma unroll
-      for (int r = 0; r < SP_MAXR; ++r) out[r] = rs * xv[r];
-      for (int a = 0; a < p; ++a) {
-        const double* ya = P.Yp + (long long)W.row[a] * k;
-        const double ra = W.r[a];
-#pragma unroll
-        for (int r = 0; r < SP_MAXR; ++r)
-          if (r < nr && lane + 32 * r < k) out[r] = fma(ra, ya[lane + 32 * r], out[r]);
-      }
+    for (int r = 0; r < SP_MAXR; ++r) xv[r] = (r < nr && lane + 32 * r < k) ? xv[r] - xbar : 0.0;
+    // q = M x'^T
+    for (int a = 0; a < p; ++a) {
+      const double* ya = P.Yp + (long long)W.row[a] * k;
+      double acc = 0.0;
 #pragma unroll
       for (int r = 0; r < SP_MAXR; ++r)
-        if (r < nr && lane + 32 * r < k) {
-          const double v = xbar + cq + sW * out[r];
-          x[lane + 32 * r] = v;
-          msum += v;
-        }
-      if (P.mean_out) {
-        msum = warp_sum(msum);
-        if (lane == 0) P.mean_out[col * nz + l] = msum * (1.0 / (double)k);
-      }
-      __syncwarp();
+        if (r < nr && lane + 32 * r < k) acc = fma(ya[lane + 32 * r], xv[r], acc);
+      acc = warp_sum(acc);
+      if (lane == 0) W.q[a] = acc * W.wgt[a];
     }
+    __syncwarp();
+    // c = q . u ;  r = Phi q = V diag(phi) V^T q, scaled by the row weights for the last product
+    double cpart = (lane < p) ? W.q[lane] * W.u[lane] : 0.0;
+    const double cq = warp_sum(cpart);
+    double tq = 0.0;
+    if (lane < p) {
+      for (int b = 0; b < p; ++b) tq = fma(W.V[b][lane], W.q[b], tq);
+      tq *= W.phi[lane];
+    }
+    __syncwarp();
+    if (lane < p) W.S[0][lane] = tq;            // S is dead: reuse its first row as scratch
+    __syncwarp();
+    if (lane < p) {
+      double rv = 0.0;
+      for (int b = 0; b < p; ++b) rv = fma(W.V[lane][b], W.S[0][b], rv);
+      W.r[lane] = rv * W.wgt[lane];
+    }
+    __syncwarp();
+    double out[SP_MAXR], msum = 0.0;
+#pragma unroll
+    for (int r = 0; r < SP_MAXR; ++r) out[r] = rs * xv[r];
+    for (int a = 0; a < p; ++a) {
+      const double* ya = P.Yp + (long long)W.row[a] * k;
+      const double ra = W.r[a];
+#pragma unroll
+      for (int r = 0; r < SP_MAXR; ++r)
+        if (r < nr && lane + 32 * r < k) out[r] = fma(ra, ya[lane + 32 * r], out[r]);
+    }
+#pragma unroll
+    for (int r = 0; r < SP_MAXR; ++r)
+      if (r < nr && lane + 32 * r < k) {
+        const double v = xbar + cq + sW * out[r];
+        x[lane + 32 * r] = v;
+        msum += v;
+      }
+    if (P.mean_out) {
+      msum = warp_sum(msum);
+      if (lane == 0) P.mean_out[col * nz + l] = msum * (1.0 / (double)k);
+    }
+    __syncwarp();
+  }
+  sweeps_out = sweeps;
+  return 0;
+}
+
+// Consumer of the packed kernel's list of small transforms (non-per-level analyses).
+__global__ void __launch_bounds__(SP_WARPS * 32) letkf_smallp_kernel(ColParams P) {
+  extern __shared__ __align__(16) unsigned char sp_smem_raw[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  SpWarpSmem& W = reinterpret_cast<SpWarpSmem*>(sp_smem_raw)[warp];
+  const int nxf = P.radius_v > 0.0 ? P.nz : 1;
+  const long long nitems = (long long)*P.small_count;
+  for (long long it = (long long)blockIdx.x * SP_WARPS + warp; it < nitems; it += (long long)gridDim.x * SP_WARPS) {
+    const long long item = P.small_items[it], col = item / nxf;
+    int p = 0, sweeps = 0;
+    const int rc = sp_transform(P, W, col, (int)(item - col * nxf), lane, p, sweeps);
     if (lane == 0) {
+      if (rc == 2) atomicAdd((unsigned long long*)&P.stats[4], 1ull);   // cannot happen: the producer counted p
       atomicAdd((unsigned long long*)&P.stats[2], (unsigned long long)sweeps);
       atomicMax(&P.stats[3], (long long)sweeps);
-      atomicAdd((unsigned long long*)&P.stats[7], 1ull);
+      if (rc == 0) atomicAdd((unsigned long long*)&P.stats[7], 1ull);
     }
+  }
+}
+
+// Per-level analyses: FIRST pass over every (column, level) transform, one warp per transform.  Transforms
+// with no or few local observations are finished here; the others go to the work list of the packed
+// k-space kernel, which then never spends a 512-thread selection on a transform it will not do.
+__global__ void __launch_bounds__(SP_WARPS * 32) letkf_smallp_classify_kernel(ColParams P) {
+  extern __shared__ __align__(16) unsigned char sp_smem_raw[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  SpWarpSmem& W = reinterpret_cast<SpWarpSmem*>(sp_smem_raw)[warp];
+  const int nxf = P.radius_v > 0.0 ? P.nz : 1;
+  const long long ncols = P.cols ? P.ncols : (long long)P.own_nx * P.own_ny;
+  // one warp per TRANSFORM (consecutive warps take the levels of one column: their index reads share L1)
+  for (long long ti = (long long)blockIdx.x * SP_WARPS + warp; ti < ncols * nxf; ti += (long long)gridDim.x * SP_WARPS) {
+    const long long ci = ti / nxf;
+    const int lt = (int)(ti - ci * nxf);
+    long long col;
+    if (P.cols) col = P.cols[ci];
+    else col = (ci / P.own_nx) * P.nx + ci % P.own_nx;
+    int p = 0, sweeps = 0;
+    const int rc = sp_transform(P, W, col, lt, lane, p, sweeps);
+    if (lane == 0) {
+      if (rc == 2) {
+        const unsigned slot = atomicAdd(P.work_count, 1u);
+        P.work_items[slot] = col * nxf + lt;
+      }
+      if (rc == 0) {
+        atomicAdd((unsigned long long*)&P.stats[7], 1ull);
+        atomicAdd((unsigned long long*)&P.stats[2], (unsigned long long)sweeps);
+        atomicMax(&P.stats[3], (long long)sweeps);
+      }
+      if (lt == 0) {
+        atomicAdd((unsigned long long*)&P.stats[0], (unsigned long long)p);
+        atomicMax(&P.stats[1], (long long)p);
+        atomicAdd((unsigned long long*)&P.stats[5], 1ull);
+      }
+    }
+    __syncwarp();
   }
 }
 

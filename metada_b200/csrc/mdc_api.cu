@@ -727,6 +727,7 @@ static int letkf_launch(mdc_ens* e, mdc_obs* o, const mdc_letkf_params* p, const
   const int sms = std::max(1, ctx->sm_count - std::max(0, std::min(p->sm_reserve, ctx->sm_count / 2)));
   cp.redo_items = nullptr; cp.redo_count = nullptr; cp.redo_consume = 0;
   cp.small_items = nullptr; cp.small_count = nullptr;
+  cp.work_items = nullptr; cp.work_count = nullptr; cp.work_consume = 0;
   if (p->mode == MDC_MODE_CANONICAL && p->solver == MDC_SOLVER_NEWTON_SCHULZ && (k < 24 || k > 128))
     MDC_FAIL(ctx, MDC_ERR_UNSUPPORTED, "letkf: the Newton-Schulz solver supports 24 <= k <= 128 (k=%d)", k);
   if (p->mode == MDC_MODE_CANONICAL && p->solver == MDC_SOLVER_NEWTON_SCHULZ_FULL && (k < 24 || k > 80))
@@ -783,19 +784,38 @@ static int letkf_launch(mdc_ens* e, mdc_obs* o, const mdc_letkf_params* p, const
     // kernel (k <= 80) or the Jacobi kernel
     const int nxf = p->radius_v > 0.0 ? e->nz : 1;
     const size_t need = (size_t)total_cols * nxf;
-    if (ctx->redo_cap < need) {      // two lists: redo (ill-conditioned) and small (few local observations)
+    if (ctx->redo_cap < need) {      // three lists: redo (ill-conditioned), small (few local observations), work
       if (ctx->redo_items) cudaFree(ctx->redo_items);
       ctx->redo_items = nullptr; ctx->redo_cap = 0;
-      MDC_CUDA(ctx, cudaMalloc((void**)&ctx->redo_items, 2 * need * sizeof(long long)));
+      MDC_CUDA(ctx, cudaMalloc((void**)&ctx->redo_items, 3 * need * sizeof(long long)));
       ctx->redo_cap = need;
     }
     cp.redo_items = ctx->redo_items;
     cp.redo_count = reinterpret_cast<unsigned*>(ctx->d_flags + 12);
-    if (!getenv("MDC_LETKF_NO_SMALLP")) {
+    MDC_CUDA(ctx, cudaMemsetAsync(ctx->d_flags + 12, 0, 3 * sizeof(unsigned), ctx->stream));
+    const bool smallp = !getenv("MDC_LETKF_NO_SMALLP");
+    const size_t smems = smallp_smem_bytes();
+    auto launch_smallp = [&](auto kern, const ColParams& cq) -> int {
+      MDC_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smems));
+      int occ = 1;
+      MDC_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, SP_WARPS * 32, smems));
+      kern<<<sms * std::max(1, occ), SP_WARPS * 32, smems, ctx->stream>>>(cq);
+      MDC_LAUNCH_CHECK(ctx);
+      return MDC_OK;
+    };
+    // Per-level analyses: a first pass (one warp per column) finishes the transforms with no or few local
+    // observations in observation space and lists the others for the k-space kernel.  Otherwise the k-space
+    // kernel defers its small transforms to the observation-space kernel after its own selection.
+    const bool classify = smallp && nxf > 1 && !dW;
+    if (classify) {
+      cp.work_items = ctx->redo_items + 2 * ctx->redo_cap;
+      cp.work_count = reinterpret_cast<unsigned*>(ctx->d_flags + 14);
+      if (int rc = launch_smallp(letkf_smallp_classify_kernel, cp)) return rc;
+      cp.work_consume = 1;
+    } else if (smallp) {
       cp.small_items = ctx->redo_items + ctx->redo_cap;
       cp.small_count = reinterpret_cast<unsigned*>(ctx->d_flags + 13);
     }
-    MDC_CUDA(ctx, cudaMemsetAsync(ctx->d_flags + 12, 0, 2 * sizeof(unsigned), ctx->stream));
     const int lch = nsp_level_chunk(k, e->nz);
     auto launchp = [&](auto kern, int nth) -> int {
       const size_t smemp = nsp_smem_bytes(k, lch, nth);
@@ -812,32 +832,27 @@ static int letkf_launch(mdc_ens* e, mdc_obs* o, const mdc_letkf_params* p, const
     };
     int rc;
     switch ((k + 7) >> 3) {   // tile rows: the kernel is specialised on the exact count
-      case 3: rc = launchp(letkf_nsp_kernel<3, 256, 2>, 256); break;
-      case 4: rc = launchp(letkf_nsp_kernel<4, 256, 2>, 256); break;
-      case 5: rc = launchp(letkf_nsp_kernel<5, 256, 2>, 256); break;
-      case 6: rc = launchp(letkf_nsp_kernel<6, 256, 2>, 256); break;
-      case 7: rc = launchp(letkf_nsp_kernel<7, 256, 2>, 256); break;
-      case 8: rc = launchp(letkf_nsp_kernel<8, 256, 2>, 256); break;
-      case 9: rc = launchp(letkf_nsp_kernel<9, 256, 2>, 256); break;
-      case 10: rc = launchp(letkf_nsp_kernel<10, 256, 2>, 256); break;   // (384 threads: 6 % slower)
-      case 11: rc = launchp(letkf_nsp_kernel<11, 512, 1>, 512); break;
-      case 12: rc = launchp(letkf_nsp_kernel<12, 512, 1>, 512); break;
-      case 13: rc = launchp(letkf_nsp_kernel<13, 512, 1>, 512); break;
-      case 14: rc = launchp(letkf_nsp_kernel<14, 512, 1>, 512); break;
-      case 15: rc = launchp(letkf_nsp_kernel<15, 512, 1>, 512); break;
-      default: rc = launchp(letkf_nsp_kernel<16, 512, 1>, 512); break;
+      case 3: rc = cp.work_consume ? launchp(letkf_nsp_kernel<3, 256, 2, true>, 256) : launchp(letkf_nsp_kernel<3, 256, 2, false>, 256); break;
+      case 4: rc = cp.work_consume ? launchp(letkf_nsp_kernel<4, 256, 2, true>, 256) : launchp(letkf_nsp_kernel<4, 256, 2, false>, 256); break;
+      case 5: rc = cp.work_consume ? launchp(letkf_nsp_kernel<5, 256, 2, true>, 256) : launchp(letkf_nsp_kernel<5, 256, 2, false>, 256); break;
+      case 6: rc = cp.work_consume ? launchp(letkf_nsp_kernel<6, 256, 2, true>, 256) : launchp(letkf_nsp_kernel<6, 256, 2, false>, 256); break;
+      case 7: rc = cp.work_consume ? launchp(letkf_nsp_kernel<7, 256, 2, true>, 256) : launchp(letkf_nsp_kernel<7, 256, 2, false>, 256); break;
+      case 8: rc = cp.work_consume ? launchp(letkf_nsp_kernel<8, 256, 2, true>, 256) : launchp(letkf_nsp_kernel<8, 256, 2, false>, 256); break;
+      case 9: rc = cp.work_consume ? launchp(letkf_nsp_kernel<9, 256, 2, true>, 256) : launchp(letkf_nsp_kernel<9, 256, 2, false>, 256); break;
+      case 10: rc = cp.work_consume ? launchp(letkf_nsp_kernel<10, 256, 2, true>, 256) : launchp(letkf_nsp_kernel<10, 256, 2, false>, 256); break;   // (384 threads: 6 % slower)
+      case 11: rc = cp.work_consume ? launchp(letkf_nsp_kernel<11, 512, 1, true>, 512) : launchp(letkf_nsp_kernel<11, 512, 1, false>, 512); break;
+      case 12: rc = cp.work_consume ? launchp(letkf_nsp_kernel<12, 512, 1, true>, 512) : launchp(letkf_nsp_kernel<12, 512, 1, false>, 512); break;
+      case 13: rc = cp.work_consume ? launchp(letkf_nsp_kernel<13, 512, 1, true>, 512) : launchp(letkf_nsp_kernel<13, 512, 1, false>, 512); break;
+      case 14: rc = cp.work_consume ? launchp(letkf_nsp_kernel<14, 512, 1, true>, 512) : launchp(letkf_nsp_kernel<14, 512, 1, false>, 512); break;
+      case 15: rc = cp.work_consume ? launchp(letkf_nsp_kernel<15, 512, 1, true>, 512) : launchp(letkf_nsp_kernel<15, 512, 1, false>, 512); break;
+      default: rc = cp.work_consume ? launchp(letkf_nsp_kernel<16, 512, 1, true>, 512) : launchp(letkf_nsp_kernel<16, 512, 1, false>, 512); break;
     }
     if (rc) return rc;
-    if (cp.small_items) {
-      const size_t smems = smallp_smem_bytes();
-      MDC_CUDA(ctx, cudaFuncSetAttribute(letkf_smallp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smems));
-      int occ = 1;
-      MDC_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, letkf_smallp_kernel, SP_WARPS * 32, smems));
-      letkf_smallp_kernel<<<sms * std::max(1, occ), SP_WARPS * 32, smems, ctx->stream>>>(cp);
-      MDC_LAUNCH_CHECK(ctx);
-    }
+    if (cp.small_items)
+      if (int rc2 = launch_smallp(letkf_smallp_kernel, cp)) return rc2;
     ColParams cq = cp;
     cq.redo_consume = 1;
+    cq.work_consume = 0;
     return k <= 80 ? launch_ns_full(cq, (long long)need) : launch_jacobi(cq, (long long)need);
   }
   if (p->mode == MDC_MODE_CANONICAL && !v1) return launch_jacobi(cp, total_cols);

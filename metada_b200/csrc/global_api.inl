@@ -6,7 +6,7 @@ int gram_reduce(mdc_ctx* ctx, mdc_obs* o, const double* B, int kb, double* d_out
   const int nout = k * k + k * kb;
   const int nb = (int)std::max<int64_t>(1, std::min<int64_t>((o->P + 255) / 256, ctx->sm_count * 2));
   double* partial = nullptr;
-  if (dev_alloc(ctx, &partial, (size_t)nb * nout)) return MDC_ERR_CUDA;
+  if (tmp_alloc(ctx, &partial, (size_t)nb * nout)) return MDC_ERR_CUDA;
   size_t smem = ((size_t)2 * GK_ROWS * k + (size_t)GK_ROWS * kb) * sizeof(double);
   MDC_CUDA(ctx, cudaFuncSetAttribute(obs_gram_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   obs_gram_kernel<<<nb, GK_THREADS, smem, ctx->stream>>>(o->Yp, B, kb, o->err, o->valid, o->P, k, partial);
@@ -14,7 +14,7 @@ int gram_reduce(mdc_ctx* ctx, mdc_obs* o, const double* B, int kb, double* d_out
   reduce_partials_kernel<<<mdc_div_up(nout, 128), 128, 0, ctx->stream>>>(partial, nb, nout, d_out);
   MDC_LAUNCH_CHECK(ctx);
   MDC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-  cudaFree(partial);
+  tmp_free(ctx, partial);
   return MDC_OK;
 }
 
@@ -28,7 +28,7 @@ int apply_transform(mdc_ctx* ctx, mdc_ens* e, const double* dW, double* spread2 
   MDC_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, global_apply_kernel, GK_THREADS, smem));
   const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((npts + GA_TP - 1) / GA_TP, (int64_t)ctx->sm_count * std::max(occ, 1)));
   double* dpart = nullptr;
-  if (spread2 && dev_alloc(ctx, &dpart, (size_t)grid * 2)) return MDC_ERR_CUDA;
+  if (spread2 && tmp_alloc(ctx, &dpart, (size_t)grid * 2)) return MDC_ERR_CUDA;
   global_apply_kernel<<<grid, GK_THREADS, smem, ctx->stream>>>(e->X, e->mean, dW, npts, k, dpart);
   MDC_LAUNCH_CHECK(ctx);
   if (spread2) {
@@ -37,7 +37,7 @@ int apply_transform(mdc_ctx* ctx, mdc_ens* e, const double* dW, double* spread2 
     MDC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     spread2[0] = spread2[1] = 0.0;
     for (int b = 0; b < grid; ++b) { spread2[0] += h[2 * b]; spread2[1] += h[2 * b + 1]; }
-    cudaFree(dpart);
+    tmp_free(ctx, dpart);
   }
   return MDC_OK;
 }
@@ -64,7 +64,7 @@ int mdc_etkf_analyse(mdc_ens* e, mdc_obs* o, double inflation) {
   if (int rc = ens_mean_device(e)) return rc;                    // ETKF.hpp:111
   if (int rc = mdc_hx_idw4(e, o)) return rc;                     // :128-141
   double *dG = nullptr, *dW = nullptr;
-  if (dev_alloc(ctx, &dG, (size_t)k * k + k) || dev_alloc(ctx, &dW, (size_t)k * k)) return MDC_ERR_CUDA;
+  if (tmp_alloc(ctx, &dG, (size_t)k * k + k) || tmp_alloc(ctx, &dW, (size_t)k * k)) return MDC_ERR_CUDA;
   int rc = gram_reduce(ctx, o, o->d, 1, dG);                      // C and g (:150, :155)
   if (!rc) {
     MDC_CUDA(ctx, cudaMemsetAsync(ctx->d_flags, 0, sizeof(int), ctx->stream));
@@ -79,7 +79,7 @@ int mdc_etkf_analyse(mdc_ens* e, mdc_obs* o, double inflation) {
   }
   if (!rc) rc = apply_transform(ctx, e, dW, nullptr);             // :163-176
   if (!rc) { MDC_CUDA(ctx, cudaStreamSynchronize(ctx->stream)); }
-  cudaFree(dG); cudaFree(dW);
+  tmp_free(ctx, dG); tmp_free(ctx, dW);
   o->have_hx = false;
   return rc;
 }
@@ -97,11 +97,11 @@ int mdc_enkf_analyse(mdc_ens* e, mdc_obs* o, double inflation, const double* Z, 
   if (int rc = mdc_hx_idw4(e, o)) return rc;                     // :168-181
   double *dZ = nullptr, *dD = nullptr, *dG = nullptr, *dW = nullptr, *dAinv = nullptr, *dsc = nullptr;
   int rc = MDC_OK;
-  auto cleanup = [&]() { cudaFree(dZ); cudaFree(dD); cudaFree(dG); cudaFree(dW); cudaFree(dAinv); cudaFree(dsc); };
-  if (dev_alloc(ctx, &dD, (size_t)P * k) || dev_alloc(ctx, &dG, (size_t)2 * k * k) || dev_alloc(ctx, &dW, (size_t)k * k) ||
-      dev_alloc(ctx, &dAinv, (size_t)k * k) || dev_alloc(ctx, &dsc, (size_t)16 + k)) { cleanup(); return MDC_ERR_CUDA; }
+  auto cleanup = [&]() { tmp_free(ctx, dZ); tmp_free(ctx, dD); tmp_free(ctx, dG); tmp_free(ctx, dW); tmp_free(ctx, dAinv); tmp_free(ctx, dsc); };
+  if (tmp_alloc(ctx, &dD, (size_t)P * k) || tmp_alloc(ctx, &dG, (size_t)2 * k * k) || tmp_alloc(ctx, &dW, (size_t)k * k) ||
+      tmp_alloc(ctx, &dAinv, (size_t)k * k) || tmp_alloc(ctx, &dsc, (size_t)16 + k)) { cleanup(); return MDC_ERR_CUDA; }
   if (Z) {
-    if (dev_alloc(ctx, &dZ, (size_t)P * k)) { cleanup(); return MDC_ERR_CUDA; }
+    if (tmp_alloc(ctx, &dZ, (size_t)P * k)) { cleanup(); return MDC_ERR_CUDA; }
     cudaError_t ce = cudaMemcpyAsync(dZ, Z, (size_t)P * k * 8, cudaMemcpyHostToDevice, s);
     if (ce != cudaSuccess) { cleanup(); MDC_FAIL(ctx, MDC_ERR_CUDA, "enkf: upload of Z failed: %s", cudaGetErrorString(ce)); }
   }
@@ -130,7 +130,7 @@ int mdc_enkf_analyse(mdc_ens* e, mdc_obs* o, double inflation, const double* Z, 
   if (!rc && want_gain_stats) {
     // K = sqrt(infl) X' A^-1 Y'^T R^-1, streamed max/min (:199-203)
     double *dM = nullptr, *dmm = nullptr;
-    if (dev_alloc(ctx, &dM, (size_t)P * k) || dev_alloc(ctx, &dmm, 2)) { cleanup(); return MDC_ERR_CUDA; }
+    if (tmp_alloc(ctx, &dM, (size_t)P * k) || tmp_alloc(ctx, &dmm, 2)) { cleanup(); return MDC_ERR_CUDA; }
     double init[2] = {-INFINITY, INFINITY};
     cudaMemcpyAsync(dmm, init, sizeof(init), cudaMemcpyHostToDevice, s);
     enkf_gain_factor_kernel<<<grid_for(ctx, P * k, 256, 8), 256, 0, s>>>(o->Yp, dAinv, o->err, o->valid, P, k, dM);
@@ -153,7 +153,7 @@ int mdc_enkf_analyse(mdc_ens* e, mdc_obs* o, double inflation, const double* Z, 
     ctx->launches++;
     cudaMemcpyAsync(ev.data(), dsc + 16, (size_t)k * 8, cudaMemcpyDeviceToHost, s);
     cudaStreamSynchronize(s);
-    if (cudaGetLastError() != cudaSuccess) { cudaFree(dM); cudaFree(dmm); cleanup(); MDC_FAIL(ctx, MDC_ERR_CUDA, "enkf: gain statistics kernels failed"); }
+    if (cudaGetLastError() != cudaSuccess) { tmp_free(ctx, dM); tmp_free(ctx, dmm); cleanup(); MDC_FAIL(ctx, MDC_ERR_CUDA, "enkf: gain statistics kernels failed"); }
     kmax = hmm[0]; kmin = hmm[1];
     if (hsc[1] == hsc[2] && hsc[1] > 0.0) {
       std::sort(ev.begin(), ev.end(), [](double a, double b) { return a > b; });
@@ -162,7 +162,7 @@ int mdc_enkf_analyse(mdc_ens* e, mdc_obs* o, double inflation, const double* Z, 
       const double lmin = (P >= k) ? 1.0 : 1.0 + ev[(size_t)P - 1] / km1;
       cond = lmax / lmin;
     }
-    cudaFree(dM); cudaFree(dmm);
+    tmp_free(ctx, dM); tmp_free(ctx, dmm);
   }
   double sp[2] = {0, 0};
   if (!rc) rc = apply_transform(ctx, e, dW, sp);                 // :215-234

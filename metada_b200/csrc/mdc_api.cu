@@ -38,6 +38,21 @@ int dev_alloc(mdc_ctx* ctx, T** p, size_t n) {
   return MDC_OK;
 }
 
+// Per-call temporaries of the global (ETKF / EnKF) paths: stream-ordered pool allocations.  Plain
+// cudaMalloc / cudaFree map and unmap device memory on every call, which made a 3 ms EnKF analysis take
+// 12 - 55 ms depending on what the process had allocated before (measured, tools/dbg_c2.py).
+template <typename T>
+int tmp_alloc(mdc_ctx* ctx, T** p, size_t n) {
+  *p = nullptr;
+  if (n == 0) n = 1;
+  MDC_CUDA(ctx, cudaMallocAsync((void**)p, n * sizeof(T), ctx->stream));
+  return MDC_OK;
+}
+template <typename T>
+void tmp_free(mdc_ctx* ctx, T* p) {
+  if (p) cudaFreeAsync((void*)p, ctx->stream);
+}
+
 int ensure_stage(mdc_ens* e, size_t elems) {
   if (e->stage_elems >= elems) return MDC_OK;
   if (e->stage) cudaFree(e->stage);
@@ -68,6 +83,13 @@ int mdc_ctx_create(int device, mdc_ctx** out) {
   ctx->sm_count = prop.multiProcessorCount;
   ctx->max_smem_optin = (int)prop.sharedMemPerBlockOptin;
   if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return MDC_ERR_CUDA; }
+  {   // keep freed temporaries in the device's default pool (tmp_alloc / tmp_free)
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+      unsigned long long keep = ~0ull;
+      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
+  }
   cudaEventCreate(&ctx->ev0);
   cudaEventCreate(&ctx->ev1);
   for (auto& e : ctx->pe) cudaEventCreate(&e);

@@ -104,6 +104,34 @@ int mdc_obs_assign(mdc_obs* obs, int64_t P, const int32_t* x, const int32_t* y, 
 int mdc_obs_destroy(mdc_obs* obs);
 int64_t mdc_obs_size(const mdc_obs* obs);       /* own + halo rows */
 
+/* ---- geographic observations and multi-variable states (the WRF-shaped case) ------------------
+ * Geography of the grid: latitude / longitude in degrees of every column, [ny][nx] (the 2-D coordinate arrays of
+ * WRFGeometry::unstaggered_info(), read by IdentityObsOperator.hpp:488-509 and WRFGeometryIterator.hpp:144), and the
+ * geometry's vertical coordinate (nlev values, or nlev = 0 / NULL: every observation sits on level 0, :515-526). */
+int mdc_ens_set_geography(mdc_ens* ens, const double* lat, const double* lon, int nlev,
+                          const double* vertical_coords);
+/* Variables of the state: a member is [var][lev][y][x] (WRFState.hpp:866-877), i.e. nz = sum of var_nlev; 3-D
+ * variables share the geometry's levels, 2-D variables have 1 level.  H reads an observation's own variable
+ * (IdentityObsOperator.hpp:681-711); every variable of a column is updated with the column's transform; with vertical
+ * localisation the distance is taken between levels inside their variables.  At most 16 variables. */
+int mdc_ens_set_variables(mdc_ens* ens, int nvar, const int32_t* var_nlev);
+/* state variable each observation observes (index into the ensemble's variables); NULL = variable 0 */
+int mdc_obs_set_variables(mdc_obs* obs, const int32_t* var);
+/* Observations with GEOGRAPHIC locations (Location(lat, lon, level, GEOGRAPHIC), Location.hpp:82-84): the local
+ * selection is Location::distance_to = haversine kilometres on a sphere of radius 6371 km (Location.hpp:213-217,
+ * 325, 349-357), so mdc_letkf_params.radius (and loc_scale) are kilometres; mdc_obs_locate finds each observation's
+ * nearest grid point and level exactly as IdentityObsOperator::convertGeographicToGrid (:484-530) -- first minimum of
+ * the Euclidean distance in degrees -- and H then interpolates at those integer coordinates (:241-248).
+ * mdc_hx_idw4 / mdc_letkf_analyse locate on demand.  Regional domains only: the selection circles must not reach a
+ * pole or wrap the whole longitude circle (MDC_ERR_UNSUPPORTED otherwise); single device (no domain decomposition);
+ * MDC_MODE_CANONICAL. */
+int mdc_obs_create_geographic(mdc_ctx* ctx, int64_t P, const double* lat, const double* lon,
+                              const double* level, const double* value, const double* err,
+                              const uint8_t* valid, const int64_t* gid, mdc_obs** out);
+int mdc_obs_locate(mdc_obs* obs, mdc_ens* ens);
+/* grid coordinates of the observations (as given, or as located); any output may be NULL */
+int mdc_obs_download_grid_coords(mdc_obs* obs, int32_t* x, int32_t* y, int32_t* z);
+
 /* ---- H(x), Y' and d: replaces k calls of ObsOperator::apply (ObsOperator.hpp:255-259 ->
  * IdentityObsOperator.hpp:154-180, 594-676) + LETKF.hpp:209-211 / ETKF.hpp:135-141 ---------- */
 int mdc_hx_idw4(mdc_ens* ens, mdc_obs* obs);

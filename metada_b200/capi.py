@@ -134,6 +134,12 @@ def load_library() -> C.CDLL:
         "mdc_ens_set_rows": (C.c_int, [vp, C.c_int]),
         "mdc_obs_destroy": (C.c_int, [vp]),
         "mdc_obs_size": (i64, [vp]),
+        "mdc_ens_set_geography": (C.c_int, [vp, vp, vp, C.c_int, vp]),
+        "mdc_ens_set_variables": (C.c_int, [vp, C.c_int, vp]),
+        "mdc_obs_set_variables": (C.c_int, [vp, vp]),
+        "mdc_obs_create_geographic": (C.c_int, [vp, i64, vp, vp, vp, vp, vp, vp, vp, C.POINTER(vp)]),
+        "mdc_obs_locate": (C.c_int, [vp, vp]),
+        "mdc_obs_download_grid_coords": (C.c_int, [vp, vp, vp, vp]),
         "mdc_hx_idw4": (C.c_int, [vp, vp]),
         "mdc_hx_download": (C.c_int, [vp, vp, vp, vp, vp]),
         "mdc_obs_pack_rows": (C.c_int, [vp, C.c_int, C.c_int, vp, i64, C.POINTER(i64)]),
@@ -283,6 +289,20 @@ class Ensemble:
         self.ctx.check(self.ctx.L.mdc_ens_download_member(self.h, m, _ptr(out)))
         return out
 
+    def set_geography(self, lat, lon, vertical_coords=None):
+        """Column coordinates in degrees, [ny, nx] (the geometry's 2-D latitude / longitude arrays), and the
+        geometry's vertical coordinate (nearest-level lookup of geographic observations)."""
+        lat = np.ascontiguousarray(lat, dtype=np.float64)
+        lon = np.ascontiguousarray(lon, dtype=np.float64)
+        assert lat.shape == (self.ny, self.nx) and lon.shape == (self.ny, self.nx), (lat.shape, lon.shape)
+        vc = np.ascontiguousarray(vertical_coords, dtype=np.float64) if vertical_coords is not None else None
+        self.ctx.check(self.ctx.L.mdc_ens_set_geography(self.h, _ptr(lat), _ptr(lon), len(vc) if vc is not None else 0, _ptr(vc)))
+
+    def set_variables(self, var_nlev):
+        """Variables of the state: a member is [var][lev][y][x], nz = sum(var_nlev)."""
+        vn = np.ascontiguousarray(var_nlev, dtype=np.int32)
+        self.ctx.check(self.ctx.L.mdc_ens_set_variables(self.h, len(vn), _ptr(vn)))
+
     def fill_synthetic(self, seed: int = 1000):
         self.ctx.check(self.ctx.L.mdc_ens_fill_synthetic(self.h, seed))
 
@@ -339,6 +359,41 @@ class Observations:
         ctx.check(ctx.L.mdc_obs_create(ctx.h, len(x), _ptr(x), _ptr(y), _ptr(z), _ptr(value),
                                        _ptr(err), _ptr(valid), _ptr(gid), C.byref(h)))
         self.h = h
+
+    @classmethod
+    def geographic(cls, ctx: Context, lat, lon, level, value, err, valid=None, gid=None) -> "Observations":
+        """Observations with GEOGRAPHIC locations (degrees, level in the geometry's vertical coordinate); the local
+        selection is then by haversine kilometres (Location.hpp:213-217)."""
+        self = cls.__new__(cls)
+        self.ctx = ctx
+        lat = np.ascontiguousarray(lat, dtype=np.float64)
+        lon = np.ascontiguousarray(lon, dtype=np.float64)
+        level = np.ascontiguousarray(level, dtype=np.float64) if level is not None else None
+        value = np.ascontiguousarray(value, dtype=np.float64)
+        err = np.ascontiguousarray(err, dtype=np.float64)
+        valid = np.ascontiguousarray(valid, dtype=np.uint8) if valid is not None else None
+        gid = np.ascontiguousarray(gid, dtype=np.int64) if gid is not None else None
+        h = C.c_void_p()
+        ctx.check(ctx.L.mdc_obs_create_geographic(ctx.h, len(lat), _ptr(lat), _ptr(lon), _ptr(level), _ptr(value),
+                                                  _ptr(err), _ptr(valid), _ptr(gid), C.byref(h)))
+        self.h = h
+        return self
+
+    def set_variables(self, var):
+        """State variable each observation observes (index into Ensemble.set_variables); None = variable 0."""
+        v = np.ascontiguousarray(var, dtype=np.int32) if var is not None else None
+        assert v is None or len(v) == self.size()
+        self.ctx.check(self.ctx.L.mdc_obs_set_variables(self.h, _ptr(v)))
+
+    def locate(self, ens: "Ensemble"):
+        """Nearest grid point and level of every geographic observation (IdentityObsOperator.hpp:484-530)."""
+        self.ctx.check(self.ctx.L.mdc_obs_locate(self.h, ens.h))
+
+    def grid_coords(self):
+        P = self.size()
+        x, y, z = (np.empty(P, np.int32) for _ in range(3))
+        self.ctx.check(self.ctx.L.mdc_obs_download_grid_coords(self.h, _ptr(x), _ptr(y), _ptr(z)))
+        return x, y, z
 
     def assign(self, x, y, z, value, err, valid=None, gid=None):
         x = np.ascontiguousarray(x, dtype=np.int32)

@@ -1,0 +1,206 @@
+// C-ABI entry points for GEOGRAPHIC observations and multi-variable states; included by
+// mdc_api.cu inside its extern "C" block, before the index / LETKF entry points that call geo_prepare_index().
+
+int mdc_ens_set_geography(mdc_ens* e, const double* lat, const double* lon, int nlev, const double* vertical_coords) {
+  mdc_ctx* ctx = e->ctx;
+  if (!lat || !lon) MDC_FAIL(ctx, MDC_ERR_INVALID, "set_geography: null coordinate arrays");
+  if (nlev < 0 || (nlev > 0 && !vertical_coords)) MDC_FAIL(ctx, MDC_ERR_INVALID, "set_geography: bad vertical coordinates");
+  MDC_CUDA(ctx, cudaSetDevice(ctx->device));
+  const size_t G = (size_t)e->nx * e->ny;
+  // extents on the host: circular mean longitude (the unwrap centre), then min / max of the unwrapped offsets
+  double sx = 0.0, sy = 0.0, latmin = 1e300, latmax = -1e300;
+  const double rad = 3.14159265358979323846 / 180.0;
+  for (size_t i = 0; i < G; ++i) {
+    if (!(lat[i] >= -90.0 && lat[i] <= 90.0) || !std::isfinite(lon[i]))
+      MDC_FAIL(ctx, MDC_ERR_INVALID, "set_geography: column %zu has latitude %g longitude %g", i, lat[i], lon[i]);
+    sx += std::cos(lon[i] * rad); sy += std::sin(lon[i] * rad);
+    latmin = std::min(latmin, lat[i]); latmax = std::max(latmax, lat[i]);
+  }
+  const double lon_c = (sx == 0.0 && sy == 0.0) ? 0.0 : std::atan2(sy, sx) / rad;
+  double umin = 1e300, umax = -1e300;
+  for (size_t i = 0; i < G; ++i) {
+    const double u = (lon[i] - lon_c) - 360.0 * std::rint((lon[i] - lon_c) / 360.0);
+    umin = std::min(umin, u); umax = std::max(umax, u);
+  }
+  if (!e->glat && (dev_alloc(ctx, &e->glat, G) || dev_alloc(ctx, &e->glon, G))) return MDC_ERR_CUDA;
+  MDC_CUDA(ctx, cudaMemcpyAsync(e->glat, lat, G * 8, cudaMemcpyHostToDevice, ctx->stream));
+  MDC_CUDA(ctx, cudaMemcpyAsync(e->glon, lon, G * 8, cudaMemcpyHostToDevice, ctx->stream));
+  if (e->vcoord) { cudaFree(e->vcoord); e->vcoord = nullptr; }
+  e->nvcoord = nlev;
+  if (nlev > 0) {
+    if (dev_alloc(ctx, &e->vcoord, (size_t)nlev)) return MDC_ERR_CUDA;
+    MDC_CUDA(ctx, cudaMemcpyAsync(e->vcoord, vertical_coords, (size_t)nlev * 8, cudaMemcpyHostToDevice, ctx->stream));
+  }
+  MDC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  e->geo = true;
+  e->geo_lon_c = lon_c; e->geo_umin = umin; e->geo_umax = umax; e->geo_latmin = latmin; e->geo_latmax = latmax;
+  return MDC_OK;
+}
+
+int mdc_ens_set_variables(mdc_ens* e, int nvar, const int32_t* var_nlev) {
+  mdc_ctx* ctx = e->ctx;
+  if (nvar < 1 || nvar > MDC_MAX_VARS || !var_nlev) MDC_FAIL(ctx, MDC_ERR_INVALID, "set_variables: 1 <= nvar <= %d", MDC_MAX_VARS);
+  int total = 0, nzg = 1;
+  for (int v = 0; v < nvar; ++v) {
+    if (var_nlev[v] < 1) MDC_FAIL(ctx, MDC_ERR_INVALID, "set_variables: variable %d has %d levels", v, var_nlev[v]);
+    total += var_nlev[v]; nzg = std::max(nzg, (int)var_nlev[v]);
+  }
+  if (total != e->nz) MDC_FAIL(ctx, MDC_ERR_INVALID, "set_variables: levels sum to %d, the ensemble has %d", total, e->nz);
+  for (int v = 0; v < nvar; ++v)
+    if (var_nlev[v] != 1 && var_nlev[v] != nzg)
+      MDC_FAIL(ctx, MDC_ERR_UNSUPPORTED, "set_variables: variable %d has %d levels; 3-D variables must share the geometry's %d levels (staggered W grids are not supported)", v, var_nlev[v], nzg);
+  MDC_CUDA(ctx, cudaSetDevice(ctx->device));
+  std::vector<int32_t> map((size_t)e->nz);
+  int off = 0;
+  for (int v = 0; v < nvar; ++v) {
+    e->var_off[v] = off; e->var_nlev[v] = var_nlev[v];
+    for (int l = 0; l < var_nlev[v]; ++l) map[(size_t)off + l] = l;
+    off += var_nlev[v];
+  }
+  if (!e->levmap && dev_alloc(ctx, &e->levmap, (size_t)e->nz)) return MDC_ERR_CUDA;
+  MDC_CUDA(ctx, cudaMemcpyAsync(e->levmap, map.data(), (size_t)e->nz * 4, cudaMemcpyHostToDevice, ctx->stream));
+  MDC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  e->nvar = nvar; e->nzg = nzg;
+  return MDC_OK;
+}
+
+int mdc_obs_set_variables(mdc_obs* o, const int32_t* var) {
+  mdc_ctx* ctx = o->ctx;
+  MDC_CUDA(ctx, cudaSetDevice(ctx->device));
+  if (o->P != o->P_own) MDC_FAIL(ctx, MDC_ERR_UNSUPPORTED, "obs_set_variables: not with halo rows");
+  if (o->var) { cudaFree(o->var); o->var = nullptr; }
+  o->var_max = 0;
+  o->have_hx = false;
+  if (!var || o->P == 0) return MDC_OK;
+  int vmax = 0;
+  for (int64_t i = 0; i < o->P; ++i) {
+    if (var[i] < 0 || var[i] >= MDC_MAX_VARS) MDC_FAIL(ctx, MDC_ERR_INVALID, "obs_set_variables: observation %lld observes variable %d", (long long)i, var[i]);
+    vmax = std::max(vmax, (int)var[i]);
+  }
+  if (dev_alloc(ctx, &o->var, (size_t)o->P)) return MDC_ERR_CUDA;
+  MDC_CUDA(ctx, cudaMemcpyAsync(o->var, var, (size_t)o->P * 4, cudaMemcpyHostToDevice, ctx->stream));
+  MDC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  o->var_max = vmax;
+  return MDC_OK;
+}
+
+int mdc_obs_create_geographic(mdc_ctx* ctx, int64_t P, const double* lat, const double* lon, const double* level,
+                              const double* value, const double* err, const uint8_t* valid, const int64_t* gid,
+                              mdc_obs** out) {
+  if (!ctx || !out) return MDC_ERR_INVALID;
+  *out = nullptr;
+  if (P > 0 && (!lat || !lon)) MDC_FAIL(ctx, MDC_ERR_INVALID, "mdc_obs_create_geographic: null coordinates");
+  for (int64_t i = 0; i < P; ++i)
+    if (!(lat[i] >= -90.0 && lat[i] <= 90.0) || !std::isfinite(lon[i]))
+      MDC_FAIL(ctx, MDC_ERR_INVALID, "mdc_obs_create_geographic: observation %lld has latitude %g longitude %g", (long long)i, lat[i], lon[i]);
+  // the grid coordinates are filled by mdc_obs_locate(); create the store with zeros
+  std::vector<int32_t> zero((size_t)std::max<int64_t>(P, 1), 0);
+  mdc_obs* o = nullptr;
+  if (int rc = mdc_obs_create(ctx, P, zero.data(), zero.data(), zero.data(), value, err, valid, gid, &o)) return rc;
+  o->geo = true;
+  const size_t n = (size_t)std::max<int64_t>(P, 1);
+  if (dev_alloc(ctx, &o->lat, n) || dev_alloc(ctx, &o->lon, n) || dev_alloc(ctx, &o->lev, n) ||
+      dev_alloc(ctx, &o->qx, n) || dev_alloc(ctx, &o->qy, n)) { mdc_obs_destroy(o); return MDC_ERR_CUDA; }
+  if (P > 0) {
+    cudaStream_t s = ctx->stream;
+    MDC_CUDA(ctx, cudaMemcpyAsync(o->lat, lat, P * 8, cudaMemcpyHostToDevice, s));
+    MDC_CUDA(ctx, cudaMemcpyAsync(o->lon, lon, P * 8, cudaMemcpyHostToDevice, s));
+    if (level) MDC_CUDA(ctx, cudaMemcpyAsync(o->lev, level, P * 8, cudaMemcpyHostToDevice, s));
+    else MDC_CUDA(ctx, cudaMemsetAsync(o->lev, 0, P * 8, s));
+    MDC_CUDA(ctx, cudaStreamSynchronize(s));
+  }
+  *out = o;
+  return MDC_OK;
+}
+
+int mdc_obs_locate(mdc_obs* o, mdc_ens* e) {
+  mdc_ctx* ctx = o->ctx;
+  if (e->ctx != ctx) MDC_FAIL(ctx, MDC_ERR_INVALID, "obs_locate: ens/obs belong to different contexts");
+  if (!o->geo) MDC_FAIL(ctx, MDC_ERR_INVALID, "obs_locate: the observations carry GRID coordinates already");
+  if (!e->geo) MDC_FAIL(ctx, MDC_ERR_INVALID, "obs_locate: the ensemble has no geography (mdc_ens_set_geography)");
+  if (e->gnx != e->nx || e->gny != e->ny)
+    MDC_FAIL(ctx, MDC_ERR_UNSUPPORTED, "obs_locate: geographic observations are not supported on a decomposed domain");
+  MDC_CUDA(ctx, cudaSetDevice(ctx->device));
+  if (o->P > 0) {
+    geo_locate_kernel<<<mdc_div_up(o->P, 256), 256, 0, ctx->stream>>>(o->P, o->lat, o->lon, o->lev, e->glat, e->glon,
+                                                                    (int64_t)e->nx * e->ny, e->nx, e->vcoord, e->nvcoord,
+                                                                    o->x, o->y, o->z);
+    MDC_LAUNCH_CHECK(ctx);
+  }
+  o->located = true;
+  o->have_hx = false;
+  o->index_valid = false;   // the index carries the located levels
+  return MDC_OK;
+}
+
+int mdc_obs_download_grid_coords(mdc_obs* o, int32_t* x, int32_t* y, int32_t* z) {
+  mdc_ctx* ctx = o->ctx;
+  if (o->geo && !o->located) MDC_FAIL(ctx, MDC_ERR_INVALID, "obs_download_grid_coords: call mdc_obs_locate first");
+  MDC_CUDA(ctx, cudaSetDevice(ctx->device));
+  const size_t P = (size_t)o->P;
+  if (x) MDC_CUDA(ctx, cudaMemcpyAsync(x, o->x, P * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  if (y) MDC_CUDA(ctx, cudaMemcpyAsync(y, o->y, P * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  if (z) MDC_CUDA(ctx, cudaMemcpyAsync(z, o->z, P * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  MDC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return MDC_OK;
+}
+
+static int index_build_impl(mdc_obs* o, int cell);
+
+// Lattice + bucket index for a haversine selection of `radius` kilometres around the columns of `e`.
+static int geo_prepare_index(mdc_obs* o, mdc_ens* e, double radius) {
+  mdc_ctx* ctx = o->ctx;
+  if (!e->geo) MDC_FAIL(ctx, MDC_ERR_INVALID, "geographic observations need an ensemble with geography (mdc_ens_set_geography)");
+  if (e->gnx != e->nx || e->gny != e->ny || e->own_nx != e->nx || e->own_ny != e->ny)
+    MDC_FAIL(ctx, MDC_ERR_UNSUPPORTED, "geographic observations are not supported on a decomposed domain");
+  if (o->P != o->P_own) MDC_FAIL(ctx, MDC_ERR_UNSUPPORTED, "geographic observations do not take halo rows");
+  MDC_CUDA(ctx, cudaSetDevice(ctx->device));
+  const double pi = 3.14159265358979323846;
+  // An observation within `radius` km (great circle, R = 6371 km, Location.hpp:325) of a column at latitude phi
+  // differs from it by at most delta = radius / R in latitude and asin(sin delta / cos phi) in longitude.
+  const double delta = std::max(radius, 0.0) / 6371.0;
+  const double phic = std::max(std::fabs(e->geo_latmin), std::fabs(e->geo_latmax)) * pi / 180.0;
+  if (!(phic + delta < 0.5 * pi * (1.0 - 1e-6)))
+    MDC_FAIL(ctx, MDC_ERR_UNSUPPORTED, "geographic selection: a %g km circle around latitude %g reaches a pole", radius, phic * 180.0 / pi);
+  const double dlat = delta * 180.0 / pi * (1.0 + 1e-9) + 1e-12;
+  const double dlon = std::asin(std::min(1.0, std::sin(delta) / std::cos(phic))) * 180.0 / pi * (1.0 + 1e-9) + 1e-12;
+  if (!(e->geo_umax + dlon < 180.0 && e->geo_umin - dlon > -180.0))
+    MDC_FAIL(ctx, MDC_ERR_UNSUPPORTED, "geographic selection: the domain (+ radius) spans the whole longitude circle; regional domains only");
+  const int R = GEO_SUB + 2;
+  GeoLattice g;
+  g.lon_c = e->geo_lon_c; g.u0 = e->geo_umin; g.lat0 = e->geo_latmin;
+  const double ext_x = e->geo_umax - e->geo_umin, ext_y = e->geo_latmax - e->geo_latmin;
+  // no finer than 1/8192 of the domain: bounds the cell count for a radius that is tiny against the domain (a coarser
+  // lattice only adds candidates; the haversine test decides)
+  const double qx = std::max({dlon / GEO_SUB, ext_x / 8192.0, 1e-9}), qy = std::max({dlat / GEO_SUB, ext_y / 8192.0, 1e-9});
+  g.inv_qx = 1.0 / qx; g.inv_qy = 1.0 / qy;
+  // columns sit in [-1, floor(ext / q) + 1] (rounding); an observation inside the radius is within R of its column
+  g.lo_x = -(double)(R + 1); g.hi_x = std::floor(ext_x * g.inv_qx) + (double)(R + 2);
+  g.lo_y = -(double)(R + 1); g.hi_y = std::floor(ext_y * g.inv_qy) + (double)(R + 2);
+  const size_t G = (size_t)e->nx * e->ny;
+  if (G > o->cq_cap) {
+    cudaFree(o->cqx); cudaFree(o->cqy);
+    o->cq_cap = 0;
+    if (dev_alloc(ctx, &o->cqx, G) || dev_alloc(ctx, &o->cqy, G)) return MDC_ERR_CUDA;
+    o->cq_cap = G;
+  }
+  geo_quantise_kernel<<<grid_for(ctx, (int64_t)G, 256, 8), 256, 0, ctx->stream>>>((int64_t)G, e->glat, e->glon, g, o->cqx, o->cqy);
+  MDC_LAUNCH_CHECK(ctx);
+  if (o->P > 0) {
+    geo_quantise_kernel<<<grid_for(ctx, o->P, 256, 8), 256, 0, ctx->stream>>>(o->P, o->lat, o->lon, g, o->qx, o->qy);
+    MDC_LAUNCH_CHECK(ctx);
+  }
+  if (int rc = index_build_impl(o, R)) return rc;
+  if ((size_t)o->P > o->sgeo_cap) {
+    cudaFree(o->slat); cudaFree(o->slon);
+    o->sgeo_cap = 0;
+    if (dev_alloc(ctx, &o->slat, (size_t)o->P) || dev_alloc(ctx, &o->slon, (size_t)o->P)) return MDC_ERR_CUDA;
+    o->sgeo_cap = (size_t)o->P;
+  }
+  if (o->P > 0) {
+    geo_gather_sorted_kernel<<<grid_for(ctx, o->P, 256, 8), 256, 0, ctx->stream>>>(o->P, o->sorted_row, o->lat, o->lon, o->slat, o->slon);
+    MDC_LAUNCH_CHECK(ctx);
+  }
+  o->geo_reach = R; o->geo_radius = radius; o->geo_ens = e;
+  return MDC_OK;
+}

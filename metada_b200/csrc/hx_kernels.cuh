@@ -10,9 +10,15 @@
 #pragma once
 #include "mdc_internal.cuh"
 
+#define MDC_MAX_VARS 16
 struct HxGeom {
-  int nx, ny, nz, k;          // local grid
+  int nx, ny, nz, k;          // local grid; nz = all levels of all variables
   int gx0, gy0, gnx, gny;     // placement in global grid
+  // multi-variable states (WRF-shaped, [var][lev][y][x] per member): the neighbour search runs on the geometry's
+  // nzg levels (IdentityObsOperator.hpp:684-690), the value is read from the observation's variable, whose 2-D
+  // fields ignore the level (:701-711).  nvar = 0: one variable of nz levels.
+  int nzg, nvar;
+  int var_off[MDC_MAX_VARS], var_nlev[MDC_MAX_VARS];
 };
 
 __device__ __forceinline__ double hx_dist2(double x, double y, int ii, int jj) {
@@ -27,7 +33,8 @@ __device__ __forceinline__ double hx_dist3(double x, double y, double z, int ii,
 template <int WARPS>
 __global__ void hx_idw4_kernel(const double* __restrict__ X, HxGeom g, int64_t P,
                                const int32_t* __restrict__ ox, const int32_t* __restrict__ oy,
-                               const int32_t* __restrict__ oz, const uint8_t* __restrict__ valid,
+                               const int32_t* __restrict__ oz, const int32_t* __restrict__ ovar,
+                               const uint8_t* __restrict__ valid,
                                const double* __restrict__ oval, double* __restrict__ Y,
                                double* __restrict__ ybar, double* __restrict__ Yp,
                                double* __restrict__ d, int* __restrict__ err_flag) {
@@ -44,11 +51,13 @@ __global__ void hx_idw4_kernel(const double* __restrict__ X, HxGeom g, int64_t P
       // clamp to the GLOBAL grid bounds (:598-600)
       double x = fmax(0.0, fmin((double)(g.gnx - 1), (double)ox[i]));
       double y = fmax(0.0, fmin((double)(g.gny - 1), (double)oy[i]));
-      double z = fmax(0.0, fmin((double)(g.nz - 1), (double)oz[i]));
+      double z = fmax(0.0, fmin((double)(g.nzg - 1), (double)oz[i]));
+      int voff = 0, vn = g.nz;
+      if (g.nvar > 0) { const int v = ovar ? ovar[i] : 0; voff = g.var_off[v]; vn = g.var_nlev[v]; }
       int i0 = (int)floor(x), j0 = (int)floor(y), k0 = (int)floor(z);
-      int i1 = min(i0 + 1, g.gnx - 1), j1 = min(j0 + 1, g.gny - 1), k1 = min(k0 + 1, g.nz - 1);
+      int i1 = min(i0 + 1, g.gnx - 1), j1 = min(j0 + 1, g.gny - 1), k1 = min(k0 + 1, g.nzg - 1);
       double dist[8];
-      if (g.nz == 1) {
+      if (g.nzg == 1) {
         ii[0] = i0; jj[0] = j0; ii[1] = i1; jj[1] = j0; ii[2] = i0; jj[2] = j1; ii[3] = i1; jj[3] = j1;
 #pragma unroll
         for (int c = 0; c < 4; ++c) { kk[c] = 0; dist[c] = hx_dist2(x, y, ii[c], jj[c]); }
@@ -81,7 +90,7 @@ __global__ void hx_idw4_kernel(const double* __restrict__ X, HxGeom g, int64_t P
           if (lane == 0) atomicExch(err_flag, 1);   // obs needs state outside this rank's tile+halo
           lx = max(0, min(g.nx - 1, lx)); ly = max(0, min(g.ny - 1, ly));
         }
-        base[c] = (((int64_t)ly * g.nx + lx) * g.nz + kk[c]) * g.k;
+        base[c] = (((int64_t)ly * g.nx + lx) * g.nz + voff + (vn > 1 ? kk[c] : 0)) * g.k;
       }
     }
     for (int m = lane; m < g.k; m += 32) {

@@ -118,7 +118,34 @@ struct IndexView {
   const int32_t* sorted_row;
   const int32_t *sx, *sy, *sz;
   int cell, ncx, ncy, xmin, ymin;
+  // GEOGRAPHIC observations (geo_kernels.cuh): the index runs on a quantised lat/lon lattice (sx, sy = lattice
+  // coordinates of the observations, cqx, cqy = of the columns, reach = conservative integer reach of the selection
+  // radius in lattice units) and the selection test is the haversine distance of the true coordinates.
+  int geo, reach;
+  const int32_t *cqx, *cqy;      // [local column]
+  const double *clat, *clon;     // [local column] degrees
+  const double *slat, *slon;     // [sorted position] degrees
+  const int32_t* levmap;         // [total level] -> level inside its variable (multi-variable states), or nullptr
 };
+
+// integer reach of the selection radius in index units, and the column's coordinates in the index
+// EXT = false is the GRID / single-variable path, compiled exactly as before these fields existed (the column
+// kernels' register allocation is fragile); EXT = true instantiations serve geographic and multi-variable analyses.
+template <bool EXT>
+__device__ __forceinline__ int index_reach(const IndexView& iv, double radius) {
+  if constexpr (EXT) return iv.geo ? iv.reach : (int)floor(radius);
+  else return (int)floor(radius);
+}
+template <bool EXT>
+__device__ __forceinline__ void index_col_coords(const IndexView& iv, long long col, int& gx, int& gy) {
+  if constexpr (EXT) { if (iv.geo) { gx = iv.cqx[col]; gy = iv.cqy[col]; } }
+}
+// level of a state level inside its variable (vertical localisation distances are per variable)
+template <bool EXT>
+__device__ __forceinline__ int index_level(const IndexView& iv, int lt) {
+  if constexpr (EXT) return iv.levmap ? iv.levmap[lt] : lt;
+  else return lt;
+}
 
 // Candidate range of one cell row for a column at global (gx, gy) and integer reach R = floor(r).
 __device__ __forceinline__ void index_row_range(const IndexView& iv, int gx, int R, int cy,
@@ -136,24 +163,55 @@ __device__ __forceinline__ void index_cy_range(const IndexView& iv, int gy, int 
   cy1 = min(y1 / iv.cell, iv.ncy - 1);
 }
 
-// Location::distance_to(...) <= radius (Location.hpp:204-211, LETKF.hpp:161-162), bit-exact:
+// Location::haversine (Location.hpp:349-357) in the reference's operation order: explicit _rn arithmetic (no FMA
+// contraction), CUDA's double sin / cos / atan2 (<= 2 ulp; glibc's are <= 1 ulp, so a distance can differ from the
+// host's in the last bits -- the selection differs only for a pair within that of the radius).
+__device__ __forceinline__ double geo_deg2rad(double deg) { return __ddiv_rn(__dmul_rn(deg, 3.14159265358979323846), 180.0); }
+__device__ __noinline__ double geo_haversine(double lat1, double lon1, double lat2, double lon2) {
+  const double dlat = geo_deg2rad(__dsub_rn(lat2, lat1)), dlon = geo_deg2rad(__dsub_rn(lon2, lon1));
+  const double s1 = sin(__ddiv_rn(dlat, 2.0)), s2 = sin(__ddiv_rn(dlon, 2.0));
+  const double a = __dadd_rn(__dmul_rn(s1, s1),
+                             __dmul_rn(__dmul_rn(__dmul_rn(cos(geo_deg2rad(lat1)), cos(geo_deg2rad(lat2))), s2), s2));
+  const double c = __dmul_rn(2.0, atan2(__dsqrt_rn(a), __dsqrt_rn(__dsub_rn(1.0, a))));
+  return __dmul_rn(6371.0, c);
+}
+// out of line and fed by plain pointers (only EXT instantiations reference it)
+__device__ __noinline__ double geo_distance(const double* __restrict__ clat, const double* __restrict__ clon,
+                                            const double* __restrict__ slat, const double* __restrict__ slon,
+                                            long long col, int a) {
+  return geo_haversine(clat[col], clon[col], slat[a], slon[a]);
+}
+
+// Location::distance_to(...) <= radius (Location.hpp:204-230, LETKF.hpp:161-162).  GRID: bit-exact --
 // dx, dy are exact integers, dx*dx+dy*dy is exact in FP64, sqrt is IEEE correctly rounded.
-__device__ __forceinline__ bool index_within(int gx, int gy, int ox, int oy, double radius,
+// GEOGRAPHIC: haversine kilometres between the column `col` and the observation at sorted position `a`.
+template <bool EXT>
+__device__ __forceinline__ bool index_within(const IndexView& iv, long long col, int a, int gx, int gy, double radius,
                                              double* dist_out) {
-  double dx = (double)(gx - ox), dy = (double)(gy - oy);
-  double dist = __dsqrt_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)));
+  double dist;
+  bool geo = false;
+  if constexpr (EXT) geo = iv.geo != 0;
+  if (geo) {
+    dist = geo_distance(iv.clat, iv.clon, iv.slat, iv.slon, col, a);
+  } else {
+    double dx = (double)(gx - iv.sx[a]), dy = (double)(gy - iv.sy[a]);
+    dist = __dsqrt_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)));
+  }
   *dist_out = dist;
   return dist <= radius;
 }
 
 // counts per owned column (tests: bit-exact against the brute-force oracle)
+template <bool EXT>
 __global__ void index_query_counts_kernel(IndexView iv, int nx, int own_nx, int own_ny, int gx0,
                                           int gy0, double radius, int32_t* __restrict__ counts) {
   int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= (int64_t)own_nx * own_ny) return;
   int lx = (int)(t % own_nx), ly = (int)(t / own_nx);
   int gx = gx0 + lx, gy = gy0 + ly;
-  int R = (int)floor(radius);
+  const long long col = (long long)ly * nx + lx;
+  index_col_coords<EXT>(iv, col, gx, gy);
+  int R = index_reach<EXT>(iv, radius);
   int cnt = 0;
   if (radius >= 0.0) {
     int cy0, cy1;
@@ -163,14 +221,15 @@ __global__ void index_query_counts_kernel(IndexView iv, int nx, int own_nx, int 
       index_row_range(iv, gx, R, cy, b, e);
       for (int a = b; a < e; ++a) {
         double dist;
-        cnt += index_within(gx, gy, iv.sx[a], iv.sy[a], radius, &dist) ? 1 : 0;
+        cnt += index_within<EXT>(iv, col, a, gx, gy, radius, &dist) ? 1 : 0;
       }
     }
   }
-  counts[(int64_t)ly * nx + lx] = cnt;
+  counts[col] = cnt;
 }
 
 // explicit lists (global ids, kernel order) for selected columns
+template <bool EXT>
 __global__ void index_query_lists_kernel(IndexView iv, const int64_t* __restrict__ gid, int nx,
                                          int gx0, int gy0, double radius,
                                          const int64_t* __restrict__ cols, int64_t ncols, int cap,
@@ -179,7 +238,8 @@ __global__ void index_query_lists_kernel(IndexView iv, const int64_t* __restrict
   if (t >= ncols) return;
   int64_t col = cols[t];
   int gx = gx0 + (int)(col % nx), gy = gy0 + (int)(col / nx);
-  int R = (int)floor(radius);
+  index_col_coords<EXT>(iv, col, gx, gy);
+  int R = index_reach<EXT>(iv, radius);
   int cnt = 0;
   if (radius >= 0.0) {
     int cy0, cy1;
@@ -189,7 +249,7 @@ __global__ void index_query_lists_kernel(IndexView iv, const int64_t* __restrict
       index_row_range(iv, gx, R, cy, b, e);
       for (int a = b; a < e; ++a) {
         double dist;
-        if (index_within(gx, gy, iv.sx[a], iv.sy[a], radius, &dist)) {
+        if (index_within<EXT>(iv, col, a, gx, gy, radius, &dist)) {
           if (cnt < cap) lists[t * cap + cnt] = gid[iv.sorted_row[a]];
           ++cnt;
         }

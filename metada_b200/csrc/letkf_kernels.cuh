@@ -227,15 +227,16 @@ __global__ void __launch_bounds__(LK_THREADS) letkf_column_kernel(ColParams P) {
   const double km1 = (double)(k - 1);
   const bool per_level = P.radius_v > 0.0;
   const int nxf = per_level ? nz : 1;
-  const int R = (int)floor(P.radius);
+  const int R = index_reach<false>(P.iv, P.radius);
   const long long ncols = P.cols ? P.ncols : (long long)P.own_nx * P.own_ny;
 
   for (long long ci = blockIdx.x; ci < ncols; ci += gridDim.x) {
     int lx, ly;
     if (P.cols) { long long c = P.cols[ci]; lx = (int)(c % P.nx); ly = (int)(c / P.nx); }
     else { lx = (int)(ci % P.own_nx); ly = (int)(ci / P.own_nx); }
-    const int gx = P.gx0 + lx, gy = P.gy0 + ly;
+    int gx = P.gx0 + lx, gy = P.gy0 + ly;
     const long long col = (long long)ly * P.nx + lx;
+    index_col_coords<false>(P.iv, col, gx, gy);
     double* Xg = P.X + col * nz * k;
     int col_sweeps = 0;
     long long col_npl = 0;
@@ -261,10 +262,10 @@ __global__ void __launch_bounds__(LK_THREADS) letkf_column_kernel(ColParams P) {
           double rho = 1.0;
           if (a < re) {
             double dist;
-            sel = index_within(gx, gy, P.iv.sx[a], P.iv.sy[a], P.radius, &dist);
+            sel = index_within<false>(P.iv, col, a, gx, gy, P.radius, &dist);
             double dv = 0.0;
             if (sel && per_level) {
-              dv = fabs((double)(P.iv.sz[a] - lt));
+              dv = fabs((double)(P.iv.sz[a] - index_level<false>(P.iv, lt)));
               sel = dv <= P.radius_v;
             }
             if (sel && P.mode == MDC_MODE_CANONICAL && P.loc != MDC_LOC_CUTOFF) {

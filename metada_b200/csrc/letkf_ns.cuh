@@ -321,7 +321,7 @@ __global__ void __launch_bounds__(NS_THREADS) letkf_ns_kernel(ColParams P, int l
   const double km1 = (double)(k - 1);
   const bool per_level = P.radius_v > 0.0;
   const int nxf = per_level ? nz : 1;
-  const int R = (int)floor(P.radius);
+  const int R = index_reach<false>(P.iv, P.radius);
   const bool redo = P.redo_consume != 0;
   const long long ncols = redo ? (long long)*P.redo_count : (P.cols ? P.ncols : (long long)P.own_nx * P.own_ny);
   const NsTiles<NTW> st = ns_tiles<NTW>(kp, warp);
@@ -334,8 +334,9 @@ __global__ void __launch_bounds__(NS_THREADS) letkf_ns_kernel(ColParams P, int l
       lx = (int)(c % P.nx); ly = (int)(c / P.nx);
     } else if (P.cols) { long long c = P.cols[ci]; lx = (int)(c % P.nx); ly = (int)(c / P.nx); }
     else { lx = (int)(ci % P.own_nx); ly = (int)(ci / P.own_nx); }
-    const int gx = P.gx0 + lx, gy = P.gy0 + ly;
+    int gx = P.gx0 + lx, gy = P.gy0 + ly;
     const long long col = (long long)ly * P.nx + lx;
+    index_col_coords<false>(P.iv, col, gx, gy);
     double* Xg = P.X + col * nz * k;
     int col_iters = 0;
     long long col_npl = 0;
@@ -364,10 +365,10 @@ __global__ void __launch_bounds__(NS_THREADS) letkf_ns_kernel(ColParams P, int l
           int orow = 0;
           if (a < re) {
             double dist;
-            sel = index_within(gx, gy, P.iv.sx[a], P.iv.sy[a], P.radius, &dist);
+            sel = index_within<false>(P.iv, col, a, gx, gy, P.radius, &dist);
             double dv = 0.0;
             if (sel && per_level) {
-              dv = fabs((double)(P.iv.sz[a] - lt));
+              dv = fabs((double)(P.iv.sz[a] - index_level<false>(P.iv, lt)));
               sel = dv <= P.radius_v;
             }
             if (sel) {

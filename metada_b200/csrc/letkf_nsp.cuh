@@ -384,7 +384,7 @@ __device__ __noinline__ int nsp_inverse_sqrt(double* Zp, double shift, double fr
 
 // WORK = true: consume the classifying pass's work list (per-level analyses); a separate instantiation
 // because the two extra live values of the list mode push the default kernel into spilling.
-template <int NT, int NTH, int MINB, bool WORK>
+template <int NT, int NTH, int MINB, bool WORK, bool EXT = false>
 __global__ void __launch_bounds__(NTH, MINB) letkf_nsp_kernel(ColParams P, int lch) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   constexpr int NW = NTH / 32;
@@ -418,7 +418,7 @@ __global__ void __launch_bounds__(NTH, MINB) letkf_nsp_kernel(ColParams P, int l
   const double sW = sqrt(km1);
   const bool per_level = P.radius_v > 0.0;
   const int nxf = per_level ? nz : 1;
-  const int R = (int)floor(P.radius);
+  const int R = index_reach<EXT>(P.iv, P.radius);
   constexpr bool work = WORK;
   const long long ncols = work ? (long long)*P.work_count : (P.cols ? P.ncols : (long long)P.own_nx * P.own_ny);
   const NspLane L = nsp_lane(lane);
@@ -432,8 +432,9 @@ __global__ void __launch_bounds__(NTH, MINB) letkf_nsp_kernel(ColParams P, int l
       lx = (int)(c % P.nx); ly = (int)(c / P.nx);
     } else if (P.cols) { long long c = P.cols[ci]; lx = (int)(c % P.nx); ly = (int)(c / P.nx); }
     else { lx = (int)(ci % P.own_nx); ly = (int)(ci / P.own_nx); }
-    const int gx = P.gx0 + lx, gy = P.gy0 + ly;
+    int gx = P.gx0 + lx, gy = P.gy0 + ly;
     const long long col = (long long)ly * P.nx + lx;
+    index_col_coords<EXT>(P.iv, col, gx, gy);
     double* Xg = P.X + col * nz * k;
     int col_iters = 0;
     long long col_npl = 0;
@@ -466,10 +467,10 @@ __global__ void __launch_bounds__(NTH, MINB) letkf_nsp_kernel(ColParams P, int l
           int orow = 0;
           if (a < re) {
             double dist;
-            sel = index_within(gx, gy, P.iv.sx[a], P.iv.sy[a], P.radius, &dist);
+            sel = index_within<EXT>(P.iv, col, a, gx, gy, P.radius, &dist);
             double dv = 0.0;
             if (sel && per_level) {
-              dv = fabs((double)(P.iv.sz[a] - lt));
+              dv = fabs((double)(P.iv.sz[a] - index_level<EXT>(P.iv, lt)));
               sel = dv <= P.radius_v;
             }
             if (sel) {

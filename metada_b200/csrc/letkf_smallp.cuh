@@ -36,14 +36,16 @@ struct SpWarpSmem {
 // One transform (col, lt) by the calling warp.  Returns 0: done in observation space (sweeps_out =
 // Jacobi sweeps), 1: no observation in reach, perturbations inflated, 2: too many local observations
 // for this route (nothing written).  p_out = number of local observations.
+template <bool EXT>
 __device__ __forceinline__ int sp_transform(const ColParams& P, SpWarpSmem& W, long long col, int lt, int lane,
                                             int& p_out, int& sweeps_out) {
   const int k = P.k, nz = P.nz, nr = (k + 31) >> 5;
   const bool per_level = P.radius_v > 0.0;
-  const int R = (int)floor(P.radius);
+  const int R = index_reach<EXT>(P.iv, P.radius);
   const double km1 = (double)(k - 1), s = km1 / P.inflation, sW = sqrt(km1), rs = 1.0 / sqrt(s);
   const int lx = (int)(col % P.nx), ly = (int)(col / P.nx);
-  const int gx = P.gx0 + lx, gy = P.gy0 + ly;
+  int gx = P.gx0 + lx, gy = P.gy0 + ly;
+  index_col_coords<EXT>(P.iv, col, gx, gy);
   double* Xg = P.X + col * nz * k;
 
     // ---- selection (same predicate and weights as the other column kernels)
@@ -61,10 +63,10 @@ __device__ __forceinline__ int sp_transform(const ColParams& P, SpWarpSmem& W, l
       int orow = 0;
       if (a < re) {
         double dist;
-        sel = index_within(gx, gy, P.iv.sx[a], P.iv.sy[a], P.radius, &dist);
+        sel = index_within<EXT>(P.iv, col, a, gx, gy, P.radius, &dist);
         double dv = 0.0;
         if (sel && per_level) {
-          dv = fabs((double)(P.iv.sz[a] - lt));
+          dv = fabs((double)(P.iv.sz[a] - index_level<EXT>(P.iv, lt)));
           sel = dv <= P.radius_v;
         }
         if (sel) {
@@ -273,6 +275,7 @@ __device__ __forceinline__ int sp_transform(const ColParams& P, SpWarpSmem& W, l
 }
 
 // Consumer of the packed kernel's list of small transforms (non-per-level analyses).
+template <bool EXT>
 __global__ void __launch_bounds__(SP_WARPS * 32) letkf_smallp_kernel(ColParams P) {
   extern __shared__ __align__(16) unsigned char sp_smem_raw[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -282,7 +285,7 @@ __global__ void __launch_bounds__(SP_WARPS * 32) letkf_smallp_kernel(ColParams P
   for (long long it = (long long)blockIdx.x * SP_WARPS + warp; it < nitems; it += (long long)gridDim.x * SP_WARPS) {
     const long long item = P.small_items[it], col = item / nxf;
     int p = 0, sweeps = 0;
-    const int rc = sp_transform(P, W, col, (int)(item - col * nxf), lane, p, sweeps);
+    const int rc = sp_transform<EXT>(P, W, col, (int)(item - col * nxf), lane, p, sweeps);
     if (lane == 0) {
       if (rc == 2) atomicAdd((unsigned long long*)&P.stats[4], 1ull);   // cannot happen: the producer counted p
       atomicAdd((unsigned long long*)&P.stats[2], (unsigned long long)sweeps);
@@ -309,7 +312,7 @@ __global__ void __launch_bounds__(SP_WARPS * 32) letkf_smallp_classify_kernel(Co
     if (P.cols) col = P.cols[ci];
     else col = (ci / P.own_nx) * P.nx + ci % P.own_nx;
     int p = 0, sweeps = 0;
-    const int rc = sp_transform(P, W, col, lt, lane, p, sweeps);
+    const int rc = sp_transform<false>(P, W, col, lt, lane, p, sweeps);
     if (lane == 0) {
       if (rc == 2) {
         const unsigned slot = atomicAdd(P.work_count, 1u);

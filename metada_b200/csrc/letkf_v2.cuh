@@ -181,7 +181,7 @@ __device__ int jacobi_blocked(double* __restrict__ M, int k, int ks, int max_swe
 
 // Thread grid (NT/16) x 16.  TM = ceil(k/16): tile width (members) of SYRK and of the update;
 // TMY = ceil(k/(NT/16)): tile height of SYRK.  MINB: CTAs per SM the register budget is cut for.
-template <int NT, int MINB, int LG, int RPL, int TM, int TMY>
+template <int NT, int MINB, int LG, int RPL, int TM, int TMY, bool EXT = false>
 __global__ void __launch_bounds__(NT, MINB) letkf_canonical_kernel(ColParams P, int lch) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   constexpr int TL = 3;  // levels per thread tile in the update
@@ -208,7 +208,7 @@ __global__ void __launch_bounds__(NT, MINB) letkf_canonical_kernel(ColParams P, 
   const double km1 = (double)(k - 1);
   const bool per_level = P.radius_v > 0.0;
   const int nxf = per_level ? nz : 1;
-  const int R = (int)floor(P.radius);
+  const int R = index_reach<EXT>(P.iv, P.radius);
   const bool redo = P.redo_consume != 0;
   const long long ncols = redo ? (long long)*P.redo_count : (P.cols ? P.ncols : (long long)P.own_nx * P.own_ny);
   const int ty = tid >> 4, tx = tid & 15;   // SYRK thread grid
@@ -221,8 +221,9 @@ __global__ void __launch_bounds__(NT, MINB) letkf_canonical_kernel(ColParams P, 
       lx = (int)(c % P.nx); ly = (int)(c / P.nx);
     } else if (P.cols) { long long c = P.cols[ci]; lx = (int)(c % P.nx); ly = (int)(c / P.nx); }
     else { lx = (int)(ci % P.own_nx); ly = (int)(ci / P.own_nx); }
-    const int gx = P.gx0 + lx, gy = P.gy0 + ly;
+    int gx = P.gx0 + lx, gy = P.gy0 + ly;
     const long long col = (long long)ly * P.nx + lx;
+    index_col_coords<EXT>(P.iv, col, gx, gy);
     double* Xg = P.X + col * nz * k;
     int col_sweeps = 0;
     long long col_npl = 0;
@@ -251,10 +252,10 @@ __global__ void __launch_bounds__(NT, MINB) letkf_canonical_kernel(ColParams P, 
           double rho = 1.0;
           if (a < re) {
             double dist;
-            sel = index_within(gx, gy, P.iv.sx[a], P.iv.sy[a], P.radius, &dist);
+            sel = index_within<EXT>(P.iv, col, a, gx, gy, P.radius, &dist);
             double dv = 0.0;
             if (sel && per_level) {
-              dv = fabs((double)(P.iv.sz[a] - lt));
+              dv = fabs((double)(P.iv.sz[a] - index_level<EXT>(P.iv, lt)));
               sel = dv <= P.radius_v;
             }
             if (sel && P.loc != MDC_LOC_CUTOFF) {

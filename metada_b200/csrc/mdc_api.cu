@@ -9,6 +9,7 @@
 
 #include "bench_kernels.cuh"
 #include "ens_kernels.cuh"
+#include "geo_kernels.cuh"
 #include "global_kernels.cuh"
 #include "hx_kernels.cuh"
 #include "index_kernels.cuh"
@@ -192,6 +193,7 @@ int mdc_ens_destroy(mdc_ens* e) {
   cudaFree(e->X);
   if (e->mean) cudaFree(e->mean);
   if (e->stage) cudaFree(e->stage);
+  cudaFree(e->glat); cudaFree(e->glon); cudaFree(e->vcoord); cudaFree(e->levmap);
   delete e;
   return MDC_OK;
 }
@@ -448,6 +450,7 @@ int mdc_obs_assign(mdc_obs* o, int64_t P, const int32_t* x, const int32_t* y, co
   mdc_ctx* ctx = o->ctx;
   if (P < 0 || P > INT32_MAX / 2) MDC_FAIL(ctx, MDC_ERR_INVALID, "mdc_obs_assign: bad P");
   if (P > 0 && (!x || !y || !value || !err)) MDC_FAIL(ctx, MDC_ERR_INVALID, "mdc_obs_assign: null arrays");
+  if (o->geo || o->var) MDC_FAIL(ctx, MDC_ERR_UNSUPPORTED, "mdc_obs_assign: not for geographic / per-variable observation stores");
   MDC_CUDA(ctx, cudaSetDevice(ctx->device));
   o->P = 0;                      // nothing to preserve when growing
   if (int rc = obs_reserve(o, std::max<int64_t>(P, 1), o->k)) return rc;
@@ -481,6 +484,8 @@ int mdc_obs_destroy(mdc_obs* o) {
   obs_free_arrays(o);
   cudaFree(o->cell_start); cudaFree(o->cell_fill); cudaFree(o->sorted_row);
   cudaFree(o->sx); cudaFree(o->sy); cudaFree(o->sz); cudaFree(o->key);
+  cudaFree(o->lat); cudaFree(o->lon); cudaFree(o->lev); cudaFree(o->var); cudaFree(o->qx); cudaFree(o->qy);
+  cudaFree(o->cqx); cudaFree(o->cqy); cudaFree(o->slat); cudaFree(o->slon);
   delete o;
   return MDC_OK;
 }
@@ -497,14 +502,21 @@ int mdc_hx_idw4(mdc_ens* e, mdc_obs* o) {
     o->P = o->P_own;
     o->index_valid = false;
   }
+  if (o->geo && !o->located)   // nearest grid point of every observation (IdentityObsOperator.hpp:241-248, 484-530)
+    if (int rc = mdc_obs_locate(o, e)) return rc;
+  if (o->var && e->nvar == 0) MDC_FAIL(ctx, MDC_ERR_INVALID, "hx: the observations name state variables, the ensemble has none (mdc_ens_set_variables)");
+  if (o->var && o->var_max >= e->nvar) MDC_FAIL(ctx, MDC_ERR_INVALID, "hx: an observation observes variable %d, the ensemble has %d", o->var_max, e->nvar);
   if (int rc = obs_reserve(o, o->cap, e->k)) return rc;
   if (o->P == 0) { o->have_hx = true; return MDC_OK; }
   constexpr int W = 8;
-  HxGeom g{e->nx, e->ny, e->nz, e->k, e->gx0, e->gy0, e->gnx, e->gny};
+  HxGeom g{};
+  g.nx = e->nx; g.ny = e->ny; g.nz = e->nz; g.k = e->k; g.gx0 = e->gx0; g.gy0 = e->gy0; g.gnx = e->gnx; g.gny = e->gny;
+  g.nzg = e->nvar > 0 ? e->nzg : e->nz; g.nvar = e->nvar;
+  for (int v = 0; v < e->nvar; ++v) { g.var_off[v] = e->var_off[v]; g.var_nlev[v] = e->var_nlev[v]; }
   MDC_CUDA(ctx, cudaMemsetAsync(ctx->d_flags, 0, sizeof(int), ctx->stream));
   size_t smem = (size_t)W * e->k * sizeof(double);
   int grid = (int)std::max<int64_t>(1, std::min<int64_t>((o->P + W - 1) / W, (int64_t)ctx->sm_count * 8));
-  hx_idw4_kernel<W><<<grid, W * 32, smem, ctx->stream>>>(e->X, g, o->P, o->x, o->y, o->z, o->valid, o->val, o->Y, o->ybar, o->Yp, o->d, ctx->d_flags);
+  hx_idw4_kernel<W><<<grid, W * 32, smem, ctx->stream>>>(e->X, g, o->P, o->x, o->y, o->z, o->var, o->valid, o->val, o->Y, o->ybar, o->Yp, o->d, ctx->d_flags);
   MDC_LAUNCH_CHECK(ctx);
   int flag = 0;
   MDC_CUDA(ctx, cudaMemcpyAsync(&flag, ctx->d_flags, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
@@ -595,6 +607,7 @@ int mdc_obs_pack_rows(mdc_obs* o, int ylo, int yhi, double* dev_rows, int64_t ca
 int mdc_obs_append_rows(mdc_obs* o, const double* dev_rows, int64_t n) {
   mdc_ctx* ctx = o->ctx;
   if (!o->have_hx) MDC_FAIL(ctx, MDC_ERR_INVALID, "append_rows: call mdc_hx_idw4 first (defines k)");
+  if (o->geo || o->var) MDC_FAIL(ctx, MDC_ERR_UNSUPPORTED, "append_rows: not for geographic / per-variable observation stores");
   if (n <= 0) return MDC_OK;
   MDC_CUDA(ctx, cudaSetDevice(ctx->device));
   if (int rc = obs_reserve(o, o->P + n, o->k)) return rc;
@@ -607,10 +620,19 @@ int mdc_obs_append_rows(mdc_obs* o, const double* dev_rows, int64_t n) {
 }
 
 // ------------------------------------------------------------------------------ bucket index
+#include "geo_api.inl"
+
 int mdc_obs_index_build(mdc_obs* o, int cell) {
+  if (o->geo) MDC_FAIL(o->ctx, MDC_ERR_UNSUPPORTED, "index_build: the index of geographic observations depends on the ensemble's geography and the radius; the query / analysis calls build it");
+  return index_build_impl(o, cell);
+}
+
+static int index_build_impl(mdc_obs* o, int cell) {
   mdc_ctx* ctx = o->ctx;
   MDC_CUDA(ctx, cudaSetDevice(ctx->device));
   if (cell <= 0) MDC_FAIL(ctx, MDC_ERR_INVALID, "index_build: cell must be > 0");
+  const int32_t* kx = o->geo ? o->qx : o->x;   // index coordinates: grid indices, or the lat/lon lattice
+  const int32_t* ky = o->geo ? o->qy : o->y;
   cudaStream_t s = ctx->stream;
   const int64_t P = o->P;
   o->cell = cell;
@@ -619,7 +641,7 @@ int mdc_obs_index_build(mdc_obs* o, int cell) {
   if (P > 0) {
     int init[4] = {INT_MAX, INT_MAX, INT_MIN, INT_MIN};
     MDC_CUDA(ctx, cudaMemcpyAsync(ctx->d_flags + 4, init, sizeof(init), cudaMemcpyHostToDevice, s));
-    index_bbox_kernel<<<grid_for(ctx, P, 256, 4), 256, 0, s>>>(o->x, o->y, P, ctx->d_flags + 4);
+    index_bbox_kernel<<<grid_for(ctx, P, 256, 4), 256, 0, s>>>(kx, ky, P, ctx->d_flags + 4);
     MDC_LAUNCH_CHECK(ctx);
     MDC_CUDA(ctx, cudaMemcpyAsync(bbox, ctx->d_flags + 4, sizeof(bbox), cudaMemcpyDeviceToHost, s));
     MDC_CUDA(ctx, cudaStreamSynchronize(s));
@@ -648,29 +670,38 @@ int mdc_obs_index_build(mdc_obs* o, int cell) {
   MDC_CUDA(ctx, cudaMemsetAsync(o->cell_start, 0, (ncell + 1) * sizeof(int32_t), s));
   if (P > 0) {
     // histogram into cell_fill, scan into cell_start, clear cell_fill, scatter, per-cell id sort
-    index_key_hist_kernel<<<grid_for(ctx, P, 256, 8), 256, 0, s>>>(o->x, o->y, P, o->xmin, o->ymin, cell, o->ncx, o->key, o->cell_fill);
+    index_key_hist_kernel<<<grid_for(ctx, P, 256, 8), 256, 0, s>>>(kx, ky, P, o->xmin, o->ymin, cell, o->ncx, o->key, o->cell_fill);
     MDC_LAUNCH_CHECK(ctx);
     index_scan_kernel<<<1, 1024, 0, s>>>(o->cell_fill, o->cell_start, (int)ncell);
     MDC_LAUNCH_CHECK(ctx);
     MDC_CUDA(ctx, cudaMemsetAsync(o->cell_fill, 0, ncell * sizeof(int32_t), s));
     index_scatter_kernel<<<grid_for(ctx, P, 256, 8), 256, 0, s>>>(o->key, P, o->cell_start, o->cell_fill, o->sorted_row);
     MDC_LAUNCH_CHECK(ctx);
-    index_cell_sort_kernel<<<mdc_div_up((int64_t)ncell, 128), 128, 0, s>>>(o->cell_start, (int)ncell, o->sorted_row, o->gid, o->x, o->y, o->z, o->sx, o->sy, o->sz);
+    index_cell_sort_kernel<<<mdc_div_up((int64_t)ncell, 128), 128, 0, s>>>(o->cell_start, (int)ncell, o->sorted_row, o->gid, kx, ky, o->z, o->sx, o->sy, o->sz);
     MDC_LAUNCH_CHECK(ctx);
   }
   o->index_valid = true;
   return MDC_OK;
 }
 
-static IndexView index_view(const mdc_obs* o) {
+static IndexView index_view(const mdc_obs* o, const mdc_ens* e) {
   IndexView iv;
   iv.cell_start = o->cell_start; iv.sorted_row = o->sorted_row;
   iv.sx = o->sx; iv.sy = o->sy; iv.sz = o->sz;
   iv.cell = o->cell; iv.ncx = o->ncx; iv.ncy = o->ncy; iv.xmin = o->xmin; iv.ymin = o->ymin;
+  iv.geo = o->geo ? 1 : 0; iv.reach = o->geo_reach;
+  iv.cqx = o->cqx; iv.cqy = o->cqy; iv.clat = e->glat; iv.clon = e->glon; iv.slat = o->slat; iv.slon = o->slon;
+  iv.levmap = e->levmap;
   return iv;
 }
 
-static int ensure_index(mdc_obs* o, double radius) {
+static int ensure_index(mdc_obs* o, mdc_ens* e, double radius) {
+  if (o->geo) {
+    if (!o->located)   // the index carries the observations' levels
+      if (int rc = mdc_obs_locate(o, e)) return rc;
+    if (o->index_valid && o->index_P == o->P && o->geo_radius == radius && o->geo_ens == e) return MDC_OK;
+    return geo_prepare_index(o, e, radius);
+  }
   if (o->index_valid && o->index_P == o->P) return MDC_OK;
   int cell = (int)std::ceil(radius);
   if (cell < 1) cell = 1;
@@ -680,13 +711,14 @@ static int ensure_index(mdc_obs* o, double radius) {
 int mdc_obs_index_query_counts(mdc_obs* o, mdc_ens* e, double radius, int32_t* host_counts) {
   mdc_ctx* ctx = o->ctx;
   MDC_CUDA(ctx, cudaSetDevice(ctx->device));
-  if (int rc = ensure_index(o, radius)) return rc;
+  if (int rc = ensure_index(o, e, radius)) return rc;
   const int64_t G = (int64_t)e->nx * e->ny;
   int32_t* dc = nullptr;
   if (dev_alloc(ctx, &dc, (size_t)G)) return MDC_ERR_CUDA;
   MDC_CUDA(ctx, cudaMemsetAsync(dc, 0xff, G * sizeof(int32_t), ctx->stream));
   const int64_t nown = (int64_t)e->own_nx * e->own_ny;
-  index_query_counts_kernel<<<mdc_div_up(nown, 128), 128, 0, ctx->stream>>>(index_view(o), e->nx, e->own_nx, e->own_ny, e->gx0, e->gy0, radius, dc);
+  auto qk = o->geo ? index_query_counts_kernel<true> : index_query_counts_kernel<false>;
+  qk<<<mdc_div_up(nown, 128), 128, 0, ctx->stream>>>(index_view(o, e), e->nx, e->own_nx, e->own_ny, e->gx0, e->gy0, radius, dc);
   MDC_LAUNCH_CHECK(ctx);
   MDC_CUDA(ctx, cudaMemcpyAsync(host_counts, dc, G * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
   MDC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -700,13 +732,14 @@ int mdc_obs_index_query_lists(mdc_obs* o, mdc_ens* e, double radius, const int64
   mdc_ctx* ctx = o->ctx;
   MDC_CUDA(ctx, cudaSetDevice(ctx->device));
   if (ncols <= 0 || cap <= 0) return MDC_OK;
-  if (int rc = ensure_index(o, radius)) return rc;
+  if (int rc = ensure_index(o, e, radius)) return rc;
   int64_t *dcols = nullptr, *dl = nullptr;
   int32_t* dc = nullptr;
   if (dev_alloc(ctx, &dcols, (size_t)ncols) || dev_alloc(ctx, &dl, (size_t)ncols * cap) || dev_alloc(ctx, &dc, (size_t)ncols)) return MDC_ERR_CUDA;
   MDC_CUDA(ctx, cudaMemcpyAsync(dcols, cols, ncols * 8, cudaMemcpyHostToDevice, ctx->stream));
   MDC_CUDA(ctx, cudaMemsetAsync(dl, 0xff, (size_t)ncols * cap * 8, ctx->stream));
-  index_query_lists_kernel<<<mdc_div_up(ncols, 64), 64, 0, ctx->stream>>>(index_view(o), o->gid, e->nx, e->gx0, e->gy0, radius, dcols, ncols, cap, dl, dc);
+  auto qk = o->geo ? index_query_lists_kernel<true> : index_query_lists_kernel<false>;
+  qk<<<mdc_div_up(ncols, 64), 64, 0, ctx->stream>>>(index_view(o, e), o->gid, e->nx, e->gx0, e->gy0, radius, dcols, ncols, cap, dl, dc);
   MDC_LAUNCH_CHECK(ctx);
   MDC_CUDA(ctx, cudaMemcpyAsync(host_lists, dl, (size_t)ncols * cap * 8, cudaMemcpyDeviceToHost, ctx->stream));
   MDC_CUDA(ctx, cudaMemcpyAsync(host_counts, dc, ncols * 4, cudaMemcpyDeviceToHost, ctx->stream));
@@ -725,6 +758,12 @@ static int letkf_launch(mdc_ens* e, mdc_obs* o, const mdc_letkf_params* p, const
   if (p->mode < 0 || p->mode > 2) MDC_FAIL(ctx, MDC_ERR_INVALID, "letkf: bad mode");
   if (p->loc < 0 || p->loc > MDC_LOC_REF_GASPARI_COHN) MDC_FAIL(ctx, MDC_ERR_INVALID, "letkf: bad localisation function");
   if (!(p->inflation > 0.0)) MDC_FAIL(ctx, MDC_ERR_INVALID, "letkf: inflation must be > 0");
+  // geographic observations / multi-variable states run on the EXT instantiations of the canonical kernels
+  const bool ext = o->geo || e->levmap != nullptr;
+  if (ext && p->mode != MDC_MODE_CANONICAL)
+    MDC_FAIL(ctx, MDC_ERR_UNSUPPORTED, "letkf: geographic observations and multi-variable states need MDC_MODE_CANONICAL");
+  if (ext && p->solver == MDC_SOLVER_NEWTON_SCHULZ_FULL)
+    MDC_FAIL(ctx, MDC_ERR_UNSUPPORTED, "letkf: geographic observations and multi-variable states run on the AUTO, JACOBI or NEWTON_SCHULZ solvers");
   const size_t smem = lk_smem_bytes(k, p->mode);
   if ((int)smem > ctx->max_smem_optin)
     MDC_FAIL(ctx, MDC_ERR_UNSUPPORTED, "letkf: k=%d mode=%d needs %zu B shared memory > %d available", k, p->mode, smem, ctx->max_smem_optin);
@@ -734,7 +773,7 @@ static int letkf_launch(mdc_ens* e, mdc_obs* o, const mdc_letkf_params* p, const
   cp.mean_out = e->mean;
   cp.nx = e->nx; cp.ny = e->ny; cp.nz = e->nz; cp.k = k; cp.own_nx = e->own_nx; cp.own_ny = e->own_ny;
   cp.gx0 = e->gx0; cp.gy0 = e->gy0;
-  cp.iv = index_view(o);
+  cp.iv = index_view(o, e);
   cp.Yp = o->Yp; cp.d = o->d; cp.err = o->err; cp.valid = o->valid;
   cp.radius = p->radius; cp.radius_v = p->radius_v; cp.inflation = p->inflation;
   cp.mode = p->mode; cp.loc = p->loc; cp.use_R = p->use_R;
@@ -791,12 +830,14 @@ static int letkf_launch(mdc_ens* e, mdc_obs* o, const mdc_letkf_params* p, const
       return MDC_OK;
     };
     // <NT, MINB, LG, RPL, TM, TMY>: NT = (k/8 block pairs) * LG lanes rounded up to whole warps
-    if (k <= 16) return launch2(letkf_canonical_kernel<32, 8, 4, 4, 1, 8>, 32);
-    if (k <= 24) return launch2(letkf_canonical_kernel<32, 8, 4, 6, 2, 12>, 32);
-    if (k <= 40) return launch2(letkf_canonical_kernel<64, 4, 8, 5, 3, 10>, 64);
-    if (k <= 64) return launch2(letkf_canonical_kernel<64, 4, 8, 8, 4, 16>, 64);
-    if (k <= 80) return launch2(letkf_canonical_kernel<160, 2, 16, 5, 5, 8>, 160);
-    return launch2(letkf_canonical_kernel<256, 1, 16, 8, 8, 8>, 256);
+#define MDC_JAC(NT, ...) (ext ? launch2(letkf_canonical_kernel<NT, __VA_ARGS__, true>, NT) : launch2(letkf_canonical_kernel<NT, __VA_ARGS__>, NT))
+    if (k <= 16) return MDC_JAC(32, 8, 4, 4, 1, 8);
+    if (k <= 24) return MDC_JAC(32, 8, 4, 6, 2, 12);
+    if (k <= 40) return MDC_JAC(64, 4, 8, 5, 3, 10);
+    if (k <= 64) return MDC_JAC(64, 4, 8, 8, 4, 16);
+    if (k <= 80) return MDC_JAC(160, 2, 16, 5, 5, 8);
+    return MDC_JAC(256, 1, 16, 8, 8, 8);
+#undef MDC_JAC
   };
   const bool v1 = getenv("MDC_LETKF_V1") != nullptr;
   if (p->mode == MDC_MODE_CANONICAL && p->solver == MDC_SOLVER_NEWTON_SCHULZ_FULL && !v1)
@@ -828,7 +869,7 @@ static int letkf_launch(mdc_ens* e, mdc_obs* o, const mdc_letkf_params* p, const
     // Per-level analyses: a first pass (one warp per column) finishes the transforms with no or few local
     // observations in observation space and lists the others for the k-space kernel.  Otherwise the k-space
     // kernel defers its small transforms to the observation-space kernel after its own selection.
-    const bool classify = smallp && nxf > 1 && !dW;
+    const bool classify = smallp && nxf > 1 && !dW && !ext;
     if (classify) {
       cp.work_items = ctx->redo_items + 2 * ctx->redo_cap;
       cp.work_count = reinterpret_cast<unsigned*>(ctx->d_flags + 14);
@@ -853,29 +894,27 @@ static int letkf_launch(mdc_ens* e, mdc_obs* o, const mdc_letkf_params* p, const
       return MDC_OK;
     };
     int rc;
-    switch ((k + 7) >> 3) {   // tile rows: the kernel is specialised on the exact count
-      case 3: rc = cp.work_consume ? launchp(letkf_nsp_kernel<3, 256, 2, true>, 256) : launchp(letkf_nsp_kernel<3, 256, 2, false>, 256); break;
-      case 4: rc = cp.work_consume ? launchp(letkf_nsp_kernel<4, 256, 2, true>, 256) : launchp(letkf_nsp_kernel<4, 256, 2, false>, 256); break;
-      case 5: rc = cp.work_consume ? launchp(letkf_nsp_kernel<5, 256, 2, true>, 256) : launchp(letkf_nsp_kernel<5, 256, 2, false>, 256); break;
-      case 6: rc = cp.work_consume ? launchp(letkf_nsp_kernel<6, 256, 2, true>, 256) : launchp(letkf_nsp_kernel<6, 256, 2, false>, 256); break;
-      case 7: rc = cp.work_consume ? launchp(letkf_nsp_kernel<7, 256, 2, true>, 256) : launchp(letkf_nsp_kernel<7, 256, 2, false>, 256); break;
-      case 8: rc = cp.work_consume ? launchp(letkf_nsp_kernel<8, 256, 2, true>, 256) : launchp(letkf_nsp_kernel<8, 256, 2, false>, 256); break;
-      case 9: rc = cp.work_consume ? launchp(letkf_nsp_kernel<9, 256, 2, true>, 256) : launchp(letkf_nsp_kernel<9, 256, 2, false>, 256); break;
-      case 10: rc = cp.work_consume ? launchp(letkf_nsp_kernel<10, 256, 2, true>, 256) : launchp(letkf_nsp_kernel<10, 256, 2, false>, 256); break;   // (384 threads: 6 % slower)
-      case 11: rc = cp.work_consume ? launchp(letkf_nsp_kernel<11, 512, 1, true>, 512) : launchp(letkf_nsp_kernel<11, 512, 1, false>, 512); break;
-      case 12: rc = cp.work_consume ? launchp(letkf_nsp_kernel<12, 512, 1, true>, 512) : launchp(letkf_nsp_kernel<12, 512, 1, false>, 512); break;
-      case 13: rc = cp.work_consume ? launchp(letkf_nsp_kernel<13, 512, 1, true>, 512) : launchp(letkf_nsp_kernel<13, 512, 1, false>, 512); break;
-      case 14: rc = cp.work_consume ? launchp(letkf_nsp_kernel<14, 512, 1, true>, 512) : launchp(letkf_nsp_kernel<14, 512, 1, false>, 512); break;
-      case 15: rc = cp.work_consume ? launchp(letkf_nsp_kernel<15, 512, 1, true>, 512) : launchp(letkf_nsp_kernel<15, 512, 1, false>, 512); break;
-      default: rc = cp.work_consume ? launchp(letkf_nsp_kernel<16, 512, 1, true>, 512) : launchp(letkf_nsp_kernel<16, 512, 1, false>, 512); break;
+#define MDC_NSP(NT, NTH, MINB)                                                                         \
+  case NT:                                                                                             \
+    rc = ext ? launchp(letkf_nsp_kernel<NT, NTH, MINB, false, true>, NTH)                              \
+             : cp.work_consume ? launchp(letkf_nsp_kernel<NT, NTH, MINB, true>, NTH)                  \
+                               : launchp(letkf_nsp_kernel<NT, NTH, MINB, false>, NTH);                \
+    break;
+    switch (std::min((k + 7) >> 3, 16)) {   // tile rows: the kernel is specialised on the exact count
+      MDC_NSP(3, 256, 2) MDC_NSP(4, 256, 2) MDC_NSP(5, 256, 2) MDC_NSP(6, 256, 2) MDC_NSP(7, 256, 2)
+      MDC_NSP(8, 256, 2) MDC_NSP(9, 256, 2) MDC_NSP(10, 256, 2)   // (nt = 10 with 384 threads: 6 % slower)
+      MDC_NSP(11, 512, 1) MDC_NSP(12, 512, 1) MDC_NSP(13, 512, 1) MDC_NSP(14, 512, 1) MDC_NSP(15, 512, 1)
+      MDC_NSP(16, 512, 1)
+      default: MDC_FAIL(ctx, MDC_ERR_UNSUPPORTED, "letkf: no packed kernel for k=%d", k);
     }
+#undef MDC_NSP
     if (rc) return rc;
     if (cp.small_items)
-      if (int rc2 = launch_smallp(letkf_smallp_kernel, cp)) return rc2;
+      if (int rc2 = ext ? launch_smallp(letkf_smallp_kernel<true>, cp) : launch_smallp(letkf_smallp_kernel<false>, cp)) return rc2;
     ColParams cq = cp;
     cq.redo_consume = 1;
     cq.work_consume = 0;
-    return k <= 80 ? launch_ns_full(cq, (long long)need) : launch_jacobi(cq, (long long)need);
+    return (k <= 80 && !ext) ? launch_ns_full(cq, (long long)need) : launch_jacobi(cq, (long long)need);
   }
   if (p->mode == MDC_MODE_CANONICAL && !v1) return launch_jacobi(cp, total_cols);
   const int nr = (k + 31) / 32;
@@ -911,7 +950,7 @@ int mdc_letkf_analyse(mdc_ens* e, mdc_obs* o, const mdc_letkf_params* p, mdc_let
     MDC_FAIL(ctx, MDC_ERR_INVALID, "letkf: Y' has k=%d, ensemble has k=%d", o->k, e->k);
   }
   MDC_CUDA(ctx, cudaEventRecord(ctx->pe[1], s));
-  if (int rc = ensure_index(o, p->radius)) return rc;
+  if (int rc = ensure_index(o, e, p->radius)) return rc;
   MDC_CUDA(ctx, cudaEventRecord(ctx->pe[2], s));
   MDC_CUDA(ctx, cudaMemsetAsync(ctx->d_stats, 0, 16 * sizeof(long long), s));
   if (int rc = letkf_launch(e, o, p, nullptr, 0, nullptr, -1)) return rc;
@@ -946,7 +985,7 @@ int mdc_letkf_column_transform(mdc_ens* e, mdc_obs* o, const mdc_letkf_params* p
   mdc_ctx* ctx = e->ctx;
   MDC_CUDA(ctx, cudaSetDevice(ctx->device));
   if (!o->have_hx) { if (int rc = mdc_hx_idw4(e, o)) return rc; }
-  if (int rc = ensure_index(o, p->radius)) return rc;
+  if (int rc = ensure_index(o, e, p->radius)) return rc;
   double* dW = nullptr;
   long long* dcol = nullptr;
   if (dev_alloc(ctx, &dW, (size_t)e->k * e->k) || dev_alloc(ctx, &dcol, 1)) return MDC_ERR_CUDA;

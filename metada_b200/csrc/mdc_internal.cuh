@@ -35,6 +35,16 @@ struct mdc_ens {
   double* stage = nullptr;                     // staging for member-major host transfers
   size_t stage_elems = 0;
   double* host_pinned = nullptr;               // pinned bounce buffer for pageable callers
+  // geography (mdc_ens_set_geography): column coordinates in degrees and the geometry's vertical coordinate
+  bool geo = false;
+  double *glat = nullptr, *glon = nullptr;     // [ny][nx]
+  double* vcoord = nullptr;                    // [nvcoord] or nullptr
+  int nvcoord = 0;
+  double geo_lon_c = 0.0, geo_umin = 0.0, geo_umax = 0.0, geo_latmin = 0.0, geo_latmax = 0.0;  // host-side extents
+  // variables (mdc_ens_set_variables): nz = sum of var_nlev; nzg = levels of the geometry (largest variable)
+  int nvar = 0, nzg = 0;
+  int var_off[16] = {0}, var_nlev[16] = {0};
+  int32_t* levmap = nullptr;                   // [nz] level inside its variable
 };
 
 struct mdc_obs {
@@ -60,6 +70,20 @@ struct mdc_obs {
   int32_t *sx = nullptr, *sy = nullptr, *sz = nullptr;  // coordinates in sorted order
   int32_t* key = nullptr;          // [P]
   size_t sorted_cap = 0;
+  // GEOGRAPHIC observations (mdc_obs_create_geographic): true coordinates; x, y, z above hold the nearest grid
+  // point once located (mdc_obs_locate).  The index then runs on the lattice coordinates qx, qy (geo_kernels.cuh).
+  bool geo = false, located = false;
+  double *lat = nullptr, *lon = nullptr, *lev = nullptr;   // [P]
+  int32_t* var = nullptr;                                  // [P] state variable observed, or nullptr (variable 0)
+  int var_max = 0;                                         // largest entry of var (host copy, checked against the ensemble)
+  int32_t *qx = nullptr, *qy = nullptr;                    // [P]
+  int32_t *cqx = nullptr, *cqy = nullptr;                  // [columns of the ensemble the index was built for]
+  size_t cq_cap = 0;
+  double *slat = nullptr, *slon = nullptr;                 // [P] coordinates in index order
+  size_t sgeo_cap = 0;
+  int geo_reach = 0;
+  double geo_radius = -1.0;
+  const mdc_ens* geo_ens = nullptr;
 };
 
 #define MDC_FAIL(ctx, code, ...)                              \

@@ -26,6 +26,15 @@ std::unique_ptr<backends::cuda::DeviceEnsemble> uploadEnsemble(Ensemble<BackendT
     ptrs.push_back(ensemble.GetMember(m).template getDataPtr<double>());
   }
   dev->upload(ptrs);
+  // a geometry with 2-D coordinate arrays (WRFGeometry::unstaggered_info(), the arrays
+  // IdentityObsOperator.hpp:488-526 searches) gives the device store its geography
+  if constexpr (requires { g.unstaggered_info().latitude_2d; g.unstaggered_info().longitude_2d; g.unstaggered_info().vertical_coords; }) {
+    const auto& info = g.unstaggered_info();
+    if (info.has_2d_coords())
+      dev->setGeography(std::vector<double>(info.latitude_2d.begin(), info.latitude_2d.end()),
+                        std::vector<double>(info.longitude_2d.begin(), info.longitude_2d.end()),
+                        std::vector<double>(info.vertical_coords.begin(), info.vertical_coords.end()));
+  }
   return dev;
 }
 

@@ -8,6 +8,7 @@
 #include <string>
 #include <vector>
 
+#include "Location.hpp"
 #include "metada_cuda_c_api.h"
 
 namespace metada::backends::cuda {
@@ -59,6 +60,19 @@ class DeviceEnsemble {
                                     "mdc_ens_download_members");
   }
   void mean(double* host) { DeviceContext::Instance().check(mdc_ens_mean(h_, host), "mdc_ens_mean"); }
+  /** Column coordinates in degrees ([ny][nx], e.g. WRFGeometry::unstaggered_info().latitude_2d / longitude_2d)
+   *  and the geometry's vertical coordinate: needed by observations with GEOGRAPHIC locations. */
+  void setGeography(const std::vector<double>& lat, const std::vector<double>& lon, const std::vector<double>& vertical) {
+    if (lat.size() != static_cast<size_t>(nx_) * ny_ || lon.size() != lat.size())
+      throw std::invalid_argument("DeviceEnsemble::setGeography: coordinate arrays do not match the grid");
+    DeviceContext::Instance().check(
+        mdc_ens_set_geography(h_, lat.data(), lon.data(), static_cast<int>(vertical.size()), vertical.empty() ? nullptr : vertical.data()),
+        "mdc_ens_set_geography");
+  }
+  /** Levels of each state variable of a [var][lev][y][x] member. */
+  void setVariables(const std::vector<int32_t>& var_nlev) {
+    DeviceContext::Instance().check(mdc_ens_set_variables(h_, static_cast<int>(var_nlev.size()), var_nlev.data()), "mdc_ens_set_variables");
+  }
 
  private:
   mdc_ens* h_ = nullptr;
@@ -72,28 +86,48 @@ class DeviceObservations {
   template <typename ObsBackend>
   explicit DeviceObservations(const ObsBackend& obs) {
     std::vector<int32_t> x, y, z;
-    std::vector<double> val, err;
+    std::vector<double> lat, lon, lev, val, err;
     std::vector<uint8_t> valid;
+    // GEOGRAPHIC locations (Location.hpp:82-84) select by haversine kilometres and are located on the grid by the
+    // device (IdentityObsOperator.hpp:241-248); GRID locations are used as they are.  A mix throws, as
+    // Location::distance_to does (Location.hpp:226-229).
+    bool geographic = false, first = true;
     for (const auto& p : obs) {
-      auto [i, j, k] = p.location.getGridCoords();   // throws for non-GRID locations, like distance_to
-      x.push_back(i); y.push_back(j); z.push_back(k);
+      const bool g = p.location.getCoordinateSystem() == framework::CoordinateSystem::GEOGRAPHIC;
+      if (first) { geographic = g; first = false; }
+      if (g != geographic) throw std::runtime_error("DeviceObservations: GRID and GEOGRAPHIC locations cannot be mixed");
+      if (g) {
+        auto [la, lo, le] = p.location.getGeographicCoords();
+        lat.push_back(la); lon.push_back(lo); lev.push_back(le);
+      } else {
+        auto [i, j, k] = p.location.getGridCoords();   // throws for other systems, like distance_to
+        x.push_back(i); y.push_back(j); z.push_back(k);
+      }
       val.push_back(p.value); err.push_back(p.error); valid.push_back(p.is_valid ? 1 : 0);
     }
-    size_ = x.size();
+    size_ = val.size();
+    geographic_ = geographic;
     auto& c = DeviceContext::Instance();
-    c.check(mdc_obs_create(c.get(), static_cast<int64_t>(size_), x.data(), y.data(), z.data(), val.data(),
-                           err.data(), valid.data(), nullptr, &h_),
-            "mdc_obs_create");
+    if (geographic)
+      c.check(mdc_obs_create_geographic(c.get(), static_cast<int64_t>(size_), lat.data(), lon.data(), lev.data(), val.data(),
+                                        err.data(), valid.data(), nullptr, &h_),
+              "mdc_obs_create_geographic");
+    else
+      c.check(mdc_obs_create(c.get(), static_cast<int64_t>(size_), x.data(), y.data(), z.data(), val.data(),
+                             err.data(), valid.data(), nullptr, &h_),
+              "mdc_obs_create");
   }
   ~DeviceObservations() { mdc_obs_destroy(h_); }
   DeviceObservations(const DeviceObservations&) = delete;
   DeviceObservations& operator=(const DeviceObservations&) = delete;
   mdc_obs* get() const { return h_; }
   size_t size() const { return size_; }
+  bool geographic() const { return geographic_; }
 
  private:
   mdc_obs* h_ = nullptr;
   size_t size_ = 0;
+  bool geographic_ = false;
 };
 
 }  // namespace metada::backends::cuda

@@ -84,3 +84,40 @@ def observations(P, gnx, gny, nz, seed=42, sigma=0.1, distinct=False):
     z = (hash64(seed, 3 * a + np.uint64(2)) % np.uint64(nz)).astype(np.int32)
     val = truth(x, y, z, gnx, gny) + sigma * noise(hash64(seed + 1, a))
     return dict(x=x, y=y, z=z, value=val, err=np.full(P, sigma), valid=np.ones(P, np.uint8))
+
+
+# ---- geography (the WRF-shaped case): curvilinear latitude / longitude arrays and geographic observations ----
+def geography(nx, ny, lat0=32.0, lon0=-104.0, dlat=0.09, dlon=0.11, curvilinear=True, wrap=True):
+    """Column coordinates in degrees, [ny, nx]: a regular latitude / longitude grid, optionally bent the way a
+    projected (Lambert) WRF grid is.  wrap: longitudes folded into [-180, 180)."""
+    j, i = np.meshgrid(np.arange(ny, dtype=np.float64), np.arange(nx, dtype=np.float64), indexing="ij")
+    lat = lat0 + dlat * j
+    lon = lon0 + dlon * i
+    if curvilinear:
+        lat = lat + 0.004 * np.sin(i / 7.0)
+        lon = lon0 + dlon * i * (1.0 + 0.002 * j) + 0.003 * np.cos(j / 5.0)
+    if wrap:
+        lon = (lon + 180.0) % 360.0 - 180.0
+    return lat, lon
+
+
+def geo_observations(P, lat, lon, vertical_coords=None, seed=42, sigma=0.1, margin=0.08, wrap=True):
+    """P observations with GEOGRAPHIC locations, uniform over the grid's bounding box grown by `margin` of its
+    size (some fall outside the domain), levels uniform over the vertical coordinate's range.  Values are drawn
+    around 0 -- the tests only need seeded, well-scaled numbers."""
+    rng = np.random.default_rng(seed)
+    u = np.unwrap(np.deg2rad(lon), axis=1)
+    u = np.rad2deg(np.unwrap(u, axis=0))
+    la0, la1, lo0, lo1 = lat.min(), lat.max(), u.min(), u.max()
+    dla, dlo = (la1 - la0) * margin, (lo1 - lo0) * margin
+    olat = rng.uniform(la0 - dla, la1 + dla, P)
+    olon = rng.uniform(lo0 - dlo, lo1 + dlo, P)
+    if wrap:
+        olon = (olon + 180.0) % 360.0 - 180.0
+    if vertical_coords is not None:
+        vc = np.asarray(vertical_coords, dtype=np.float64)
+        lev = rng.uniform(vc.min() - 0.1 * np.ptp(vc), vc.max() + 0.1 * np.ptp(vc), P)
+    else:
+        lev = np.zeros(P)
+    return {"lat": olat, "lon": olon, "level": lev, "value": sigma * 5.0 * rng.standard_normal(P),
+            "err": np.full(P, sigma), "valid": np.ones(P, dtype=np.uint8)}

@@ -10,6 +10,7 @@
  */
 #include "metada_oracle.h"
 
+#include <float.h>
 #include <math.h>
 #include <stdlib.h>
 #include <string.h>
@@ -61,11 +62,91 @@ void orc_select_counts(int nx, int ny, int64_t P, const int32_t* ox, const int32
   (void)nthreads;
 }
 
+/* framework/base/Location.hpp:213-217 (GEOGRAPHIC x GEOGRAPHIC: horizontal great circle, level ignored) with
+ * deg2rad (:333) and haversine (:349-357), kEarthRadiusKm = 6371.0 (:325); result in kilometres */
+static double orc_deg2rad(double deg) { return deg * 3.14159265358979323846 / 180.0; }
+double orc_distance_geo(double lat1, double lon1, double lat2, double lon2) {
+  double dlat = orc_deg2rad(lat2 - lat1);
+  double dlon = orc_deg2rad(lon2 - lon1);
+  double a = sin(dlat / 2) * sin(dlat / 2) +
+             cos(orc_deg2rad(lat1)) * cos(orc_deg2rad(lat2)) * sin(dlon / 2) * sin(dlon / 2);
+  double c = 2 * atan2(sqrt(a), sqrt(1 - a));
+  return 6371.0 * c;
+}
+
+/* LETKF.hpp:159-165 with GEOGRAPHIC locations: ascending obs index, inclusive <= (kilometres) */
+int64_t orc_select_local_geo(double clat, double clon, int64_t P, const double* olat, const double* olon,
+                             double radius, int32_t* idx_out, double* min_margin) {
+  int64_t c = 0;
+  for (int64_t i = 0; i < P; ++i) {
+    double distance = orc_distance_geo(clat, clon, olat[i], olon[i]);
+    if (min_margin) {
+      double m = fabs(distance - radius);
+      if (m < *min_margin) *min_margin = m;
+    }
+    if (distance <= radius) {
+      if (idx_out) idx_out[c] = (int32_t)i;
+      ++c;
+    }
+  }
+  return c;
+}
+
+void orc_select_counts_geo(int nx, int ny, const double* glat, const double* glon, int64_t P,
+                           const double* olat, const double* olon, double radius, int32_t* counts,
+                           double* min_margin) {
+  double mm = INFINITY;
+#ifdef _OPENMP
+#pragma omp parallel for schedule(dynamic, 16) reduction(min : mm)
+#endif
+  for (int64_t g = 0; g < (int64_t)nx * ny; ++g) {
+    double m = INFINITY;
+    counts[g] = (int32_t)orc_select_local_geo(glat[g], glon[g], P, olat, olon, radius, NULL, &m);
+    if (m < mm) mm = m;
+  }
+  if (min_margin) *min_margin = mm;
+}
+
+/* backends/common/obsoperator/IdentityObsOperator.hpp:484-530 (convertGeographicToGrid, the branch for a
+ * geometry with 2-D coordinate arrays): FIRST minimum of the Euclidean distance in degrees over the grid in
+ * linear (y-outer, x-inner) order, then the first minimum of |level - vertical_coords[z]| (k = 0 without
+ * vertical coordinates). */
+void orc_geo_locate(int64_t P, const double* olat, const double* olon, const double* olev,
+                    const double* glat, const double* glon, int nx, int ny, const double* vcoord,
+                    int nlev, int32_t* ox, int32_t* oy, int32_t* oz) {
+  const int64_t G = (int64_t)nx * ny;
+#ifdef _OPENMP
+#pragma omp parallel for schedule(static)
+#endif
+  for (int64_t i = 0; i < P; ++i) {
+    const double lat = olat[i], lon = olon[i];
+    double min_dist = DBL_MAX;
+    int64_t min_idx = 0;
+    for (int64_t idx = 0; idx < G; ++idx) {
+      double grid_lon = glon[idx], grid_lat = glat[idx];
+      double dist = sqrt((lon - grid_lon) * (lon - grid_lon) + (lat - grid_lat) * (lat - grid_lat));
+      if (dist < min_dist) { min_dist = dist; min_idx = idx; }
+    }
+    int k = 0;
+    if (vcoord && nlev > 0) {
+      double level = olev ? olev[i] : 0.0, min_vert_dist = DBL_MAX;
+      for (int z = 0; z < nlev; ++z) {
+        double dist = fabs(level - vcoord[z]);
+        if (dist < min_vert_dist) { min_vert_dist = dist; k = z; }
+      }
+    }
+    ox[i] = (int32_t)(min_idx % nx); oy[i] = (int32_t)(min_idx / nx); oz[i] = k;
+  }
+}
+
 /* ------------------------------------------------------------------ H(x): 4-point IDW */
 
 /* backends/common/obsoperator/IdentityObsOperator.hpp:594-638 (find4NearestGridPoints) and
  * :643-676 (idw4Interpolation), linear index kk*(ny*nx) + jj*nx + ii. */
-static double hx_one(const double* s, int nx, int ny, int nz, int oxi, int oyi, int ozi) {
+/* Multi-variable states (:681-711, idw4InterpolationVariable): the neighbours are searched on the geometry's
+ * nz levels, the value is read from the observation's variable -- `s` points at that variable's block and
+ * var_nlev is its level count (a 2-D variable ignores the level, :706-707). */
+static double hx_one_var(const double* s, int nx, int ny, int nz, int var_nlev, int oxi, int oyi, int ozi) {
   double x = (double)oxi, y = (double)oyi, z = (double)ozi;
   x = fmax(0.0, fmin((double)(nx - 1), x));
   y = fmax(0.0, fmin((double)(ny - 1), y));
@@ -108,11 +189,15 @@ static double hx_one(const double* s, int nx, int ny, int nz, int oxi, int oyi, 
   double weighted_sum = 0.0, weight_sum = 0.0;
   for (int c = 0; c < cnt; ++c) {
     double w = (dist[c] == 0.0) ? 1e12 : 1.0 / dist[c];
-    size_t linear_index = kk[c] * ((size_t)ny * nx) + jj[c] * (size_t)nx + ii[c];
+    size_t linear_index = (var_nlev > 1 ? kk[c] : 0) * ((size_t)ny * nx) + jj[c] * (size_t)nx + ii[c];
     weighted_sum += w * s[linear_index];
     weight_sum += w;
   }
   return weighted_sum / weight_sum;
+}
+
+static double hx_one(const double* s, int nx, int ny, int nz, int oxi, int oyi, int ozi) {
+  return hx_one_var(s, nx, ny, nz, nz, oxi, oyi, ozi);
 }
 
 /* IdentityObsOperator.hpp:154-180 : invalid obs -> 0.0 */
@@ -151,6 +236,33 @@ void orc_obs_space(const double* X, int nx, int ny, int nz, int k, int64_t P, co
     if (ybar) ybar[i] = mean;
     if (Yp) for (int m = 0; m < k; ++m) Yp[i * k + m] = Y[i * k + m] - mean;
     if (d) d[i] = oval[i] - mean;
+  }
+}
+
+/* Y, Y', d for a multi-variable state: member layout [var][lev][y][x], observation i reads variable ovar[i]
+ * (IdentityObsOperator.hpp:236-281, 681-711); nzg = levels of the geometry (the largest variable). */
+static void obs_space_ext(const double* X, int nx, int ny, int nz, int k, int64_t P, const int32_t* ox,
+                          const int32_t* oy, const int32_t* oz, const uint8_t* valid, const double* oval,
+                          const orc_ext* ext, double* Y, double* Yp, double* d) {
+  const int64_t G = (int64_t)nx * ny, n = G * nz;
+  int off[64] = {0}, nzg = 1;
+  for (int v = 0; v < ext->nvar; ++v) {
+    off[v + 1] = off[v] + ext->var_nlev[v];
+    if (ext->var_nlev[v] > nzg) nzg = ext->var_nlev[v];
+  }
+  for (int m = 0; m < k; ++m)
+    for (int64_t i = 0; i < P; ++i) {
+      if (valid && !valid[i]) { Y[i * k + m] = 0.0; continue; }
+      const int v = ext->ovar ? ext->ovar[i] : 0;
+      Y[i * k + m] = hx_one_var(X + (int64_t)m * n + (int64_t)off[v] * G, nx, ny, nzg, ext->var_nlev[v], ox[i],
+                                oy[i], oz ? oz[i] : 0);
+    }
+  for (int64_t i = 0; i < P; ++i) {
+    double s = 0.0;
+    for (int m = 0; m < k; ++m) s += Y[i * k + m];
+    double mean = s / (double)k;
+    for (int m = 0; m < k; ++m) Yp[i * k + m] = Y[i * k + m] - mean;
+    d[i] = oval[i] - mean;
   }
 }
 
@@ -484,7 +596,7 @@ static void store_W(int mode, int k, const xform_ws* w, double* Wo) {
 
 /* ------------------------------------------------------------------ LETKF drivers */
 
-static int letkf_snapshot(const orc_letkf_params* p, double* X, const int32_t* ox,
+static int letkf_snapshot(const orc_letkf_params* p, const orc_ext* ext, double* X, const int32_t* ox,
                           const int32_t* oy, const int32_t* oz, const double* oval,
                           const double* oerr, const uint8_t* valid, const int64_t* cols_sel,
                           int64_t ncols_sel, int32_t* counts_out, double* W_out) {
@@ -494,7 +606,18 @@ static int letkf_snapshot(const orc_letkf_params* p, double* X, const int32_t* o
   double* Y = (double*)malloc(sizeof(double) * (size_t)(P > 0 ? P : 1) * k);
   double* Yp = (double*)malloc(sizeof(double) * (size_t)(P > 0 ? P : 1) * k);
   double* d = (double*)malloc(sizeof(double) * (size_t)(P > 0 ? P : 1));
-  orc_obs_space(X, nx, ny, nz, k, P, ox, oy, oz, valid, oval, Y, NULL, Yp, d);
+  const int geo = ext && ext->glat;            /* GEOGRAPHIC locations: haversine kilometres */
+  int* levmap = (int*)malloc(sizeof(int) * (size_t)nz);   /* level of a state level inside its variable */
+  for (int l = 0; l < nz; ++l) levmap[l] = l;
+  if (ext && ext->nvar > 0) {
+    int tot = 0;
+    for (int v = 0; v < ext->nvar; ++v)
+      for (int l = 0; l < ext->var_nlev[v]; ++l) if (tot < nz) levmap[tot++] = l;
+    if (tot != nz) { free(Y); free(Yp); free(d); free(levmap); return -4; }
+    obs_space_ext(X, nx, ny, nz, k, P, ox, oy, oz, valid, oval, ext, Y, Yp, d);
+  } else {
+    orc_obs_space(X, nx, ny, nz, k, P, ox, oy, oz, valid, oval, Y, NULL, Yp, d);
+  }
   free(Y);
   const int64_t ncols = cols_sel ? ncols_sel : G;
   int rc_all = 0;
@@ -516,7 +639,9 @@ static int letkf_snapshot(const orc_letkf_params* p, double* X, const int32_t* o
     for (int64_t ci = 0; ci < ncols; ++ci) {
       const int64_t g = cols_sel ? cols_sel[ci] : ci;
       const int gx = (int)(g % nx), gy = (int)(g / nx);
-      const int64_t ph = orc_select_local(gx, gy, P, ox, oy, p->radius, idx);
+      const int64_t ph = geo ? orc_select_local_geo(ext->glat[g], ext->glon[g], P, ext->olat, ext->olon,
+                                                    p->radius, idx, NULL)
+                             : orc_select_local(gx, gy, P, ox, oy, p->radius, idx);
       if (counts_out) counts_out[g] = (int32_t)ph;
       if (ph > cap) {
         cap = ph * 2; free(Yl); free(dl); free(rinv);
@@ -534,13 +659,16 @@ static int letkf_snapshot(const orc_letkf_params* p, double* X, const int32_t* o
           const int32_t i = idx[a];
           double rho = 1.0;
           if (per_level) {
-            double dv = fabs((double)(oz[i] - lt));
+            double dv = fabs((double)(oz[i] - levmap[lt]));
             if (!(dv <= p->radius_v)) continue;
             if (p->mode == ORC_MODE_CANONICAL && p->loc != ORC_LOC_CUTOFF)
               rho *= orc_loc_weight(p->loc, dv, p->radius_v, p->radius_v * (loc_scale / p->radius));
           }
           if (p->mode == ORC_MODE_CANONICAL && p->loc != ORC_LOC_CUTOFF)
-            rho *= orc_loc_weight(p->loc, orc_distance_grid(gx, gy, ox[i], oy[i]), p->radius, loc_scale);
+            rho *= orc_loc_weight(p->loc,
+                                  geo ? orc_distance_geo(ext->glat[g], ext->glon[g], ext->olat[i], ext->olon[i])
+                                      : orc_distance_grid(gx, gy, ox[i], oy[i]),
+                                  p->radius, loc_scale);
           idl[pl] = i;
           double var = oerr[i] * oerr[i]; /* GridObservation.hpp:239-252 */
           if (valid && !valid[i]) var = INFINITY;
@@ -581,7 +709,7 @@ static int letkf_snapshot(const orc_letkf_params* p, double* X, const int32_t* o
     }
     free(idx); free(idl); free(Yl); free(dl); free(rinv); ws_free(&w);
   }
-  free(Yp); free(d);
+  free(Yp); free(d); free(levmap);
   return rc_all;
 }
 
@@ -643,8 +771,19 @@ int orc_letkf(const orc_letkf_params* p, double* X, const int32_t* ox, const int
               const int64_t* cols_sel, int64_t ncols_sel, int32_t* counts_out, double* W_out) {
   if (p->semantics == ORC_SEM_AS_WRITTEN)
     return letkf_as_written(p, X, ox, oy, oz, oval, oerr, valid, counts_out);
-  return letkf_snapshot(p, X, ox, oy, oz, oval, oerr, valid, cols_sel, ncols_sel, counts_out,
+  return letkf_snapshot(p, NULL, X, ox, oy, oz, oval, oerr, valid, cols_sel, ncols_sel, counts_out,
                         W_out);
+}
+
+/* Snapshot LETKF with GEOGRAPHIC observation / grid locations and / or a multi-variable state (the WRF-shaped
+ * case: Location.hpp:213-217 distances, IdentityObsOperator.hpp:236-281 variable access).  ox, oy, oz are the
+ * observations' nearest grid points (orc_geo_locate). */
+int orc_letkf_ext(const orc_letkf_params* p, const orc_ext* ext, double* X, const int32_t* ox,
+                  const int32_t* oy, const int32_t* oz, const double* oval, const double* oerr,
+                  const uint8_t* valid, const int64_t* cols_sel, int64_t ncols_sel, int32_t* counts_out,
+                  double* W_out) {
+  if (ext && ext->nvar > 63) return -4;
+  return letkf_snapshot(p, ext, X, ox, oy, oz, oval, oerr, valid, cols_sel, ncols_sel, counts_out, W_out);
 }
 
 /* ------------------------------------------------------------------ global ETKF */

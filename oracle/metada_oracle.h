@@ -95,6 +95,39 @@ int orc_letkf(const orc_letkf_params* p, double* X, const int32_t* ox, const int
               const int32_t* oz, const double* oval, const double* oerr, const uint8_t* valid,
               const int64_t* cols_sel, int64_t ncols_sel, int32_t* counts_out, double* W_out);
 
+/* ---- GEOGRAPHIC locations and multi-variable states (the WRF-shaped case) ---------------------- */
+
+/* Location::distance_to for two GEOGRAPHIC locations: haversine kilometres, R = 6371 km
+ * (Location.hpp:213-217, 325, 333, 349-357). */
+double orc_distance_geo(double lat1, double lon1, double lat2, double lon2);
+
+/* LETKF.hpp:159-165 with GEOGRAPHIC locations.  min_margin (optional, in/out): smallest |distance - radius|
+ * seen -- the tests use it to show that no pair sits within rounding of the cutoff. */
+int64_t orc_select_local_geo(double clat, double clon, int64_t P, const double* olat, const double* olon,
+                             double radius, int32_t* idx_out, double* min_margin);
+void orc_select_counts_geo(int nx, int ny, const double* glat, const double* glon, int64_t P,
+                           const double* olat, const double* olon, double radius, int32_t* counts,
+                           double* min_margin);
+
+/* IdentityObsOperator::convertGeographicToGrid (IdentityObsOperator.hpp:484-530): nearest grid point (first
+ * minimum of the Euclidean distance in degrees over glat/glon [ny][nx]) and nearest vertical level. */
+void orc_geo_locate(int64_t P, const double* olat, const double* olon, const double* olev,
+                    const double* glat, const double* glon, int nx, int ny, const double* vcoord,
+                    int nlev, int32_t* ox, int32_t* oy, int32_t* oz);
+
+typedef struct {
+  const double *glat, *glon;   /* [ny][nx] column coordinates in degrees; NULL: GRID distances            */
+  const double *olat, *olon;   /* [P] observation coordinates in degrees (with glat)                     */
+  int nvar;                    /* variables of the state, member layout [var][lev][y][x]; 0: one variable */
+  const int32_t* var_nlev;     /* [nvar] levels per variable (sum = nz)                                   */
+  const int32_t* ovar;         /* [P] variable each observation observes, NULL: variable 0               */
+} orc_ext;
+
+int orc_letkf_ext(const orc_letkf_params* p, const orc_ext* ext, double* X, const int32_t* ox,
+                  const int32_t* oy, const int32_t* oz, const double* oval, const double* oerr,
+                  const uint8_t* valid, const int64_t* cols_sel, int64_t ncols_sel, int32_t* counts_out,
+                  double* W_out);
+
 /* Global ETKF (ETKF.hpp:100-179). X in place. */
 int orc_etkf(double* X, int nx, int ny, int nz, int k, int64_t P, const int32_t* ox,
              const int32_t* oy, const int32_t* oz, const double* oval, const double* oerr,

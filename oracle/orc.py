@@ -64,6 +64,9 @@ def lib() -> C.CDLL:
         _lib.orc_loc_weight.argtypes = [C.c_int, C.c_double, C.c_double, C.c_double]
         _lib.orc_select_local.restype = C.c_int64
         _lib.orc_max_threads.restype = C.c_int
+        _lib.orc_distance_geo.restype = C.c_double
+        _lib.orc_distance_geo.argtypes = [C.c_double] * 4
+        _lib.orc_select_local_geo.restype = C.c_int64
     return _lib
 
 
@@ -174,6 +177,79 @@ def letkf(X, ox, oy, oz, oval, oerr, valid=None, *, radius, inflation=1.0, mode=
     if want_W:
         out["W"] = W
     return out
+
+
+class Ext(C.Structure):
+    _fields_ = [("glat", C.POINTER(C.c_double)), ("glon", C.POINTER(C.c_double)),
+                ("olat", C.POINTER(C.c_double)), ("olon", C.POINTER(C.c_double)),
+                ("nvar", C.c_int), ("var_nlev", C.POINTER(C.c_int32)), ("ovar", C.POINTER(C.c_int32))]
+
+
+def distance_geo(lat1, lon1, lat2, lon2) -> float:
+    """Location::distance_to, GEOGRAPHIC (haversine km)."""
+    return lib().orc_distance_geo(float(lat1), float(lon1), float(lat2), float(lon2))
+
+
+def select_local_geo(clat, clon, olat, olon, radius):
+    olat, olon = _f64(olat), _f64(olon)
+    out = np.empty(len(olat), dtype=np.int32)
+    c = lib().orc_select_local_geo(C.c_double(clat), C.c_double(clon), C.c_int64(len(olat)), _p(olat, C.c_double),
+                                   _p(olon, C.c_double), C.c_double(radius), _p(out, C.c_int32), None)
+    return out[:c].copy()
+
+
+def select_counts_geo(glat, glon, olat, olon, radius):
+    """Returns (counts [ny, nx], smallest |distance - radius| over all column/observation pairs)."""
+    glat, glon, olat, olon = _f64(glat), _f64(glon), _f64(olat), _f64(olon)
+    ny, nx = glat.shape
+    out = np.empty(nx * ny, dtype=np.int32)
+    mm = C.c_double(np.inf)
+    lib().orc_select_counts_geo(C.c_int(nx), C.c_int(ny), _p(glat, C.c_double), _p(glon, C.c_double),
+                                C.c_int64(len(olat)), _p(olat, C.c_double), _p(olon, C.c_double),
+                                C.c_double(radius), _p(out, C.c_int32), C.byref(mm))
+    return out.reshape(ny, nx), mm.value
+
+
+def geo_locate(olat, olon, olev, glat, glon, vcoord=None):
+    """IdentityObsOperator::convertGeographicToGrid: nearest grid point (x, y) and level z of every observation."""
+    glat, glon, olat, olon = _f64(glat), _f64(glon), _f64(olat), _f64(olon)
+    ny, nx = glat.shape
+    P = len(olat)
+    olev = _f64(olev) if olev is not None else None
+    vc = _f64(vcoord) if vcoord is not None else None
+    ox, oy, oz = (np.empty(P, np.int32) for _ in range(3))
+    lib().orc_geo_locate(C.c_int64(P), _p(olat, C.c_double), _p(olon, C.c_double), _p(olev, C.c_double),
+                         _p(glat, C.c_double), _p(glon, C.c_double), C.c_int(nx), C.c_int(ny),
+                         _p(vc, C.c_double), C.c_int(len(vc) if vc is not None else 0),
+                         _p(ox, C.c_int32), _p(oy, C.c_int32), _p(oz, C.c_int32))
+    return ox, oy, oz
+
+
+def letkf_ext(X, ox, oy, oz, oval, oerr, valid=None, *, radius, glat=None, glon=None, olat=None, olon=None,
+              var_nlev=None, ovar=None, inflation=1.0, loc=LOC_GASPARI_COHN, use_R=1, radius_v=0.0, nthreads=0,
+              loc_scale=0.0):
+    """Canonical snapshot LETKF with GEOGRAPHIC locations (glat/glon [ny, nx], olat/olon [P]; radius in km) and / or
+    a multi-variable state (var_nlev, ovar).  ox, oy, oz: nearest grid points (geo_locate).  Returns dict(Xa, counts)."""
+    Xa = _f64(X).copy()
+    k, nz, ny, nx = Xa.shape
+    ox, oy, oz = _i32(ox), _i32(oy), _i32(oz)
+    oval, oerr = _f64(oval), _f64(oerr)
+    P = len(ox)
+    v = np.ascontiguousarray(valid, dtype=np.uint8) if valid is not None else None
+    keep = [_f64(a) if a is not None else None for a in (glat, glon, olat, olon)]
+    vn = _i32(var_nlev) if var_nlev is not None else None
+    ov = _i32(ovar) if ovar is not None else None
+    ext = Ext(_p(keep[0], C.c_double), _p(keep[1], C.c_double), _p(keep[2], C.c_double), _p(keep[3], C.c_double),
+              len(vn) if vn is not None else 0, _p(vn, C.c_int32), _p(ov, C.c_int32))
+    prm = LetkfParams(nx, ny, nz, k, P, radius, radius_v, inflation, MODE_CANONICAL, loc, use_R, SEM_SNAPSHOT,
+                      nthreads, loc_scale)
+    counts = np.full(nx * ny, -1, dtype=np.int32)
+    rc = lib().orc_letkf_ext(C.byref(prm), C.byref(ext), _p(Xa, C.c_double), _p(ox, C.c_int32), _p(oy, C.c_int32),
+                             _p(oz, C.c_int32), _p(oval, C.c_double), _p(oerr, C.c_double), _p(v, C.c_uint8),
+                             None, C.c_int64(0), _p(counts, C.c_int32), None)
+    if rc:
+        raise RuntimeError(f"orc_letkf_ext failed rc={rc}")
+    return {"Xa": Xa, "counts": counts.reshape(ny, nx)}
 
 
 def etkf(X, ox, oy, oz, oval, oerr, valid=None, *, inflation=1.0):

@@ -129,15 +129,39 @@ def metrics_case(tmp):
             "mean": b[5:5 + n].reshape(nz, ny, nx).copy(), "spread": b[5 + n:5 + 2 * n].reshape(nz, ny, nx).copy()}
 
 
+def location_case(tmp):
+    """The reference's Location::distance_to (oracle/_ref/ref_location) on seeded GEOGRAPHIC pairs: regional pairs
+    (the LETKF selection regime), global pairs, dateline crossings, identical and antipodal points."""
+    rng = np.random.default_rng(2024)
+    n = 4000
+    a = np.empty((n, 4))
+    a[:, 0] = rng.uniform(-89, 89, n); a[:, 1] = rng.uniform(-180, 180, n)
+    a[:1500, 2] = a[:1500, 0] + rng.uniform(-1.5, 1.5, 1500)            # regional: within ~200 km
+    a[:1500, 3] = a[:1500, 1] + rng.uniform(-2.0, 2.0, 1500)
+    a[1500:, 2] = rng.uniform(-90, 90, n - 1500); a[1500:, 3] = rng.uniform(-180, 180, n - 1500)
+    a[:, 2] = np.clip(a[:, 2], -90, 90)
+    a[3000:3200, 1] = rng.uniform(178, 180, 200); a[3000:3200, 3] = rng.uniform(-180, -178, 200)   # dateline
+    a[3200:3300, 2:] = a[3200:3300, :2]                                   # identical points
+    a[3300:3400, 2] = -a[3300:3400, 0]; a[3300:3400, 3] = a[3300:3400, 1] + 180.0   # antipodes
+    inp, out = os.path.join(tmp, "l_in.bin"), os.path.join(tmp, "l_out.bin")
+    with open(inp, "wb") as f:
+        f.write(struct.pack("<q", n))
+        f.write(np.ascontiguousarray(a).tobytes())
+    subprocess.check_call([os.path.join(ROOT, "oracle", "_ref", "ref_location"), inp, out])
+    return {"pairs": a, "km": np.frombuffer(open(out, "rb").read(), dtype="<f8").copy()}
+
+
 def main():
     subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle"), "ref"], stdout=subprocess.DEVNULL)
     with tempfile.TemporaryDirectory() as tmp:
         np.savez_compressed(os.path.join(OUT, "metrics_7x11x6x3.npz"), **metrics_case(tmp))
     with tempfile.TemporaryDirectory() as tmp:
+        np.savez_compressed(os.path.join(OUT, "location_geographic.npz"), **location_case(tmp))
+    with tempfile.TemporaryDirectory() as tmp:
         np.savez_compressed(os.path.join(OUT, "tutorial_36x18.npz"), **tutorial(tmp))
     with tempfile.TemporaryDirectory() as tmp:
         np.savez_compressed(os.path.join(OUT, "synthetic_23x17.npz"), **synthetic_case(tmp))
-    for f in ("tutorial_36x18.npz", "synthetic_23x17.npz", "metrics_7x11x6x3.npz"):
+    for f in ("tutorial_36x18.npz", "synthetic_23x17.npz", "metrics_7x11x6x3.npz", "location_geographic.npz"):
         g = np.load(os.path.join(OUT, f))
         print(f, {k: (g[k].shape if g[k].ndim else g[k].item()) for k in g.files})
 

@@ -1,0 +1,180 @@
+"""GPU parity for GEOGRAPHIC observations and multi-variable states, through the C ABI.
+
+Bars: nearest grid point / level of every observation bit-exact (IdentityObsOperator.hpp:484-530); local-observation
+counts and sets bit-exact against the brute-force haversine scan of the oracle (LETKF.hpp:159-165 with
+Location.hpp:213-217) -- the device's sin / cos / atan2 are not glibc's, so each test also shows that no pair sits
+within 1e-9 km of the cutoff; Y, Y', d bit-exact; analysis mean and perturbations relative <= 1e-10.
+"""
+import numpy as np
+import pytest
+
+import metada_b200 as mb
+from metada_b200 import capi, synthetic as syn
+from oracle import orc
+from tests.common import analysis_errors
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-10
+VC = np.array([1000.0, 925.0, 850.0, 700.0, 500.0, 300.0])
+
+
+def _geo_case(nx, ny, nz, k, P, seed, vc=None, **geo):
+    lat, lon = syn.geography(nx, ny, **geo)
+    o = syn.geo_observations(P, lat, lon, vc, seed=seed)
+    X = syn.ensemble(k, nx, ny, nz, seed=900 + seed)
+    return lat, lon, o, X
+
+
+def _setup(ctx, X, lat, lon, o, vc=None):
+    k, nz, ny, nx = X.shape
+    ens = mb.Ensemble(ctx, nx, ny, nz, k)
+    ens.upload(X)
+    ens.set_geography(lat, lon, vc)
+    obs = mb.Observations.geographic(ctx, o["lat"], o["lon"], o["level"], o["value"], o["err"], o["valid"])
+    return ens, obs
+
+
+def test_locate_bit_exact_with_ties_and_levels(ctx):
+    lat, lon, o, X = _geo_case(37, 29, 6, 4, 3000, seed=1, vc=VC)
+    ens, obs = _setup(ctx, X, lat, lon, o, VC)
+    obs.locate(ens)
+    x, y, z = obs.grid_coords()
+    ex, ey, ez = orc.geo_locate(o["lat"], o["lon"], o["level"], lat, lon, VC)
+    assert np.array_equal(x, ex) and np.array_equal(y, ey) and np.array_equal(z, ez)
+    ens.close(); obs.close()
+    # exact ties on a regular grid with representable spacing: the first grid point in linear order wins;
+    # more grid points (2 x 2048 + ...) than one shared-memory tile
+    lat, lon = syn.geography(96, 50, lat0=10.0, lon0=20.0, dlat=0.25, dlon=0.5, curvilinear=False)
+    rng = np.random.default_rng(3)
+    olat = 10.0 + 0.125 * rng.integers(-2, 2 * 50 + 2, 2000)
+    olon = 20.0 + 0.25 * rng.integers(-2, 2 * 96 + 2, 2000)
+    ens = mb.Ensemble(ctx, 96, 50, 1, 2)
+    ens.set_geography(lat, lon)
+    obs = mb.Observations.geographic(ctx, olat, olon, None, np.zeros(2000), np.ones(2000))
+    obs.locate(ens)
+    x, y, z = obs.grid_coords()
+    ex, ey, ez = orc.geo_locate(olat, olon, None, lat, lon, None)
+    assert np.array_equal(x, ex) and np.array_equal(y, ey) and (z == 0).all()
+    ens.close(); obs.close()
+
+
+@pytest.mark.parametrize("radius", [0.0, 12.0, 45.0, 110.0])
+@pytest.mark.parametrize("lon0", [-104.0, 176.5])
+def test_haversine_selection_counts_and_sets_bit_exact(ctx, radius, lon0):
+    """lon0 = 176.5: the domain crosses the dateline (columns at +179.9 and -179.9 degrees are neighbours)."""
+    lat, lon, o, X = _geo_case(45, 31, 1, 2, 1500, seed=2, lon0=lon0)
+    if lon0 > 0:
+        assert lon.min() < -175 and lon.max() > 175
+    ens, obs = _setup(ctx, X, lat, lon, o)
+    counts = obs.query_counts(ens, radius)
+    ref, margin = orc.select_counts_geo(lat, lon, o["lat"], o["lon"], radius)
+    assert margin > 1e-9, margin                  # no pair within rounding of the cutoff: the sets are well defined
+    assert np.array_equal(counts, ref)
+    if radius > 40:
+        assert ref.max() > 20
+    cols = np.array([0, 44, 45 * 15 + 20, 45 * 31 - 1, 777], np.int64)
+    lists, cnt = obs.query_lists(ens, radius, cols, cap=1500)
+    for c, lst, n in zip(cols, lists, cnt):
+        want = orc.select_local_geo(lat.ravel()[c], lon.ravel()[c], o["lat"], o["lon"], radius)
+        assert n == len(want)
+        assert sorted(lst.tolist()) == want.tolist()
+    ens.close(); obs.close()
+
+
+def _check_analysis(ctx, X, lat, lon, o, vc, radius, var_nlev=None, ovar=None, solver=mb.SOLVER_AUTO, radius_v=0.0,
+                    loc=mb.LOC_GASPARI_COHN, inflation=1.0):
+    ens, obs = _setup(ctx, X, lat, lon, o, vc)
+    if var_nlev is not None:
+        ens.set_variables(var_nlev)
+        obs.set_variables(ovar)
+    obs.hx(ens)
+    x, y, z = obs.grid_coords()
+    ex, ey, ez = orc.geo_locate(o["lat"], o["lon"], o["level"], lat, lon, vc)
+    assert np.array_equal(x, ex) and np.array_equal(y, ey) and np.array_equal(z, ez)
+    st = capi.letkf_analyse(ens, obs, capi.make_params(radius, inflation, mb.MODE_CANONICAL, loc, solver=solver,
+                                                      radius_v=radius_v))
+    Xa = ens.download()
+    ref = orc.letkf_ext(X, ex, ey, ez, o["value"], o["err"], o["valid"], radius=radius, glat=lat, glon=lon,
+                        olat=o["lat"], olon=o["lon"], var_nlev=var_nlev, ovar=ovar, radius_v=radius_v, loc=loc,
+                        inflation=inflation)
+    if radius_v == 0.0:      # (with per-level transforms the device counts the level-0 sets)
+        assert st["sum_local_obs"] == int(ref["counts"].sum())
+        assert st["max_local_obs"] == int(ref["counts"].max())
+    em, ep = analysis_errors(Xa, ref["Xa"])
+    assert em < TOL and ep < TOL, (em, ep)
+    assert np.abs(ref["Xa"] - X).max() > 1e-3
+    ens.close(); obs.close()
+    return st
+
+
+@pytest.mark.parametrize("k,solver", [(12, mb.SOLVER_AUTO), (40, mb.SOLVER_AUTO), (40, mb.SOLVER_JACOBI), (80, mb.SOLVER_AUTO)])
+def test_geographic_letkf_matches_oracle(ctx, k, solver):
+    """k = 12: Jacobi kernel; k = 40, 80: packed Newton-Schulz kernel (+ the observation-space kernel for the columns
+    with few local observations at the domain edge)."""
+    lat, lon, o, X = _geo_case(30, 22, 3, k, 900, seed=4, vc=VC[:3])
+    st = _check_analysis(ctx, X, lat, lon, o, VC[:3], radius=55.0, solver=solver)
+    assert st["columns"] == 30 * 22
+
+
+def test_geographic_few_local_observations_take_the_observation_space_kernel(ctx):
+    """Sparse observations: most columns have p_loc <= 24 and 2 p_loc <= k, which the packed kernel hands to the
+    observation-space kernel (its EXT instantiation); some columns have no local observation at all."""
+    lat, lon, o, X = _geo_case(28, 21, 2, 64, 120, seed=9, vc=VC[:2])
+    st = _check_analysis(ctx, X, lat, lon, o, VC[:2], radius=30.0, inflation=1.02)
+    assert st["small_transforms"] > 100, st
+
+
+def test_geographic_letkf_across_the_dateline_with_reference_localisation_function(ctx):
+    lat, lon, o, X = _geo_case(26, 20, 2, 24, 700, seed=5, vc=VC[:2], lon0=178.6, lat0=-48.0)
+    _check_analysis(ctx, X, lat, lon, o, VC[:2], radius=60.0, loc=mb.LOC_GAUSSIAN, inflation=1.05)
+
+
+@pytest.mark.parametrize("radius_v", [0.0, 1.5])
+def test_geographic_multivariable_state(ctx, radius_v):
+    """Three variables ([nzg, nzg, 1] levels: two 3-D fields and a surface field), each observation reads its own
+    variable; with vertical localisation the level distance is taken inside the variables."""
+    var_nlev = [4, 4, 1]
+    lat, lon, o, X = _geo_case(24, 18, sum(var_nlev), 32, 800, seed=6, vc=VC[:4])
+    ovar = np.random.default_rng(8).integers(0, 3, 800).astype(np.int32)
+    st = _check_analysis(ctx, X, lat, lon, o, VC[:4], radius=50.0, var_nlev=var_nlev, ovar=ovar, radius_v=radius_v)
+    assert st["columns"] == 24 * 18
+
+
+def test_grid_observations_on_a_multivariable_state(ctx):
+    """GRID coordinates (integer distances) with per-observation variables: H and Y' bit-exact, analysis <= 1e-10."""
+    nx, ny, k, P = 21, 17, 24, 500
+    var_nlev = [3, 1, 3]
+    nz = sum(var_nlev)
+    X = syn.ensemble(k, nx, ny, nz, seed=4321)
+    o = syn.observations(P, nx, ny, 3, seed=12)
+    ovar = np.random.default_rng(9).integers(0, 3, P).astype(np.int32)
+    ens = mb.Ensemble(ctx, nx, ny, nz, k)
+    ens.upload(X)
+    ens.set_variables(var_nlev)
+    obs = mb.Observations(ctx, o["x"], o["y"], o["z"], o["value"], o["err"], o["valid"])
+    obs.set_variables(ovar)
+    for radius_v in (0.0, 1.0):
+        ens.upload(X)
+        st = capi.letkf_analyse(ens, obs, capi.make_params(4.0, 1.0, mb.MODE_CANONICAL, mb.LOC_GASPARI_COHN, radius_v=radius_v))
+        ref = orc.letkf_ext(X, o["x"], o["y"], o["z"], o["value"], o["err"], o["valid"], radius=4.0,
+                            var_nlev=var_nlev, ovar=ovar, radius_v=radius_v)
+        if radius_v == 0.0:
+            assert st["sum_local_obs"] == int(ref["counts"].sum())
+        em, ep = analysis_errors(ens.download(), ref["Xa"])
+        assert em < TOL and ep < TOL, (radius_v, em, ep)
+    ens.close(); obs.close()
+
+
+def test_unsupported_geographic_requests_fail_loudly(ctx):
+    lat, lon, o, X = _geo_case(12, 10, 1, 8, 50, seed=7)
+    ens, obs = _setup(ctx, X, lat, lon, o)
+    with pytest.raises(mb.MdcError, match="CANONICAL"):
+        capi.letkf_analyse(ens, obs, capi.make_params(50.0, 1.0, mb.MODE_REF_COMPAT, mb.LOC_CUTOFF))
+    with pytest.raises(mb.MdcError, match="pole"):
+        obs.query_counts(ens, 7000.0)
+    with pytest.raises(mb.MdcError, match="index"):
+        obs.index_build(8)
+    plain = mb.Ensemble(ctx, 12, 10, 1, 8)
+    with pytest.raises(mb.MdcError, match="geography"):
+        obs.locate(plain)
+    plain.close(); ens.close(); obs.close()

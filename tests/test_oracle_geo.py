@@ -1,0 +1,136 @@
+"""CPU checks of the oracle's GEOGRAPHIC / multi-variable restatement.
+
+Pin: orc_distance_geo against the reference's own Location.hpp (tests/golden/location_geographic.npz, made by
+oracle/_ref/ref_location from the unmodified header) -- bit-exact, NaNs at antipodes included.  The nearest-grid-point
+search (IdentityObsOperator.hpp:484-530) sits in a class that needs the WRF/NetCDF geometry and cannot be compiled
+here; it is restated and cross-checked against an independent NumPy restatement."""
+import os
+
+import numpy as np
+
+from metada_b200 import synthetic as syn
+from oracle import orc
+from tests import np_twin
+from tests.common import rel_err
+
+G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def test_haversine_matches_reference_location_header_bit_exactly():
+    g = np.load(os.path.join(G, "location_geographic.npz"))
+    got = np.array([orc.distance_geo(*r) for r in g["pairs"]])
+    same = (got == g["km"]) | (np.isnan(got) & np.isnan(g["km"]))
+    assert same.all(), np.nonzero(~same)[0][:10]
+    assert np.isnan(g["km"]).sum() > 0          # the reference returns NaN for (near-)antipodal pairs: a > 1
+    # closed-form sanity: one degree of latitude on a 6371 km sphere
+    assert abs(orc.distance_geo(10.0, 20.0, 11.0, 20.0) - 6371.0 * np.pi / 180.0) < 1e-9
+    assert orc.distance_geo(10.0, 179.5, 10.0, -179.5) < 120.0   # across the dateline
+
+
+def _np_locate(olat, olon, olev, glat, glon, vc):
+    d = np.sqrt((olon[:, None] - glon.ravel()[None, :]) ** 2 + (olat[:, None] - glat.ravel()[None, :]) ** 2)
+    idx = d.argmin(1)                            # numpy argmin = first minimum, as the strict '<' scan
+    nx = glat.shape[1]
+    z = np.abs(olev[:, None] - vc[None, :]).argmin(1) if vc is not None else np.zeros(len(olat), int)
+    return idx % nx, idx // nx, z
+
+
+def test_geo_locate_first_minimum_and_levels():
+    lat, lon = syn.geography(31, 23)
+    vc = np.array([1000.0, 925.0, 850.0, 700.0, 500.0, 300.0])
+    o = syn.geo_observations(400, lat, lon, vc, seed=5)
+    ox, oy, oz = orc.geo_locate(o["lat"], o["lon"], o["level"], lat, lon, vc)
+    ex, ey, ez = _np_locate(o["lat"], o["lon"], o["level"], lat, lon, vc)
+    assert np.array_equal(ox, ex) and np.array_equal(oy, ey) and np.array_equal(oz, ez)
+    # exact ties (regular grid with representable spacing, observations on cell corners / edge midpoints):
+    # the FIRST grid point in linear order wins
+    lat, lon = syn.geography(9, 7, lat0=10.0, lon0=20.0, dlat=0.25, dlon=0.5, curvilinear=False)
+    olat = np.array([10.125, 10.125, 10.25, 11.5 + 0.125])
+    olon = np.array([20.25, 20.5, 20.75, 24.0 + 0.25])
+    ox, oy, oz = orc.geo_locate(olat, olon, None, lat, lon, None)
+    assert list(zip(ox, oy)) == [(0, 0), (1, 0), (1, 1), (8, 6)]
+    assert (oz == 0).all()
+
+
+def _np_letkf_geo(X, o, ox, oy, lat, lon, radius, var_nlev=None, ovar=None, oz=None):
+    """Independent NumPy restatement: canonical transform per column (numpy.linalg.eigh), haversine selection,
+    Gaspari-Cohn weights, H by 4-point IDW at the located integer coordinates (exact hit: weight 1e12)."""
+    k, nz, ny, nx = X.shape
+    var_nlev = [nz] if var_nlev is None else list(var_nlev)
+    off = np.concatenate([[0], np.cumsum(var_nlev)])
+    nzg = max(var_nlev)
+    P = len(ox)
+    Y = np.empty((P, k))
+    for i in range(P):
+        v = 0 if ovar is None else int(ovar[i])
+        x = float(np.clip(ox[i], 0, nx - 1)); y = float(np.clip(oy[i], 0, ny - 1))
+        z = float(np.clip(oz[i] if oz is not None else 0, 0, nzg - 1))
+        i0, j0, k0 = int(x), int(y), int(z)
+        i1, j1, k1 = min(i0 + 1, nx - 1), min(j0 + 1, ny - 1), min(k0 + 1, nzg - 1)
+        if nzg == 1:
+            nb = [(i0, j0, 0), (i1, j0, 0), (i0, j1, 0), (i1, j1, 0)]
+        else:
+            c8 = [(i0, j0, k0), (i1, j0, k0), (i0, j1, k0), (i1, j1, k0), (i0, j0, k1), (i1, j0, k1), (i0, j1, k1), (i1, j1, k1)]
+            nb = sorted(c8, key=lambda c: np.sqrt((x - c[0]) ** 2 + (y - c[1]) ** 2 + (z - c[2]) ** 2))[:4]   # stable
+        ws = wsum = 0.0
+        for (ii, jj, kk) in nb:
+            dd = np.sqrt((x - ii) ** 2 + (y - jj) ** 2 + (z - kk) ** 2)
+            w = 1e12 if dd == 0.0 else 1.0 / dd
+            lev = off[v] + (kk if var_nlev[v] > 1 else 0)
+            ws = ws + w * X[:, lev, jj, ii]
+            wsum += w
+        Y[i] = ws / wsum
+    Yp = Y - Y.mean(1, keepdims=True)
+    d = o["value"] - Y.mean(1)
+    Xa = X.copy()
+    for gy in range(ny):
+        for gx in range(nx):
+            dist = np.array([orc.distance_geo(lat[gy, gx], lon[gy, gx], a, b) for a, b in zip(o["lat"], o["lon"])])
+            idx = np.nonzero(dist <= radius)[0]
+            if len(idx) == 0:
+                continue
+            rho = np.array([np_twin.gaspari_cohn(dd / (0.5 * radius)) for dd in dist[idx]])
+            rinv = rho / o["err"][idx] ** 2
+            Yl = Yp[idx]
+            A = (Yl.T * rinv) @ Yl + (k - 1) * np.eye(k)
+            ev, V = np.linalg.eigh(A)
+            wa = V @ ((V.T @ ((Yl.T * rinv) @ d[idx])) / ev)
+            Wa = (V * np.sqrt((k - 1) / ev)) @ V.T
+            x = X[:, :, gy, gx]                       # [k, nz]
+            m = x.mean(0)
+            Xa[:, :, gy, gx] = m[None, :] + (wa[:, None] + Wa).T @ (x - m[None, :])   # Xa = xbar + X'(w 1^T + W)
+    return Xa
+
+
+def test_letkf_ext_geographic_multivariable_against_numpy():
+    nx, ny, k = 12, 9, 10
+    var_nlev = [3, 3, 1]
+    nz = sum(var_nlev)
+    lat, lon = syn.geography(nx, ny, lat0=44.0, lon0=170.0, dlat=0.4, dlon=1.1)   # crosses the dateline
+    assert lon.min() < -170 and lon.max() > 170
+    vc = np.array([1000.0, 850.0, 500.0])
+    o = syn.geo_observations(60, lat, lon, vc, seed=11)
+    rng = np.random.default_rng(1)
+    ovar = rng.integers(0, 3, 60).astype(np.int32)
+    X = syn.ensemble(k, nx, ny, nz, seed=1234)
+    ox, oy, oz = orc.geo_locate(o["lat"], o["lon"], o["level"], lat, lon, vc)
+    radius = 150.0
+    r = orc.letkf_ext(X, ox, oy, oz, o["value"], o["err"], o["valid"], radius=radius, glat=lat, glon=lon,
+                      olat=o["lat"], olon=o["lon"], var_nlev=var_nlev, ovar=ovar)
+    counts, margin = orc.select_counts_geo(lat, lon, o["lat"], o["lon"], radius)
+    assert np.array_equal(r["counts"], counts) and counts.max() > 3 and margin > 1e-9
+    ref = _np_letkf_geo(X, o, ox, oy, lat, lon, radius, var_nlev, ovar, oz)
+    assert rel_err(r["Xa"], ref) < 1e-11
+    assert np.abs(r["Xa"] - X).max() > 1e-3      # the analysis did something
+
+
+def test_letkf_ext_without_extensions_is_orc_letkf():
+    X = syn.ensemble(8, 10, 7, 2, seed=77)
+    o = syn.observations(40, 10, 7, 2, seed=5)
+    a = orc.letkf(X, o["x"], o["y"], o["z"], o["value"], o["err"], o["valid"], radius=3.0, radius_v=1.0)
+    b = orc.letkf_ext(X, o["x"], o["y"], o["z"], o["value"], o["err"], o["valid"], radius=3.0, radius_v=1.0)
+    assert np.array_equal(a["Xa"], b["Xa"]) and np.array_equal(a["counts"], b["counts"])
+    # one declared variable spanning every level is the same thing
+    c = orc.letkf_ext(X, o["x"], o["y"], o["z"], o["value"], o["err"], o["valid"], radius=3.0, radius_v=1.0,
+                      var_nlev=[2], ovar=np.zeros(40, np.int32))
+    assert np.array_equal(a["Xa"], c["Xa"])

@@ -61,7 +61,9 @@ __device__ __forceinline__ double lk_gaspari_cohn(double z) {
   z = fabs(z);
   if (z >= 2.0) return 0.0;
   if (z <= 1.0) return (((-0.25 * z + 0.5) * z + 0.625) * z - 5.0 / 3.0) * z * z + 1.0;
-  return ((((z / 12.0 - 0.5) * z + 0.625) * z + 5.0 / 3.0) * z - 5.0) * z + 4.0 - 2.0 / (3.0 * z);
+  // close to the end of the support the polynomial cancels to a few 1e-16 of either sign; the taper is >= 0 and the
+  // kernels take the square root of the weight
+  return fmax(((((z / 12.0 - 0.5) * z + 0.625) * z + 5.0 / 3.0) * z - 5.0) * z + 4.0 - 2.0 / (3.0 * z), 0.0);
 }
 
 // The reference's localisation functions (LWEnKF.hpp:597-635).  Not inlined: two double-precision

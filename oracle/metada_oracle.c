@@ -271,7 +271,8 @@ double orc_gaspari_cohn(double z) {
   if (z >= 2.0) return 0.0;
   if (z <= 1.0)
     return (((-0.25 * z + 0.5) * z + 0.625) * z - 5.0 / 3.0) * z * z + 1.0;
-  return ((((z / 12.0 - 0.5) * z + 0.625) * z + 5.0 / 3.0) * z - 5.0) * z + 4.0 - 2.0 / (3.0 * z);
+  /* close to z = 2 the polynomial cancels to a few 1e-16 of either sign; the taper itself is >= 0 */
+  return fmax(((((z / 12.0 - 0.5) * z + 0.625) * z + 5.0 / 3.0) * z - 5.0) * z + 4.0 - 2.0 / (3.0 * z), 0.0);
 }
 
 /* LWEnKF.hpp:597-621 (switch over LocalizationFunction) and :624-635 (the reference's own

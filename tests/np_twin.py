@@ -9,7 +9,7 @@ def gaspari_cohn(z):
         return 0.0
     if z <= 1:
         return (((-0.25 * z + 0.5) * z + 0.625) * z - 5.0 / 3.0) * z * z + 1.0
-    return ((((z / 12.0 - 0.5) * z + 0.625) * z + 5.0 / 3.0) * z - 5.0) * z + 4.0 - 2.0 / (3.0 * z)
+    return max(((((z / 12.0 - 0.5) * z + 0.625) * z + 5.0 / 3.0) * z - 5.0) * z + 4.0 - 2.0 / (3.0 * z), 0.0)
 
 
 def hx_idw4_2d(member, ox, oy):

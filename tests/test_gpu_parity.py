@@ -382,3 +382,23 @@ def test_streamed_host_pipeline_is_bit_identical_to_one_shot(ctx, slab_rows, wor
     sl.close()
     assert np.array_equal(host, one_shot)
     assert st2["columns"] == nx * ny and st2["sum_local_obs"] == st1["sum_local_obs"]
+
+
+@pytest.mark.parametrize("k", [12, 40])
+def test_gaspari_cohn_weight_at_the_edge_of_its_support_is_not_negative(ctx, k):
+    """radius = 5 (1 + 1e-10): observations at distance exactly 5 (offsets (5, 0), (3, 4), ...) sit 1e-10 inside the
+    support, where the taper's polynomial cancels to -2.8e-16; the kernels take sqrt(rho), so an unclamped weight
+    turned the whole column into NaN."""
+    nx, ny, nz, P = 24, 19, 2, 600
+    X, o = make_case(nx, ny, nz, k, P, seed=21)
+    radius = 5.0000000005
+    z = 5.0 / (0.5 * radius)
+    assert z < 2.0 and ((((z / 12.0 - 0.5) * z + 0.625) * z + 5.0 / 3.0) * z - 5.0) * z + 4.0 - 2.0 / (3.0 * z) < 0.0
+    ens, obs = _setup(ctx, X, o)
+    capi.letkf_analyse(ens, obs, capi.make_params(radius, 1.0, mb.MODE_CANONICAL, mb.LOC_GASPARI_COHN))
+    Xa = ens.download()
+    assert np.isfinite(Xa).all()
+    ref = orc.letkf(X, o["x"], o["y"], o["z"], o["value"], o["err"], o["valid"], radius=radius)
+    em, ep = analysis_errors(Xa, ref["Xa"])
+    assert em < TOL and ep < TOL, (em, ep)
+    ens.close(); obs.close()

@@ -14,10 +14,10 @@ from metada_b200 import capi, synthetic as syn
 def main():
     ctx = mb.Context(0)
     out = []
-    for name, nx, ny, var_nlev, k, P, radius in (("wrf-300", 300, 300, [30, 30, 30, 1], 40, 60000, 40.0),
-                                                 ("wrf-600", 600, 600, [30, 30, 1], 80, 250000, 40.0)):
+    for name, nx, ny, var_nlev, k, P, radius, dlat, dlon in (("wrf-300", 300, 300, [30, 30, 30, 1], 40, 60000, 40.0, 0.09, 0.11),
+                                                             ("wrf-600", 600, 600, [30, 30, 1], 80, 250000, 20.0, 0.045, 0.055)):
         nz = sum(var_nlev)
-        lat, lon = syn.geography(nx, ny)
+        lat, lon = syn.geography(nx, ny, dlat=dlat, dlon=dlon)
         vc = np.linspace(1000.0, 100.0, max(var_nlev))
         o = syn.geo_observations(P, lat, lon, vc, seed=42)
         ens = mb.Ensemble(ctx, nx, ny, nz, k)
@@ -25,7 +25,7 @@ def main():
         ens.set_variables(var_nlev)
         obs = mb.Observations.geographic(ctx, o["lat"], o["lon"], o["level"], o["value"], o["err"], o["valid"])
         obs.set_variables(np.random.default_rng(1).integers(0, len(var_nlev), P).astype(np.int32))
-        rec = {"case": name, "nx": nx, "ny": ny, "var_nlev": var_nlev, "k": k, "P": P, "radius_km": radius}
+        rec = {"case": name, "nx": nx, "ny": ny, "var_nlev": var_nlev, "k": k, "P": P, "radius_km": radius, "grid_spacing_deg": [dlat, dlon]}
         for it in range(3):
             ens.fill_synthetic(1000)
             ctx.sync()

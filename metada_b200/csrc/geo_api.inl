@@ -8,13 +8,14 @@ int mdc_ens_set_geography(mdc_ens* e, const double* lat, const double* lon, int 
   MDC_CUDA(ctx, cudaSetDevice(ctx->device));
   const size_t G = (size_t)e->nx * e->ny;
   // extents on the host: circular mean longitude (the unwrap centre), then min / max of the unwrapped offsets
-  double sx = 0.0, sy = 0.0, latmin = 1e300, latmax = -1e300;
+  double sx = 0.0, sy = 0.0, latmin = 1e300, latmax = -1e300, lonmin = 1e300, lonmax = -1e300;
   const double rad = 3.14159265358979323846 / 180.0;
   for (size_t i = 0; i < G; ++i) {
     if (!(lat[i] >= -90.0 && lat[i] <= 90.0) || !std::isfinite(lon[i]))
       MDC_FAIL(ctx, MDC_ERR_INVALID, "set_geography: column %zu has latitude %g longitude %g", i, lat[i], lon[i]);
     sx += std::cos(lon[i] * rad); sy += std::sin(lon[i] * rad);
     latmin = std::min(latmin, lat[i]); latmax = std::max(latmax, lat[i]);
+    lonmin = std::min(lonmin, lon[i]); lonmax = std::max(lonmax, lon[i]);
   }
   const double lon_c = (sx == 0.0 && sy == 0.0) ? 0.0 : std::atan2(sy, sx) / rad;
   double umin = 1e300, umax = -1e300;
@@ -30,6 +31,35 @@ int mdc_ens_set_geography(mdc_ens* e, const double* lat, const double* lon, int 
   if (nlev > 0) {
     if (dev_alloc(ctx, &e->vcoord, (size_t)nlev)) return MDC_ERR_CUDA;
     MDC_CUDA(ctx, cudaMemcpyAsync(e->vcoord, vertical_coords, (size_t)nlev * 8, cudaMemcpyHostToDevice, ctx->stream));
+  }
+  // cells for the nearest-grid-point search: squares of the raw (lon, lat) plane holding ~4 grid points on average
+  {
+    const double ext_x = std::max(lonmax - lonmin, 1e-9), ext_y = std::max(latmax - latmin, 1e-9);
+    double c = std::max(std::sqrt(ext_x * ext_y / (double)G * 4.0), std::max(ext_x, ext_y) / 8192.0);
+    while ((std::floor(ext_x / c) + 1.0) * (std::floor(ext_y / c) + 1.0) > 16777216.0) c *= 2.0;
+    e->gc_lon0 = lonmin; e->gc_lat0 = latmin; e->gc_c = c;
+    e->gc_ncx = (int)std::floor(ext_x / c) + 1; e->gc_ncy = (int)std::floor(ext_y / c) + 1;
+    const size_t ncell = (size_t)e->gc_ncx * e->gc_ncy;
+    cudaFree(e->gc_start); cudaFree(e->gc_pts); cudaFree(e->gc_plat); cudaFree(e->gc_plon);
+    e->gc_start = nullptr; e->gc_pts = nullptr; e->gc_plat = nullptr; e->gc_plon = nullptr;
+    int32_t *key = nullptr, *fill = nullptr;
+    if (dev_alloc(ctx, &e->gc_start, ncell + 1) || dev_alloc(ctx, &e->gc_pts, G) || dev_alloc(ctx, &e->gc_plat, G) ||
+        dev_alloc(ctx, &e->gc_plon, G) || dev_alloc(ctx, &key, G) || dev_alloc(ctx, &fill, ncell))
+      return MDC_ERR_CUDA;
+    cudaStream_t s = ctx->stream;
+    GeoCells gc{e->gc_lon0, e->gc_lat0, 1.0 / c, c, e->gc_ncx, e->gc_ncy};
+    MDC_CUDA(ctx, cudaMemsetAsync(fill, 0, ncell * sizeof(int32_t), s));
+    geo_cell_key_kernel<<<grid_for(ctx, (int64_t)G, 256, 8), 256, 0, s>>>((int64_t)G, e->glat, e->glon, gc, key, fill);
+    MDC_LAUNCH_CHECK(ctx);
+    index_scan_kernel<<<1, 1024, 0, s>>>(fill, e->gc_start, (int)ncell);
+    MDC_LAUNCH_CHECK(ctx);
+    MDC_CUDA(ctx, cudaMemsetAsync(fill, 0, ncell * sizeof(int32_t), s));
+    index_scatter_kernel<<<grid_for(ctx, (int64_t)G, 256, 8), 256, 0, s>>>(key, (int64_t)G, e->gc_start, fill, e->gc_pts);
+    MDC_LAUNCH_CHECK(ctx);
+    geo_cell_gather_kernel<<<grid_for(ctx, (int64_t)G, 256, 8), 256, 0, s>>>((int64_t)G, e->gc_pts, e->glat, e->glon, e->gc_plat, e->gc_plon);
+    MDC_LAUNCH_CHECK(ctx);
+    MDC_CUDA(ctx, cudaStreamSynchronize(s));
+    cudaFree(key); cudaFree(fill);
   }
   MDC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   e->geo = true;
@@ -121,10 +151,16 @@ int mdc_obs_locate(mdc_obs* o, mdc_ens* e) {
   if (e->gnx != e->nx || e->gny != e->ny)
     MDC_FAIL(ctx, MDC_ERR_UNSUPPORTED, "obs_locate: geographic observations are not supported on a decomposed domain");
   MDC_CUDA(ctx, cudaSetDevice(ctx->device));
-  if (o->P > 0) {
+  if (o->P > 0 && getenv("MDC_GEO_LOCATE_BRUTE")) {   // the reference's O(P G) scan, kept as a cross-check
     geo_locate_kernel<<<mdc_div_up(o->P, 256), 256, 0, ctx->stream>>>(o->P, o->lat, o->lon, o->lev, e->glat, e->glon,
                                                                     (int64_t)e->nx * e->ny, e->nx, e->vcoord, e->nvcoord,
                                                                     o->x, o->y, o->z);
+    MDC_LAUNCH_CHECK(ctx);
+  } else if (o->P > 0) {                                // ring walk over the bucketed grid points, same result
+    GeoCells gc{e->gc_lon0, e->gc_lat0, 1.0 / e->gc_c, e->gc_c, e->gc_ncx, e->gc_ncy};
+    geo_locate_ring_kernel<<<mdc_div_up(o->P, 128), 128, 0, ctx->stream>>>(o->P, o->lat, o->lon, o->lev, gc, e->gc_start, e->gc_pts,
+                                                                         e->gc_plat, e->gc_plon, e->nx, e->vcoord, e->nvcoord,
+                                                                         o->x, o->y, o->z);
     MDC_LAUNCH_CHECK(ctx);
   }
   o->located = true;

@@ -72,6 +72,100 @@ __global__ void __launch_bounds__(256) geo_locate_kernel(int64_t P, const double
   oz[i] = kz;
 }
 
+// ---- O(P) nearest grid point: the grid points are bucketed once per geometry into square cells of the raw
+// (longitude, latitude) plane (the reference's metric is the plain Euclidean distance in degrees, no wrap), an
+// observation walks the rings of cells around its own.  Before ring rho every unvisited point lies in a cell at
+// Chebyshev distance >= rho, i.e. at least (rho - 1) c away (the observation can sit anywhere in its own cell), so the
+// walk stops as soon as the best distance is below (rho - 1) c (1 - 1e-9) -- the margin covers the rounding of the
+// cell assignment.  Ties are resolved as the reference's
+// linear scan does (strict '<' in index order = smallest linear index among equal rounded distances), so the result
+// is bit-identical to geo_locate_kernel.
+struct GeoCells {
+  double lon0, lat0, inv_c, c;
+  int ncx, ncy;
+};
+
+__device__ __forceinline__ void geo_cell_of(const GeoCells& gc, double lat, double lon, int& cx, int& cy) {
+  const double fx = floor((lon - gc.lon0) * gc.inv_c), fy = floor((lat - gc.lat0) * gc.inv_c);
+  cx = (int)fmin(fmax(fx, 0.0), (double)(gc.ncx - 1));
+  cy = (int)fmin(fmax(fy, 0.0), (double)(gc.ncy - 1));
+}
+
+__global__ void geo_cell_key_kernel(int64_t G, const double* __restrict__ glat, const double* __restrict__ glon,
+                                    GeoCells gc, int32_t* __restrict__ key, int32_t* __restrict__ hist) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < G; i += (int64_t)gridDim.x * blockDim.x) {
+    int cx, cy;
+    geo_cell_of(gc, glat[i], glon[i], cx, cy);
+    const int kk = cy * gc.ncx + cx;
+    key[i] = kk;
+    atomicAdd(hist + kk, 1);
+  }
+}
+
+// coordinates in cell order next to the linear grid index: the ring walk then reads three sequential arrays
+__global__ void geo_cell_gather_kernel(int64_t G, const int32_t* __restrict__ pts, const double* __restrict__ glat,
+                                       const double* __restrict__ glon, double* __restrict__ plat,
+                                       double* __restrict__ plon) {
+  for (int64_t a = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; a < G; a += (int64_t)gridDim.x * blockDim.x) {
+    const int32_t g = pts[a];
+    plat[a] = glat[g]; plon[a] = glon[g];
+  }
+}
+
+__global__ void __launch_bounds__(128) geo_locate_ring_kernel(int64_t P, const double* __restrict__ olat,
+                                                              const double* __restrict__ olon,
+                                                              const double* __restrict__ olev, GeoCells gc,
+                                                              const int32_t* __restrict__ cell_start,
+                                                              const int32_t* __restrict__ pts,
+                                                              const double* __restrict__ plat,
+                                                              const double* __restrict__ plon, int nx,
+                                                              const double* __restrict__ vcoord, int nlev,
+                                                              int32_t* __restrict__ ox, int32_t* __restrict__ oy,
+                                                              int32_t* __restrict__ oz) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= P) return;
+  const double lat = olat[i], lon = olon[i];
+  int cx, cy;
+  geo_cell_of(gc, lat, lon, cx, cy);
+  double best = DBL_MAX, best2 = INFINITY;
+  int best_idx = 0x7fffffff;
+  const int rho_max = max(max(cx, gc.ncx - 1 - cx), max(cy, gc.ncy - 1 - cy));
+  for (int rho = 0; rho <= rho_max; ++rho) {
+    if (rho > 1 && best < (double)(rho - 1) * gc.c * (1.0 - 1e-9)) break;   // rings >= rho are at least (rho - 1) c away
+    const int y0 = cy - rho, y1 = cy + rho;
+    for (int yy = max(y0, 0); yy <= min(y1, gc.ncy - 1); ++yy) {
+      const bool edge_row = (yy == y0 || yy == y1);
+      // full row of the ring on its top / bottom edge, the two end cells otherwise
+      const int step = edge_row ? 1 : max(2 * rho, 1);
+      for (int xx = cx - rho; xx <= cx + rho; xx += step) {
+        if (xx < 0 || xx >= gc.ncx) continue;
+        const int cell = yy * gc.ncx + xx;
+        for (int a = cell_start[cell]; a < cell_start[cell + 1]; ++a) {
+          const double dx = __dsub_rn(lon, plon[a]), dy = __dsub_rn(lat, plat[a]);
+          const double d2 = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));
+          if (d2 <= best2 * (1.0 + 1e-15)) {   // (a larger d2 can still round to the same root and win on its index)
+            const double dd = __dsqrt_rn(d2);
+            const int g = pts[a];
+            if (dd < best || (dd == best && g < best_idx)) { best = dd; best2 = d2; best_idx = g; }
+          }
+        }
+      }
+    }
+  }
+  int kz = 0;
+  if (vcoord && nlev > 0) {
+    const double level = olev ? olev[i] : 0.0;
+    double mv = DBL_MAX;
+    for (int z = 0; z < nlev; ++z) {
+      const double dist = fabs(__dsub_rn(level, vcoord[z]));
+      if (dist < mv) { mv = dist; kz = z; }
+    }
+  }
+  ox[i] = best_idx % nx;
+  oy[i] = best_idx / nx;
+  oz[i] = kz;
+}
+
 struct GeoLattice {
   double lon_c;              // unwrap centre: u = (lon - lon_c) - 360 rint((lon - lon_c) / 360) in [-180, 180]
   double u0, lat0;           // lattice origin (minimum over the columns)

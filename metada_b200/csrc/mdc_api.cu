@@ -54,6 +54,17 @@ void tmp_free(mdc_ctx* ctx, T* p) {
   if (p) cudaFreeAsync((void*)p, ctx->stream);
 }
 
+int ensure_copy_stream(mdc_ctx* ctx) {
+  if (ctx->copy_stream) return MDC_OK;
+  MDC_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+  for (int i = 0; i < 2; ++i) {
+    MDC_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_full[i], cudaEventDisableTiming));
+    MDC_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_free[i], cudaEventDisableTiming));
+  }
+  MDC_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_start, cudaEventDisableTiming));
+  return MDC_OK;
+}
+
 int ensure_stage(mdc_ens* e, size_t elems) {
   if (e->stage_elems >= elems) return MDC_OK;
   if (e->stage) cudaFree(e->stage);
@@ -116,6 +127,12 @@ int mdc_ctx_destroy(mdc_ctx* ctx) {
   cudaEventDestroy(ctx->ev0);
   cudaEventDestroy(ctx->ev1);
   for (auto& e : ctx->pe) cudaEventDestroy(e);
+  if (ctx->copy_stream) {
+    cudaStreamSynchronize(ctx->copy_stream);
+    for (int i = 0; i < 2; ++i) { cudaEventDestroy(ctx->ev_full[i]); cudaEventDestroy(ctx->ev_free[i]); }
+    cudaEventDestroy(ctx->ev_start);
+    cudaStreamDestroy(ctx->copy_stream);
+  }
   cudaStreamDestroy(ctx->stream);
   delete ctx;
   return MDC_OK;
@@ -194,6 +211,7 @@ int mdc_ens_destroy(mdc_ens* e) {
   if (e->mean) cudaFree(e->mean);
   if (e->stage) cudaFree(e->stage);
   cudaFree(e->glat); cudaFree(e->glon); cudaFree(e->vcoord); cudaFree(e->levmap);
+  cudaFree(e->gc_start); cudaFree(e->gc_pts); cudaFree(e->gc_plat); cudaFree(e->gc_plon);
   delete e;
   return MDC_OK;
 }
@@ -272,16 +290,30 @@ int mdc_ens_upload_members_rows(mdc_ens* e, int m0, int count, const double* con
   MDC_CUDA(ctx, cudaSetDevice(ctx->device));
   const int64_t G = (int64_t)e->nx * e->ny, n = G * e->nz;
   const size_t width = (size_t)e->ny * e->nx * sizeof(double), spitch = (size_t)host_ny * e->nx * sizeof(double);
-  for (int mb = 0; mb < count; mb += kMemberBatch) {
-    const int cb = std::min(kMemberBatch, count - mb);
-    if (int rc = ensure_stage(e, (size_t)n * cb)) return rc;
+  // Double-buffered staging: the H2D copies of batch b + 1 run on the copy stream while the transpose of batch b
+  // runs on the context's stream (one buffer and one stream serialised them: 6.2 ms per 8-member batch of a C5 slab
+  // instead of the 4.1 ms the copy alone takes).
+  if (int rc = ensure_copy_stream(ctx)) return rc;
+  const size_t half = (size_t)n * std::min(kMemberBatch, count);
+  if (int rc = ensure_stage(e, 2 * half)) return rc;
+  cudaStream_t ms = ctx->stream, cs = ctx->copy_stream;
+  MDC_CUDA(ctx, cudaEventRecord(ctx->ev_start, ms));            // earlier work on the stream may still read the staging buffer
+  MDC_CUDA(ctx, cudaStreamWaitEvent(cs, ctx->ev_start, 0));
+  int b = 0;
+  for (int mb = 0; mb < count; mb += kMemberBatch, ++b) {
+    const int cb = std::min(kMemberBatch, count - mb), h = b & 1;
+    double* st = e->stage + (size_t)h * half;
+    if (b >= 2) MDC_CUDA(ctx, cudaStreamWaitEvent(cs, ctx->ev_free[h], 0));   // the transpose of batch b - 2 has read this half
     for (int c = 0; c < cb; ++c)
-      MDC_CUDA(ctx, cudaMemcpy2DAsync(e->stage + (int64_t)c * n, width, hosts[mb + c] + (int64_t)host_y0 * e->nx, spitch, width,
-                                      (size_t)e->nz, cudaMemcpyHostToDevice, ctx->stream));
-    ens_scatter_members_kernel<<<mdc_div_up(n, 256), 256, 0, ctx->stream>>>(e->X, e->stage, 0, n, G, e->nz, e->k, m0 + mb, cb);
+      MDC_CUDA(ctx, cudaMemcpy2DAsync(st + (int64_t)c * n, width, hosts[mb + c] + (int64_t)host_y0 * e->nx, spitch, width,
+                                      (size_t)e->nz, cudaMemcpyHostToDevice, cs));
+    MDC_CUDA(ctx, cudaEventRecord(ctx->ev_full[h], cs));
+    MDC_CUDA(ctx, cudaStreamWaitEvent(ms, ctx->ev_full[h], 0));
+    ens_scatter_members_kernel<<<mdc_div_up(n, 256), 256, 0, ms>>>(e->X, st, 0, n, G, e->nz, e->k, m0 + mb, cb);
     MDC_LAUNCH_CHECK(ctx);
+    MDC_CUDA(ctx, cudaEventRecord(ctx->ev_free[h], ms));
   }
-  return MDC_OK;
+  return MDC_OK;   // everything the caller may wait for is on the context's stream
 }
 
 int mdc_ens_download_members_rows(mdc_ens* e, int m0, int count, double* const* hosts, int host_ny,
@@ -293,17 +325,27 @@ int mdc_ens_download_members_rows(mdc_ens* e, int m0, int count, double* const* 
   const int64_t G = (int64_t)e->nx * e->ny, n = G * e->nz;
   const size_t spitch = (size_t)e->ny * e->nx * sizeof(double), dpitch = (size_t)host_ny * e->nx * sizeof(double);
   const size_t width = (size_t)nrows * e->nx * sizeof(double);
-  for (int mb = 0; mb < count; mb += kMemberBatch) {
-    const int cb = std::min(kMemberBatch, count - mb);
-    if (int rc = ensure_stage(e, (size_t)n * cb)) return rc;
-    ens_gather_members_kernel<<<mdc_div_up(n, 256), 256, 0, ctx->stream>>>(e->X, e->stage, 0, n, G, e->nz, e->k, m0 + mb, cb);
+  // double-buffered like the upload: the transpose of batch b + 1 overlaps the D2H copies of batch b
+  if (int rc = ensure_copy_stream(ctx)) return rc;
+  const size_t half = (size_t)n * std::min(kMemberBatch, count);
+  if (int rc = ensure_stage(e, 2 * half)) return rc;
+  cudaStream_t ms = ctx->stream, cs = ctx->copy_stream;
+  int b = 0;
+  for (int mb = 0; mb < count; mb += kMemberBatch, ++b) {
+    const int cb = std::min(kMemberBatch, count - mb), h = b & 1;
+    double* st = e->stage + (size_t)h * half;
+    if (b >= 2) MDC_CUDA(ctx, cudaStreamWaitEvent(ms, ctx->ev_free[h], 0));   // the copies of batch b - 2 have drained this half
+    ens_gather_members_kernel<<<mdc_div_up(n, 256), 256, 0, ms>>>(e->X, st, 0, n, G, e->nz, e->k, m0 + mb, cb);
     MDC_LAUNCH_CHECK(ctx);
+    MDC_CUDA(ctx, cudaEventRecord(ctx->ev_full[h], ms));
+    MDC_CUDA(ctx, cudaStreamWaitEvent(cs, ctx->ev_full[h], 0));
     for (int c = 0; c < cb; ++c)
-      MDC_CUDA(ctx, cudaMemcpy2DAsync(hosts[mb + c] + (int64_t)host_y0 * e->nx, dpitch, e->stage + (int64_t)c * n, spitch, width,
-                                      (size_t)e->nz, cudaMemcpyDeviceToHost, ctx->stream));
-    // the next batch reuses the staging buffer: same stream, so ordered after these copies
+      MDC_CUDA(ctx, cudaMemcpy2DAsync(hosts[mb + c] + (int64_t)host_y0 * e->nx, dpitch, st + (int64_t)c * n, spitch, width,
+                                      (size_t)e->nz, cudaMemcpyDeviceToHost, cs));
+    MDC_CUDA(ctx, cudaEventRecord(ctx->ev_free[h], cs));
   }
-  MDC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  MDC_CUDA(ctx, cudaStreamSynchronize(cs));
+  MDC_CUDA(ctx, cudaStreamSynchronize(ms));
   return MDC_OK;
 }
 

@@ -20,6 +20,9 @@ struct mdc_ctx {
   size_t flush_bytes = 0;
   int* d_flags = nullptr;      // [16] device scratch for error flags / counters
   long long* d_stats = nullptr;  // [16]
+  // second stream + events of the double-buffered row-slab transfers (copies overlap the member transposes)
+  cudaStream_t copy_stream = nullptr;
+  cudaEvent_t ev_full[2] = {nullptr, nullptr}, ev_free[2] = {nullptr, nullptr}, ev_start = nullptr;
   long long* redo_items = nullptr;  // transforms handed from the packed Newton-Schulz kernel to its fallback
   size_t redo_cap = 0;
 };
@@ -41,6 +44,11 @@ struct mdc_ens {
   double* vcoord = nullptr;                    // [nvcoord] or nullptr
   int nvcoord = 0;
   double geo_lon_c = 0.0, geo_umin = 0.0, geo_umax = 0.0, geo_latmin = 0.0, geo_latmax = 0.0;  // host-side extents
+  // grid points bucketed in the (longitude, latitude) plane for the nearest-grid-point search (geo_kernels.cuh)
+  double gc_lon0 = 0.0, gc_lat0 = 0.0, gc_c = 0.0;
+  int gc_ncx = 0, gc_ncy = 0;
+  int32_t *gc_start = nullptr, *gc_pts = nullptr;
+  double *gc_plat = nullptr, *gc_plon = nullptr;
   // variables (mdc_ens_set_variables): nz = sum of var_nlev; nzg = levels of the geometry (largest variable)
   int nvar = 0, nzg = 0;
   int var_off[16] = {0}, var_nlev[16] = {0};

@@ -34,7 +34,7 @@ from . import capi
 
 
 class StreamedLetkf:
-    def __init__(self, device, gnx, gny, nz, k, radius, slab_rows=32, slots=4, sm_reserve=4, workers=None,
+    def __init__(self, device, gnx, gny, nz, k, radius, slab_rows=32, slots=4, sm_reserve=8, workers=None,
                  row_range=None):
         """row_range = (Y0, Y1): analyse only the global rows [Y0, Y1) (one rank's share of a
         column-sharded job, parallel.py); default: the whole grid."""

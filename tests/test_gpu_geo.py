@@ -34,8 +34,16 @@ def _setup(ctx, X, lat, lon, o, vc=None):
     return ens, obs
 
 
-def test_locate_bit_exact_with_ties_and_levels(ctx):
-    lat, lon, o, X = _geo_case(37, 29, 6, 4, 3000, seed=1, vc=VC)
+@pytest.mark.parametrize("brute", [False, True])
+def test_locate_bit_exact_with_ties_and_levels(ctx, brute, monkeypatch):
+    """brute = False: ring walk over the bucketed grid points (the default); True: the reference's O(P G) scan."""
+    if brute:
+        monkeypatch.setenv("MDC_GEO_LOCATE_BRUTE", "1")
+    else:
+        monkeypatch.delenv("MDC_GEO_LOCATE_BRUTE", raising=False)
+    lat, lon = syn.geography(37, 29)
+    o = syn.geo_observations(3000, lat, lon, VC, seed=1, margin=0.35)     # a third of them outside the domain
+    X = syn.ensemble(4, 37, 29, 6, seed=901)
     ens, obs = _setup(ctx, X, lat, lon, o, VC)
     obs.locate(ens)
     x, y, z = obs.grid_coords()
@@ -56,6 +64,18 @@ def test_locate_bit_exact_with_ties_and_levels(ctx):
     ex, ey, ez = orc.geo_locate(olat, olon, None, lat, lon, None)
     assert np.array_equal(x, ex) and np.array_equal(y, ey) and (z == 0).all()
     ens.close(); obs.close()
+    # a domain across the dateline (raw longitudes jump from +180 to -180) and a single-row grid
+    for nx, ny, kw in ((45, 31, {"lon0": 176.5}), (40, 1, {"curvilinear": False})):
+        lat, lon = syn.geography(nx, ny, **kw)
+        o = syn.geo_observations(1500, lat, lon, None, seed=2, margin=0.2)
+        ens = mb.Ensemble(ctx, nx, ny, 1, 2)
+        ens.set_geography(lat, lon)
+        obs = mb.Observations.geographic(ctx, o["lat"], o["lon"], None, o["value"], o["err"])
+        obs.locate(ens)
+        x, y, z = obs.grid_coords()
+        ex, ey, ez = orc.geo_locate(o["lat"], o["lon"], None, lat, lon, None)
+        assert np.array_equal(x, ex) and np.array_equal(y, ey)
+        ens.close(); obs.close()
 
 
 @pytest.mark.parametrize("radius", [0.0, 12.0, 45.0, 110.0])

@@ -32,34 +32,41 @@ int mdc_ens_set_geography(mdc_ens* e, const double* lat, const double* lon, int 
     if (dev_alloc(ctx, &e->vcoord, (size_t)nlev)) return MDC_ERR_CUDA;
     MDC_CUDA(ctx, cudaMemcpyAsync(e->vcoord, vertical_coords, (size_t)nlev * 8, cudaMemcpyHostToDevice, ctx->stream));
   }
-  // cells for the nearest-grid-point search: squares of the raw (lon, lat) plane holding ~4 grid points on average
+  // cells for the nearest-grid-point search: squares of the raw (lon, lat) plane holding ~4 grid points on average,
+  // and a second level of GEO_COARSE x GEO_COARSE times larger ones
   {
     const double ext_x = std::max(lonmax - lonmin, 1e-9), ext_y = std::max(latmax - latmin, 1e-9);
     double c = std::max(std::sqrt(ext_x * ext_y / (double)G * 4.0), std::max(ext_x, ext_y) / 8192.0);
     while ((std::floor(ext_x / c) + 1.0) * (std::floor(ext_y / c) + 1.0) > 16777216.0) c *= 2.0;
-    e->gc_lon0 = lonmin; e->gc_lat0 = latmin; e->gc_c = c;
-    e->gc_ncx = (int)std::floor(ext_x / c) + 1; e->gc_ncy = (int)std::floor(ext_y / c) + 1;
-    const size_t ncell = (size_t)e->gc_ncx * e->gc_ncy;
-    cudaFree(e->gc_start); cudaFree(e->gc_pts); cudaFree(e->gc_plat); cudaFree(e->gc_plon);
-    e->gc_start = nullptr; e->gc_pts = nullptr; e->gc_plat = nullptr; e->gc_plon = nullptr;
-    int32_t *key = nullptr, *fill = nullptr;
-    if (dev_alloc(ctx, &e->gc_start, ncell + 1) || dev_alloc(ctx, &e->gc_pts, G) || dev_alloc(ctx, &e->gc_plat, G) ||
-        dev_alloc(ctx, &e->gc_plon, G) || dev_alloc(ctx, &key, G) || dev_alloc(ctx, &fill, ncell))
-      return MDC_ERR_CUDA;
+    e->gc_lon0 = lonmin; e->gc_lat0 = latmin; e->gc_lon1 = lonmax; e->gc_lat1 = latmax;
     cudaStream_t s = ctx->stream;
-    GeoCells gc{e->gc_lon0, e->gc_lat0, 1.0 / c, c, e->gc_ncx, e->gc_ncy};
-    MDC_CUDA(ctx, cudaMemsetAsync(fill, 0, ncell * sizeof(int32_t), s));
-    geo_cell_key_kernel<<<grid_for(ctx, (int64_t)G, 256, 8), 256, 0, s>>>((int64_t)G, e->glat, e->glon, gc, key, fill);
-    MDC_LAUNCH_CHECK(ctx);
-    index_scan_kernel<<<1, 1024, 0, s>>>(fill, e->gc_start, (int)ncell);
-    MDC_LAUNCH_CHECK(ctx);
-    MDC_CUDA(ctx, cudaMemsetAsync(fill, 0, ncell * sizeof(int32_t), s));
-    index_scatter_kernel<<<grid_for(ctx, (int64_t)G, 256, 8), 256, 0, s>>>(key, (int64_t)G, e->gc_start, fill, e->gc_pts);
-    MDC_LAUNCH_CHECK(ctx);
-    geo_cell_gather_kernel<<<grid_for(ctx, (int64_t)G, 256, 8), 256, 0, s>>>((int64_t)G, e->gc_pts, e->glat, e->glon, e->gc_plat, e->gc_plon);
-    MDC_LAUNCH_CHECK(ctx);
-    MDC_CUDA(ctx, cudaStreamSynchronize(s));
-    cudaFree(key); cudaFree(fill);
+    int32_t* key = nullptr;
+    if (dev_alloc(ctx, &key, G)) return MDC_ERR_CUDA;
+    for (int lv = 0; lv < 2; ++lv, c *= GEO_COARSE) {
+      e->gc_c[lv] = c;
+      e->gc_ncx[lv] = (int)std::floor(ext_x / c) + 1; e->gc_ncy[lv] = (int)std::floor(ext_y / c) + 1;
+      const size_t ncell = (size_t)e->gc_ncx[lv] * e->gc_ncy[lv];
+      cudaFree(e->gc_start[lv]); cudaFree(e->gc_pts[lv]); cudaFree(e->gc_plat[lv]); cudaFree(e->gc_plon[lv]);
+      e->gc_start[lv] = nullptr; e->gc_pts[lv] = nullptr; e->gc_plat[lv] = nullptr; e->gc_plon[lv] = nullptr;
+      int32_t* fill = nullptr;
+      if (dev_alloc(ctx, &e->gc_start[lv], ncell + 1) || dev_alloc(ctx, &e->gc_pts[lv], G) || dev_alloc(ctx, &e->gc_plat[lv], G) ||
+          dev_alloc(ctx, &e->gc_plon[lv], G) || dev_alloc(ctx, &fill, ncell))
+        return MDC_ERR_CUDA;
+      GeoCells gc{lonmin, latmin, lonmax, latmax, 1.0 / c, c, e->gc_ncx[lv], e->gc_ncy[lv], nullptr, nullptr, nullptr, nullptr};
+      MDC_CUDA(ctx, cudaMemsetAsync(fill, 0, ncell * sizeof(int32_t), s));
+      geo_cell_key_kernel<<<grid_for(ctx, (int64_t)G, 256, 8), 256, 0, s>>>((int64_t)G, e->glat, e->glon, gc, key, fill);
+      MDC_LAUNCH_CHECK(ctx);
+      index_scan_kernel<<<1, 1024, 0, s>>>(fill, e->gc_start[lv], (int)ncell);
+      MDC_LAUNCH_CHECK(ctx);
+      MDC_CUDA(ctx, cudaMemsetAsync(fill, 0, ncell * sizeof(int32_t), s));
+      index_scatter_kernel<<<grid_for(ctx, (int64_t)G, 256, 8), 256, 0, s>>>(key, (int64_t)G, e->gc_start[lv], fill, e->gc_pts[lv]);
+      MDC_LAUNCH_CHECK(ctx);
+      geo_cell_gather_kernel<<<grid_for(ctx, (int64_t)G, 256, 8), 256, 0, s>>>((int64_t)G, e->gc_pts[lv], e->glat, e->glon, e->gc_plat[lv], e->gc_plon[lv]);
+      MDC_LAUNCH_CHECK(ctx);
+      MDC_CUDA(ctx, cudaStreamSynchronize(s));
+      cudaFree(fill);
+    }
+    cudaFree(key);
   }
   MDC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   e->geo = true;
@@ -157,10 +164,12 @@ int mdc_obs_locate(mdc_obs* o, mdc_ens* e) {
                                                                     o->x, o->y, o->z);
     MDC_LAUNCH_CHECK(ctx);
   } else if (o->P > 0) {                                // ring walk over the bucketed grid points, same result
-    GeoCells gc{e->gc_lon0, e->gc_lat0, 1.0 / e->gc_c, e->gc_c, e->gc_ncx, e->gc_ncy};
-    geo_locate_ring_kernel<<<mdc_div_up(o->P, 128), 128, 0, ctx->stream>>>(o->P, o->lat, o->lon, o->lev, gc, e->gc_start, e->gc_pts,
-                                                                         e->gc_plat, e->gc_plon, e->nx, e->vcoord, e->nvcoord,
-                                                                         o->x, o->y, o->z);
+    GeoCells lv[2];
+    for (int l = 0; l < 2; ++l)
+      lv[l] = GeoCells{e->gc_lon0, e->gc_lat0, e->gc_lon1, e->gc_lat1, 1.0 / e->gc_c[l], e->gc_c[l], e->gc_ncx[l], e->gc_ncy[l],
+                       e->gc_start[l], e->gc_pts[l], e->gc_plat[l], e->gc_plon[l]};
+    geo_locate_ring_kernel<<<mdc_div_up(o->P, 128), 128, 0, ctx->stream>>>(o->P, o->lat, o->lon, o->lev, lv[0], lv[1], e->nx,
+                                                                         e->vcoord, e->nvcoord, o->x, o->y, o->z);
     MDC_LAUNCH_CHECK(ctx);
   }
   o->located = true;

@@ -73,16 +73,25 @@ __global__ void __launch_bounds__(256) geo_locate_kernel(int64_t P, const double
 }
 
 // ---- O(P) nearest grid point: the grid points are bucketed once per geometry into square cells of the raw
-// (longitude, latitude) plane (the reference's metric is the plain Euclidean distance in degrees, no wrap), an
-// observation walks the rings of cells around its own.  Before ring rho every unvisited point lies in a cell at
-// Chebyshev distance >= rho, i.e. at least (rho - 1) c away (the observation can sit anywhere in its own cell), so the
-// walk stops as soon as the best distance is below (rho - 1) c (1 - 1e-9) -- the margin covers the rounding of the
-// cell assignment.  Ties are resolved as the reference's
-// linear scan does (strict '<' in index order = smallest linear index among equal rounded distances), so the result
-// is bit-identical to geo_locate_kernel.
+// (longitude, latitude) plane (the reference's metric is the plain Euclidean distance in degrees, no wrap) at two
+// resolutions -- ~4 points per fine cell, 16 x 16 fine cells per coarse cell.  An observation walks the rings of
+// cells around its own (clamped into the cell grid when it lies outside).  Before ring rho every unvisited point
+// lies in a cell at Chebyshev distance >= rho, so it is at least
+//     LB(rho) = sqrt(min((dx_out + (rho-1) c)^2 + dy_out^2, dx_out^2 + (dy_out + (rho-1) c)^2))
+// away, dx_out / dy_out being the observation's distance to the grid's bounding box along each axis (0 inside); the
+// walk stops once the best distance is below LB(rho) (1 - 1e-9) -- the margin covers the rounding of the cell
+// assignment.  Observations that are not settled within GEO_FINE_RINGS fine rings (far outside the domain, or in an
+// empty corner of a projected grid's bounding box) finish on the coarse cells, whose rings grow 16 times faster.
+// Ties are resolved as the reference's linear scan does (strict '<' in index order = smallest linear index among
+// equal rounded distances), so the result is bit-identical to geo_locate_kernel.
+#define GEO_FINE_RINGS 4
+#define GEO_COARSE 16
 struct GeoCells {
-  double lon0, lat0, inv_c, c;
+  double lon0, lat0, lon1, lat1;   // bounding box of the grid points
+  double inv_c, c;
   int ncx, ncy;
+  const int32_t *start, *pts;      // [ncx*ncy + 1], [G] linear grid index in cell order
+  const double *plat, *plon;       // [G] coordinates in cell order
 };
 
 __device__ __forceinline__ void geo_cell_of(const GeoCells& gc, double lat, double lon, int& cx, int& cy) {
@@ -112,46 +121,61 @@ __global__ void geo_cell_gather_kernel(int64_t G, const int32_t* __restrict__ pt
   }
 }
 
-__global__ void __launch_bounds__(128) geo_locate_ring_kernel(int64_t P, const double* __restrict__ olat,
-                                                              const double* __restrict__ olon,
-                                                              const double* __restrict__ olev, GeoCells gc,
-                                                              const int32_t* __restrict__ cell_start,
-                                                              const int32_t* __restrict__ pts,
-                                                              const double* __restrict__ plat,
-                                                              const double* __restrict__ plon, int nx,
-                                                              const double* __restrict__ vcoord, int nlev,
-                                                              int32_t* __restrict__ ox, int32_t* __restrict__ oy,
-                                                              int32_t* __restrict__ oz) {
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= P) return;
-  const double lat = olat[i], lon = olon[i];
+// rings 0 .. rho_cap of one cell level; true when the search is settled (bound met or every cell visited)
+__device__ __forceinline__ bool geo_ring_walk(const GeoCells& gc, double lat, double lon, int rho_cap, double& best,
+                                              double& best2, int& best_idx) {
   int cx, cy;
   geo_cell_of(gc, lat, lon, cx, cy);
-  double best = DBL_MAX, best2 = INFINITY;
-  int best_idx = 0x7fffffff;
+  const double dx_out = fmax(0.0, fmax(gc.lon0 - lon, lon - gc.lon1));
+  const double dy_out = fmax(0.0, fmax(gc.lat0 - lat, lat - gc.lat1));
   const int rho_max = max(max(cx, gc.ncx - 1 - cx), max(cy, gc.ncy - 1 - cy));
   for (int rho = 0; rho <= rho_max; ++rho) {
-    if (rho > 1 && best < (double)(rho - 1) * gc.c * (1.0 - 1e-9)) break;   // rings >= rho are at least (rho - 1) c away
+    if (rho > 1) {
+      const double w = (double)(rho - 1) * gc.c;
+      const double lb2 = fmin((dx_out + w) * (dx_out + w) + dy_out * dy_out, dx_out * dx_out + (dy_out + w) * (dy_out + w));
+      if (best < sqrt(lb2) * (1.0 - 1e-9)) return true;
+    }
+    if (rho > rho_cap) return false;
     const int y0 = cy - rho, y1 = cy + rho;
     for (int yy = max(y0, 0); yy <= min(y1, gc.ncy - 1); ++yy) {
+      // the whole row on the ring's top / bottom edge, its two end cells otherwise
       const bool edge_row = (yy == y0 || yy == y1);
-      // full row of the ring on its top / bottom edge, the two end cells otherwise
       const int step = edge_row ? 1 : max(2 * rho, 1);
-      for (int xx = cx - rho; xx <= cx + rho; xx += step) {
-        if (xx < 0 || xx >= gc.ncx) continue;
+      int xx = cx - rho;
+      if (edge_row && xx < 0) xx = 0;
+      for (; xx <= min(cx + rho, gc.ncx - 1); xx += step) {
+        if (xx < 0) continue;
         const int cell = yy * gc.ncx + xx;
-        for (int a = cell_start[cell]; a < cell_start[cell + 1]; ++a) {
-          const double dx = __dsub_rn(lon, plon[a]), dy = __dsub_rn(lat, plat[a]);
+        const int b = gc.start[cell], e = gc.start[cell + 1];
+        for (int a = b; a < e; ++a) {
+          const double dx = __dsub_rn(lon, gc.plon[a]), dy = __dsub_rn(lat, gc.plat[a]);
           const double d2 = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));
           if (d2 <= best2 * (1.0 + 1e-15)) {   // (a larger d2 can still round to the same root and win on its index)
             const double dd = __dsqrt_rn(d2);
-            const int g = pts[a];
+            const int g = gc.pts[a];
             if (dd < best || (dd == best && g < best_idx)) { best = dd; best2 = d2; best_idx = g; }
           }
         }
       }
     }
   }
+  return true;
+}
+
+__global__ void __launch_bounds__(128) geo_locate_ring_kernel(int64_t P, const double* __restrict__ olat,
+                                                              const double* __restrict__ olon,
+                                                              const double* __restrict__ olev, GeoCells fine,
+                                                              GeoCells coarse, int nx,
+                                                              const double* __restrict__ vcoord, int nlev,
+                                                              int32_t* __restrict__ ox, int32_t* __restrict__ oy,
+                                                              int32_t* __restrict__ oz) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= P) return;
+  const double lat = olat[i], lon = olon[i];
+  double best = DBL_MAX, best2 = INFINITY;
+  int best_idx = 0x7fffffff;
+  if (!geo_ring_walk(fine, lat, lon, GEO_FINE_RINGS, best, best2, best_idx))
+    geo_ring_walk(coarse, lat, lon, 0x7fffffff, best, best2, best_idx);
   int kz = 0;
   if (vcoord && nlev > 0) {
     const double level = olev ? olev[i] : 0.0;

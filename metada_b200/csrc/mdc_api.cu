@@ -54,6 +54,27 @@ void tmp_free(mdc_ctx* ctx, T* p) {
   if (p) cudaFreeAsync((void*)p, ctx->stream);
 }
 
+__global__ void small_copy_kernel(const unsigned long long* __restrict__ src, unsigned long long* __restrict__ dst, int n) {
+  if ((int)threadIdx.x < n) dst[threadIdx.x] = src[threadIdx.x];
+}
+__global__ void fill4_kernel(int* dst, int a, int b, int c, int d) {
+  if (threadIdx.x == 0) { dst[0] = a; dst[1] = b; dst[2] = c; dst[3] = d; }
+}
+
+// Read `bytes` (a multiple of 8, <= 256) of device memory back to the host and synchronise the stream -- without the
+// copy engine: inside the streamed pipeline its queue holds tens of milliseconds of member transfers.
+int read_small(mdc_ctx* ctx, const void* dsrc, void* hdst, size_t bytes) {
+  if (!ctx->h_small) {
+    MDC_CUDA(ctx, cudaHostAlloc(&ctx->h_small, 256, cudaHostAllocMapped));
+    MDC_CUDA(ctx, cudaHostGetDevicePointer(&ctx->d_small, ctx->h_small, 0));
+  }
+  small_copy_kernel<<<1, 32, 0, ctx->stream>>>((const unsigned long long*)dsrc, (unsigned long long*)ctx->d_small, (int)(bytes / 8));
+  MDC_LAUNCH_CHECK(ctx);
+  MDC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  memcpy(hdst, ctx->h_small, bytes);
+  return MDC_OK;
+}
+
 int ensure_copy_stream(mdc_ctx* ctx) {
   if (ctx->copy_stream) return MDC_OK;
   MDC_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
@@ -121,6 +142,7 @@ int mdc_ctx_destroy(mdc_ctx* ctx) {
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
   if (ctx->flush_buf) cudaFree(ctx->flush_buf);
+  if (ctx->h_small) cudaFreeHost(ctx->h_small);
   cudaFree(ctx->d_flags);
   if (ctx->redo_items) cudaFree(ctx->redo_items);
   cudaFree(ctx->d_stats);
@@ -211,7 +233,7 @@ int mdc_ens_destroy(mdc_ens* e) {
   if (e->mean) cudaFree(e->mean);
   if (e->stage) cudaFree(e->stage);
   cudaFree(e->glat); cudaFree(e->glon); cudaFree(e->vcoord); cudaFree(e->levmap);
-  cudaFree(e->gc_start); cudaFree(e->gc_pts); cudaFree(e->gc_plat); cudaFree(e->gc_plon);
+  for (int l = 0; l < 2; ++l) { cudaFree(e->gc_start[l]); cudaFree(e->gc_pts[l]); cudaFree(e->gc_plat[l]); cudaFree(e->gc_plon[l]); }
   delete e;
   return MDC_OK;
 }
@@ -560,9 +582,9 @@ int mdc_hx_idw4(mdc_ens* e, mdc_obs* o) {
   int grid = (int)std::max<int64_t>(1, std::min<int64_t>((o->P + W - 1) / W, (int64_t)ctx->sm_count * 8));
   hx_idw4_kernel<W><<<grid, W * 32, smem, ctx->stream>>>(e->X, g, o->P, o->x, o->y, o->z, o->var, o->valid, o->val, o->Y, o->ybar, o->Yp, o->d, ctx->d_flags);
   MDC_LAUNCH_CHECK(ctx);
-  int flag = 0;
-  MDC_CUDA(ctx, cudaMemcpyAsync(&flag, ctx->d_flags, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-  MDC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  int flag2[2] = {0, 0};
+  if (int rc = read_small(ctx, ctx->d_flags, flag2, 8)) return rc;
+  const int flag = flag2[0];
   if (flag) MDC_FAIL(ctx, MDC_ERR_INVALID, "hx: an observation needs state outside this ensemble's local grid (+halo)");
   o->have_hx = true;
   return MDC_OK;
@@ -640,8 +662,7 @@ int mdc_obs_pack_rows(mdc_obs* o, int ylo, int yhi, double* dev_rows, int64_t ca
     MDC_LAUNCH_CHECK(ctx);
   }
   unsigned long long h = 0;
-  MDC_CUDA(ctx, cudaMemcpyAsync(&h, counter, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
-  MDC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  if (int rc = read_small(ctx, counter, &h, 8)) return rc;
   if (n) *n = (int64_t)h;   // caller compares with cap; rows beyond cap were dropped
   return MDC_OK;
 }
@@ -681,12 +702,11 @@ static int index_build_impl(mdc_obs* o, int cell) {
   o->index_P = P;
   int bbox[4] = {0, 0, 0, 0};
   if (P > 0) {
-    int init[4] = {INT_MAX, INT_MAX, INT_MIN, INT_MIN};
-    MDC_CUDA(ctx, cudaMemcpyAsync(ctx->d_flags + 4, init, sizeof(init), cudaMemcpyHostToDevice, s));
+    fill4_kernel<<<1, 32, 0, s>>>(ctx->d_flags + 4, INT_MAX, INT_MAX, INT_MIN, INT_MIN);
+    MDC_LAUNCH_CHECK(ctx);
     index_bbox_kernel<<<grid_for(ctx, P, 256, 4), 256, 0, s>>>(kx, ky, P, ctx->d_flags + 4);
     MDC_LAUNCH_CHECK(ctx);
-    MDC_CUDA(ctx, cudaMemcpyAsync(bbox, ctx->d_flags + 4, sizeof(bbox), cudaMemcpyDeviceToHost, s));
-    MDC_CUDA(ctx, cudaStreamSynchronize(s));
+    if (int rc = read_small(ctx, ctx->d_flags + 4, bbox, sizeof(bbox))) return rc;
   }
   // cell boundaries sit at global multiples of `cell` (not at this store's bounding box), so a
   // column sees its candidates in the same (cell, global id) order on every rank / slab
@@ -998,8 +1018,7 @@ int mdc_letkf_analyse(mdc_ens* e, mdc_obs* o, const mdc_letkf_params* p, mdc_let
   if (int rc = letkf_launch(e, o, p, nullptr, 0, nullptr, -1)) return rc;
   MDC_CUDA(ctx, cudaEventRecord(ctx->pe[3], s));
   long long h[16];
-  MDC_CUDA(ctx, cudaMemcpyAsync(h, ctx->d_stats, sizeof(h), cudaMemcpyDeviceToHost, s));
-  MDC_CUDA(ctx, cudaStreamSynchronize(s));
+  if (int rc = read_small(ctx, ctx->d_stats, h, sizeof(h))) return rc;
   o->have_hx = false;  // the ensemble changed: Y' is stale for a next cycle
   if (st) {
     memset(st, 0, sizeof(*st));

@@ -23,6 +23,10 @@ struct mdc_ctx {
   // second stream + events of the double-buffered row-slab transfers (copies overlap the member transposes)
   cudaStream_t copy_stream = nullptr;
   cudaEvent_t ev_full[2] = {nullptr, nullptr}, ev_free[2] = {nullptr, nullptr}, ev_start = nullptr;
+  // small results (flags, counters, statistics) come back through mapped pinned memory written by a tiny kernel:
+  // a cudaMemcpy D2H of a few bytes queues on the copy engine behind the streamed pipeline's 190 MB member batches
+  void* h_small = nullptr;       // host pointer, 256 bytes
+  void* d_small = nullptr;       // its device alias
   long long* redo_items = nullptr;  // transforms handed from the packed Newton-Schulz kernel to its fallback
   size_t redo_cap = 0;
 };
@@ -45,10 +49,11 @@ struct mdc_ens {
   int nvcoord = 0;
   double geo_lon_c = 0.0, geo_umin = 0.0, geo_umax = 0.0, geo_latmin = 0.0, geo_latmax = 0.0;  // host-side extents
   // grid points bucketed in the (longitude, latitude) plane for the nearest-grid-point search (geo_kernels.cuh)
-  double gc_lon0 = 0.0, gc_lat0 = 0.0, gc_c = 0.0;
-  int gc_ncx = 0, gc_ncy = 0;
-  int32_t *gc_start = nullptr, *gc_pts = nullptr;
-  double *gc_plat = nullptr, *gc_plon = nullptr;
+  // ([0] fine cells, [1] coarse cells)
+  double gc_lon0 = 0.0, gc_lat0 = 0.0, gc_lon1 = 0.0, gc_lat1 = 0.0, gc_c[2] = {0.0, 0.0};
+  int gc_ncx[2] = {0, 0}, gc_ncy[2] = {0, 0};
+  int32_t *gc_start[2] = {nullptr, nullptr}, *gc_pts[2] = {nullptr, nullptr};
+  double *gc_plat[2] = {nullptr, nullptr}, *gc_plon[2] = {nullptr, nullptr};
   // variables (mdc_ens_set_variables): nz = sum of var_nlev; nzg = levels of the geometry (largest variable)
   int nvar = 0, nzg = 0;
   int var_off[16] = {0}, var_nlev[16] = {0};

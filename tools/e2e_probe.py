@@ -31,7 +31,7 @@ def main():
         ens.download_ptrs(0, ptrs)
         ctx.sync()
 
-    configs = [(32, 4, 8), (32, 4, 4), (32, 5, 8), (32, 5, 16), (64, 4, 8), (16, 6, 8)]
+    configs = [(32, 4, 8), (32, 4, 4), (32, 5, 12), (48, 4, 8)]
     first = True
     for slab_rows, slots, smr in configs:
         ens2 = None

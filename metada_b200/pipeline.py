@@ -7,9 +7,11 @@ The column grid is cut into row slabs that flow through the GPU as a three-stage
     compute:     H(x) of slab s+1, obs-halo append, analyse slab s (their slots' streams)
     downloader:  member transpose + D2H copy of slab s-1           (its slot's stream)
 
-Each slab lives in one of a few reusable SLOTS (library context = CUDA stream, ensemble slab,
-observation store); three host threads hand slots to each other through queues, so both PCIe
-directions and the SMs are busy at the same time and the device only ever holds a few slabs.  The
+Each slab lives in one of a few reusable SLOTS (library context = CUDA stream + copy stream, ensemble
+slab); three host threads hand slots to each other through queues, so both PCIe directions and the SMs
+are busy at the same time and the device only ever holds a few slabs.  Every slab has its own (small)
+observation store, uploaded before the member traffic starts: a small copy issued in the steady state
+would wait on the copy engine behind ~190 MB member batches.  The
 persistent column kernel leaves a few SMs free (`sm_reserve`) so the bandwidth-bound transposes of
 the other two stages are not queued behind it.  A slab needs (i) one read-only halo row above it
 for the 4-point IDW stencil of H, uploaded with it, and (ii) the Y' rows of observations within

@@ -150,3 +150,32 @@ def test_letkf_driver_canonical_3d(tmp_path):
     ref = orc.letkf(X, o["x"], o["y"], o["z"], o["value"], np.full(P, 0.25), radius=4.0, inflation=1.0)
     em, ep = analysis_errors(Xa, ref["Xa"])
     assert em < 1e-10 and ep < 1e-10, (em, ep)
+
+
+@pytest.mark.gpu
+def test_host_layer_geographic_observations(tmp_path):
+    """C++ host layer with the reference's Location(lat, lon, level, GEOGRAPHIC): DeviceObservations +
+    DeviceEnsemble::setGeography + mdc_letkf_analyse (metada_b200/host/apps/geo_letkf_cuda.cpp) against the oracle."""
+    import struct
+    from metada_b200 import synthetic as syn
+    from oracle import orc
+    nx, ny, nz, k, P, radius = 18, 13, 3, 24, 300, 60.0
+    lat, lon = syn.geography(nx, ny)
+    vc = np.array([1000.0, 850.0, 500.0])
+    o = syn.geo_observations(P, lat, lon, vc, seed=31)
+    o["valid"][::11] = 0
+    X = syn.ensemble(k, nx, ny, nz, seed=88)
+    inp, out = str(tmp_path / "in.bin"), str(tmp_path / "out.bin")
+    with open(inp, "wb") as f:
+        f.write(struct.pack("<6qd", nx, ny, nz, k, P, len(vc), radius))
+        for a in (lat, lon, vc, X, o["lat"], o["lon"], o["level"], o["value"], o["err"], o["valid"].astype(np.float64)):
+            f.write(np.ascontiguousarray(a, dtype="<f8").tobytes())
+    r = subprocess.run([_need("geo_letkf_cuda"), inp, out], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr + r.stdout
+    Xa = np.frombuffer(open(out, "rb").read(), dtype="<f8").reshape(k, nz, ny, nx)
+    ex, ey, ez = orc.geo_locate(o["lat"], o["lon"], o["level"], lat, lon, vc)
+    ref = orc.letkf_ext(X, ex, ey, ez, o["value"], o["err"], o["valid"], radius=radius, glat=lat, glon=lon,
+                        olat=o["lat"], olon=o["lon"])
+    em, ep = analysis_errors(Xa, ref["Xa"])
+    assert em < 1e-10 and ep < 1e-10, (em, ep)
+    assert "columns %d" % (nx * ny) in r.stdout

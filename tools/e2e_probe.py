@@ -32,17 +32,14 @@ def main():
         ctx.sync()
 
     configs = [(32, 4, 8), (32, 4, 4), (32, 5, 12), (48, 4, 8)]
-    first = True
     for slab_rows, slots, smr in configs:
-        ens2 = None
         sl = mb.StreamedLetkf(0, nx, ny, nz, k, radius, slab_rows=slab_rows, slots=slots, sm_reserve=smr)
         rec = {"slab_rows": slab_rows, "slots": slots, "sm_reserve": smr, "s": []}
-        for it in range(2 if first else 1):
+        for it in range(2):               # every configuration allocates its own slots and stores: first pass = warm-up
             refill()
             t0 = time.perf_counter()
             sl.analyse(ptrs, o, params)
             rec["s"].append(time.perf_counter() - t0)
-        first = False
         dur = {}
         for kind, s, w, a, b in sl.trace:
             dur.setdefault(kind, []).append(b - a)

@@ -266,6 +266,24 @@ static void obs_space_ext(const double* X, int nx, int ny, int nz, int k, int64_
   }
 }
 
+/* H(x) of ONE member of a multi-variable state at located (integer) observation coordinates: the body of
+ * obs_space_ext exposed for the pin against the reference's IdentityObsOperator (oracle/ref_obsop_geo.cpp). */
+void orc_hx_ext(const double* member, int nx, int ny, int nz, const orc_ext* ext, int64_t P, const int32_t* ox,
+                const int32_t* oy, const int32_t* oz, const uint8_t* valid, double* out) {
+  const int64_t G = (int64_t)nx * ny;
+  int off[64] = {0}, nzg = 1;
+  (void)nz;
+  for (int v = 0; v < ext->nvar && v < 63; ++v) {
+    off[v + 1] = off[v] + ext->var_nlev[v];
+    if (ext->var_nlev[v] > nzg) nzg = ext->var_nlev[v];
+  }
+  for (int64_t i = 0; i < P; ++i) {
+    if (valid && !valid[i]) { out[i] = 0.0; continue; }
+    const int v = ext->ovar ? ext->ovar[i] : 0;
+    out[i] = hx_one_var(member + (int64_t)off[v] * G, nx, ny, nzg, ext->var_nlev[v], ox[i], oy[i], oz ? oz[i] : 0);
+  }
+}
+
 double orc_gaspari_cohn(double z) {
   z = fabs(z);
   if (z >= 2.0) return 0.0;

@@ -123,6 +123,11 @@ typedef struct {
   const int32_t* ovar;         /* [P] variable each observation observes, NULL: variable 0               */
 } orc_ext;
 
+/* IdentityObsOperator::apply for one member of a multi-variable state at located observation coordinates
+ * (IdentityObsOperator.hpp:154-180, 236-281, 681-711). */
+void orc_hx_ext(const double* member, int nx, int ny, int nz, const orc_ext* ext, int64_t P, const int32_t* ox,
+                const int32_t* oy, const int32_t* oz, const uint8_t* valid, double* out);
+
 int orc_letkf_ext(const orc_letkf_params* p, const orc_ext* ext, double* X, const int32_t* ox,
                   const int32_t* oy, const int32_t* oz, const double* oval, const double* oerr,
                   const uint8_t* valid, const int64_t* cols_sel, int64_t ncols_sel, int32_t* counts_out,

@@ -225,6 +225,20 @@ def geo_locate(olat, olon, olev, glat, glon, vcoord=None):
     return ox, oy, oz
 
 
+def hx_ext(member, ox, oy, oz, var_nlev, ovar, valid=None):
+    """H(x) of one member [nz_total, ny, nx] of a multi-variable state at located observation coordinates."""
+    member = _f64(member)
+    nz, ny, nx = member.shape
+    ox, oy, oz = _i32(ox), _i32(oy), _i32(oz)
+    vn, ov = _i32(var_nlev), _i32(ovar)
+    v = np.ascontiguousarray(valid, dtype=np.uint8) if valid is not None else None
+    ext = Ext(None, None, None, None, len(vn), _p(vn, C.c_int32), _p(ov, C.c_int32))
+    out = np.empty(len(ox))
+    lib().orc_hx_ext(_p(member, C.c_double), C.c_int(nx), C.c_int(ny), C.c_int(nz), C.byref(ext), C.c_int64(len(ox)),
+                     _p(ox, C.c_int32), _p(oy, C.c_int32), _p(oz, C.c_int32), _p(v, C.c_uint8), _p(out, C.c_double))
+    return out
+
+
 def letkf_ext(X, ox, oy, oz, oval, oerr, valid=None, *, radius, glat=None, glon=None, olat=None, olon=None,
               var_nlev=None, ovar=None, inflation=1.0, loc=LOC_GASPARI_COHN, use_R=1, radius_v=0.0, nthreads=0,
               loc_scale=0.0):

@@ -151,6 +151,34 @@ def location_case(tmp):
     return {"pairs": a, "km": np.frombuffer(open(out, "rb").read(), dtype="<f8").copy()}
 
 
+def obsop_geo_case(tmp):
+    """The reference's IdentityObsOperator (oracle/_ref/ref_obsop_geo, mock WRF-type backends) on GEOGRAPHIC
+    observations of a three-variable state ([5, 5, 1] levels) on a curvilinear grid: nearest grid point / level
+    (convertGeographicToGrid) + 4-of-8 IDW in the observation's own variable."""
+    nx, ny, var_nlev, P = 23, 17, [5, 5, 1], 600
+    nz = max(var_nlev)
+    lat, lon = syn.geography(nx, ny)
+    vc = np.array([1000.0, 925.0, 850.0, 700.0, 500.0])
+    o = syn.geo_observations(P, lat, lon, vc, seed=77, margin=0.3)
+    rng = np.random.default_rng(5)
+    ovar = rng.integers(0, 3, P)
+    valid = (rng.random(P) > 0.05)
+    state = syn.ensemble(1, nx, ny, sum(var_nlev), seed=31)[0]              # [11][ny][nx]
+    # a few observations exactly on grid points and exactly half way between two (ties)
+    o["lat"][:5], o["lon"][:5] = lat[3, 4:9], lon[3, 4:9]
+    o["lat"][5:9], o["lon"][5:9] = 0.5 * (lat[6, 2:6] + lat[6, 3:7]), 0.5 * (lon[6, 2:6] + lon[6, 3:7])
+    inp, out = os.path.join(tmp, "h_in.bin"), os.path.join(tmp, "h_out.bin")
+    with open(inp, "wb") as f:
+        f.write(struct.pack("<5q", nx, ny, nz, len(var_nlev), P))
+        f.write(struct.pack("<%dq" % len(var_nlev), *var_nlev))
+        for a in (lat, lon, vc, state, o["lat"], o["lon"], o["level"], ovar.astype(np.float64), valid.astype(np.float64)):
+            f.write(np.ascontiguousarray(a, dtype="<f8").tobytes())
+    subprocess.check_call([os.path.join(ROOT, "oracle", "_ref", "ref_obsop_geo"), inp, out])
+    return {"lat": lat, "lon": lon, "vc": vc, "state": state, "var_nlev": np.array(var_nlev, np.int32),
+            "olat": o["lat"], "olon": o["lon"], "olev": o["level"], "ovar": ovar.astype(np.int32),
+            "valid": valid.astype(np.uint8), "HX": np.frombuffer(open(out, "rb").read(), dtype="<f8").copy()}
+
+
 def main():
     subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle"), "ref"], stdout=subprocess.DEVNULL)
     with tempfile.TemporaryDirectory() as tmp:
@@ -158,10 +186,12 @@ def main():
     with tempfile.TemporaryDirectory() as tmp:
         np.savez_compressed(os.path.join(OUT, "location_geographic.npz"), **location_case(tmp))
     with tempfile.TemporaryDirectory() as tmp:
+        np.savez_compressed(os.path.join(OUT, "obsop_geographic.npz"), **obsop_geo_case(tmp))
+    with tempfile.TemporaryDirectory() as tmp:
         np.savez_compressed(os.path.join(OUT, "tutorial_36x18.npz"), **tutorial(tmp))
     with tempfile.TemporaryDirectory() as tmp:
         np.savez_compressed(os.path.join(OUT, "synthetic_23x17.npz"), **synthetic_case(tmp))
-    for f in ("tutorial_36x18.npz", "synthetic_23x17.npz", "metrics_7x11x6x3.npz", "location_geographic.npz"):
+    for f in ("tutorial_36x18.npz", "synthetic_23x17.npz", "metrics_7x11x6x3.npz", "location_geographic.npz", "obsop_geographic.npz"):
         g = np.load(os.path.join(OUT, f))
         print(f, {k: (g[k].shape if g[k].ndim else g[k].item()) for k in g.files})
 

@@ -78,6 +78,24 @@ def test_locate_bit_exact_with_ties_and_levels(ctx, brute, monkeypatch):
         ens.close(); obs.close()
 
 
+def test_device_h_matches_reference_obs_operator_golden_bit_exactly(ctx):
+    """tests/golden/obsop_geographic.npz: output of the reference's own IdentityObsOperator.hpp (mock WRF-type
+    backends, oracle/_ref/ref_obsop_geo) -- the device's location + per-variable H reproduce it bit for bit."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "obsop_geographic.npz"))
+    nz, ny, nx = g["state"].shape
+    ens = mb.Ensemble(ctx, nx, ny, nz, 1)
+    ens.upload(g["state"][None])
+    ens.set_geography(g["lat"], g["lon"], g["vc"])
+    ens.set_variables(g["var_nlev"])
+    P = len(g["olat"])
+    obs = mb.Observations.geographic(ctx, g["olat"], g["olon"], g["olev"], np.zeros(P), np.ones(P), g["valid"])
+    obs.set_variables(g["ovar"])
+    obs.hx(ens)
+    assert np.array_equal(obs.hx_download(("Y",))["Y"][:, 0], g["HX"])
+    ens.close(); obs.close()
+
+
 @pytest.mark.parametrize("radius", [0.0, 12.0, 45.0, 110.0])
 @pytest.mark.parametrize("lon0", [-104.0, 176.5])
 def test_haversine_selection_counts_and_sets_bit_exact(ctx, radius, lon0):

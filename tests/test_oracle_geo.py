@@ -1,9 +1,10 @@
 """CPU checks of the oracle's GEOGRAPHIC / multi-variable restatement.
 
-Pin: orc_distance_geo against the reference's own Location.hpp (tests/golden/location_geographic.npz, made by
-oracle/_ref/ref_location from the unmodified header) -- bit-exact, NaNs at antipodes included.  The nearest-grid-point
-search (IdentityObsOperator.hpp:484-530) sits in a class that needs the WRF/NetCDF geometry and cannot be compiled
-here; it is restated and cross-checked against an independent NumPy restatement."""
+Pins: orc_distance_geo against the reference's own Location.hpp (tests/golden/location_geographic.npz, made by
+oracle/_ref/ref_location from the unmodified header) -- bit-exact, NaNs at antipodes included; orc_geo_locate + the
+per-variable H against the reference's own IdentityObsOperator.hpp driven through mock WRF-type backends
+(tests/golden/obsop_geographic.npz, made by oracle/_ref/ref_obsop_geo) -- bit-exact.  An independent NumPy
+restatement cross-checks both."""
 import os
 
 import numpy as np
@@ -25,6 +26,24 @@ def test_haversine_matches_reference_location_header_bit_exactly():
     # closed-form sanity: one degree of latitude on a 6371 km sphere
     assert abs(orc.distance_geo(10.0, 20.0, 11.0, 20.0) - 6371.0 * np.pi / 180.0) < 1e-9
     assert orc.distance_geo(10.0, 179.5, 10.0, -179.5) < 120.0   # across the dateline
+
+
+def test_locate_and_variable_h_match_reference_obs_operator_bit_exactly():
+    """IdentityObsOperator::apply on GEOGRAPHIC observations of a [5, 5, 1]-level three-variable state: nearest grid
+    point and level (:484-530), 4-of-8 IDW (:594-638) in the observation's own variable (:681-711), invalid -> 0."""
+    g = np.load(os.path.join(G, "obsop_geographic.npz"))
+    ox, oy, oz = orc.geo_locate(g["olat"], g["olon"], g["olev"], g["lat"], g["lon"], g["vc"])
+    h = orc.hx_ext(g["state"], ox, oy, oz, g["var_nlev"], g["ovar"], g["valid"])
+    assert np.array_equal(h, g["HX"])
+    assert (g["HX"][g["valid"] == 0] == 0.0).all() and len(np.unique(oz)) == 5
+    # the first five observations sit exactly on grid points (3, 4..8): H is that point's value to 1e-11
+    # (weight 1e12 against three neighbours of weight <= 1)
+    for i in range(5):
+        if g["valid"][i]:
+            v, off = int(g["ovar"][i]), int(np.concatenate([[0], np.cumsum(g["var_nlev"])])[g["ovar"][i]])
+            lev = off + (int(oz[i]) if g["var_nlev"][v] > 1 else 0)
+            assert (ox[i], oy[i]) == (4 + i, 3)
+            assert abs(h[i] - g["state"][lev, 3, 4 + i]) < 1e-10
 
 
 def _np_locate(olat, olon, olev, glat, glon, vc):

@@ -628,7 +628,16 @@ static int letkf_snapshot(const orc_letkf_params* p, const orc_ext* ext, double*
   const int geo = ext && ext->glat;            /* GEOGRAPHIC locations: haversine kilometres */
   int* levmap = (int*)malloc(sizeof(int) * (size_t)nz);   /* level of a state level inside its variable */
   for (int l = 0; l < nz; ++l) levmap[l] = l;
-  if (ext && ext->nvar > 0) {
+  if (ext && ext->Xobs) {
+    /* Staggered grids: the analysed ensemble X lives on its own column set (e.g. the U grid, with its own glat /
+     * glon), the observations are operated on the ensemble Xobs of the grid that holds the observed variables
+     * (nx_obs x ny_obs, nz_obs levels in all; var_nlev / ovar describe ITS variables).  X is one variable. */
+    if (ext->nvar > 0) {
+      obs_space_ext(ext->Xobs, ext->nx_obs, ext->ny_obs, ext->nz_obs, k, P, ox, oy, oz, valid, oval, ext, Y, Yp, d);
+    } else {
+      orc_obs_space(ext->Xobs, ext->nx_obs, ext->ny_obs, ext->nz_obs, k, P, ox, oy, oz, valid, oval, Y, NULL, Yp, d);
+    }
+  } else if (ext && ext->nvar > 0) {
     int tot = 0;
     for (int v = 0; v < ext->nvar; ++v)
       for (int l = 0; l < ext->var_nlev[v]; ++l) if (tot < nz) levmap[tot++] = l;

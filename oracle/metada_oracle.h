@@ -121,6 +121,10 @@ typedef struct {
   int nvar;                    /* variables of the state, member layout [var][lev][y][x]; 0: one variable */
   const int32_t* var_nlev;     /* [nvar] levels per variable (sum = nz)                                   */
   const int32_t* ovar;         /* [P] variable each observation observes, NULL: variable 0               */
+  /* staggered grids: H is evaluated on this ensemble ([k][nz_obs][ny_obs][nx_obs], the grid that holds the     */
+  /* observed variables -- var_nlev / ovar then describe it) instead of the analysed X; NULL: on X itself       */
+  const double* Xobs;
+  int nx_obs, ny_obs, nz_obs;
 } orc_ext;
 
 /* IdentityObsOperator::apply for one member of a multi-variable state at located observation coordinates

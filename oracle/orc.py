@@ -182,7 +182,8 @@ def letkf(X, ox, oy, oz, oval, oerr, valid=None, *, radius, inflation=1.0, mode=
 class Ext(C.Structure):
     _fields_ = [("glat", C.POINTER(C.c_double)), ("glon", C.POINTER(C.c_double)),
                 ("olat", C.POINTER(C.c_double)), ("olon", C.POINTER(C.c_double)),
-                ("nvar", C.c_int), ("var_nlev", C.POINTER(C.c_int32)), ("ovar", C.POINTER(C.c_int32))]
+                ("nvar", C.c_int), ("var_nlev", C.POINTER(C.c_int32)), ("ovar", C.POINTER(C.c_int32)),
+                ("Xobs", C.POINTER(C.c_double)), ("nx_obs", C.c_int), ("ny_obs", C.c_int), ("nz_obs", C.c_int)]
 
 
 def distance_geo(lat1, lon1, lat2, lon2) -> float:
@@ -232,7 +233,7 @@ def hx_ext(member, ox, oy, oz, var_nlev, ovar, valid=None):
     ox, oy, oz = _i32(ox), _i32(oy), _i32(oz)
     vn, ov = _i32(var_nlev), _i32(ovar)
     v = np.ascontiguousarray(valid, dtype=np.uint8) if valid is not None else None
-    ext = Ext(None, None, None, None, len(vn), _p(vn, C.c_int32), _p(ov, C.c_int32))
+    ext = Ext(None, None, None, None, len(vn), _p(vn, C.c_int32), _p(ov, C.c_int32), None, 0, 0, 0)
     out = np.empty(len(ox))
     lib().orc_hx_ext(_p(member, C.c_double), C.c_int(nx), C.c_int(ny), C.c_int(nz), C.byref(ext), C.c_int64(len(ox)),
                      _p(ox, C.c_int32), _p(oy, C.c_int32), _p(oz, C.c_int32), _p(v, C.c_uint8), _p(out, C.c_double))
@@ -241,9 +242,11 @@ def hx_ext(member, ox, oy, oz, var_nlev, ovar, valid=None):
 
 def letkf_ext(X, ox, oy, oz, oval, oerr, valid=None, *, radius, glat=None, glon=None, olat=None, olon=None,
               var_nlev=None, ovar=None, inflation=1.0, loc=LOC_GASPARI_COHN, use_R=1, radius_v=0.0, nthreads=0,
-              loc_scale=0.0):
+              loc_scale=0.0, Xobs=None):
     """Canonical snapshot LETKF with GEOGRAPHIC locations (glat/glon [ny, nx], olat/olon [P]; radius in km) and / or
-    a multi-variable state (var_nlev, ovar).  ox, oy, oz: nearest grid points (geo_locate).  Returns dict(Xa, counts)."""
+    a multi-variable state (var_nlev, ovar).  ox, oy, oz: nearest grid points (geo_locate).  Xobs [k, nz', ny', nx']:
+    staggered grids -- H is evaluated on this ensemble (whose variables var_nlev / ovar then describe) and the
+    transforms are applied to X, a single variable on its own column set glat / glon.  Returns dict(Xa, counts)."""
     Xa = _f64(X).copy()
     k, nz, ny, nx = Xa.shape
     ox, oy, oz = _i32(ox), _i32(oy), _i32(oz)
@@ -253,8 +256,12 @@ def letkf_ext(X, ox, oy, oz, oval, oerr, valid=None, *, radius, glat=None, glon=
     keep = [_f64(a) if a is not None else None for a in (glat, glon, olat, olon)]
     vn = _i32(var_nlev) if var_nlev is not None else None
     ov = _i32(ovar) if ovar is not None else None
+    xo = _f64(Xobs) if Xobs is not None else None
+    if xo is not None:
+        assert xo.shape[0] == k
     ext = Ext(_p(keep[0], C.c_double), _p(keep[1], C.c_double), _p(keep[2], C.c_double), _p(keep[3], C.c_double),
-              len(vn) if vn is not None else 0, _p(vn, C.c_int32), _p(ov, C.c_int32))
+              len(vn) if vn is not None else 0, _p(vn, C.c_int32), _p(ov, C.c_int32), _p(xo, C.c_double),
+              xo.shape[3] if xo is not None else 0, xo.shape[2] if xo is not None else 0, xo.shape[1] if xo is not None else 0)
     prm = LetkfParams(nx, ny, nz, k, P, radius, radius_v, inflation, MODE_CANONICAL, loc, use_R, SEM_SNAPSHOT,
                       nthreads, loc_scale)
     counts = np.full(nx * ny, -1, dtype=np.int32)

@@ -203,6 +203,36 @@ def test_grid_observations_on_a_multivariable_state(ctx):
     ens.close(); obs.close()
 
 
+@pytest.mark.parametrize("k", [10, 32])
+def test_staggered_grid_is_its_own_column_set_sharing_the_mass_grid_h(ctx, k):
+    """U-staggered variable (17 x 12 columns with their own coordinates) next to a mass grid (16 x 12, variables T and
+    QV): H(x) is evaluated on the mass-grid ensemble, the U columns are analysed with that Y' (mdc_hx_idw4 on one
+    store, mdc_letkf_analyse on the other), then the mass grid itself."""
+    from tests.test_oracle_geo import _staggered_case
+    lat, lon, ulat, ulon, vc, o, ovar, Xm, Xu = _staggered_case(k)
+    mass = mb.Ensemble(ctx, 16, 12, 6, k)
+    mass.upload(Xm); mass.set_geography(lat, lon, vc); mass.set_variables([3, 3])
+    ugrid = mb.Ensemble(ctx, 17, 12, 3, k)
+    ugrid.upload(Xu); ugrid.set_geography(ulat, ulon, vc)
+    obs = mb.Observations.geographic(ctx, o["lat"], o["lon"], o["level"], o["value"], o["err"], o["valid"])
+    obs.set_variables(ovar)
+    prm = capi.make_params(120.0, 1.0, mb.MODE_CANONICAL, mb.LOC_GASPARI_COHN)
+    obs.hx(mass)
+    st_u = capi.letkf_analyse(ugrid, obs, prm)          # Y' from the mass grid, columns and coordinates of the U grid
+    obs.hx(mass)                                        # (an analysis drops Y'; the mass background is still untouched)
+    st_m = capi.letkf_analyse(mass, obs, prm)
+    ox, oy, oz = orc.geo_locate(o["lat"], o["lon"], o["level"], lat, lon, vc)
+    kw = dict(radius=120.0, olat=o["lat"], olon=o["lon"], var_nlev=[3, 3], ovar=ovar)
+    ref_u = orc.letkf_ext(Xu, ox, oy, oz, o["value"], o["err"], o["valid"], glat=ulat, glon=ulon, Xobs=Xm, **kw)
+    ref_m = orc.letkf_ext(Xm, ox, oy, oz, o["value"], o["err"], o["valid"], glat=lat, glon=lon, **kw)
+    assert st_u["columns"] == 17 * 12 and st_u["sum_local_obs"] == int(ref_u["counts"].sum())
+    assert st_m["columns"] == 16 * 12 and st_m["sum_local_obs"] == int(ref_m["counts"].sum())
+    for got, ref in ((ugrid.download(), ref_u["Xa"]), (mass.download(), ref_m["Xa"])):
+        em, ep = analysis_errors(got, ref)
+        assert em < TOL and ep < TOL, (em, ep)
+    mass.close(); ugrid.close(); obs.close()
+
+
 def test_unsupported_geographic_requests_fail_loudly(ctx):
     lat, lon, o, X = _geo_case(12, 10, 1, 8, 50, seed=7)
     ens, obs = _setup(ctx, X, lat, lon, o)

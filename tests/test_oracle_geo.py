@@ -71,9 +71,12 @@ def test_geo_locate_first_minimum_and_levels():
     assert (oz == 0).all()
 
 
-def _np_letkf_geo(X, o, ox, oy, lat, lon, radius, var_nlev=None, ovar=None, oz=None):
+def _np_letkf_geo(X, o, ox, oy, lat, lon, radius, var_nlev=None, ovar=None, oz=None, Xobs=None):
     """Independent NumPy restatement: canonical transform per column (numpy.linalg.eigh), haversine selection,
     Gaspari-Cohn weights, H by 4-point IDW at the located integer coordinates (exact hit: weight 1e12)."""
+    Xa_grid = X                                     # the ensemble that is analysed (its own column set lat / lon)
+    if Xobs is not None:
+        X = Xobs                                    # staggered grids: H reads the ensemble that holds the variables
     k, nz, ny, nx = X.shape
     var_nlev = [nz] if var_nlev is None else list(var_nlev)
     off = np.concatenate([[0], np.cumsum(var_nlev)])
@@ -101,6 +104,8 @@ def _np_letkf_geo(X, o, ox, oy, lat, lon, radius, var_nlev=None, ovar=None, oz=N
         Y[i] = ws / wsum
     Yp = Y - Y.mean(1, keepdims=True)
     d = o["value"] - Y.mean(1)
+    X = Xa_grid
+    k, nz, ny, nx = X.shape
     Xa = X.copy()
     for gy in range(ny):
         for gx in range(nx):
@@ -153,3 +158,34 @@ def test_letkf_ext_without_extensions_is_orc_letkf():
     c = orc.letkf_ext(X, o["x"], o["y"], o["z"], o["value"], o["err"], o["valid"], radius=3.0, radius_v=1.0,
                       var_nlev=[2], ovar=np.zeros(40, np.int32))
     assert np.array_equal(a["Xa"], c["Xa"])
+
+
+def _staggered_case(k=10):
+    """Mass grid 16 x 12 with variables T, QV ([3, 3] levels); U grid 17 x 12 (one more column, half a cell to the
+    west) holding the single variable U; observations of T and QV."""
+    nx, ny, P = 16, 12, 120
+    lat, lon = syn.geography(nx, ny, lat0=40.0, lon0=5.0, dlat=0.3, dlon=0.4)
+    j, i = np.meshgrid(np.arange(ny, dtype=np.float64), np.arange(nx + 1, dtype=np.float64) - 0.5, indexing="ij")
+    ulat = 40.0 + 0.3 * j + 0.004 * np.sin(i / 7.0)
+    ulon = 5.0 + 0.4 * i * (1.0 + 0.002 * j) + 0.003 * np.cos(j / 5.0)
+    vc = np.array([1000.0, 850.0, 500.0])
+    o = syn.geo_observations(P, lat, lon, vc, seed=21)
+    ovar = np.random.default_rng(2).integers(0, 2, P).astype(np.int32)
+    Xm = syn.ensemble(k, nx, ny, 6, seed=400)
+    Xu = syn.ensemble(k, nx + 1, ny, 3, seed=401)
+    return lat, lon, ulat, ulon, vc, o, ovar, Xm, Xu
+
+
+def test_staggered_grid_analysis_reads_h_from_the_mass_grid():
+    lat, lon, ulat, ulon, vc, o, ovar, Xm, Xu = _staggered_case()
+    ox, oy, oz = orc.geo_locate(o["lat"], o["lon"], o["level"], lat, lon, vc)
+    kw = dict(radius=120.0, olat=o["lat"], olon=o["lon"], var_nlev=[3, 3], ovar=ovar)
+    r = orc.letkf_ext(Xu, ox, oy, oz, o["value"], o["err"], o["valid"], glat=ulat, glon=ulon, Xobs=Xm, **kw)
+    ref = _np_letkf_geo(Xu, o, ox, oy, ulat, ulon, 120.0, [3, 3], ovar, oz, Xobs=Xm)
+    assert rel_err(r["Xa"], ref) < 1e-11 and np.abs(r["Xa"] - Xu).max() > 1e-3
+    counts, _ = orc.select_counts_geo(ulat, ulon, o["lat"], o["lon"], 120.0)
+    assert np.array_equal(r["counts"], counts)
+    # H on the analysed ensemble itself through the same entry is the ordinary analysis
+    a = orc.letkf_ext(Xm, ox, oy, oz, o["value"], o["err"], o["valid"], glat=lat, glon=lon, **kw)
+    b = orc.letkf_ext(Xm, ox, oy, oz, o["value"], o["err"], o["valid"], glat=lat, glon=lon, Xobs=Xm, **kw)
+    assert np.array_equal(a["Xa"], b["Xa"])

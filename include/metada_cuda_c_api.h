@@ -124,7 +124,9 @@ int mdc_obs_set_variables(mdc_obs* obs, const int32_t* var);
  * the Euclidean distance in degrees -- and H then interpolates at those integer coordinates (:241-248).
  * mdc_hx_idw4 / mdc_letkf_analyse locate on demand.  Regional domains only: the selection circles must not reach a
  * pole or wrap the whole longitude circle (MDC_ERR_UNSUPPORTED otherwise); single device (no domain decomposition);
- * MDC_MODE_CANONICAL. */
+ * MDC_MODE_CANONICAL.  Staggered (U / V) variables: give the staggered grid its own ensemble store and geography,
+ * run mdc_hx_idw4(mass_grid_ens, obs) and then mdc_letkf_analyse(staggered_ens, obs, ...) -- the analysis uses the
+ * Y' already in the store and the columns / coordinates of the ensemble it is given. */
 int mdc_obs_create_geographic(mdc_ctx* ctx, int64_t P, const double* lat, const double* lon,
                               const double* level, const double* value, const double* err,
                               const uint8_t* valid, const int64_t* gid, mdc_obs** out);

@@ -49,6 +49,9 @@ int mdc_timer_stop(mdc_ctx* ctx, float* ms);
 /* number of kernels this library has launched on ctx since creation (bench.py gpu_launches) */
 int64_t mdc_ctx_launch_count(const mdc_ctx* ctx);
 int mdc_ctx_sm_count(const mdc_ctx* ctx);
+/* the 16 raw device counters of the last analysis on ctx (development diagnostics: [8..15] hold per-phase clock
+ * ticks when the column kernel is built with -DNSP_PROFILE, zeros otherwise) */
+int mdc_ctx_last_stats(mdc_ctx* ctx, int64_t out[16]);
 /* writes > L2-size bytes to evict the L2 between timed iterations */
 int mdc_ctx_flush_l2(mdc_ctx* ctx);
 /* plain device buffers (halo staging between observation stores on one device) */

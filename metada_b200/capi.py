@@ -22,9 +22,12 @@ MODE_REF_COMPAT, MODE_REF_ETKF, MODE_CANONICAL = 0, 1, 2
 LOC_CUTOFF, LOC_GASPARI_COHN, LOC_GAUSSIAN, LOC_EXPONENTIAL, LOC_REF_GASPARI_COHN = 0, 1, 2, 3, 4
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-              "-shared", "-Xcompiler", "-fPIC", "-cudart", "shared",
-              "-Xlinker", "-rpath=/usr/local/cuda/lib64"]   # (no -split-compile: parallel ptxas made the column
+              "-Xcompiler", "-fPIC", "-cudart", "shared"]   # (no -split-compile: parallel ptxas made the column
 # kernels' register allocation, hence their spills and speed, vary from build to build)
+LINK_FLAGS = ["-shared", "-cudart", "shared", "-Xlinker", "-rpath=/usr/local/cuda/lib64"]
+# translation units: the API + every kernel except the packed Newton-Schulz column kernel, whose 42 instantiations
+# are spread over six units (csrc/nsp_tu.cu compiled with a tile-count range each, csrc/nsp_launch.h) built in parallel
+NSP_GROUPS = [(3, 6), (7, 9), (10, 10), (11, 12), (13, 14), (15, 16)]
 
 
 class MdcError(RuntimeError):
@@ -70,14 +73,36 @@ def lib_path() -> str:
 
 
 def build_library(force: bool = False, verbose: bool = False) -> str:
-    """nvcc cross-compiles for sm_100a (works without a GPU)."""
-    srcs = [os.path.join(_HERE, "csrc", f) for f in os.listdir(os.path.join(_HERE, "csrc"))] + [_HEADER]
+    """nvcc cross-compiles for sm_100a (works without a GPU): objects in metada_b200/_obj, units in parallel."""
+    from concurrent.futures import ThreadPoolExecutor
+    csrc = os.path.join(_HERE, "csrc")
+    srcs = [os.path.join(csrc, f) for f in os.listdir(csrc)] + [_HEADER]
     newest = max(os.path.getmtime(s) for s in srcs)
-    if force or not os.path.exists(_LIB) or os.path.getmtime(_LIB) < newest:
-        cmd = ["nvcc", *NVCC_FLAGS, "-o", _LIB, _SRC]
-        if verbose:
-            cmd.insert(1, "-Xptxas=-v")
-        subprocess.check_call(cmd)
+    objdir = os.path.join(_HERE, "_obj")
+    os.makedirs(objdir, exist_ok=True)
+    units = [("mdc_api.o", _SRC, [])]
+    units += [(f"nsp_{lo}_{hi}.o", os.path.join(csrc, "nsp_tu.cu"), [f"-DNSP_LO={lo}", f"-DNSP_HI={hi}"]) for lo, hi in NSP_GROUPS]
+    only = os.environ.get("MDC_BUILD_ONLY")          # development: rebuild just these objects (comma-separated)
+
+    def compile_unit(u):
+        obj, src, defs = u
+        out = os.path.join(objdir, obj)
+        stale = force or not os.path.exists(out) or os.path.getmtime(out) < newest
+        if only is not None:
+            stale = obj in only.split(",") or not os.path.exists(out)
+        if stale:
+            cmd = ["nvcc", *NVCC_FLAGS, *defs, "-c", "-o", out, src]
+            if os.environ.get("MDC_NSP_PROFILE") and obj.startswith("nsp_"):
+                cmd.insert(1, "-DNSP_PROFILE")          # per-phase clock ticks (tools/nsp_phase_profile.py)
+            if verbose:
+                cmd.insert(1, "-Xptxas=-v")
+            subprocess.check_call(cmd)
+        return out, stale
+
+    with ThreadPoolExecutor(max_workers=min(len(units), os.cpu_count() or 1)) as ex:
+        res = list(ex.map(compile_unit, units))
+    if any(st for _, st in res) or not os.path.exists(_LIB):
+        subprocess.check_call(["nvcc", *LINK_FLAGS, "-o", _LIB, *[o for o, _ in res]])
     return _LIB
 
 
@@ -111,6 +136,7 @@ def load_library() -> C.CDLL:
         "mdc_timer_stop": (C.c_int, [vp, C.POINTER(C.c_float)]),
         "mdc_ctx_launch_count": (i64, [vp]),
         "mdc_ctx_sm_count": (C.c_int, [vp]),
+        "mdc_ctx_last_stats": (C.c_int, [vp, C.POINTER(C.c_int64)]),
         "mdc_ctx_flush_l2": (C.c_int, [vp]),
         "mdc_ens_create": (C.c_int, [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(vp)]),
         "mdc_ens_destroy": (C.c_int, [vp]),
@@ -202,6 +228,11 @@ class Context:
 
     def sm_count(self) -> int:
         return int(self.L.mdc_ctx_sm_count(self.h))
+
+    def last_stats(self):
+        out = (C.c_int64 * 16)()
+        self.check(self.L.mdc_ctx_last_stats(self.h, out))
+        return [int(v) for v in out]
 
     def flush_l2(self):
         self.check(self.L.mdc_ctx_flush_l2(self.h))

@@ -16,7 +16,7 @@
 // Off-diagonal tiles are stored once (no mirrored store).
 //
 // Forcing symmetry is only stable while cond(A) is moderate (letkf_ns.cuh); a column (or level, with
-// per-level transforms) whose rigorous bound (shift + ||C||_F) / shift exceeds NS_SYM_COND_MAX is appended to a
+// per-level transforms) whose rigorous condition bound exceeds NSP_KAPPA_MAX is appended to a
 // redo list, which a second launch of the full-product kernel (k <= 80) or the Jacobi kernel
 // (k > 80) consumes.
 #pragma once
@@ -25,6 +25,19 @@
 
 #include "letkf_ns.cuh"
 #include "letkf_smallp.cuh"
+#include "ns_schedule_table.h"
+
+// -DNSP_PROFILE: thread 0 of every CTA adds the clock64() ticks it spends per phase to stats[8..15]
+// (8 selection, 9 gather + SYRK, 10 norm / A store / start look-up, 11 products, 12 iteration epilogues,
+// 13 w = Z Z g, 14 update, 15 whole column); read with mdc_ctx_last_stats.  Development only.
+#ifdef NSP_PROFILE
+#define NSP_T0() long long nsp_t_ = clock64()
+#define NSP_TICK(slot) do { const long long n_ = clock64(); if (threadIdx.x == 0) atomicAdd((unsigned long long*)&nsp_prof_[slot], (unsigned long long)(n_ - nsp_t_)); nsp_t_ = n_; } while (0)
+__device__ long long* nsp_prof_;
+#else
+#define NSP_T0() do {} while (0)
+#define NSP_TICK(slot) do {} while (0)
+#endif
 
 __host__ __device__ inline int nsp_ntiles(int k) { const int nt = (k + 7) >> 3; return nt * (nt + 1) / 2; }
 __device__ __forceinline__ int nsp_row_start(int I, int nt) { return (I * (2 * nt - I + 1)) >> 1; }
@@ -252,11 +265,46 @@ __device__ __forceinline__ NsTiles<NTA> nsp_rect_tiles(int ntr, int nt, int warp
   return w;
 }
 
-// Z <- A^{-1/2} for the A held in the T buffer.  Deliberately NOT inlined: the column loop around it
-// keeps ~60 registers of state alive, and under the 128-register cap ptxas then serialises every
-// fragment load behind the MMA that frees its register; as a separate function the products get
-// the whole budget (the caller's state is saved once per column).  Returns the iterations used,
-// -1 if the iteration did not converge.
+// ---- schedule look-ups (ns_schedule_table.h): all threads compute the same index (constant-memory broadcasts)
+__device__ __forceinline__ int nss_start_index(double kappa) {
+  // kappa grid: kappa_i - 1 = 1e-3 * 1.12^i; smallest i with kappa_i >= kappa
+  int i = (int)ceilf(__log2f(fmaxf((float)(kappa - 1.0), 1e-3f) * 1e3f) * (1.0f / 0.16349873f));
+  i = max(0, min(i, NSS_NKAPPA - 1));
+  while (i > 0 && nss_starts[i - 1].kappa >= kappa) --i;
+  while (i < NSS_NKAPPA - 1 && nss_starts[i].kappa < kappa) ++i;
+  return (nss_starts[i].kappa >= kappa) ? i : -1;
+}
+__device__ __forceinline__ int nss_step_index(double rho) {
+  // rho grid (descending): 2 rho_i / (1 - rho_i) = 4000 * 0.88^i; largest i with rho_i >= rho
+  if (!(rho <= nss_steps[0].rho)) return -1;
+  const float gq = (float)(2.0 * rho / (1.0 - rho));
+  int i = (int)floorf(__log2f(fmaxf(gq, 1e-12f) * (1.0f / 4000.0f)) * (1.0f / -0.18442457f));
+  i = max(0, min(i, NSS_NRHO - 1));
+  while (i < NSS_NRHO - 1 && nss_steps[i + 1].rho >= rho) ++i;
+  while (i > 0 && nss_steps[i].rho < rho) --i;
+  return i;
+}
+
+// largest condition bound (Schatten-4 bound of the spectrum / shift) the packed kernel takes; beyond it the
+// transform goes to the redo list.  Symmetric-tile products assume the iterates commute; with the short composite
+// minimax schedule (13 - 20 products) the rounding defect stays small much longer than with plain Newton-Schulz:
+// error of Z against the eigen-decomposition (numpy emulation of these very tile products on C5-like matrices)
+// 5e-15 at cond 50, 7e-15 at 200, 1.5e-14 at 530, 3.3e-14 at 1200, 1.4e-13 at 3500.
+#define NSP_KAPPA_MAX 2000.0
+
+// Z <- A^{-1/2} for the A held in the T buffer, by the composite minimax polynomial iteration of
+// tools/gen_ns_schedule.py: state Z and the residual E = I - Z^2 A (in the Y buffer), spectrum(E) in [-rho, rho];
+//   start  (degree 0..2 in A, chosen by the condition bound kappa):  Z0 = q(A), E0 = I - Z0 (A Z0)
+//   stage  (degree d = 1..3):  T = sum c_i E^i,  Z <- Z T,  E <- I - T^2 + E T^2       d + 2 products
+//   finish (degree f = 1..3):  Z <- Z sum c_i E^i                                       f products
+// with the minimax coefficients for the interval the spectrum is known to lie in and the degree sequence that
+// minimises the product count (13 - 14 products at C5's conditioning; Chebyshev start + Newton-Schulz + series
+// finish took 17 - 20).  rho is tracked a priori (rigorous while spectrum(A) is inside [shift, shift kappa]) and
+// cross-checked against the measured ||E||_F after every stage.
+// Deliberately NOT inlined: the column loop around it keeps ~60 registers of state alive, and under the
+// 128-register cap ptxas then serialises every fragment load behind the MMA that frees its register; as a
+// separate function the products get the whole budget (the caller's state is saved once per column).
+// Returns the number of k x k products used, -1 if the iteration failed, -2 if kappa is beyond NSP_KAPPA_MAX.
 template <int NT, int NTH>
 __device__ __noinline__ int nsp_inverse_sqrt(double* Zp, double shift, double fro, int k) {
   constexpr int NW = NTH / 32, NTW = (NT * (NT + 1) / 2 + NW - 1) / NW, nt = NT, kp = 8 * NT;
@@ -268,118 +316,161 @@ __device__ __noinline__ int nsp_inverse_sqrt(double* Zp, double shift, double fr
   const unsigned zs = (unsigned)__cvta_generic_to_shared(Zp), ys = zs + msz * 8, ts = ys + msz * 8;
   const NspLane L = nsp_lane(lane);
   const NspTiles<NTW> st = nsp_tiles<NTW, NTH>(nt, warp);
-  bool ok = true;
-    // The iteration as a state machine around the single product site:
-    //   A2: Y <- A A, spectral bound, Z0 = q(A)      Y0: Y <- A Z0
-    //   ZY: T <- (3I - Z Y)/2, residual              YT: Y <- Y T     TZ: Z <- T Z
-    // Y and Z are overwritten in place after a barrier (the product is held in the accumulator
-    // registers meanwhile), so three matrices suffice.
-    // Finish.  With E = I - Z Y the exact answer is Z (I - E)^{-1/2} = Z (I + E/2 + 3/8 E^2 + 5/16 E^3 + ...);
-    // Newton-Schulz applies the first-order factor each iteration.  Once the residual r = ||E||_F
-    // (>= the spectral norm; max|E_ij| underestimates it by up to 35x on these matrices) is small the
-    // series is applied ONCE to the order that suffices, by Horner's rule on B = E/2
-    // (W <- c1 I + c2 B, then m times W <- I + B W, then Z <- W Z); truncation errors are rigorous:
-    //   r < 3e-7: I + B                       1 product  (3/8 r^2   < 4e-14)
-    //   r < 5e-5: I + B + 1.5 B^2             2 products (5/16 r^3  < 4e-14)
-    //   r < 6e-4: I + B + 1.5 B^2 + 2.5 B^3   3 products (35/128 r^4 < 4e-14)
-    // instead of one more full iteration (3 products) plus the first-order finish (2).
-    //   HB: W <- I + B W (W in the Y buffer, dead by then)      FZ: Z <- W Z
-    enum { OP_A2, OP_Y0, OP_ZY, OP_YT, OP_TZ, OP_HB, OP_FZ };
-    double acc[NTW][2];
-    int op = OP_A2, it = 0, horner = 0;
-    bool done = false;
-#pragma unroll 1
-    while (true) {
-      const unsigned pb = (op == OP_ZY) ? zs : (op == OP_YT || op == OP_FZ) ? ys : ts;
-      const unsigned qb = (op == OP_A2 || op == OP_YT) ? ts : (op == OP_ZY || op == OP_HB) ? ys : zs;
-      nsp_mm_any<NT, NW, NTW>(pb, qb, warp, st, L, acc);
-      if (op == OP_A2) {
-        nsp_store<NTW>(ys, nt, st, L, acc);
-        // tighter upper end of the spectrum from the product just made: lmax(C)^2 <= ||C^2||_F
-        // (Schatten-4 norm of C; C^2 = A^2 - 2 shift A + shift^2 I), typically 2-3x below ||C||_F
-        double f4 = 0.0;
+  // the lane's accumulator pair of tile n sits at byte offset cb(n) of every packed matrix; dg(n): 0 = off the
+  // diagonal, 1 = first element on it, 2 = second
+  auto cb = [&](int n) { return nsp_cbase(st.ti[n], st.tj[n], nt, L); };
+  auto dg = [&](int n) { const int i = st.ti[n] * 8 + g, j = st.tj[n] * 8 + 2 * t; return i == j ? 1 : (i == j + 1 ? 2 : 0); };
+  auto own = [&](const double* M, int n) { return *reinterpret_cast<const double2*>(reinterpret_cast<const unsigned char*>(M) + cb(n)); };
+  // The iteration is a small state machine around the SINGLE product site (nsp_mm_any; its per-warp specialised
+  // bodies must exist once for the instruction cache).  Operands by op:
+  enum { OP_A2, OP_Y0, OP_M0, OP_E2, OP_E3, OP_ZT, OP_T2, OP_ET };
+  double acc[NTW][2];
+  double rho_ap = 0.0;
+  int op = OP_A2, nprod = 0, step = 0;     // step: index of the current stage / finish in nss_steps
+  int rc = -1;
+  // next step from the residual bound: loads the coefficients, returns the first op of the step (-1: failure)
+  auto plan = [&](double rmeas) -> int {
+    if (!(rmeas < 1e6)) return -1;                                  // NaN / divergence guard
+    const int j = nss_step_index(fmin(rho_ap, rmeas));
+    if (j < 0) return -1;
+    step = j;
+    rho_ap = nss_steps[j].rho_out * 1.002;
+    if (nss_steps[j].kind % 10 == 1) {                              // T = c0 I + c1 E straight into the T buffer
+      const double c0 = nss_steps[j].c[0], c1 = nss_steps[j].c[1];
 #pragma unroll
-        for (int n = 0; n < NTW; ++n)
-          if (n < st.n) {
-            const int i = st.ti[n] * 8 + g, j = st.tj[n] * 8 + 2 * t;
-            const double2 a = *reinterpret_cast<const double2*>(
-                reinterpret_cast<const unsigned char*>(Tp) + nsp_cbase(st.ti[n], st.tj[n], nt, L));
-            const double w = (st.ti[n] != st.tj[n]) ? 2.0 : 1.0;
-            const double c0 = acc[n][0] - 2.0 * shift * a.x + (i == j ? shift * shift : 0.0);
-            const double c1 = acc[n][1] - 2.0 * shift * a.y + (i == j + 1 ? shift * shift : 0.0);
-            if (i < k && j < k) f4 = fma(w * c0, c0, f4);
-            if (i < k && j + 1 < k) f4 = fma(w * c1, c1, f4);
-          }
-        f4 = nsp_block_reduce<NTH>(f4, false, red);            // (its barriers also publish A^2)
-        const double hi = shift + fro;
-        const NsStart q0 = ns_chebyshev_start(shift, fmin(hi, shift + sqrt(sqrt(f4) + 1e-13 * hi * hi)));
-        for (int e = tid; e < msz; e += NTH) Zp[e] = fma(q0.a2, Yp[e], q0.a1 * Tp[e]);
-        __syncthreads();
-        if (tid < kp) Zp[nsp_elem(tid, tid, nt)] += q0.a0;      // Z0 = q(A)
-        __syncthreads();
-        op = OP_Y0;
-      } else if (op == OP_Y0) {
-        nsp_store<NTW>(ys, nt, st, L, acc);                     // (A^2 no longer read: barrier above)
-        __syncthreads();
-        op = OP_ZY;
-      } else if (op == OP_ZY) {
-        double r = 0.0;                                          // ||E||_F >= ||E||_2, E = I - Z Y
-#pragma unroll
-        for (int n = 0; n < NTW; ++n)
-          if (n < st.n) {
-            const int i = st.ti[n] * 8 + g, j = st.tj[n] * 8 + 2 * t;
-            const double d0 = (i == j ? 1.0 : 0.0), d1 = (i == j + 1 ? 1.0 : 0.0);
-            const double e0 = d0 - acc[n][0], e1 = d1 - acc[n][1];
-            const double w = (st.ti[n] != st.tj[n]) ? 2.0 : 1.0;
-            r = fma(w * e0, e0, fma(w * e1, e1, r));
-            sts_f64x2(ts + nsp_cbase(st.ti[n], st.tj[n], nt, L), d0 + 0.5 * e0, d1 + 0.5 * e1);   // T = (3I - ZY)/2
-          }
-        r = sqrt(nsp_block_reduce<NTH>(r, false, red));         // also publishes T
-        if (!(r < 1e6)) { ok = false; break; }                   // NaN guard (divergence runs into the cap)
-        done = r < 6e-4;
-        if (r < 3e-7) {
-          op = OP_TZ;                                            // first-order finish: Z <- T Z
-        } else if (done) {
-          // B = T - I in place, W0 = c1 I + c2 B into the Y buffer (Y is dead from here on)
-          const double c1 = (r < 5e-5) ? 1.0 : 1.5, c2 = (r < 5e-5) ? 1.5 : 2.5;
-          horner = (r < 5e-5) ? 1 : 2;
-          if (tid < kp) Tp[nsp_elem(tid, tid, nt)] -= 1.0;
-          __syncthreads();
-          for (int e = tid; e < msz; e += NTH) Yp[e] = c2 * Tp[e];
-          __syncthreads();
-          if (tid < kp) Yp[nsp_elem(tid, tid, nt)] += c1;
-          __syncthreads();
-          op = OP_HB;
-        } else {
-          op = OP_YT;
+      for (int n = 0; n < NTW; ++n)
+        if (n < st.n) {
+          const double2 e = own(Yp, n);
+          const int d = dg(n);
+          sts_f64x2(ts + cb(n), fma(c1, e.x, d == 1 ? c0 : 0.0), fma(c1, e.y, d == 2 ? c0 : 0.0));
         }
-      } else if (op == OP_HB || op == OP_FZ) {
-        const unsigned dst = (op == OP_HB) ? ys : zs;
-        __syncthreads();                                         // everyone is done reading W (or Z)
+      __syncthreads();
+      return OP_ZT;
+    }
+    return OP_E2;
+  };
+  NSP_T0();
+#pragma unroll 1
+  while (true) {
+    const unsigned pb = (op == OP_A2 || op == OP_Y0 || op == OP_T2) ? ts : (op == OP_M0 || op == OP_ZT) ? zs : ys;
+    const unsigned qb = (op == OP_Y0) ? zs : (op == OP_M0 || op == OP_E2) ? ys : ts;
+    NSP_TICK(12);
+    nsp_mm_any<NT, NW, NTW>(pb, qb, warp, st, L, acc);
+    NSP_TICK(11);
+    ++nprod;
+    if (op == OP_A2) {
+      // tighter upper end of the spectrum from the product just made: lmax(C)^2 <= ||C^2||_F
+      // (Schatten-4 norm of C; C^2 = A^2 - 2 shift A + shift^2 I), typically 2-3x below ||C||_F
+      double f4 = 0.0;
+#pragma unroll
+      for (int n = 0; n < NTW; ++n)
+        if (n < st.n) {
+          const int i = st.ti[n] * 8 + g, j = st.tj[n] * 8 + 2 * t, d = dg(n);
+          const double2 a = own(Tp, n);
+          const double w = (st.ti[n] != st.tj[n]) ? 2.0 : 1.0;
+          const double q0 = acc[n][0] - 2.0 * shift * a.x + (d == 1 ? shift * shift : 0.0);
+          const double q1 = acc[n][1] - 2.0 * shift * a.y + (d == 2 ? shift * shift : 0.0);
+          if (i < k && j < k) f4 = fma(w * q0, q0, f4);
+          if (i < k && j + 1 < k) f4 = fma(w * q1, q1, f4);
+        }
+      f4 = nsp_block_reduce<NTH>(f4, false, red);
+      const double hi = shift + fro;
+      const double kappa = fmax(fmin(hi, shift + sqrt(sqrt(f4) + 1e-13 * hi * hi)) / shift, 1.0) * (1.0 + 1e-9);
+      const int si = (kappa <= NSP_KAPPA_MAX) ? nss_start_index(kappa) : -1;
+      if (si < 0) { rc = -2; break; }
+      const int sdeg = nss_starts[si].degree;
+      rho_ap = nss_starts[si].rho0 * 1.002;
+      const double rs = rsqrt(shift), is = 1.0 / shift;
+      const double z0 = nss_starts[si].a[0] * rs, z1 = nss_starts[si].a[1] * rs * is, z2 = nss_starts[si].a[2] * rs * is * is;
+      // Z0 = q(A) -> Z buffer; degree 0: E0 = I - z0^2 A, degree 1: Y0 = A Z0 = z0 A + z1 A^2 -> Y buffer (no product)
+#pragma unroll
+      for (int n = 0; n < NTW; ++n)
+        if (n < st.n) {
+          const double2 a = own(Tp, n);
+          const int d = dg(n);
+          const double dx = (d == 1 ? 1.0 : 0.0), dy = (d == 2 ? 1.0 : 0.0);
+          sts_f64x2(zs + cb(n), fma(z2, acc[n][0], fma(z1, a.x, z0 * dx)), fma(z2, acc[n][1], fma(z1, a.y, z0 * dy)));
+          if (sdeg == 0) sts_f64x2(ys + cb(n), dx - z0 * z0 * a.x, dy - z0 * z0 * a.y);
+          else if (sdeg == 1) sts_f64x2(ys + cb(n), fma(z1, acc[n][0], z0 * a.x), fma(z1, acc[n][1], z0 * a.y));
+        }
+      __syncthreads();
+      if (sdeg == 0) {
+        // (||E0||_F is not measured: rho0 = (kappa - 1) / (kappa + 1) is exact for the bound)
+        op = plan(rho_ap);
+        if (op < 0) break;
+      } else {
+        op = (sdeg == 1) ? OP_M0 : OP_Y0;
+      }
+    } else if (op == OP_Y0) {
+      nsp_store<NTW>(ys, nt, st, L, acc);                       // Y0 = A Z0 (the Y buffer is free)
+      __syncthreads();
+      op = OP_M0;
+    } else if (op == OP_M0 || op == OP_ET) {
+      // E = I - Z0 Y0, or E <- I - T^2 + E T^2 (T^2 is in the T buffer); ||E||_F on the way
+      double r = 0.0;
+#pragma unroll
+      for (int n = 0; n < NTW; ++n)
+        if (n < st.n) {
+          const int d = dg(n);
+          double e0 = (d == 1 ? 1.0 : 0.0), e1 = (d == 2 ? 1.0 : 0.0);
+          if (op == OP_ET) { const double2 t2 = own(Tp, n); e0 = (e0 - t2.x) + acc[n][0]; e1 = (e1 - t2.y) + acc[n][1]; }
+          else { e0 -= acc[n][0]; e1 -= acc[n][1]; }
+          const double w = (st.ti[n] != st.tj[n]) ? 2.0 : 1.0;
+          r = fma(w * e0, e0, fma(w * e1, e1, r));
+          acc[n][0] = e0; acc[n][1] = e1;
+        }
+      r = sqrt(nsp_block_reduce<NTH>(r, false, red));           // (its barriers: everyone is done reading Y)
+      nsp_store<NTW>(ys, nt, st, L, acc);
+      __syncthreads();
+      op = plan(r);
+      if (op < 0) break;
+    } else if (op == OP_E2) {
+      if (nss_steps[step].kind % 10 == 2) {                      // T = c0 I + c1 E + c2 E^2 (the T buffer is free)
+        const double c0 = nss_steps[step].c[0], c1 = nss_steps[step].c[1], c2 = nss_steps[step].c[2];
 #pragma unroll
         for (int n = 0; n < NTW; ++n)
           if (n < st.n) {
-            const int i = st.ti[n] * 8 + g, j = st.tj[n] * 8 + 2 * t;
-            const double d0 = (op == OP_HB && i == j) ? 1.0 : 0.0, d1 = (op == OP_HB && i == j + 1) ? 1.0 : 0.0;
-            sts_f64x2(dst + nsp_cbase(st.ti[n], st.tj[n], nt, L), acc[n][0] + d0, acc[n][1] + d1);
+            const double2 ev = own(Yp, n);
+            const int d = dg(n);
+            sts_f64x2(ts + cb(n), fma(c2, acc[n][0], fma(c1, ev.x, d == 1 ? c0 : 0.0)),
+                      fma(c2, acc[n][1], fma(c1, ev.y, d == 2 ? c0 : 0.0)));
           }
         __syncthreads();
-        if (op == OP_FZ) { ++it; break; }
-        if (--horner == 0) op = OP_FZ;
-      } else if (op == OP_YT) {
-        __syncthreads();                                         // everyone is done reading Y
-        nsp_store<NTW>(ys, nt, st, L, acc);                     // in place; T Z does not read Y
-        op = OP_TZ;
+        op = OP_ZT;
       } else {
-        __syncthreads();                                         // everyone is done reading Z
-        nsp_store<NTW>(zs, nt, st, L, acc);
+        nsp_store<NTW>(ts, nt, st, L, acc);                     // E^2 -> T buffer
         __syncthreads();
-        ++it;
-        if (done || it >= NS_MAX_ITERS) break;
-        op = OP_ZY;
+        op = OP_E3;
       }
+    } else if (op == OP_E3) {
+      const double c0 = nss_steps[step].c[0], c1 = nss_steps[step].c[1], c2 = nss_steps[step].c[2], c3 = nss_steps[step].c[3];
+#pragma unroll
+      for (int n = 0; n < NTW; ++n)
+        if (n < st.n) {
+          const double2 ev = own(Yp, n), e2 = own(Tp, n);
+          const int d = dg(n);
+          acc[n][0] = fma(c3, acc[n][0], fma(c2, e2.x, fma(c1, ev.x, d == 1 ? c0 : 0.0)));
+          acc[n][1] = fma(c3, acc[n][1], fma(c2, e2.y, fma(c1, ev.y, d == 2 ? c0 : 0.0)));
+        }
+      __syncthreads();                                           // everyone is done reading E^2
+      nsp_store<NTW>(ts, nt, st, L, acc);
+      __syncthreads();
+      op = OP_ZT;
+    } else if (op == OP_ZT) {
+      __syncthreads();                                           // everyone is done reading Z
+      nsp_store<NTW>(zs, nt, st, L, acc);
+      if (nss_steps[step].kind > 10) { __syncthreads(); rc = nprod; break; }
+      op = OP_T2;                                                // (T^2 reads the T buffer only)
+    } else {  // OP_T2
+      __syncthreads();                                           // everyone is done reading T (and Z is published)
+      nsp_store<NTW>(ts, nt, st, L, acc);
+      __syncthreads();
+      op = OP_ET;
     }
-  return (ok && done) ? it : -1;
+    if (nprod >= 64) break;                                      // cannot happen: every stage contracts rho
+  }
+  NSP_TICK(12);
+  return rc;
 }
 
 // WORK = true: consume the classifying pass's work list (per-level analyses); a separate instantiation
@@ -445,6 +536,11 @@ __global__ void __launch_bounds__(NTH, MINB) letkf_nsp_kernel(ColParams P, int l
     const int lt_e = work ? lt_b + 1 : nxf;
     for (int lt = lt_b; lt < lt_e; ++lt) {
       // ---------------- 1. selection, gather, C += Yw^T Yw on the FP64 tensor path, g += Yw^T dw
+#ifdef NSP_PROFILE
+      if (threadIdx.x == 0) nsp_prof_ = P.stats;
+      const long long nsp_col_t0 = clock64();
+#endif
+      NSP_T0();
       double cacc[NTW][2];
 #pragma unroll
       for (int n = 0; n < NTW; ++n) { cacc[n][0] = 0.0; cacc[n][1] = 0.0; }
@@ -527,6 +623,7 @@ __global__ void __launch_bounds__(NTH, MINB) letkf_nsp_kernel(ColParams P, int l
           break;
         }
 #endif
+        NSP_TICK(8);
         for (int c0 = 0; c0 < nsel; c0 += PCH) {
           const int rows = min(PCH, nsel - c0), rows4 = (rows + 3) & ~3;
           // gather: warp w stages rows w, w + NW, ...; all loads issued before the stores
@@ -574,6 +671,7 @@ __global__ void __launch_bounds__(NTH, MINB) letkf_nsp_kernel(ColParams P, int l
           }
           __syncthreads();
         }
+        NSP_TICK(9);
         npl += nsel;
         if (tid == 0 && nsel) s_int[0] = 0;      // (nsel == 0: already 0, and no barrier since it was read)
         __syncthreads();
@@ -597,8 +695,9 @@ __global__ void __launch_bounds__(NTH, MINB) letkf_nsp_kernel(ColParams P, int l
             if (i < k && j + 1 < k) fro = fma(w * cacc[n][1], cacc[n][1], fro);
           }
         fro = sqrt(nsp_block_reduce<NTH>(fro, false, red));
-        if (!((shift + fro) < NS_SYM_COND_MAX * shift)) {
-          // symmetric tiles are not stable at this conditioning: hand over to the full-product kernel
+        // (||C||_F is typically 2 - 3x the Schatten-4 bound the iteration works with: a transform far beyond the
+        // limit is handed over without spending the A^2 product on it)
+        if (!((shift + fro) < 8.0 * NSP_KAPPA_MAX * shift)) {
           if (tid == 0) {
             const unsigned slot = atomicAdd(P.redo_count, 1u);
             P.redo_items[slot] = col * nxf + lt;
@@ -617,7 +716,20 @@ __global__ void __launch_bounds__(NTH, MINB) letkf_nsp_kernel(ColParams P, int l
           }
         if (tid < k) gvec[tid] = gacc;
         __syncthreads();
-        const int it = nsp_inverse_sqrt<NT, NTH>(Zp, shift, fro, k);
+        NSP_TICK(10);
+        const int it = nsp_inverse_sqrt<NT, NTH>(Zp, shift, fro, k);   // products used
+#ifdef NSP_PROFILE
+        nsp_t_ = clock64();
+#endif
+        if (it == -2) {
+          // condition bound beyond NSP_KAPPA_MAX: symmetric tiles are not trusted there, the full-product
+          // kernel (k <= 80) or the Jacobi kernel redoes this transform
+          if (tid == 0) {
+            const unsigned slot = atomicAdd(P.redo_count, 1u);
+            P.redo_items[slot] = col * nxf + lt;
+          }
+          continue;
+        }
         if (it < 0) ok = false;
         col_iters = max(col_iters, it);
         // w = Z (Z g): warp per tile row, lanes read Z in the fragment pattern (row g, columns t, 4 + t
@@ -646,6 +758,7 @@ __global__ void __launch_bounds__(NTH, MINB) letkf_nsp_kernel(ColParams P, int l
           }
         }
       }
+      NSP_TICK(13);
       if (!ok) col_fail = true;
 
       if (P.W_out && P.w_col == col && lt == 0) {
@@ -740,6 +853,10 @@ __global__ void __launch_bounds__(NTH, MINB) letkf_nsp_kernel(ColParams P, int l
           __syncthreads();
         }
       }
+      NSP_TICK(14);
+#ifdef NSP_PROFILE
+      if (threadIdx.x == 0) atomicAdd((unsigned long long*)&P.stats[15], (unsigned long long)(clock64() - nsp_col_t0));
+#endif
     }  // lt
     if (tid == 0) {
       if (!work) {                       // (work mode: the classifying pass counted the columns)

@@ -16,6 +16,7 @@
 #include "letkf_kernels.cuh"
 #include "letkf_ns.cuh"
 #include "letkf_nsp.cuh"
+#include "nsp_launch.h"
 #include "letkf_v2.cuh"
 #include "metrics_kernels.cuh"
 #include "mdc_internal.cuh"
@@ -179,6 +180,13 @@ int mdc_timer_stop(mdc_ctx* ctx, float* ms) {
 }
 int64_t mdc_ctx_launch_count(const mdc_ctx* ctx) { return ctx->launches; }
 int mdc_ctx_sm_count(const mdc_ctx* ctx) { return ctx->sm_count; }
+int mdc_ctx_last_stats(mdc_ctx* ctx, int64_t out[16]) {
+  MDC_CUDA(ctx, cudaSetDevice(ctx->device));
+  long long h[16];
+  if (int rc = read_small(ctx, ctx->d_stats, h, sizeof(h))) return rc;
+  for (int i = 0; i < 16; ++i) out[i] = h[i];
+  return MDC_OK;
+}
 
 int mdc_ctx_flush_l2(mdc_ctx* ctx) {
   MDC_CUDA(ctx, cudaSetDevice(ctx->device));
@@ -942,34 +950,14 @@ static int letkf_launch(mdc_ens* e, mdc_obs* o, const mdc_letkf_params* p, const
       cp.small_count = reinterpret_cast<unsigned*>(ctx->d_flags + 13);
     }
     const int lch = nsp_level_chunk(k, e->nz);
-    auto launchp = [&](auto kern, int nth) -> int {
-      const size_t smemp = nsp_smem_bytes(k, lch, nth);
-      if ((int)smemp > ctx->max_smem_optin)
-        MDC_FAIL(ctx, MDC_ERR_UNSUPPORTED, "letkf: k=%d needs %zu B shared memory > %d available", k, smemp, ctx->max_smem_optin);
-      MDC_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemp));
-      int occ = 1;
-      MDC_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, nth, smemp));
-      if (occ < 1) occ = 1;
-      int grid = (int)std::max<long long>(1, std::min<long long>(total_cols, (long long)sms * occ));
-      kern<<<grid, nth, smemp, ctx->stream>>>(cp, lch);
-      MDC_LAUNCH_CHECK(ctx);
-      return MDC_OK;
-    };
-    int rc;
-#define MDC_NSP(NT, NTH, MINB)                                                                         \
-  case NT:                                                                                             \
-    rc = ext ? launchp(letkf_nsp_kernel<NT, NTH, MINB, false, true>, NTH)                              \
-             : cp.work_consume ? launchp(letkf_nsp_kernel<NT, NTH, MINB, true>, NTH)                  \
-                               : launchp(letkf_nsp_kernel<NT, NTH, MINB, false>, NTH);                \
-    break;
-    switch (std::min((k + 7) >> 3, 16)) {   // tile rows: the kernel is specialised on the exact count
-      MDC_NSP(3, 256, 2) MDC_NSP(4, 256, 2) MDC_NSP(5, 256, 2) MDC_NSP(6, 256, 2) MDC_NSP(7, 256, 2)
-      MDC_NSP(8, 256, 2) MDC_NSP(9, 256, 2) MDC_NSP(10, 256, 2)   // (nt = 10 with 384 threads: 6 % slower)
-      MDC_NSP(11, 512, 1) MDC_NSP(12, 512, 1) MDC_NSP(13, 512, 1) MDC_NSP(14, 512, 1) MDC_NSP(15, 512, 1)
-      MDC_NSP(16, 512, 1)
-      default: MDC_FAIL(ctx, MDC_ERR_UNSUPPORTED, "letkf: no packed kernel for k=%d", k);
-    }
-#undef MDC_NSP
+    // the kernel's instantiations live in their own translation units (nsp_tu.cu, nsp_launch.h)
+    const int ntile = std::min((k + 7) >> 3, 16);   // tile rows: the kernel is specialised on the exact count
+    int rc = NSP_NOT_MINE;
+#define MDC_NSP_TRY(LO, HI) \
+    if (rc == NSP_NOT_MINE) rc = nsp_launch_##LO##_##HI(ntile, &cp, lch, sms, ext ? 1 : 0, cp.work_consume, total_cols, ctx);
+    NSP_GROUPS(MDC_NSP_TRY)
+#undef MDC_NSP_TRY
+    if (rc == NSP_NOT_MINE) MDC_FAIL(ctx, MDC_ERR_UNSUPPORTED, "letkf: no packed kernel for k=%d", k);
     if (rc) return rc;
     if (cp.small_items)
       if (int rc2 = ext ? launch_smallp(letkf_smallp_kernel<true>, cp) : launch_smallp(letkf_smallp_kernel<false>, cp)) return rc2;

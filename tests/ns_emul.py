@@ -1,0 +1,100 @@
+"""NumPy emulation of the packed Newton-Schulz kernel's iteration (metada_b200/csrc/letkf_nsp.cuh,
+nsp_inverse_sqrt): the same schedule tables (parsed from the generated header), the same look-up rules, the
+same products -- only the upper-triangular 8 x 8 tiles of every product are formed, the lower ones implied by
+symmetry.  Used by tests/test_ns_schedule.py; also documents the accuracy claims made in the kernel's comments."""
+import os
+import re
+
+import numpy as np
+
+HEADER = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "metada_b200", "csrc", "ns_schedule_table.h")
+KAPPA_MAX = 2000.0
+
+
+def load_tables(path=HEADER):
+    txt = open(path).read()
+    steps_txt = txt[txt.index("nss_steps[NSS_NRHO] = {"):txt.index("};\n", txt.index("nss_steps[NSS_NRHO] = {"))]
+    starts_txt = txt[txt.index("nss_starts[NSS_NKAPPA] = {"):]
+    num = r"[-+0-9.eE]+"
+    steps = [(float(v[0]), float(v[1]), [float(x) for x in v[2:6]], int(v[6]), int(v[7]))
+             for v in re.findall(r"\{(%s), (%s), \{(%s), (%s), (%s), (%s)\}, (\d+), (\d+)\}" % ((num,) * 6), steps_txt)]
+    starts = [(float(v[0]), float(v[1]), [float(x) for x in v[2:5]], int(v[5]), int(v[6]))
+              for v in re.findall(r"\{(%s), (%s), \{(%s), (%s), (%s)\}, (\d+), (\d+)\}" % ((num,) * 5), starts_txt)]
+    return steps, starts
+
+
+def tile_sym_product(P, Q):
+    """upper-triangular tiles of the true product, lower tiles by symmetry (what the kernel stores)"""
+    R = P @ Q
+    nt = R.shape[0] // 8
+    for I in range(nt):
+        for J in range(I):
+            R[8 * I:8 * I + 8, 8 * J:8 * J + 8] = R[8 * J:8 * J + 8, 8 * I:8 * I + 8].T
+    return R
+
+
+def start_index(starts, kappa):
+    kap = np.array([s[0] for s in starts])
+    i = int(np.searchsorted(kap, kappa))
+    return i if i < len(kap) else -1
+
+
+def step_index(steps, rho):
+    rg = np.array([s[0] for s in steps])
+    if not rho <= rg[0]:
+        return -1
+    return int(np.searchsorted(-rg, -rho, side="right")) - 1
+
+
+def inverse_sqrt(A, shift, tables=None, product=tile_sym_product):
+    """returns (Z, products, trace) or (None, products, reason)"""
+    steps, starts = tables or load_tables()
+    n = A.shape[0]
+    I = np.eye(n)
+    fro = np.linalg.norm(A - shift * I, "fro")
+    nprod = 1
+    A2 = product(A, A)
+    C2 = A2 - 2 * shift * A + shift * shift * I
+    hi = shift + fro
+    kappa = max(min(hi, shift + np.sqrt(np.linalg.norm(C2, "fro") + 1e-13 * hi * hi)) / shift, 1.0) * (1 + 1e-9)
+    si = start_index(starts, kappa) if kappa <= KAPPA_MAX else -1
+    if si < 0:
+        return None, nprod, "kappa"
+    _, rho0, a, sdeg, _ = starts[si]
+    rs = 1.0 / np.sqrt(shift)
+    z0, z1, z2 = a[0] * rs, a[1] * rs / shift, a[2] * rs / shift ** 2
+    Z = z0 * I + z1 * A + z2 * A2
+    rho_ap = rho0 * 1.002
+    if sdeg == 0:
+        E, r = I - z0 * z0 * A, rho_ap
+    else:
+        if sdeg == 1:
+            Y = z0 * A + z1 * A2
+        else:
+            Y = product(A, Z); nprod += 1
+        E = I - product(Z, Y); nprod += 1
+        r = np.linalg.norm(E, "fro")
+    trace = [("start", sdeg, kappa, rho0)]
+    while nprod < 64:
+        if not r < 1e6:
+            return None, nprod, "diverged"
+        j = step_index(steps, min(rho_ap, r))
+        if j < 0:
+            return None, nprod, "rho"
+        _, rout, c, kind, _ = steps[j]
+        d = kind % 10
+        T = c[0] * I + c[1] * E
+        if d >= 2:
+            E2 = product(E, E); nprod += 1
+            T = T + c[2] * E2
+        if d == 3:
+            T = T + c[3] * product(E, E2); nprod += 1
+        Z = product(Z, T); nprod += 1
+        trace.append((kind, min(rho_ap, r), r))
+        if kind > 10:
+            return Z, nprod, trace
+        T2 = product(T, T); nprod += 1
+        E = (I - T2) + product(E, T2); nprod += 1
+        r = np.linalg.norm(E, "fro")
+        rho_ap = rout * 1.002
+    return None, nprod, "products"

@@ -1,0 +1,89 @@
+"""The schedule of the composite minimax polynomial iteration (tools/gen_ns_schedule.py ->
+metada_b200/csrc/ns_schedule_table.h): every table entry is checked by direct evaluation, and the kernel's
+iteration is emulated in NumPy (tests/ns_emul.py) against the eigen-decomposition."""
+import numpy as np
+import pytest
+
+from tests import ns_emul
+
+LD = np.longdouble
+
+
+def _image(c, rho):
+    u = np.cos(np.pi * np.arange(6001) / 6000).astype(LD)
+    e = -LD(rho) * u
+    t = np.zeros_like(e)
+    for ci in c[::-1]:
+        t = t * e + LD(ci)
+    return (LD(1) - e) * t * t
+
+
+def test_every_step_entry_contracts_as_claimed():
+    steps, _ = ns_emul.load_tables()
+    rho = np.array([s[0] for s in steps])
+    assert np.all(np.diff(rho) < 0) and rho[0] > 0.999 and rho[-1] < 3e-7
+    for rg, rout, c, kind, togo in steps:
+        p = _image(c, rg)
+        got = float(max(1 - p.min(), p.max() - 1))
+        assert got <= rout * (1 + 1e-6) + 1e-15, (rg, kind, got, rout)   # (coefficients are rounded to double)
+        if kind > 10:
+            assert rout <= 4e-14 and togo == kind - 10
+        else:
+            assert rout * 1.002 < rg                       # a stage always contracts
+    # products_to_go is what following the policy costs
+    for i, (rg, rout, c, kind, togo) in enumerate(steps):
+        n, j = 0, i
+        while True:
+            _, ro, _, kd, _ = steps[j]
+            if kd > 10:
+                n += kd - 10
+                break
+            n += kd + 2
+            j = ns_emul.step_index(steps, ro * 1.002)
+            assert j > i or j >= 0
+        assert n == togo, (i, n, togo)
+
+
+def test_every_start_entry():
+    steps, starts = ns_emul.load_tables()
+    kap = np.array([s[0] for s in starts])
+    assert np.all(np.diff(kap) > 0) and kap[-1] >= ns_emul.KAPPA_MAX
+    for kg, rho0, a, deg, total in starts:
+        xi = (LD(1) + LD(kg - 1) * (np.cos(np.pi * np.arange(6001) / 6000).astype(LD) + 1) / 2)
+        q = LD(a[0]) + LD(a[1]) * xi + LD(a[2]) * xi * xi
+        p = xi * q * q
+        assert float(max(1 - p.min(), p.max() - 1)) <= rho0 * (1 + 1e-6) + 1e-15
+        j = ns_emul.step_index(steps, rho0 * 1.002)
+        assert j >= 0 and total == 1 + deg + steps[j][4]
+
+
+def _c5_like(rng, k, p, sigma):
+    Y = 0.5 * rng.standard_normal((p, k))
+    Y -= Y.mean(1, keepdims=True)
+    w = rng.uniform(0, 1, p) ** 2 / sigma ** 2
+    Yw = Y * np.sqrt(w)[:, None]
+    return (k - 1.0) * np.eye(k) + Yw.T @ Yw
+
+
+@pytest.mark.parametrize("k,p,sigma,max_products,tol", [
+    (80, 87, 0.3, 11, 3e-14), (80, 87, 0.1, 14, 3e-14), (80, 140, 0.1, 15, 3e-14), (40, 93, 0.1, 15, 3e-14),
+    (128, 90, 0.1, 14, 3e-14), (80, 87, 0.05, 16, 5e-14), (80, 87, 0.03, 18, 1e-13), (80, 87, 0.02, 20, 2e-13),
+    (24, 5, 0.1, 14, 3e-14), (80, 30, 1.0, 10, 3e-14)])
+def test_emulated_kernel_iteration_matches_the_eigendecomposition(k, p, sigma, max_products, tol):
+    rng = np.random.default_rng(k * 1000 + p)
+    tables = ns_emul.load_tables()
+    for _ in range(4):
+        A = _c5_like(rng, k, p, sigma)
+        Z, nprod, trace = ns_emul.inverse_sqrt(A, k - 1.0, tables)
+        assert Z is not None, trace
+        w, V = np.linalg.eigh(A)
+        ref = (V / np.sqrt(w)) @ V.T
+        assert np.abs(Z - ref).max() / np.abs(ref).max() < tol, trace
+        assert nprod <= max_products, (nprod, trace)
+
+
+def test_condition_bound_beyond_the_limit_is_refused():
+    rng = np.random.default_rng(5)
+    A = _c5_like(rng, 80, 87, 0.004)
+    Z, _, why = ns_emul.inverse_sqrt(A, 79.0)
+    assert Z is None and why == "kappa"

@@ -120,10 +120,11 @@ def load_library() -> C.CDLL:
     global _lib
     if _lib is not None:
         return _lib
-    if not os.path.exists(_LIB):
-        raise MdcError(f"{_LIB} is missing: build it with metada_b200.build_library() "
+    path = os.environ.get("MDC_LIB", _LIB)     # development: an instrumented build of the same sources (tools/build_prof.sh)
+    if not os.path.exists(path):
+        raise MdcError(f"{path} is missing: build it with metada_b200.build_library() "
                        "(__graft_entry__.build()); there is no CPU fallback")
-    L = C.CDLL(_LIB)
+    L = C.CDLL(path)
     vp, i64, dbl = C.c_void_p, C.c_int64, C.c_double
     pd = C.POINTER(C.c_double)
     sig = {

@@ -19,6 +19,7 @@ int launchp(K kern, int nth, const ColParams& cp, int lch, int sms, long long to
   int occ = 1;
   MDC_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, nth, smemp));
   if (occ < 1) occ = 1;
+  if (const char* e = getenv("MDC_NSP_CTAS_PER_SM")) occ = std::max(1, std::min(occ, atoi(e)));   // development: co-residency experiments
   int grid = (int)std::max<long long>(1, std::min<long long>(total_cols, (long long)sms * occ));
   kern<<<grid, nth, smemp, ctx->stream>>>(cp, lch);
   MDC_LAUNCH_CHECK(ctx);
@@ -28,7 +29,11 @@ int launchp(K kern, int nth, const ColParams& cp, int lch, int sms, long long to
 template <int NT>
 int launch_nt(const ColParams& cp, int lch, int sms, int ext, int work, long long total_cols, mdc_ctx* ctx) {
   // k <= 80: 8 warps, two columns per SM (nt = 10 with 384 threads measured 6 % slower); above: 16 warps, one per SM
+#ifdef NSP_DEV_MINB1      // development: one CTA per SM, no register cap (what ptxas does with the products then)
+  constexpr int NTH = NT <= 10 ? 256 : 512, MINB = 1;
+#else
   constexpr int NTH = NT <= 10 ? 256 : 512, MINB = NT <= 10 ? 2 : 1;
+#endif
   if (ext) return launchp(letkf_nsp_kernel<NT, NTH, MINB, false, true>, NTH, cp, lch, sms, total_cols, ctx);
   if (work) return launchp(letkf_nsp_kernel<NT, NTH, MINB, true>, NTH, cp, lch, sms, total_cols, ctx);
   return launchp(letkf_nsp_kernel<NT, NTH, MINB, false>, NTH, cp, lch, sms, total_cols, ctx);

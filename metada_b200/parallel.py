@@ -151,6 +151,8 @@ class SlabLetkf:
             self.ctx.sync()
         # observations change every assimilation cycle, so the bucket index belongs to the step:
         # rebuild it even when this object is reused with the same observations (bench.py)
+        if int(math.floor(params.radius)) > self.reach:
+            raise ValueError(f"SlabLetkf was planned for radius < {self.reach + 1}; analyse() got {params.radius}")
         self.obs.index_build(max(1, int(math.ceil(params.radius))))
         return capi.letkf_analyse(self.ens, self.obs, params)
 

@@ -45,11 +45,18 @@ class StreamedLetkf:
         self.Y0, self.Y1 = (0, gny) if row_range is None else row_range
         rows = self.Y1 - self.Y0
         self.nslab = max(1, (rows + slab_rows - 1) // slab_rows)
-        self.nslots = max(3, slots if workers is None else workers) if self.nslab > 1 else 1
-        self.sm_reserve = sm_reserve
-        self.ctxs = [capi.Context(device) for _ in range(self.nslots)]
         self.bounds = [(self.Y0 + (rows * s) // self.nslab, self.Y0 + (rows * (s + 1)) // self.nslab)
                        for s in range(self.nslab)]
+        # slabs whose observations a slab's columns can reach: every slab within `reach` rows, not only the two
+        # adjacent ones (a slab lower than the reach leaves the slab after next inside it).  self.depth = how many
+        # slabs ahead must have gone through H before a slab is analysed; they all hold a slot meanwhile.
+        self.neigh = [[d for d, (d0, d1) in enumerate(self.bounds)
+                       if d != s and d0 < y1 + self.reach and d1 > y0 - self.reach]
+                      for s, (y0, y1) in enumerate(self.bounds)]
+        self.depth = max([abs(d - s) for s, ds in enumerate(self.neigh) for d in ds] or [0])
+        self.nslots = max(3, slots if workers is None else workers, self.depth + 2) if self.nslab > 1 else 1
+        self.sm_reserve = sm_reserve
+        self.ctxs = [capi.Context(device) for _ in range(self.nslots)]
         self._ens = [None] * self.nslots
         self._obs = [None] * self.nslab         # one observation store per slab, on the context of slot s % nslots
         self._pool = None
@@ -75,7 +82,10 @@ class StreamedLetkf:
         observation rows received from the ranks above / below this row range; they are appended to
         the slabs within reach of that edge.  Returns summed stats."""
         import metada_b200 as mb
-        S, R, K = self.nslab, self.reach, self.nslots
+        S, R, K, D = self.nslab, self.reach, self.nslots, self.depth
+        if int(math.floor(params.radius)) > R:
+            raise ValueError(f"StreamedLetkf was planned for radius < {R + 1}; analyse() got {params.radius}: the "
+                             "observation halos would miss rows")
         host_ny = self.gny if host_ny is None else host_ny
         prm = copy.copy(params)
         if S > 1:
@@ -89,10 +99,9 @@ class StreamedLetkf:
             own_idx.append(idx)
             ys = obs["y"][idx]
             cnt = {}
-            for dst in (s - 1, s + 1):
-                if 0 <= dst < S:
-                    d0, d1 = self.bounds[dst]
-                    cnt[dst] = (d0 - R, d1 + R, int(np.count_nonzero((ys >= d0 - R) & (ys < d1 + R))))
+            for dst in self.neigh[s]:
+                d0, d1 = self.bounds[dst]
+                cnt[dst] = (d0 - R, d1 + R, int(np.count_nonzero((ys >= d0 - R) & (ys < d1 + R))))
             halo_n.append(cnt)
         rd = self.k + 8
         max_rows = max(y1 - y0 for (y0, y1) in self.bounds) + 1
@@ -168,7 +177,7 @@ class StreamedLetkf:
             try:
                 loaded = -1
                 for s in range(S):
-                    while loaded < min(s + 1, S - 1):      # slab s+1 must be on the device: its H feeds s
+                    while loaded < min(s + D, S - 1):      # slabs s+1 .. s+D must be on the device: their H feeds s
                         item = q_up.get()
                         if item is None or errors:
                             return
@@ -180,8 +189,8 @@ class StreamedLetkf:
                     w = slot_of[s]
                     ob = self._obs[s]
                     t0 = time.perf_counter()
-                    for src in (s - 1, s + 1):
-                        if 0 <= src < S and s in halo_buf[src]:
+                    for src in self.neigh[s]:
+                        if s in halo_buf[src]:
                             p, n = halo_buf[src][s]
                             ob.append_rows(p, n)
                     if self.bounds[s][0] - R < self.Y0:        # rows from other ranks: supersets are harmless

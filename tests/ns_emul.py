@@ -18,8 +18,8 @@ def load_tables(path=HEADER):
     num = r"[-+0-9.eE]+"
     steps = [(float(v[0]), float(v[1]), [float(x) for x in v[2:6]], int(v[6]), int(v[7]))
              for v in re.findall(r"\{(%s), (%s), \{(%s), (%s), (%s), (%s)\}, (\d+), (\d+)\}" % ((num,) * 6), steps_txt)]
-    starts = [(float(v[0]), float(v[1]), [float(x) for x in v[2:5]], int(v[5]), int(v[6]))
-              for v in re.findall(r"\{(%s), (%s), \{(%s), (%s), (%s)\}, (\d+), (\d+)\}" % ((num,) * 5), starts_txt)]
+    starts = [(float(v[0]), float(v[1]), [float(x) for x in v[2:5]], int(v[5]), int(v[6]), [int(x) for x in v[8].split(",")][:int(v[7])])
+              for v in re.findall(r"\{(%s), (%s), \{(%s), (%s), (%s)\}, (\d+), (\d+), (\d+), \{([0-9, ]+)\}\}" % ((num,) * 5), starts_txt)]
     return steps, starts
 
 
@@ -60,29 +60,27 @@ def inverse_sqrt(A, shift, tables=None, product=tile_sym_product):
     si = start_index(starts, kappa) if kappa <= KAPPA_MAX else -1
     if si < 0:
         return None, nprod, "kappa"
-    _, rho0, a, sdeg, _ = starts[si]
+    _, rho0, a, sdeg, _, seq = starts[si]
     rs = 1.0 / np.sqrt(shift)
     z0, z1, z2 = a[0] * rs, a[1] * rs / shift, a[2] * rs / shift ** 2
     Z = z0 * I + z1 * A + z2 * A2
-    rho_ap = rho0 * 1.002
     if sdeg == 0:
-        E, r = I - z0 * z0 * A, rho_ap
+        E = I - z0 * z0 * A
     else:
         if sdeg == 1:
             Y = z0 * A + z1 * A2
         else:
             Y = product(A, Z); nprod += 1
         E = I - product(Z, Y); nprod += 1
-        r = np.linalg.norm(E, "fro")
     trace = [("start", sdeg, kappa, rho0)]
-    while nprod < 64:
-        if not r < 1e6:
-            return None, nprod, "diverged"
-        j = step_index(steps, min(rho_ap, r))
-        if j < 0:
-            return None, nprod, "rho"
-        _, rout, c, kind, _ = steps[j]
+    # the steps listed by the start entry, in order (the kernel copies their coefficients to shared memory once)
+    for j in seq:
+        rg, rout, c, kind, _ = steps[j]
         d = kind % 10
+        if kind > 10:
+            r = np.linalg.norm(E, "fro")
+            if not r * r <= n * (rg * 1.01) ** 2:
+                return None, nprod, "residual"
         T = c[0] * I + c[1] * E
         if d >= 2:
             E2 = product(E, E); nprod += 1
@@ -90,11 +88,9 @@ def inverse_sqrt(A, shift, tables=None, product=tile_sym_product):
         if d == 3:
             T = T + c[3] * product(E, E2); nprod += 1
         Z = product(Z, T); nprod += 1
-        trace.append((kind, min(rho_ap, r), r))
+        trace.append((kind, rg, float(np.linalg.norm(E, 2))))
         if kind > 10:
             return Z, nprod, trace
         T2 = product(T, T); nprod += 1
         E = (I - T2) + product(E, T2); nprod += 1
-        r = np.linalg.norm(E, "fro")
-        rho_ap = rout * 1.002
-    return None, nprod, "products"
+    return None, nprod, "sequence"

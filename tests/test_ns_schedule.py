@@ -48,13 +48,23 @@ def test_every_start_entry():
     steps, starts = ns_emul.load_tables()
     kap = np.array([s[0] for s in starts])
     assert np.all(np.diff(kap) > 0) and kap[-1] >= ns_emul.KAPPA_MAX
-    for kg, rho0, a, deg, total in starts:
+    for kg, rho0, a, deg, total, seq in starts:
         xi = (LD(1) + LD(kg - 1) * (np.cos(np.pi * np.arange(6001) / 6000).astype(LD) + 1) / 2)
         q = LD(a[0]) + LD(a[1]) * xi + LD(a[2]) * xi * xi
         p = xi * q * q
         assert float(max(1 - p.min(), p.max() - 1)) <= rho0 * (1 + 1e-6) + 1e-15
         j = ns_emul.step_index(steps, rho0 * 1.002)
         assert j >= 0 and total == 1 + deg + steps[j][4]
+        # the listed sequence is what following the a-priori bounds step by step gives, and it ends with a finish whose
+        # design interval covers the bound carried into it
+        want = [j]
+        while steps[want[-1]][3] <= 10:
+            want.append(ns_emul.step_index(steps, steps[want[-1]][1] * 1.002))
+        assert seq == want and len(seq) <= 8, (kg, seq, want)
+        rho = rho0 * 1.002
+        for jj in seq:
+            assert steps[jj][0] >= rho                      # the step was designed for an interval that contains rho
+            rho = steps[jj][1] * 1.002
 
 
 def _c5_like(rng, k, p, sigma):

@@ -12,8 +12,9 @@ one for the interval the spectrum is known to lie in (equal-ripple x t(x)^2 on [
 image is centred on 1), and the sequence of degrees is chosen by dynamic programming over rho so that the number
 of k x k products is minimal: 13-14 products where Chebyshev start + Newton-Schulz + series finish needs 17-20
 (condition bounds 40-80).  Everything depends on one scalar (kappa for the start, rho afterwards), so the schedule
-is two small tables looked up at run time; the kernel measures ||E||_F after every stage and uses
-min(a-priori rho, measured) -- the a-priori bound is rigorous as long as spectrum(A) lies in [lmin, lmin kappa].
+is two small tables; the start entry (chosen by kappa) lists the steps that follow, so the kernel reads all of a
+column's coefficients at once.  The a-priori bounds are rigorous as long as spectrum(A) lies in [lmin, lmin kappa];
+the kernel checks ||E||_F <= sqrt(k) rho before the finishing step.
 """
 import os
 import sys
@@ -165,7 +166,17 @@ def build():
             c = 1 + s + J[j]
             if best is None or c < best[0]:
                 best = (c, s, a, rho0)
-        starts.append(best)
+        # the whole sequence of steps follows from the start (every a-priori rho does): list it, so that the kernel
+        # reads its coefficients once per column instead of looking a step up after every stage
+        seq, j = [], idx_of(best[3])
+        while True:
+            seq.append(j)
+            kind, d, ce, ro = act[j]
+            if kind == "finish":
+                break
+            j = idx_of(ro)
+        assert len(seq) <= 8
+        starts.append(best + (seq,))
     return rho_grid, J, act, kap, starts
 
 
@@ -178,16 +189,20 @@ def emit(path):
         f.write("// per rho-grid entry (descending rho): rho, image half-width after the step, c0..c3 (in E = I - M), and\n"
                 "// kind: 1..3 = stage of that degree, 11..13 = finish of degree kind - 10\n")
         f.write("struct NssStep { double rho, rho_out, c[4]; int kind, products_to_go; };\n")
-        f.write("struct NssStart { double kappa, rho0, a[3]; int degree, products_total; };\n")
+        f.write("// per kappa-grid entry: start polynomial, and the indices of the steps that follow (nsteps of them, the last\n"
+                "// one a finish)\n")
+        f.write("struct NssStart { double kappa, rho0, a[3]; int degree, products_total; int nsteps; unsigned char step[8]; };\n")
         f.write("__constant__ NssStep nss_steps[NSS_NRHO] = {\n")
         for i, rho in enumerate(rho_grid):
             kind, d, ce, ro = act[i]
             c = list(ce) + [0.0] * (4 - len(ce))
             f.write("  {%.17g, %.17g, {%.17g, %.17g, %.17g, %.17g}, %d, %d},\n" % (rho, ro, *c, d + (10 if kind == "finish" else 0), J[i]))
         f.write("};\n__constant__ NssStart nss_starts[NSS_NKAPPA] = {\n")
-        for kp, (c, s, a, rho0) in zip(kap, starts):
+        for kp, (c, s, a, rho0, seq) in zip(kap, starts):
             aa = list(a) + [0.0] * (3 - len(a))
-            f.write("  {%.17g, %.17g, {%.17g, %.17g, %.17g}, %d, %d},\n" % (kp, rho0, *aa, s, c))
+            sq = list(seq) + [0] * (8 - len(seq))
+            f.write("  {%.17g, %.17g, {%.17g, %.17g, %.17g}, %d, %d, %d, {%s}},\n"
+                    % (kp, rho0, *aa, s, c, len(seq), ", ".join(str(v) for v in sq)))
         f.write("};\n")
     return rho_grid, J, act, kap, starts
 

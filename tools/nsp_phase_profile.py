@@ -10,7 +10,11 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import metada_b200 as mb
 from metada_b200 import capi, synthetic as syn
 
-NAMES = {8: "selection", 9: "gather+syrk", 10: "norm/A/start", 11: "products", 12: "iteration epilogues", 13: "w=ZZg",
+if os.environ.get("NSP_PROFILE_UPDATE"):
+    NAMES = {8: "selection..start", 9: "iteration", 10: "update products", 11: "state wait", 12: "level means", 13: "w=ZZg",
+             14: "stores+mean", 15: "column total"}
+else:
+  NAMES = {8: "selection", 9: "gather+syrk", 10: "norm/A/start", 11: "products", 12: "iteration epilogues", 13: "w=ZZg",
          14: "update", 15: "column total"}
 
 

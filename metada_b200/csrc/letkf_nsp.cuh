@@ -40,22 +40,34 @@ __device__ long long* nsp_prof_;
 #endif
 // -DNSP_PROFILE -DNSP_PROFILE_UPDATE: slots 10 / 11 / 12 are re-used for the update's product, state wait and level
 // mean passes (8 then holds everything before the iteration, 9 the iteration, 13 w, 14 the stores)
+// -DNSP_PROFILE -DNSP_PROFILE_EPI: slots 8 / 9 = wait at the first barrier / store + second barrier of the Z T and T T
+// epilogues (the Gram phase's ticks are off)
+#if defined(NSP_PROFILE) && defined(NSP_PROFILE_EPI)
+#define NSP_TICK3(slot) NSP_TICK(slot)
+#else
+#define NSP_TICK3(slot) do {} while (0)
+#endif
 #if defined(NSP_PROFILE) && defined(NSP_PROFILE_UPDATE)
 #define NSP_TICK2(slot) NSP_TICK(slot)
 #define NSP_SLOT_PRE(slot) 8
 #define NSP_SLOT_IT(slot) 9
 #else
-#define NSP_SLOT_PRE(slot) slot
 #define NSP_SLOT_IT(slot) slot
 #define NSP_TICK2(slot) do {} while (0)
+#if defined(NSP_PROFILE_EPI)
+#define NSP_SLOT_PRE(slot) 10
+#else
+#define NSP_SLOT_PRE(slot) slot
+#endif
 #endif
 
 __host__ __device__ inline int nsp_ntiles(int k) { const int nt = (k + 7) >> 3; return nt * (nt + 1) / 2; }
-// doubles of the staging region: three packed matrices, or NSP_GCH gathered rows, or one matrix + lch staged levels
+// doubles of the staging region: three packed matrices, or NSP_GCH_OF(nt) gathered rows, or one matrix + lch staged levels
 __host__ __device__ inline int nsp_region_doubles(int k, int lch) {
   const int kp = (k + 7) & ~7, ks = kp + 4, m = nsp_ntiles(k) * 64;
   int r = 3 * m;
-  if (128 * ks > r) r = 128 * ks;
+  const int gch = (kp >> 3) <= 5 ? 112 : 128;                  // NSP_GCH_OF
+  if (gch * ks > r) r = gch * ks;
   if (m + lch * ks > r) r = m + lch * ks;
   return r;
 }
@@ -615,13 +627,17 @@ __device__ NSP_ISQ_INLINE int nsp_inverse_sqrt(double* Zp, double* red, double* 
       op = OP_ZT;
     } else if (op == OP_ZT) {
       __syncthreads();                                           // everyone is done reading Z
+      NSP_TICK3(8);
       nsp_store_run<NTW>(zs + cb0, st.n, acc);
+      NSP_TICK3(9);
       if ((int)sc[5 * sn] > 10) { __syncthreads(); rc = nprod; break; }
       op = OP_T2;                                                // (T^2 reads the T buffer only)
     } else {  // OP_T2
       __syncthreads();                                           // everyone is done reading T (and Z is published)
+      NSP_TICK3(8);
       nsp_store_run<NTW>(ts + cb0, st.n, acc);
       __syncthreads();
+      NSP_TICK3(9);
       op = OP_ET;
     }
     if (nprod >= 64) break;                                      // cannot happen: the sequence ends with a finish
@@ -630,12 +646,53 @@ __device__ NSP_ISQ_INLINE int nsp_inverse_sqrt(double* Zp, double* red, double* 
   return rc;
 }
 
-#define NSP_GCH 128      /* observation rows staged per gather round */
+// ---- update product U = X' Z for 32 staged levels (4 row tiles) when every warp's tiles lie in one row tile and one
+// group of NTA column tiles (NT % NTA == 0, 4 NT % NW == 0; k = 80: 5 tiles, two groups): compile-time tile offsets
+// into the packed Z, the same explicit software pipeline as the iteration's products.  xa: shared address of
+// X'[row tile of the warp, row g][t]; CG: the warp's column group.
+template <int NT, int NTA, int CG>
+__device__ __forceinline__ void nsp_upd_warp(unsigned xa, unsigned zbase, const NspLane& L, double (&uacc)[NTA][2]) {
+  constexpr int TOT = NT * NTA;
+#pragma unroll 1
+  for (int h = 0; h < 2; ++h) {
+    const unsigned zd = zbase + L.offd + (h ? L.dh : 0u), zt = zbase + L.offt + ((unsigned)h << 8);
+    const unsigned xh = xa + (unsigned)h * 32u;
+    double ar[2], br[3];
+    ar[0] = nsp_lds_v<0>(xh);
+    br[0] = nsp_frag_v<NT, CG * NTA, 0>(zd, zt);
+    if constexpr (TOT > 1) br[1] = nsp_frag_v<NT, CG * NTA + 1 % NTA, 1 / NTA>(zd, zt);
+    nsp_static_for<0, TOT>([&](auto i_c) {
+      constexpr int idx = decltype(i_c)::value, K = idx / NTA, n = idx % NTA;
+      if constexpr (idx + 2 < TOT) {
+        constexpr int K2 = (idx + 2) / NTA, n2 = (idx + 2) % NTA;
+        br[(idx + 2) % 3] = nsp_frag_v<NT, CG * NTA + n2, K2>(zd, zt);
+      }
+      if constexpr (K + 1 < NT && n == 0) ar[(K + 1) & 1] = nsp_lds_v<(K + 1) * 64>(xh);
+      NSP_DMMA(uacc[n], ar[K & 1], br[idx % 3]);
+    });
+  }
+}
+template <int NT, int NTA, int... CGs>
+__device__ __forceinline__ void nsp_upd_dispatch(std::integer_sequence<int, CGs...>, int cg, unsigned xa, unsigned zbase,
+                                                 const NspLane& L, double (&uacc)[NTA][2]) {
+  ((cg == CGs ? (nsp_upd_warp<NT, NTA, CGs>(xa, zbase, L, uacc), 0) : 0), ...);
+}
+
+// (the generic tile walk of the larger ensembles keeps many registers of its own: there the iteration is better
+// off as a called function)
+template <int NT, int NTH>
+__device__ __noinline__ int nsp_inverse_sqrt_call(double* Zp, double* red, double* sc, int& rbuf, double shift, double rs,
+                                                  double fro, int k) {
+  return nsp_inverse_sqrt<NT, NTH>(Zp, red, sc, rbuf, shift, rs, fro, k);
+}
+
+/* observation rows staged per gather round: 128, 112 for the small ensembles that run four CTAs per SM */
+#define NSP_GCH_OF(NT) ((NT) <= 5 ? 112 : 128)
 #define NSP_LCH_CAP 64   /* levels staged per update round */
 #define NSP_LSUB 32      /* levels per update product (accumulator tiles per warp) */
 #define NSP_SC_FRO 46    /* slot of the schedule scratch that carries ||C||_F from the Gram phase to the iteration */
 
-// Shared memory: one staging region [max(3 matrices, NSP_GCH rows, matrix + lch levels)] that holds, in turn,
+// Shared memory: one staging region [max(3 matrices, NSP_GCH_OF(nt) rows, matrix + lch levels)] that holds, in turn,
 //   phase 1  the gathered Y' rows of the column's local observations (stride k + 4, bulk copies, one per row),
 //   phase 2  the three packed matrices Z | Y(E) | T of the iteration,
 //   phase 3  Z | the column's state block [lch][k + 4] (bulk copies, one per level), overwritten in place by the
@@ -690,7 +747,7 @@ __device__ __noinline__ int nsp_phase_gram(const ColParams& P, int lch, long lon
   const NspSm<NT> S(k, lch);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int g = lane >> 2, t = lane & 3;
-  double* Ych = S.Zp;          // [NSP_GCH][ks] staged rows (no matrix is live)
+  double* Ych = S.Zp;          // [NSP_GCH_OF(NT)][ks] staged rows (no matrix is live)
   double* gpart = S.Zp;        // [NW][kp] per-warp partial sums of g
   const bool tma = (k & 1) == 0;                               // 16-byte aligned rows
   unsigned mph = (unsigned)S.par[0];
@@ -785,9 +842,9 @@ __device__ __noinline__ int nsp_phase_gram(const ColParams& P, int lch, long lon
       return nsel | (1 << 28);
     }
 #endif
-    NSP_TICK(8);
-    for (int c0 = 0; c0 < nsel; c0 += NSP_GCH) {
-      const int rows = min(NSP_GCH, nsel - c0), rows4 = (rows + 3) & ~3;
+    NSP_TICK(NSP_SLOT_PRE(8));
+    for (int c0 = 0; c0 < nsel; c0 += NSP_GCH_OF(NT)) {
+      const int rows = min(NSP_GCH_OF(NT), nsel - c0), rows4 = (rows + 3) & ~3;
       // gather: one bulk copy per row, all in flight at once, completion counted in bytes by the mbarrier
       if (tma) {
         fence_proxy_async();                                 // earlier generic accesses of the staging first
@@ -1030,6 +1087,16 @@ __device__ __noinline__ void nsp_phase_update(const ColParams& P, int lch, long 
       double uacc[NTA][2];
 #pragma unroll
       for (int n = 0; n < NTA; ++n) { uacc[n][0] = 0.0; uacc[n][1] = 0.0; }
+      if constexpr ((4 * NT) % NW == 0 && NT % NTA == 0 && NT <= NSP_FIXED_MAX_NT) {
+        if (ntr == 4) {
+          // full round: the warp's NTA tiles are row tile warp / (NT / NTA), column group warp % (NT / NTA)
+          constexpr int NG = NT / NTA;
+          const unsigned xa_s = S.ys + (unsigned)(((s0 + (warp / NG) * 8 + g) * ks + t) * 8);
+          nsp_upd_dispatch<NT, NTA>(std::make_integer_sequence<int, NG>{}, warp % NG, xa_s, S.zs, L, uacc);
+          goto update_product_done;
+        }
+      }
+      {
       const double* xa = Xt + (s0 + g) * ks + t;
       NspWalk zw[NTA];
 #pragma unroll
@@ -1050,6 +1117,8 @@ __device__ __noinline__ void nsp_phase_update(const ColParams& P, int lch, long 
 #pragma unroll
         for (int n = 0; n < NTA; ++n) zw[n].next(K, nt);
       }
+      }
+    update_product_done:
       __syncthreads();                                     // every warp is done with these rows of X'
       // the analysed rows go, dense, over the perturbations just consumed (row l at l k <= l ks)
 #pragma unroll
@@ -1071,11 +1140,13 @@ __device__ __noinline__ void nsp_phase_update(const ColParams& P, int lch, long 
       for (int e = tid; e < nl * k; e += NTH) Xg[(long long)l0 * k + e] = Xt[e];
     }
     if (P.mean_out) {
-      for (int l = warp; l < nl; l += NW) {
+      for (int lb = 0; lb < nl; lb += NTH >> 2) {
+        const int l = lb + (tid >> 2), q = tid & 3;
         double s = 0.0;
-        for (int j = lane; j < k; j += 32) s += Xt[l * k + j];
-        s = warp_sum(s);
-        if (lane == 0) P.mean_out[col * nz + l0 + l] = s * (1.0 / (double)k);
+        if (l < nl) for (int j = q; j < k; j += 4) s += Xt[l * k + j];
+        s += __shfl_xor_sync(0xffffffffu, s, 1);
+        s += __shfl_xor_sync(0xffffffffu, s, 2);
+        if (l < nl && q == 0) P.mean_out[col * nz + l0 + l] = s * (1.0 / (double)k);
       }
     }
   }
@@ -1132,7 +1203,11 @@ __global__ void __launch_bounds__(NTH, MINB) letkf_nsp_kernel(const __grid_const
         const NspSm<NT> S(k, lch);
         int rbuf = 0;
         const double shift = (double)(k - 1) / P.inflation;
-        const int it = nsp_inverse_sqrt<NT, NTH>(S.Zp, S.red, S.sc, rbuf, shift, rsqrt(shift), S.sc[NSP_SC_FRO], k);
+        int it;
+        if constexpr (NT <= NSP_FIXED_MAX_NT)
+          it = nsp_inverse_sqrt<NT, NTH>(S.Zp, S.red, S.sc, rbuf, shift, rsqrt(shift), S.sc[NSP_SC_FRO], k);
+        else
+          it = nsp_inverse_sqrt_call<NT, NTH>(S.Zp, S.red, S.sc, rbuf, shift, rsqrt(shift), S.sc[NSP_SC_FRO], k);
         if (it == -2) {
           // condition bound beyond NSP_KAPPA_MAX: symmetric tiles are not trusted there, the full-product
           // kernel (k <= 80) or the Jacobi kernel redoes this transform

@@ -32,7 +32,9 @@ int launch_nt(const ColParams& cp, int lch, int sms, int ext, int work, long lon
 #ifdef NSP_DEV_MINB1      // development: one CTA per SM, no register cap (what ptxas does with the products then)
   constexpr int NTH = NT <= 10 ? 256 : 512, MINB = 1;
 #else
-  constexpr int NTH = NT <= 10 ? 256 : 512, MINB = NT <= 10 ? 2 : 1;
+  // k <= 40: 4 warps, four columns per SM (products of 15 tiles: the fixed cost per product dominates, more CTAs
+  // interleave); k <= 80: 8 warps, two per SM (nt = 10 with 384 threads measured 6 % slower); above: 16 warps, one
+  constexpr int NTH = NT <= 5 ? 128 : NT <= 10 ? 256 : 512, MINB = NT <= 5 ? 4 : NT <= 10 ? 2 : 1;
 #endif
   if (ext) return launchp(letkf_nsp_kernel<NT, NTH, MINB, false, true>, NTH, cp, lch, sms, total_cols, ctx);
   if (work) return launchp(letkf_nsp_kernel<NT, NTH, MINB, true>, NTH, cp, lch, sms, total_cols, ctx);

@@ -57,6 +57,8 @@ int mdc_ctx_flush_l2(mdc_ctx* ctx);
 /* plain device buffers (halo staging between observation stores on one device) */
 int mdc_dev_malloc(mdc_ctx* ctx, int64_t bytes, void** out);
 int mdc_dev_free(mdc_ctx* ctx, void* p);
+/* kind 1: host -> device, 2: device -> host (synchronous on the context's stream) */
+int mdc_dev_copy(mdc_ctx* ctx, void* dst, const void* src, int64_t bytes, int kind);
 
 /* ---- ensemble store: replaces framework/adapters/Ensemble.hpp:42-194 (vector<State>) ------
  * Device layout: X[col][lev][member], col = y*nx + x  (one contiguous nz*k block per column).
@@ -235,6 +237,53 @@ typedef struct {
   double rmse, bias, correlation, crps, avg_spread;
 } mdc_metrics;
 int mdc_ens_metrics(mdc_ens* ens, mdc_ens* truth, mdc_metrics* out, double* host_spread);
+
+/* ---- streaming and sharding runtime (csrc/mdc_runtime.cpp) -----------------------------------------------
+ * The reference's LETKF<Tag>::Analyse (LETKF.hpp:63-119) walks one in-memory ensemble; its members are host vectors
+ * reached through State::getDataPtr<double>() (State.hpp:229-242).  mdc_stream_analyse takes exactly those pointers
+ * and streams the rows [row0, row1) of the grid through the device in slabs on three host threads (upload ||
+ * H + halo between slabs + column analysis || download, one CUDA stream per slab in flight), in place, so an
+ * ensemble larger than the device (BASELINE C5: 86 GB) is analysed by the same call; the result is bit-identical to
+ * mdc_letkf_analyse on the whole grid.  MDC_MODE_CANONICAL and the REF modes; GRID observations.
+ *
+ * Column sharding: one process per GPU, rank r owns the rows of slab_bounds(gny, r, nranks) =
+ * [gny r / nranks, gny (r + 1) / nranks); mdc_comm_init attaches an NCCL communicator (id from
+ * mdc_comm_get_unique_id on rank 0, handed to the other ranks by the launcher) and mdc_stream_analyse then starts
+ * with the observation halo exchange: H on the rank's edge strips, rows of the observations other ranks' columns
+ * can reach packed per destination (Y'[k], d, value, err, valid, x, y, z, gid) and carried by one group of
+ * ncclSend / ncclRecv over NVLink; no other communication.  Every rank passes the GLOBAL observation arrays (the
+ * message sizes follow from them, no count exchange) and its own rows of the members. */
+typedef struct mdc_stream mdc_stream;
+typedef struct {
+  int gnx, gny, nz, k;
+  int row0, row1;     /* global rows analysed through this handle; the whole grid: 0, gny                    */
+  int slab_rows;      /* rows per slab; <= 0: chosen so that the range has >= 24 slabs of 8..32 rows         */
+  int slots;          /* slabs in flight (>= 3; raised when a slab is lower than the localisation reach)     */
+  int sm_reserve;     /* SMs the column kernel leaves to the transposes of the neighbouring slabs (8)        */
+  double radius;      /* largest horizontal radius mdc_stream_analyse will be given                          */
+} mdc_stream_config;
+int mdc_stream_create(int device, const mdc_stream_config* cfg, mdc_stream** out);
+int mdc_stream_destroy(mdc_stream* s);
+const char* mdc_stream_last_error(const mdc_stream* s);
+int mdc_stream_slabs(const mdc_stream* s);
+int mdc_stream_slots(const mdc_stream* s);
+/* members: k host pointers (pinned for full PCIe speed) to [nz][host_ny][gnx] arrays whose first row is global row
+ * host_row0; they must cover [row0, min(row1 + 1, gny)) (H reads one row above the range).  ox .. ovalid: the global
+ * observation set (oz, ovalid may be NULL).  Updated in place; returns when every slab is back. */
+int mdc_stream_analyse(mdc_stream* s, double* const* members, int host_row0, int host_ny, int64_t P,
+                       const int32_t* ox, const int32_t* oy, const int32_t* oz, const double* oval,
+                       const double* oerr, const uint8_t* ovalid, const mdc_letkf_params* params,
+                       mdc_letkf_stats* out);
+/* wall-clock milliseconds of the last call's halo prologue and slab pipeline, rows received from other ranks */
+int mdc_stream_timings(const mdc_stream* s, double* edge_halo_ms, double* stream_ms, int64_t* halo_rows);
+/* 128-byte NCCL unique id (rank 0) */
+int mdc_comm_get_unique_id(void* id, int bytes);
+int mdc_comm_init(mdc_stream* s, const void* id, int rank, int nranks);
+/* after a sharded analysis on FULL host members [nz][gny][gnx] (host_row0 = 0): every rank's analysed rows are passed
+ * to all the others, so that each process ends with the whole analysed ensemble (what a drop-in driver saves) */
+int mdc_comm_allgather_rows(mdc_stream* s, double* const* members);
+/* max over ranks of *value (device-side ncclAllReduce); single rank: unchanged */
+int mdc_comm_max(mdc_stream* s, double* value);
 
 /* ---- microbenchmarks used for the roofline denominators (profiles/) ------------------------ */
 int mdc_bench_fp64_fma(mdc_ctx* ctx, double* tflops);

@@ -7,7 +7,7 @@ There is no CPU fallback: loading fails loudly if the library is missing, and cr
 fails without a CUDA device.
 """
 from .capi import (  # noqa: F401
-    Context, Ensemble, Observations, LetkfParams, LetkfStats, EnkfDiag, Metrics, MdcError,
+    Context, Ensemble, Observations, Stream, LetkfParams, LetkfStats, EnkfDiag, Metrics, MdcError,
     MODE_REF_COMPAT, MODE_REF_ETKF, MODE_CANONICAL, LOC_CUTOFF, LOC_GASPARI_COHN, LOC_GAUSSIAN, LOC_EXPONENTIAL, LOC_REF_GASPARI_COHN,
     SOLVER_AUTO, SOLVER_JACOBI, SOLVER_NEWTON_SCHULZ, SOLVER_NEWTON_SCHULZ_FULL,
     lib_path, load_library, build_library, exported_symbols,

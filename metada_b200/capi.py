@@ -24,7 +24,7 @@ LOC_CUTOFF, LOC_GASPARI_COHN, LOC_GAUSSIAN, LOC_EXPONENTIAL, LOC_REF_GASPARI_COH
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-cudart", "shared"]   # (no -split-compile: parallel ptxas made the column
 # kernels' register allocation, hence their spills and speed, vary from build to build)
-LINK_FLAGS = ["-shared", "-cudart", "shared", "-Xlinker", "-rpath=/usr/local/cuda/lib64"]
+LINK_FLAGS = ["-shared", "-cudart", "shared", "-Xlinker", "-rpath=/usr/local/cuda/lib64", "-lpthread", "-ldl"]
 # translation units: the API + every kernel except the packed Newton-Schulz column kernel, whose 42 instantiations
 # are spread over six units (csrc/nsp_tu.cu compiled with a tile-count range each, csrc/nsp_launch.h) built in parallel
 NSP_GROUPS = [(3, 6), (7, 9), (10, 10), (11, 12), (13, 14), (15, 16)]
@@ -68,6 +68,11 @@ class EnkfDiag(C.Structure):
         return {n: getattr(self, n) for n, _ in self._fields_}
 
 
+class StreamConfig(C.Structure):
+    _fields_ = [("gnx", C.c_int), ("gny", C.c_int), ("nz", C.c_int), ("k", C.c_int), ("row0", C.c_int), ("row1", C.c_int),
+                ("slab_rows", C.c_int), ("slots", C.c_int), ("sm_reserve", C.c_int), ("radius", C.c_double)]
+
+
 def lib_path() -> str:
     return _LIB
 
@@ -80,7 +85,7 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
     newest = max(os.path.getmtime(s) for s in srcs)
     objdir = os.path.join(_HERE, "_obj")
     os.makedirs(objdir, exist_ok=True)
-    units = [("mdc_api.o", _SRC, [])]
+    units = [("mdc_api.o", _SRC, []), ("mdc_runtime.o", os.path.join(csrc, "mdc_runtime.cpp"), [])]
     units += [(f"nsp_{lo}_{hi}.o", os.path.join(csrc, "nsp_tu.cu"), [f"-DNSP_LO={lo}", f"-DNSP_HI={hi}"]) for lo, hi in NSP_GROUPS]
     only = os.environ.get("MDC_BUILD_ONLY")          # development: rebuild just these objects (comma-separated)
 
@@ -179,6 +184,19 @@ def load_library() -> C.CDLL:
         "mdc_letkf_column_transform": (C.c_int, [vp, vp, C.POINTER(LetkfParams), i64, vp]),
         "mdc_etkf_analyse": (C.c_int, [vp, vp, dbl]),
         "mdc_enkf_analyse": (C.c_int, [vp, vp, dbl, vp, C.c_uint64, C.c_int, C.POINTER(EnkfDiag)]),
+        "mdc_dev_copy": (C.c_int, [vp, vp, vp, i64, C.c_int]),
+        "mdc_stream_create": (C.c_int, [C.c_int, C.POINTER(StreamConfig), C.POINTER(vp)]),
+        "mdc_stream_destroy": (C.c_int, [vp]),
+        "mdc_stream_last_error": (C.c_char_p, [vp]),
+        "mdc_stream_slabs": (C.c_int, [vp]),
+        "mdc_stream_slots": (C.c_int, [vp]),
+        "mdc_stream_analyse": (C.c_int, [vp, C.POINTER(vp), C.c_int, C.c_int, i64, vp, vp, vp, vp, vp, vp,
+                                          C.POINTER(LetkfParams), C.POINTER(LetkfStats)]),
+        "mdc_stream_timings": (C.c_int, [vp, pd, pd, C.POINTER(i64)]),
+        "mdc_comm_get_unique_id": (C.c_int, [vp, C.c_int]),
+        "mdc_comm_init": (C.c_int, [vp, vp, C.c_int, C.c_int]),
+        "mdc_comm_max": (C.c_int, [vp, pd]),
+        "mdc_comm_allgather_rows": (C.c_int, [vp, C.POINTER(vp)]),
         "mdc_bench_fp64_fma": (C.c_int, [vp, pd]),
         "mdc_bench_fp64_dmma": (C.c_int, [vp, pd]),
         "mdc_bench_hbm_copy": (C.c_int, [vp, pd]),
@@ -531,3 +549,72 @@ def enkf_analyse(ens: Ensemble, obs: Observations, inflation: float, Z=None, see
     ens.ctx.check(ens.ctx.L.mdc_enkf_analyse(ens.h, obs.h, inflation, _ptr(Zc), seed,
                                              int(want_gain_stats), C.byref(d)))
     return d.asdict()
+
+
+class Stream:
+    """mdc_stream: the C++ streaming / sharding runtime (csrc/mdc_runtime.cpp).  Host members in, analysed in place."""
+
+    def __init__(self, device, gnx, gny, nz, k, radius, row_range=None, slab_rows=0, slots=4, sm_reserve=8):
+        self.L = load_library()
+        r0, r1 = (0, gny) if row_range is None else row_range
+        self.cfg = StreamConfig(gnx, gny, nz, k, r0, r1, slab_rows, slots, sm_reserve, float(radius))
+        h = C.c_void_p()
+        rc = self.L.mdc_stream_create(device, C.byref(self.cfg), C.byref(h))
+        if rc:
+            raise MdcError(f"mdc_stream_create rc={rc}")
+        self.h = h
+
+    def check(self, rc):
+        if rc:
+            raise MdcError(f"rc={rc}: {self.L.mdc_stream_last_error(self.h).decode()}")
+
+    @property
+    def nslab(self):
+        return self.L.mdc_stream_slabs(self.h)
+
+    @property
+    def nslots(self):
+        return self.L.mdc_stream_slots(self.h)
+
+    @staticmethod
+    def unique_id() -> bytes:
+        buf = C.create_string_buffer(128)
+        rc = load_library().mdc_comm_get_unique_id(buf, 128)
+        if rc:
+            raise MdcError(f"mdc_comm_get_unique_id rc={rc} (NCCL missing?)")
+        return buf.raw
+
+    def comm_init(self, uid: bytes, rank: int, world: int):
+        buf = C.create_string_buffer(uid, 128)
+        self.check(self.L.mdc_comm_init(self.h, buf, rank, world))
+
+    def allgather_rows(self, member_ptrs):
+        arr = (C.c_void_p * len(member_ptrs))(*member_ptrs)
+        self.check(self.L.mdc_comm_allgather_rows(self.h, arr))
+
+    def comm_max(self, v: float) -> float:
+        x = C.c_double(v)
+        self.check(self.L.mdc_comm_max(self.h, C.byref(x)))
+        return x.value
+
+    def analyse(self, member_ptrs, obs: dict, params, host_row0=0, host_ny=None) -> dict:
+        host_ny = self.cfg.gny if host_ny is None else host_ny
+        arr = (C.c_void_p * len(member_ptrs))(*member_ptrs)
+        x = np.ascontiguousarray(obs["x"], np.int32); y = np.ascontiguousarray(obs["y"], np.int32)
+        z = np.ascontiguousarray(obs["z"], np.int32) if obs.get("z") is not None else None
+        v = np.ascontiguousarray(obs["value"], np.float64); e = np.ascontiguousarray(obs["err"], np.float64)
+        ok = np.ascontiguousarray(obs["valid"], np.uint8) if obs.get("valid") is not None else None
+        st = LetkfStats()
+        self.check(self.L.mdc_stream_analyse(self.h, arr, host_row0, host_ny, len(x), _ptr(x), _ptr(y), _ptr(z), _ptr(v), _ptr(e),
+                                             _ptr(ok), C.byref(params), C.byref(st)))
+        return st.asdict()
+
+    def timings(self) -> dict:
+        a, b, n = C.c_double(), C.c_double(), C.c_int64()
+        self.L.mdc_stream_timings(self.h, C.byref(a), C.byref(b), C.byref(n))
+        return {"edge_halo_ms": a.value, "stream_ms": b.value, "halo_rows": n.value}
+
+    def close(self):
+        if self.h:
+            self.L.mdc_stream_destroy(self.h)
+            self.h = None

@@ -212,6 +212,14 @@ int mdc_dev_free(mdc_ctx* ctx, void* p) {
   return MDC_OK;
 }
 
+int mdc_dev_copy(mdc_ctx* ctx, void* dst, const void* src, int64_t bytes, int kind) {
+  if (!dst || !src || bytes < 0 || (kind != 1 && kind != 2)) MDC_FAIL(ctx, MDC_ERR_INVALID, "dev_copy: bad arguments");
+  MDC_CUDA(ctx, cudaSetDevice(ctx->device));
+  MDC_CUDA(ctx, cudaMemcpyAsync(dst, src, (size_t)bytes, kind == 1 ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToHost, ctx->stream));
+  MDC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return MDC_OK;
+}
+
 // ------------------------------------------------------------------------------ ensemble
 int mdc_ens_create(mdc_ctx* ctx, int nx, int ny, int nz, int k, mdc_ens** out) {
   if (!ctx || !out) return MDC_ERR_INVALID;

@@ -10,7 +10,20 @@
 //                          (canonical only; default gaspari_cohn; the last three are LWEnKF.hpp:597-635)
 //   localization_scale:    length scale of the last three (default: localization_radius)
 //   vertical_radius: levels (canonical only; default 0 = none)
+//   streaming: "auto" (default) | "on" | "off" -- "on" / "auto" with GRID observations: the members' host arrays
+//              (State::getDataPtr) go through mdc_stream_analyse in row slabs, in place (an ensemble larger than
+//              the device is fine); "off" or geographic observations: upload all, analyse, download all
+//   slab_rows: rows per slab of the streamed path (default: chosen by the runtime)
+// Several processes (one per GPU; column sharding with the NCCL observation halo): environment MDC_RANK,
+// MDC_WORLD_SIZE, MDC_COMM_ID_FILE (rank 0 writes the NCCL id there, the others wait for it), MDC_DEVICE (default:
+// rank).  Every process reads the whole ensemble, analyses its rows, and receives the others' rows afterwards
+// (mdc_comm_allgather_rows), so saveEnsemble() writes the same files on every rank (give them different
+// output_base_file, or save on rank 0 only).
+#include <chrono>
+#include <cstdlib>
+#include <fstream>
 #include <string>
+#include <thread>
 
 #include "Config.hpp"
 #include "DeviceAnalysis.hpp"
@@ -44,6 +57,10 @@ class LETKF {
     try { loc = config.Get("localization_function").asString(); } catch (...) {}
     try { params_.radius_v = config.Get("vertical_radius").asFloat(); } catch (...) {}
     try { params_.loc_scale = config.Get("localization_scale").asFloat(); } catch (...) {}
+    try { streaming_ = config.Get("streaming").asString(); } catch (...) {}
+    try { slab_rows_ = config.Get("slab_rows").asInt(); } catch (...) {}
+    if (streaming_ != "auto" && streaming_ != "on" && streaming_ != "off")
+      throw std::invalid_argument("LETKF: streaming must be auto, on or off");
     if (mode == "ref_compat") params_.mode = MDC_MODE_REF_COMPAT;
     else if (mode == "ref_etkf") params_.mode = MDC_MODE_REF_ETKF;
     else if (mode == "canonical") {
@@ -61,11 +78,13 @@ class LETKF {
 
   void Analyse() {
     logger_.Info() << "LETKF analysis started";
-    auto dev = device::uploadEnsemble(ensemble_);
-    backends::cuda::DeviceObservations dobs(obs_.backend());
-    auto& ctx = backends::cuda::DeviceContext::Instance();
-    ctx.check(mdc_letkf_analyse(dev->get(), dobs.get(), &params_, &stats_), "mdc_letkf_analyse");
-    device::downloadEnsemble(*dev, ensemble_);
+    if (!(streaming_ != "off" && analyseStreamed())) {
+      auto dev = device::uploadEnsemble(ensemble_);
+      backends::cuda::DeviceObservations dobs(obs_.backend());
+      auto& ctx = backends::cuda::DeviceContext::Instance();
+      ctx.check(mdc_letkf_analyse(dev->get(), dobs.get(), &params_, &stats_), "mdc_letkf_analyse");
+      device::downloadEnsemble(*dev, ensemble_);
+    }
     ensemble_.RecomputeMean();                       // LETKF.hpp:116
     logger_.Info() << "LETKF analysis completed: " << stats_.columns << " columns, mean local obs "
                    << (stats_.columns ? static_cast<double>(stats_.sum_local_obs) / stats_.columns : 0.0)
@@ -83,6 +102,69 @@ class LETKF {
   const mdc_letkf_stats& deviceStats() const { return stats_; }
 
  private:
+  // Streamed (and, with MDC_WORLD_SIZE > 1, sharded) analysis straight from the members' host arrays.  false: not
+  // applicable (geographic observations / geography, or a plain "auto" run that fits one shot) -- the caller falls back.
+  bool analyseStreamed() {
+    const auto* geometry = ensemble_.GetMember(0).geometry();
+    if (!geometry) throw std::runtime_error("Geometry pointer is null in device analysis");
+    const auto& g = geometry->backend();
+    std::vector<int32_t> x, y, z;
+    std::vector<double> val, err;
+    std::vector<uint8_t> valid;
+    for (const auto& p : obs_.backend()) {
+      if (p.location.getCoordinateSystem() != framework::CoordinateSystem::GRID) return false;   // (haversine path: one shot)
+      auto [i, j, l] = p.location.getGridCoords();
+      x.push_back(i); y.push_back(j); z.push_back(l);
+      val.push_back(p.value); err.push_back(p.error); valid.push_back(p.is_valid ? 1 : 0);
+    }
+    const char* ws = std::getenv("MDC_WORLD_SIZE");
+    const int world = ws ? std::atoi(ws) : 1, rank = std::getenv("MDC_RANK") ? std::atoi(std::getenv("MDC_RANK")) : 0;
+    const int gnx = static_cast<int>(g.x_dim()), gny = static_cast<int>(g.y_dim()), nz = static_cast<int>(g.z_dim());
+    const int k = static_cast<int>(ensemble_.Size());
+    const double bytes = 8.0 * gnx * gny * nz * k;
+    if (streaming_ == "auto" && world == 1 && bytes < 2e9) return false;      // small: the one-shot path has less overhead
+    mdc_stream_config cfg{};
+    cfg.gnx = gnx; cfg.gny = gny; cfg.nz = nz; cfg.k = k;
+    cfg.row0 = static_cast<int>((static_cast<long long>(gny) * rank) / world);
+    cfg.row1 = static_cast<int>((static_cast<long long>(gny) * (rank + 1)) / world);
+    cfg.slab_rows = slab_rows_; cfg.slots = 4; cfg.sm_reserve = 8; cfg.radius = params_.radius;
+    const int device = std::getenv("MDC_DEVICE") ? std::atoi(std::getenv("MDC_DEVICE")) : (world > 1 ? rank : 0);
+    mdc_stream* st = nullptr;
+    if (mdc_stream_create(device, &cfg, &st)) throw std::runtime_error("mdc_stream_create failed");
+    auto fail = [&](const char* what) {
+      std::string msg = std::string(what) + ": " + mdc_stream_last_error(st);
+      mdc_stream_destroy(st);
+      throw std::runtime_error(msg);
+    };
+    if (world > 1) {
+      const char* idfile = std::getenv("MDC_COMM_ID_FILE");
+      if (!idfile) fail("MDC_WORLD_SIZE > 1 needs MDC_COMM_ID_FILE");
+      char id[128];
+      if (rank == 0) {
+        if (mdc_comm_get_unique_id(id, 128)) fail("mdc_comm_get_unique_id");
+        std::ofstream(std::string(idfile) + ".tmp", std::ios::binary).write(id, 128);
+        std::rename((std::string(idfile) + ".tmp").c_str(), idfile);
+      } else {
+        for (int tries = 0;; ++tries) {
+          std::ifstream f(idfile, std::ios::binary);
+          if (f.read(id, 128)) break;
+          if (tries > 6000) fail("timed out waiting for MDC_COMM_ID_FILE");
+          std::this_thread::sleep_for(std::chrono::milliseconds(10));
+        }
+      }
+      if (mdc_comm_init(st, id, rank, world)) fail("mdc_comm_init");
+    }
+    std::vector<double*> ptrs;
+    for (int m = 0; m < k; ++m) ptrs.push_back(ensemble_.GetMember(m).template getDataPtr<double>());
+    if (mdc_stream_analyse(st, ptrs.data(), 0, gny, static_cast<int64_t>(val.size()), x.data(), y.data(), z.data(), val.data(),
+                           err.data(), valid.data(), &params_, &stats_))
+      fail("mdc_stream_analyse");
+    if (world > 1 && mdc_comm_allgather_rows(st, ptrs.data())) fail("mdc_comm_allgather_rows");
+    logger_.Info() << "LETKF streamed analysis: " << mdc_stream_slabs(st) << " slabs, rank " << rank << " of " << world;
+    mdc_stream_destroy(st);
+    return true;
+  }
+
   Ensemble<BackendTag>& ensemble_;
   Observation<BackendTag>& obs_;
   const ObsOperator<BackendTag>& obs_op_;
@@ -92,6 +174,8 @@ class LETKF {
   std::string format_ = "nc";
   mdc_letkf_params params_{};
   mdc_letkf_stats stats_{};
+  std::string streaming_ = "auto";
+  int slab_rows_ = 0;
   Logger<BackendTag>& logger_ = Logger<BackendTag>::Instance();
 };
 

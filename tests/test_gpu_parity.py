@@ -402,3 +402,40 @@ def test_gaspari_cohn_weight_at_the_edge_of_its_support_is_not_negative(ctx, k):
     em, ep = analysis_errors(Xa, ref["Xa"])
     assert em < TOL and ep < TOL, (em, ep)
     ens.close(); obs.close()
+
+
+@pytest.mark.parametrize("slab_rows,radius", [(6, 4.0), (3, 4.0), (0, 4.0), (2, 5.5), (64, 4.0)])
+def test_c_runtime_streamed_analysis_is_bit_identical_to_one_shot(ctx, slab_rows, radius):
+    """mdc_stream_analyse (csrc/mdc_runtime.cpp: slab pipeline on three host threads, halos between every pair of
+    slabs within reach) on HOST members against the one-shot device analysis: same bits.  Slabs lower than the
+    localisation reach (3 and 2 rows for reach 4 / 5) need rows from the slab after next."""
+    nx, ny, nz, k, P = 19, 43, 2, 24, 460
+    X, o = make_case(nx, ny, nz, k, P, seed=43, out_of_grid=6)
+    ens, obs = _setup(ctx, X, o)
+    params = capi.make_params(radius, 1.05, mb.MODE_CANONICAL, mb.LOC_GASPARI_COHN)
+    st1 = capi.letkf_analyse(ens, obs, params)
+    one_shot = ens.download()
+    ens.close(); obs.close()
+    host = X.copy()
+    sl = mb.Stream(0, nx, ny, nz, k, radius, slab_rows=slab_rows, slots=3)
+    st = sl.analyse([host[m].ctypes.data for m in range(k)], o, params)
+    assert sl.nslab == (max(1, -(-ny // slab_rows)) if slab_rows else max(1, -(-ny // 8)))
+    sl.close()
+    assert np.array_equal(host, one_shot)
+    assert st["columns"] == nx * ny == st1["columns"]
+    assert st["sum_local_obs"] == st1["sum_local_obs"] and st["max_local_obs"] == st1["max_local_obs"]
+    # a radius beyond the plan is refused, not silently truncated
+    sl = mb.Stream(0, nx, ny, nz, k, 2.0, slab_rows=4)
+    with pytest.raises(mb.MdcError):
+        sl.analyse([host[m].ctypes.data for m in range(k)], o, params)
+    sl.close()
+
+
+def test_c_runtime_row_range_needs_its_halo_row(ctx):
+    nx, ny, nz, k = 9, 20, 1, 8
+    X, o = make_case(nx, ny, nz, k, 60, seed=3)
+    sl = mb.Stream(0, nx, ny, nz, k, 3.0, row_range=(5, 12), slab_rows=4)
+    part = np.ascontiguousarray(X[:, :, 5:12, :])            # no halo row 12
+    with pytest.raises(mb.MdcError):
+        sl.analyse([part[m].ctypes.data for m in range(k)], o, capi.make_params(3.0), host_row0=5, host_ny=7)
+    sl.close()

@@ -347,3 +347,53 @@ def cholesky_lower(A):
     if lib().orc_cholesky_lower(C.c_int(A.shape[0]), _p(A, C.c_double), _p(out, C.c_double)):
         raise RuntimeError("not SPD")
     return out
+
+
+# ---- the CPU arm of bench.py (oracle/cpu_baseline.c): built -O3 -march=native ON THE MACHINE THAT RUNS IT (the
+# file name carries a hash of the CPU flags, so a library built in the build container is not reused on the GPU box)
+class CpubParams(C.Structure):
+    _fields_ = [("nx", C.c_int), ("ny", C.c_int), ("nz", C.c_int), ("k", C.c_int), ("P", C.c_int64),
+                ("radius", C.c_double), ("inflation", C.c_double), ("nthreads", C.c_int)]
+
+
+_cpub = None
+
+
+def cpu_baseline_lib() -> C.CDLL:
+    global _cpub
+    if _cpub is None:
+        import hashlib
+        try:
+            flags = [ln for ln in open("/proc/cpuinfo") if ln.startswith("flags")][0]
+        except Exception:  # noqa: BLE001
+            flags = "unknown"
+        tag = hashlib.sha1(flags.encode()).hexdigest()[:10]
+        src = os.path.join(_HERE, "cpu_baseline.c")
+        out = os.path.join(_HERE, f"_cpub_{tag}.so")
+        if not os.path.exists(out) or os.path.getmtime(out) < os.path.getmtime(src):
+            cc = "gcc"
+            subprocess.check_call([cc, "-O3", "-march=native", "-fopenmp", "-fPIC", "-shared", "-std=c11", "-o", out, src, "-lm"])
+        _cpub = C.CDLL(out)
+        _cpub.cpub_max_threads.restype = C.c_int
+    return _cpub
+
+
+def cpu_baseline_letkf(X, ox, oy, oz, oval, oerr, valid=None, *, radius, inflation=1.0, nthreads=0, cols=None,
+                       inplace=False):
+    """Canonical LETKF (Gaspari-Cohn, symmetric square root) by the performance-minded host code.  Returns
+    (Xa, sum of local observation counts).  X is not modified unless inplace (a C-contiguous float64 array)."""
+    Xa = X if inplace else _f64(X).copy()
+    assert Xa.dtype == np.float64 and Xa.flags.c_contiguous
+    k, nz, ny, nx = Xa.shape
+    ox, oy, oz = _i32(ox), _i32(oy), _i32(oz)
+    oval, oerr = _f64(oval), _f64(oerr)
+    v = np.ascontiguousarray(valid, dtype=np.uint8) if valid is not None else None
+    prm = CpubParams(nx, ny, nz, k, len(ox), radius, inflation, nthreads)
+    cs = np.ascontiguousarray(cols, dtype=np.int64) if cols is not None else None
+    tot = C.c_int64(0)
+    rc = cpu_baseline_lib().cpub_letkf(C.byref(prm), _p(Xa, C.c_double), _p(ox, C.c_int32), _p(oy, C.c_int32), _p(oz, C.c_int32),
+                                       _p(oval, C.c_double), _p(oerr, C.c_double), _p(v, C.c_uint8), _p(cs, C.c_int64),
+                                       C.c_int64(len(cs) if cs is not None else 0), C.byref(tot))
+    if rc:
+        raise RuntimeError(f"cpub_letkf failed rc={rc}")
+    return Xa, int(tot.value)

@@ -1009,3 +1009,151 @@ int orc_enkf(double* X, int nx, int ny, int nz, int k, int64_t P, const int32_t*
   free(mean); free(Y); free(Yp); free(d); free(S); free(Lm); free(B); free(C);
   return rc;
 }
+
+/* ------------------------------------------------------------------ LWEnKF (locally weighted EnKF) */
+
+/* LWEnKF.hpp:603-636: the localisation function of the NORMALISED distance */
+static double lw_loc_fn(int fn, double distance, double radius) {
+  const double nd = distance / radius;
+  switch (fn) {
+    case ORC_LOC_GAUSSIAN: return exp(-0.5 * nd * nd);
+    case ORC_LOC_EXPONENTIAL: return exp(-nd);
+    case ORC_LOC_CUTOFF: return nd <= 1.0 ? 1.0 : 0.0;
+    case ORC_LOC_REF_GASPARI_COHN:
+      if (nd >= 2.0) return 0.0;
+      if (nd >= 1.0) { const double z = nd - 1.0; return ((-0.25 * z + 0.5) * z + 0.625) * z + 0.125; }
+      return (((-0.25 * nd + 0.5) * nd + 0.625) * nd - 5.0) * nd + 4.0;
+    default: return exp(-0.5 * nd * nd);
+  }
+}
+
+/* LWEnKF<Tag>::Analyse, LWEnKF.hpp:207-334 (+ computeWeights :400-531, computeWeightedCovariance :537-551,
+ * applyLocalization :556-574, applyLocalizationToGain :579-598, applyInflation :641-660,
+ * generateObservationPerturbations :665-685 with the N(0,1) draws Z supplied).  Everything is global and dense, as
+ * written: S is P x P, K is n x P, the "distances" of both localisations are INDEX distances |i - j| / dim.
+ * X: [k][n] in place.  weighting: 0 uniform, 1 adaptive, 2 inverse_var, 3 likelihood.  diag: [9] innovation_norm,
+ * background_spread, analysis_spread, max K, min K, cond(S), max w, min w, var w. */
+int orc_lwenkf(double* X, int nx, int ny, int nz, int k, int64_t P, const int32_t* ox, const int32_t* oy,
+               const int32_t* oz, const double* oval, const double* oerr, const uint8_t* valid, double inflation,
+               double radius, int loc_fn, int weighting, const double* Z, double* diag) {
+  const int64_t n = (int64_t)nx * ny * nz;
+  double* mean = (double*)malloc(sizeof(double) * (size_t)n);
+  orc_ensemble_mean(X, k, n, mean);                                            /* :219 */
+  double* Xp = (double*)malloc(sizeof(double) * (size_t)n * k);               /* [k][n] perturbations :220-231 */
+  for (int m = 0; m < k; ++m)
+    for (int64_t i = 0; i < n; ++i) Xp[(int64_t)m * n + i] = X[(int64_t)m * n + i] - mean[i];
+  double* Y = (double*)malloc(sizeof(double) * (size_t)P * k);
+  double* Yp = (double*)malloc(sizeof(double) * (size_t)P * k);
+  double* d = (double*)malloc(sizeof(double) * (size_t)P);
+  orc_obs_space(X, nx, ny, nz, k, P, ox, oy, oz, valid, oval, Y, NULL, Yp, d); /* :241-255 */
+  /* ---- weights (:400-436) */
+  double* w = (double*)malloc(sizeof(double) * (size_t)k);
+  for (int m = 0; m < k; ++m) {
+    double sq = 0.0;
+    for (int64_t i = 0; i < n; ++i) sq += Xp[(int64_t)m * n + i] * Xp[(int64_t)m * n + i];
+    if (weighting == 0) w[m] = 1.0 / k;
+    else if (weighting == 1) w[m] = 1.0 / (sqrt(sq) + 1e-8);
+    else if (weighting == 2) w[m] = 1.0 / (sq + 1e-8);
+    else {
+      double q = 0.0;                                                          /* :514-529, R^-1 of a diagonal R */
+      for (int64_t a = 0; a < P; ++a) {
+        const double in = oval[a] - Y[a * k + m];
+        const double var = (valid && !valid[a]) ? INFINITY : oerr[a] * oerr[a];
+        q += in * ((1.0 / var) * in);
+      }
+      w[m] = exp(-0.5 * q);
+    }
+  }
+  if (weighting == 1 || weighting == 2) {                                      /* :457-466 / :490-499 */
+    double s = 0.0;
+    for (int m = 0; m < k; ++m) s += w[m];
+    for (int m = 0; m < k; ++m) w[m] /= s;
+  }
+  {
+    double s = 0.0;                                                            /* :425-428 */
+    for (int m = 0; m < k; ++m) s += w[m];
+    for (int m = 0; m < k; ++m) w[m] /= s;
+  }
+  double wmax = w[0], wmin = w[0], wvar = 0.0;
+  for (int m = 0; m < k; ++m) {
+    if (w[m] > wmax) wmax = w[m];
+    if (w[m] < wmin) wmin = w[m];
+    const double df = w[m] - 1.0 / k;
+    wvar += df * df;
+  }
+  wvar /= k;
+  /* ---- inflation (:641-660) */
+  const double sqi = sqrt(inflation);
+  double bs = 0.0;
+  for (int64_t e = 0; e < n * k; ++e) { Xp[e] *= sqi; bs += Xp[e] * Xp[e]; }
+  const double background_spread = sqrt(bs / ((double)n * k));
+  double dn = 0.0;
+  for (int64_t a = 0; a < P; ++a) dn += d[a] * d[a];
+  /* ---- S = (sum_m w_m y'_m y'_m^T) o L + R (:263-275) */
+  double* S = (double*)malloc(sizeof(double) * (size_t)P * P);
+  for (int64_t a = 0; a < P; ++a)
+    for (int64_t b = 0; b < P; ++b) {
+      double s = 0.0;
+      for (int m = 0; m < k; ++m) s += w[m] * Yp[a * k + m] * Yp[b * k + m];
+      s *= lw_loc_fn(loc_fn, fabs((double)(a - b)) / (double)P, radius);
+      if (a == b) s += (valid && !valid[a]) ? INFINITY : oerr[a] * oerr[a];
+      S[a * P + b] = s;
+    }
+  double* Sinv = (double*)malloc(sizeof(double) * (size_t)P * P);
+  int rc = orc_lu_inverse((int)P, S, Sinv);                                    /* S.inverse() :279 */
+  /* cond(S) from its singular values = |eigenvalues| of the symmetric S (:289-292) */
+  double cond = NAN;
+  if (!rc) {
+    double* ev = (double*)malloc(sizeof(double) * (size_t)P);
+    double* V = (double*)malloc(sizeof(double) * (size_t)P * P);
+    if (!orc_jacobi_eigh((int)P, S, ev, V, NULL)) {
+      double lo = INFINITY, hi = 0.0;
+      for (int64_t a = 0; a < P; ++a) { const double v = fabs(ev[a]); if (v < lo) lo = v; if (v > hi) hi = v; }
+      cond = hi / lo;
+    }
+    free(ev); free(V);
+  }
+  double kmax = -INFINITY, kmin = INFINITY;
+  if (!rc) {
+    /* K = ((X' Y'^T) S^-1) / (k - 1), then o Lg (:278-282); xa_m = xb + x'_m + K (yo + eps_m - Yb_m) (:299-310) */
+    const int64_t dim = n > P ? n : P;
+    double* XY = (double*)malloc(sizeof(double) * (size_t)P);
+    double* Krow = (double*)malloc(sizeof(double) * (size_t)P);
+    for (int64_t i = 0; i < n; ++i) {
+      for (int64_t a = 0; a < P; ++a) {
+        double s = 0.0;
+        for (int m = 0; m < k; ++m) s += Xp[(int64_t)m * n + i] * Yp[a * k + m];
+        XY[a] = s;
+      }
+      for (int64_t b = 0; b < P; ++b) {
+        double s = 0.0;
+        for (int64_t a = 0; a < P; ++a) s += XY[a] * Sinv[a * P + b];
+        s = s / (double)(k - 1) * lw_loc_fn(loc_fn, fabs((double)(i - b)) / (double)dim, radius);
+        Krow[b] = s;
+        if (s > kmax) kmax = s;
+        if (s < kmin) kmin = s;
+      }
+      for (int m = 0; m < k; ++m) {
+        double s = 0.0;
+        for (int64_t b = 0; b < P; ++b) {
+          const double sd = (valid && !valid[b]) ? INFINITY : sqrt(oerr[b] * oerr[b]);
+          s += Krow[b] * ((oval[b] + sd * Z[b * k + m]) - Y[b * k + m]);
+        }
+        X[(int64_t)m * n + i] = mean[i] + (Xp[(int64_t)m * n + i] + s);
+      }
+    }
+    free(XY); free(Krow);
+  }
+  double as = 0.0;
+  if (!rc) {
+    orc_ensemble_mean(X, k, n, mean);                                          /* :320-333 */
+    for (int m = 0; m < k; ++m)
+      for (int64_t i = 0; i < n; ++i) { const double v = X[(int64_t)m * n + i] - mean[i]; as += v * v; }
+  }
+  if (diag) {
+    diag[0] = sqrt(dn); diag[1] = background_spread; diag[2] = sqrt(as / ((double)k * n));
+    diag[3] = kmax; diag[4] = kmin; diag[5] = cond; diag[6] = wmax; diag[7] = wmin; diag[8] = wvar;
+  }
+  free(mean); free(Xp); free(Y); free(Yp); free(d); free(w); free(S); free(Sinv);
+  return rc;
+}

@@ -150,6 +150,9 @@ typedef struct {
 /* Global stochastic EnKF (EnKF.hpp:139-256) with supplied standard-normal draws Z (P x k,
  * row-major; obs_pert = sqrt(R_ii) * Z, EnKF.hpp:340-361).  X in place.
  * want_gain_stats: form K explicitly to get max/min (O(n*P) memory). */
+int orc_lwenkf(double* X, int nx, int ny, int nz, int k, int64_t P, const int32_t* ox, const int32_t* oy,
+               const int32_t* oz, const double* oval, const double* oerr, const uint8_t* valid, double inflation,
+               double radius, int loc_fn, int weighting, const double* Z, double* diag);
 int orc_enkf(double* X, int nx, int ny, int nz, int k, int64_t P, const int32_t* ox,
              const int32_t* oy, const int32_t* oz, const double* oval, const double* oerr,
              const uint8_t* valid, double inflation, const double* Z, int want_gain_stats,

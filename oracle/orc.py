@@ -307,6 +307,30 @@ def enkf(X, ox, oy, oz, oval, oerr, Z, valid=None, *, inflation=1.0, want_gain_s
     return Xa, {n: getattr(diag, n) for n, _ in EnkfDiag._fields_}
 
 
+LW_UNIFORM, LW_ADAPTIVE, LW_INVERSE_VAR, LW_LIKELIHOOD = 0, 1, 2, 3
+LW_WEIGHTING = {"uniform": 0, "adaptive": 1, "inverse_var": 2, "likelihood": 3}
+LW_LOCFN = {"gaussian": 2, "exponential": 3, "cutoff": 0, "gaspari_cohn": 4}     # LOC_* codes
+
+
+def lwenkf(X, ox, oy, oz, oval, oerr, Z, valid=None, *, inflation=1.0, radius=1.0, loc_fn=2, weighting=0):
+    """LWEnKF<Tag>::Analyse (LWEnKF.hpp:207-334).  Returns (Xa, diag[9])."""
+    Xa = _f64(X).copy()
+    k, nz, ny, nx = Xa.shape
+    ox, oy, oz = _i32(ox), _i32(oy), _i32(oz)
+    oval, oerr, Z = _f64(oval), _f64(oerr), _f64(Z)
+    v = np.ascontiguousarray(valid, dtype=np.uint8) if valid is not None else None
+    diag = np.zeros(9)
+    f = lib().orc_lwenkf
+    f.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int64] + [C.c_void_p] * 6 + [C.c_double, C.c_double, C.c_int,
+                  C.c_int, C.c_void_p, C.c_void_p]
+    rc = f(Xa.ctypes.data, nx, ny, nz, k, len(ox), ox.ctypes.data, oy.ctypes.data, oz.ctypes.data, oval.ctypes.data,
+           oerr.ctypes.data, v.ctypes.data if v is not None else None, inflation, radius, loc_fn, weighting, Z.ctypes.data,
+           diag.ctypes.data)
+    if rc:
+        raise RuntimeError(f"orc_lwenkf failed rc={rc}")
+    return Xa, diag
+
+
 def metrics(X, truth):
     """Metrics<double>::CalculateAll (Metrics.hpp:74-103).  X: [k, ...state], truth: [...state]."""
     X = _f64(X)

@@ -23,6 +23,7 @@
 #include <vector>
 
 #include "EnKF.hpp"
+#include "LWEnKF.hpp"
 #include "ETKF.hpp"
 #include "LETKF.hpp"
 
@@ -178,13 +179,30 @@ static int run(const std::string& mode, int argc, char** argv, const std::string
                   r.min_kalman_gain, r.condition_number, r.inflation_factor});
     return 0;
   }
+  if (mode == "lwenkf") {
+    fwk::LWEnKF<Tag> lw(ensemble, observations, obs_operator, config);
+    lw.Analyse();
+    write_vec(f, dump_members(ensemble));
+    // the N(0,1) draws LWEnKF.hpp:666-679 consumed (same generator, same fixed seed, same order)
+    std::random_device rd;   // -> metada_fixed_random_device via ref_fixed_seed.hpp
+    std::mt19937 gen(rd());
+    std::normal_distribution<double> dist(0.0, 1.0);
+    std::vector<double> Z(static_cast<size_t>(P * k));
+    for (int64_t i = 0; i < P; ++i)
+      for (int64_t j = 0; j < k; ++j) Z[static_cast<size_t>(i * k + j)] = dist(gen);
+    write_vec(f, Z);
+    auto r = lw.getAnalysisResults();
+    write_vec(f, {r.innovation_norm, r.background_spread, r.analysis_spread, r.max_kalman_gain, r.min_kalman_gain,
+                  r.condition_number, r.max_weight, r.min_weight, r.weight_variance});
+    return 0;
+  }
   std::cerr << "unknown mode " << mode << std::endl;
   return 2;
 }
 
 int main(int argc, char** argv) {
   if (argc != 4) {
-    std::cerr << "usage: ref_driver <hx|letkf|letkf_snapshot|etkf|enkf> <config.json> <out.bin>" << std::endl;
+    std::cerr << "usage: ref_driver <hx|letkf|letkf_snapshot|etkf|enkf|lwenkf> <config.json> <out.bin>" << std::endl;
     return 2;
   }
   const std::string mode = argv[1], out = argv[3];

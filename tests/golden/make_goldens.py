@@ -23,6 +23,12 @@ DRIVER = os.path.join(ROOT, "oracle", "_ref", "ref_driver")
 OUT = os.path.dirname(os.path.abspath(__file__))
 
 
+# (weighting_scheme, localization_function, localization_radius): the radius normalises LWEnKF's INDEX distance
+# |i - j| / dim (LWEnKF.hpp:569, 593), so values below 1 are what makes the localisation bite
+LWENKF_CASES = [("uniform", "gaussian", 0.3), ("adaptive", "gaspari_cohn", 0.4), ("inverse_var", "exponential", 0.25),
+                ("likelihood", "cutoff", 0.5), ("uniform", "gaussian", 10.0)]
+
+
 def read_dump(path):
     b = open(path, "rb").read()
     k, n, P = struct.unpack_from("<qqq", b, 0)
@@ -61,6 +67,17 @@ def collect(cfg, tmp, nx, ny):
         if mode == "enkf":
             g["enkf_Z"] = v[1].reshape(P, k)
             g["enkf_diag"] = v[2]
+    # LWEnKF<SimpleBackendTag>::Analyse (LWEnKF.hpp:207-334) for every weighting scheme / localisation function
+    for i, (weighting, locfn, radius) in enumerate(LWENKF_CASES):
+        c = json.loads(json.dumps(cfg))
+        c["analysis"].update(weighting_scheme=weighting, localization_function=locfn, localization_radius=radius)
+        cp = os.path.join(tmp, f"cfg_lw{i}.json")
+        json.dump(c, open(cp, "w"))
+        _, _, _, v = run("lwenkf", cp, tmp)
+        g[f"lwenkf{i}_Xa"] = v[0].reshape(k, 1, ny, nx)
+        g[f"lwenkf{i}_Z"] = v[1].reshape(P, k)
+        g[f"lwenkf{i}_diag"] = v[2]        # innovation_norm, background_spread, analysis_spread, max/min K, cond, max/min w, var w
+    g["lwenkf_cases"] = np.array(json.dumps(LWENKF_CASES))
     return g
 
 

@@ -11,7 +11,7 @@ import numpy as np
 import pytest
 
 from oracle import orc
-from tests.common import rel_err
+from tests.common import analysis_errors, rel_err
 
 G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 CASES = ["tutorial_36x18.npz", "synthetic_23x17.npz"]
@@ -103,3 +103,28 @@ def test_metrics_match_reference_header_bit_exactly():
     X, t = g["X"], g["truth"]
     assert abs(m["rmse"] - np.sqrt(((X.mean(0) - t) ** 2).mean())) < 1e-14
     assert abs(m["avg_spread"] - X.std(0, ddof=1).mean()) < 1e-14
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_lwenkf_matches_reference(name):
+    """LWEnKF<SimpleBackendTag>::Analyse (the reference's own, unmodified LWEnKF.hpp) for every weighting scheme and
+    localisation function; the likelihood weights underflow to 0 / 0 on the tutorial set in the reference too."""
+    import json
+    g = load(name)
+    cases = json.loads(str(g["lwenkf_cases"]))
+    for i, (weighting, locfn, radius) in enumerate(cases):
+        want, wdiag = g[f"lwenkf{i}_Xa"], g[f"lwenkf{i}_diag"]
+        Xa, diag = orc.lwenkf(g["X"], g["ox"], g["oy"], g["oz"], g["yo"], np.sqrt(g["var"]), g[f"lwenkf{i}_Z"],
+                              inflation=float(g["inflation"]), radius=float(np.float32(radius)),   # ConfigValue.hpp:108 narrowing
+                              loc_fn=orc.LW_LOCFN[locfn],
+                              weighting=orc.LW_WEIGHTING[weighting])
+        if np.isnan(want).any():
+            assert np.isnan(Xa).any(), (name, weighting)
+            continue
+        cond = wdiag[5]
+        tol = max(1e-10, 3e-15 * cond)                  # explicit inverse of S: forward error ~ cond(S) eps
+        em, ep = analysis_errors(Xa, want)
+        assert em < tol and ep < tol, (name, weighting, locfn, em, ep, cond)
+        for j, nm in enumerate(("innovation_norm", "background_spread", "analysis_spread", "max_kalman_gain", "min_kalman_gain",
+                                "condition_number", "max_weight", "min_weight", "weight_variance")):
+            assert abs(diag[j] - wdiag[j]) <= max(1e-9, 3e-14 * cond) * max(abs(wdiag[j]), 1e-30) + (1e-30 if j == 8 else 0), (nm, diag[j], wdiag[j])

@@ -227,6 +227,21 @@ typedef struct {
 int mdc_enkf_analyse(mdc_ens* ens, mdc_obs* obs, double inflation, const double* Z, uint64_t seed,
                      int want_gain_stats, mdc_enkf_diag* diag);
 
+/* ---- locally weighted EnKF: replaces LWEnKF<Tag>::Analyse (LWEnKF.hpp:207-334) ------------------------------
+ * As written in the reference: global and dense (S = (sum_m w_m y'_m y'_m^T) o L + R is P x P; K = X' Y'^T S^-1 /
+ * (k - 1) is Schur-multiplied by a second localisation matrix; both use INDEX distances |i - j| / dim normalised by
+ * loc_radius, LWEnKF.hpp:566-570, 589-594), member weights by `weighting` (:400-531), multiplicative inflation of
+ * the perturbations (:641-660), perturbed observations (:665-685; Z as for mdc_enkf_analyse).  loc_fn: MDC_LOC_CUTOFF,
+ * MDC_LOC_GAUSSIAN, MDC_LOC_EXPONENTIAL or MDC_LOC_REF_GASPARI_COHN (the reference's "gaspari_cohn").  K is never
+ * stored.  Needs libcusolver at run time (LU of S, eigenvalues for cond(S)). */
+enum { MDC_LW_UNIFORM = 0, MDC_LW_ADAPTIVE = 1, MDC_LW_INVERSE_VAR = 2, MDC_LW_LIKELIHOOD = 3 };
+typedef struct {
+  double innovation_norm, background_spread, analysis_spread, max_kalman_gain, min_kalman_gain, condition_number;
+  double max_weight, min_weight, weight_variance;
+} mdc_lwenkf_diag;
+int mdc_lwenkf_analyse(mdc_ens* ens, mdc_obs* obs, double inflation, double loc_radius, int loc_fn, int weighting,
+                       const double* Z, uint64_t seed, mdc_lwenkf_diag* diag);
+
 /* ---- verification metrics against a truth state -------------------------------------------------
  * Replaces framework/algorithms/Metrics.hpp:74-290 (Metrics<T>::CalculateAll): ensemble mean and
  * spread (unbiased standard deviation) per state point, RMSE / bias / correlation of the mean

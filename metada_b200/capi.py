@@ -68,6 +68,15 @@ class EnkfDiag(C.Structure):
         return {n: getattr(self, n) for n, _ in self._fields_}
 
 
+class LwenkfDiag(C.Structure):
+    _fields_ = [(n, C.c_double) for n in (
+        "innovation_norm", "background_spread", "analysis_spread", "max_kalman_gain", "min_kalman_gain",
+        "condition_number", "max_weight", "min_weight", "weight_variance")]
+
+    def asdict(self):
+        return {n: getattr(self, n) for n, _ in self._fields_}
+
+
 class StreamConfig(C.Structure):
     _fields_ = [("gnx", C.c_int), ("gny", C.c_int), ("nz", C.c_int), ("k", C.c_int), ("row0", C.c_int), ("row1", C.c_int),
                 ("slab_rows", C.c_int), ("slots", C.c_int), ("sm_reserve", C.c_int), ("radius", C.c_double)]
@@ -197,6 +206,7 @@ def load_library() -> C.CDLL:
         "mdc_comm_init": (C.c_int, [vp, vp, C.c_int, C.c_int]),
         "mdc_comm_max": (C.c_int, [vp, pd]),
         "mdc_comm_allgather_rows": (C.c_int, [vp, C.POINTER(vp)]),
+        "mdc_lwenkf_analyse": (C.c_int, [vp, vp, dbl, dbl, C.c_int, C.c_int, vp, C.c_uint64, C.POINTER(LwenkfDiag)]),
         "mdc_bench_fp64_fma": (C.c_int, [vp, pd]),
         "mdc_bench_fp64_dmma": (C.c_int, [vp, pd]),
         "mdc_bench_hbm_copy": (C.c_int, [vp, pd]),
@@ -548,6 +558,16 @@ def enkf_analyse(ens: Ensemble, obs: Observations, inflation: float, Z=None, see
     d = EnkfDiag()
     ens.ctx.check(ens.ctx.L.mdc_enkf_analyse(ens.h, obs.h, inflation, _ptr(Zc), seed,
                                              int(want_gain_stats), C.byref(d)))
+    return d.asdict()
+
+LW_UNIFORM, LW_ADAPTIVE, LW_INVERSE_VAR, LW_LIKELIHOOD = 0, 1, 2, 3
+
+
+def lwenkf_analyse(ens: Ensemble, obs: Observations, inflation: float, loc_radius: float, loc_fn: int, weighting: int,
+                   Z=None, seed: int = 7) -> dict:
+    Zc = np.ascontiguousarray(Z, dtype=np.float64) if Z is not None else None
+    d = LwenkfDiag()
+    ens.ctx.check(ens.ctx.L.mdc_lwenkf_analyse(ens.h, obs.h, inflation, loc_radius, loc_fn, weighting, _ptr(Zc), seed, C.byref(d)))
     return d.asdict()
 
 

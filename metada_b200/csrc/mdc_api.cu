@@ -11,6 +11,7 @@
 #include "ens_kernels.cuh"
 #include "geo_kernels.cuh"
 #include "global_kernels.cuh"
+#include "lwenkf_kernels.cuh"
 #include "hx_kernels.cuh"
 #include "index_kernels.cuh"
 #include "letkf_kernels.cuh"
@@ -1153,3 +1154,4 @@ int mdc_bench_hbm_copy(mdc_ctx* ctx, double* gbs) {
 }  // extern "C"
 
 #include "global_api.inl"
+#include "lwenkf_api.inl"

@@ -3,7 +3,7 @@
 // 261,287): same AnalysisResults fields, same config keys (analysis.inflation, inflation_method,
 // output_base_file, format).  Analyse() = mdc_enkf_analyse.  The reference draws its observation
 // perturbations from an unseeded mt19937 (EnKF.hpp:346-347); here they come from a counter-based
-// device generator seeded by the optional key analysis.seed (default 7), or from
+// device generator seeded by the optional key analysis.seed (default 7) mixed with a per-call counter, or from
 // setObservationPerturbations() for reproducible comparisons.
 #include <string>
 #include <vector>
@@ -61,7 +61,8 @@ class EnKF {
       throw std::invalid_argument("EnKF: observation perturbations must be [obs][member]");
     mdc_enkf_diag d{};
     backends::cuda::DeviceContext::Instance().check(
-        mdc_enkf_analyse(dev->get(), dobs.get(), inflation_factor_, Z_.empty() ? nullptr : Z_.data(), seed_, 1, &d),
+        mdc_enkf_analyse(dev->get(), dobs.get(), inflation_factor_, Z_.empty() ? nullptr : Z_.data(),
+                         seed_ + 0x9E3779B97F4A7C15ull * calls_++ /* a fresh stream every cycle */, 1, &d),
         "mdc_enkf_analyse");
     device::downloadEnsemble(*dev, ensemble_);
     ensemble_.RecomputeMean();       // EnKF.hpp:237
@@ -102,7 +103,7 @@ class EnKF {
   double inflation_factor_ = 1.0;
   std::string output_base_file_;
   std::string format_ = "txt";
-  uint64_t seed_ = 7;
+  uint64_t seed_ = 7, calls_ = 0;
   std::vector<double> Z_;
   mdc_enkf_diag diag_{};
   Logger<BackendTag>& logger_ = Logger<BackendTag>::Instance();

@@ -197,3 +197,24 @@ def test_letkf_driver_streamed_equals_one_shot(tmp_path, mode):
         assert r.returncode == 0, r.stderr + r.stdout
         dumps.append(open(dump, "rb").read())
     assert dumps[0] == dumps[1]
+
+
+@pytest.mark.gpu
+def test_lwenkf_driver_matches_reference(tmp_path):
+    """lwenkf_cuda <config> (LWEnKF<CudaBackendTag>, the reference's config keys) against the reference's own
+    LWEnKF.hpp output for the adaptive-weight / polynomial-localisation case."""
+    g = load(CASES[1])
+    cases = json.loads(str(g["lwenkf_cases"]))
+    i = 1
+    weighting, fn, radius = cases[i]
+    zf = str(tmp_path / "Z.bin")
+    np.ascontiguousarray(g[f"lwenkf{i}_Z"], dtype="<f8").tofile(zf)
+    cfg = write_case(g, str(tmp_path), "ref_compat", {"perturbation_file": zf, "weighting_scheme": weighting,
+                                                       "localization_function": fn, "localization_radius": radius})
+    dump = str(tmp_path / "xa.bin")
+    r = subprocess.run([_need("lwenkf_cuda"), cfg, "--dump", dump], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr + r.stdout
+    em, ep = analysis_errors(read_dump(dump, int(g["ny"]), int(g["nx"])), g[f"lwenkf{i}_Xa"])
+    tol = max(1e-10, 1e-14 * float(g[f"lwenkf{i}_diag"][5]))
+    assert em < tol and ep < tol, (em, ep)
+    assert "LWEnKF diagnostics" in r.stdout

@@ -77,15 +77,24 @@ int mdc_ens_set_geography(mdc_ens* e, const double* lat, const double* lon, int 
 int mdc_ens_set_variables(mdc_ens* e, int nvar, const int32_t* var_nlev) {
   mdc_ctx* ctx = e->ctx;
   if (nvar < 1 || nvar > MDC_MAX_VARS || !var_nlev) MDC_FAIL(ctx, MDC_ERR_INVALID, "set_variables: 1 <= nvar <= %d", MDC_MAX_VARS);
-  int total = 0, nzg = 1;
+  // The geometry's level count nzg is that of the mass-level variables = the smallest multi-level count; a variable
+  // staggered in the vertical (WRF's W, PH, PHB: WRFState.hpp:89-93, 445-449) has nzg + 1.  H searches its neighbours
+  // on the geometry's nzg levels and reads var[kk][jj][ii] with the variable's own dimensions
+  // (IdentityObsOperator.hpp:684-711), so it never touches a staggered variable's top level; the column update
+  // transforms every level of every variable.
+  int total = 0, nzg = 0;
   for (int v = 0; v < nvar; ++v) {
     if (var_nlev[v] < 1) MDC_FAIL(ctx, MDC_ERR_INVALID, "set_variables: variable %d has %d levels", v, var_nlev[v]);
-    total += var_nlev[v]; nzg = std::max(nzg, (int)var_nlev[v]);
+    total += var_nlev[v];
+    if (var_nlev[v] > 1) nzg = nzg ? std::min(nzg, (int)var_nlev[v]) : (int)var_nlev[v];
   }
+  if (!nzg) nzg = 1;
   if (total != e->nz) MDC_FAIL(ctx, MDC_ERR_INVALID, "set_variables: levels sum to %d, the ensemble has %d", total, e->nz);
+  if (e->nvcoord > 0 && nzg > 1 && e->nvcoord != nzg)
+    MDC_FAIL(ctx, MDC_ERR_INVALID, "set_variables: the geometry has %d vertical coordinates, the mass-level variables %d levels", e->nvcoord, nzg);
   for (int v = 0; v < nvar; ++v)
-    if (var_nlev[v] != 1 && var_nlev[v] != nzg)
-      MDC_FAIL(ctx, MDC_ERR_UNSUPPORTED, "set_variables: variable %d has %d levels; 3-D variables must share the geometry's %d levels (staggered W grids are not supported)", v, var_nlev[v], nzg);
+    if (var_nlev[v] != 1 && var_nlev[v] != nzg && var_nlev[v] != nzg + 1)
+      MDC_FAIL(ctx, MDC_ERR_UNSUPPORTED, "set_variables: variable %d has %d levels; a 3-D variable has the geometry's %d levels or one more (vertically staggered)", v, var_nlev[v], nzg);
   MDC_CUDA(ctx, cudaSetDevice(ctx->device));
   std::vector<int32_t> map((size_t)e->nz);
   int off = 0;

@@ -240,16 +240,20 @@ void orc_obs_space(const double* X, int nx, int ny, int nz, int k, int64_t P, co
 }
 
 /* Y, Y', d for a multi-variable state: member layout [var][lev][y][x], observation i reads variable ovar[i]
- * (IdentityObsOperator.hpp:236-281, 681-711); nzg = levels of the geometry (the largest variable). */
+ * (IdentityObsOperator.hpp:236-281, 681-711); nzg = levels of the geometry (the smallest multi-level variable; a vertically
+ * staggered one has nzg + 1). */
 static void obs_space_ext(const double* X, int nx, int ny, int nz, int k, int64_t P, const int32_t* ox,
                           const int32_t* oy, const int32_t* oz, const uint8_t* valid, const double* oval,
                           const orc_ext* ext, double* Y, double* Yp, double* d) {
   const int64_t G = (int64_t)nx * ny, n = G * nz;
-  int off[64] = {0}, nzg = 1;
+  /* geometry levels = the mass-level variables' count = the smallest multi-level one; a vertically staggered variable
+   * (W: nz + 1 levels) is read with its own dimensions but searched on the geometry's levels (:684-711) */
+  int off[64] = {0}, nzg = 0;
   for (int v = 0; v < ext->nvar; ++v) {
     off[v + 1] = off[v] + ext->var_nlev[v];
-    if (ext->var_nlev[v] > nzg) nzg = ext->var_nlev[v];
+    if (ext->var_nlev[v] > 1 && (nzg == 0 || ext->var_nlev[v] < nzg)) nzg = ext->var_nlev[v];
   }
+  if (nzg == 0) nzg = 1;
   for (int m = 0; m < k; ++m)
     for (int64_t i = 0; i < P; ++i) {
       if (valid && !valid[i]) { Y[i * k + m] = 0.0; continue; }
@@ -271,12 +275,13 @@ static void obs_space_ext(const double* X, int nx, int ny, int nz, int k, int64_
 void orc_hx_ext(const double* member, int nx, int ny, int nz, const orc_ext* ext, int64_t P, const int32_t* ox,
                 const int32_t* oy, const int32_t* oz, const uint8_t* valid, double* out) {
   const int64_t G = (int64_t)nx * ny;
-  int off[64] = {0}, nzg = 1;
+  int off[64] = {0}, nzg = 0;
   (void)nz;
   for (int v = 0; v < ext->nvar && v < 63; ++v) {
     off[v + 1] = off[v] + ext->var_nlev[v];
-    if (ext->var_nlev[v] > nzg) nzg = ext->var_nlev[v];
+    if (ext->var_nlev[v] > 1 && (nzg == 0 || ext->var_nlev[v] < nzg)) nzg = ext->var_nlev[v];
   }
+  if (nzg == 0) nzg = 1;
   for (int64_t i = 0; i < P; ++i) {
     if (valid && !valid[i]) { out[i] = 0.0; continue; }
     const int v = ext->ovar ? ext->ovar[i] : 0;

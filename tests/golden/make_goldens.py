@@ -168,12 +168,12 @@ def location_case(tmp):
     return {"pairs": a, "km": np.frombuffer(open(out, "rb").read(), dtype="<f8").copy()}
 
 
-def obsop_geo_case(tmp):
+def obsop_geo_case(tmp, var_nlev=(5, 5, 1)):
     """The reference's IdentityObsOperator (oracle/_ref/ref_obsop_geo, mock WRF-type backends) on GEOGRAPHIC
     observations of a three-variable state ([5, 5, 1] levels) on a curvilinear grid: nearest grid point / level
     (convertGeographicToGrid) + 4-of-8 IDW in the observation's own variable."""
-    nx, ny, var_nlev, P = 23, 17, [5, 5, 1], 600
-    nz = max(var_nlev)
+    nx, ny, var_nlev, P = 23, 17, list(var_nlev), 600
+    nz = min(v for v in var_nlev if v > 1)        # the geometry's (mass) levels; a W-staggered variable has nz + 1
     lat, lon = syn.geography(nx, ny)
     vc = np.array([1000.0, 925.0, 850.0, 700.0, 500.0])
     o = syn.geo_observations(P, lat, lon, vc, seed=77, margin=0.3)
@@ -204,6 +204,8 @@ def main():
         np.savez_compressed(os.path.join(OUT, "location_geographic.npz"), **location_case(tmp))
     with tempfile.TemporaryDirectory() as tmp:
         np.savez_compressed(os.path.join(OUT, "obsop_geographic.npz"), **obsop_geo_case(tmp))
+    with tempfile.TemporaryDirectory() as tmp:    # second variable staggered in the vertical (WRF's W: nz + 1 levels)
+        np.savez_compressed(os.path.join(OUT, "obsop_geographic_wstag.npz"), **obsop_geo_case(tmp, (5, 6, 1)))
     with tempfile.TemporaryDirectory() as tmp:
         np.savez_compressed(os.path.join(OUT, "tutorial_36x18.npz"), **tutorial(tmp))
     with tempfile.TemporaryDirectory() as tmp:

@@ -78,11 +78,13 @@ def test_locate_bit_exact_with_ties_and_levels(ctx, brute, monkeypatch):
         ens.close(); obs.close()
 
 
-def test_device_h_matches_reference_obs_operator_golden_bit_exactly(ctx):
-    """tests/golden/obsop_geographic.npz: output of the reference's own IdentityObsOperator.hpp (mock WRF-type
-    backends, oracle/_ref/ref_obsop_geo) -- the device's location + per-variable H reproduce it bit for bit."""
+@pytest.mark.parametrize("fname", ["obsop_geographic.npz", "obsop_geographic_wstag.npz"])
+def test_device_h_matches_reference_obs_operator_golden_bit_exactly(ctx, fname):
+    """tests/golden/obsop_geographic*.npz: output of the reference's own IdentityObsOperator.hpp (mock WRF-type
+    backends, oracle/_ref/ref_obsop_geo) -- the device's location + per-variable H reproduce it bit for bit, also
+    with a variable staggered in the vertical (wstag: 6 levels on a 5-level geometry)."""
     import os
-    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "obsop_geographic.npz"))
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", fname))
     nz, ny, nx = g["state"].shape
     ens = mb.Ensemble(ctx, nx, ny, nz, 1)
     ens.upload(g["state"][None])
@@ -176,6 +178,22 @@ def test_geographic_multivariable_state(ctx, radius_v):
     ovar = np.random.default_rng(8).integers(0, 3, 800).astype(np.int32)
     st = _check_analysis(ctx, X, lat, lon, o, VC[:4], radius=50.0, var_nlev=var_nlev, ovar=ovar, radius_v=radius_v)
     assert st["columns"] == 24 * 18
+
+
+@pytest.mark.parametrize("radius_v", [0.0, 1.5])
+def test_geographic_state_with_a_vertically_staggered_variable(ctx, radius_v):
+    """WRF's W / PH (WRFState.hpp:89-93, 445-449): nz + 1 levels on an nz-level geometry.  H never reads the top level
+    (the neighbour search runs on the geometry's levels), the column update transforms all nz + 1."""
+    var_nlev = [4, 5, 1]
+    lat, lon, o, X = _geo_case(22, 17, sum(var_nlev), 24, 700, seed=16, vc=VC[:4])
+    ovar = np.random.default_rng(18).integers(0, 3, 700).astype(np.int32)
+    st = _check_analysis(ctx, X, lat, lon, o, VC[:4], radius=50.0, var_nlev=var_nlev, ovar=ovar, radius_v=radius_v)
+    assert st["columns"] == 22 * 17
+    # a variable that is neither on the geometry's levels nor staggered by one is refused
+    ens = mb.Ensemble(ctx, 5, 4, 4 + 7 + 1, 3)
+    with pytest.raises(mb.MdcError):
+        ens.set_variables([4, 7, 1])
+    ens.close()
 
 
 def test_grid_observations_on_a_multivariable_state(ctx):

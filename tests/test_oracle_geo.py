@@ -8,6 +8,7 @@ restatement cross-checks both."""
 import os
 
 import numpy as np
+import pytest
 
 from metada_b200 import synthetic as syn
 from oracle import orc
@@ -28,10 +29,12 @@ def test_haversine_matches_reference_location_header_bit_exactly():
     assert orc.distance_geo(10.0, 179.5, 10.0, -179.5) < 120.0   # across the dateline
 
 
-def test_locate_and_variable_h_match_reference_obs_operator_bit_exactly():
+@pytest.mark.parametrize("fname", ["obsop_geographic.npz", "obsop_geographic_wstag.npz"])
+def test_locate_and_variable_h_match_reference_obs_operator_bit_exactly(fname):
     """IdentityObsOperator::apply on GEOGRAPHIC observations of a [5, 5, 1]-level three-variable state: nearest grid
-    point and level (:484-530), 4-of-8 IDW (:594-638) in the observation's own variable (:681-711), invalid -> 0."""
-    g = np.load(os.path.join(G, "obsop_geographic.npz"))
+    point and level (:484-530), 4-of-8 IDW (:594-638) in the observation's own variable (:681-711), invalid -> 0.
+    wstag: the second variable is staggered in the vertical (6 levels on a 5-level geometry, WRF's W)."""
+    g = np.load(os.path.join(G, fname))
     ox, oy, oz = orc.geo_locate(g["olat"], g["olon"], g["olev"], g["lat"], g["lon"], g["vc"])
     h = orc.hx_ext(g["state"], ox, oy, oz, g["var_nlev"], g["ovar"], g["valid"])
     assert np.array_equal(h, g["HX"])

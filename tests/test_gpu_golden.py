@@ -50,11 +50,11 @@ def test_etkf_and_enkf_vs_reference(ctx, name):
     ens, obs = _setup(ctx, g)
     diag = capi.enkf_analyse(ens, obs, float(g["inflation"]), Z=g["enkf_Z"], want_gain_stats=True)
     em, ep = analysis_errors(ens.download(), g["Xa_enkf"])
-    assert em < 1e-10 and ep < 1e-9, (em, ep)
+    assert em < 1e-10 and ep < 1e-10, (em, ep)
     ref = dict(zip(("innovation_norm", "background_spread", "analysis_spread", "max_kalman_gain",
                     "min_kalman_gain", "condition_number"), g["enkf_diag"]))
     for key, v in ref.items():
-        assert abs(diag[key] - v) <= 1e-8 * abs(v), (key, diag[key], v)
+        assert abs(diag[key] - v) <= 1e-10 * abs(v), (key, diag[key], v)
     ens.close(); obs.close()
 
 

@@ -110,7 +110,7 @@ def test_etkf_and_enkf_drivers_match_reference(tmp_path):
     r = subprocess.run([_need("enkf_cuda"), cfg, "--dump", dump], capture_output=True, text=True)
     assert r.returncode == 0, r.stderr + r.stdout
     em, ep = analysis_errors(read_dump(dump, int(g["ny"]), int(g["nx"])), g["Xa_enkf"])
-    assert em < 1e-10 and ep < 1e-9, (em, ep)
+    assert em < 1e-10 and ep < 1e-10, (em, ep)
     assert "EnKF diagnostics" in r.stdout
 
 

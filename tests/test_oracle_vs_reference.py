@@ -83,11 +83,11 @@ def test_enkf_matches_reference_with_its_own_draws(name):
     g = load(name)
     Xa, diag = orc.enkf(g["X"], g["ox"], g["oy"], g["oz"], g["yo"], g["err"], g["enkf_Z"],
                         inflation=float(g["inflation"]), want_gain_stats=True)
-    assert rel_err(Xa, g["Xa_enkf"]) < 1e-9
+    assert rel_err(Xa, g["Xa_enkf"]) < 1e-12
     ref = dict(zip(("innovation_norm", "background_spread", "analysis_spread", "max_kalman_gain",
                     "min_kalman_gain", "condition_number"), g["enkf_diag"]))
     for key, v in ref.items():
-        assert abs(diag[key] - v) <= 1e-8 * abs(v), (key, diag[key], v)
+        assert abs(diag[key] - v) <= 1e-12 * abs(v), (key, diag[key], v)
 
 
 def test_metrics_match_reference_header_bit_exactly():

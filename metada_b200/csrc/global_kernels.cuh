@@ -44,7 +44,8 @@ obs_gram_kernel(const double* __restrict__ Yp, const double* __restrict__ B, int
       Ac[e] = v;
       Ar[e] = v * rinv;
     }
-    for (int e = tid; e < rows * kb; e += nt) Br[e] = B[(base + e / kb) * kb + e % kb];
+    // (an invalid observation has weight 0; its innovation may be NaN -- a missing value -- and 0 * NaN would spread)
+    for (int e = tid; e < rows * kb; e += nt) Br[e] = valid[base + e / kb] ? B[(base + e / kb) * kb + e % kb] : 0.0;
     __syncthreads();
     for (int e = tid; e < nout; e += nt) {
       double s = out[e];

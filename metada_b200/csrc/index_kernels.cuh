@@ -89,7 +89,7 @@ __global__ void index_scatter_kernel(const int32_t* __restrict__ key, int64_t P,
   }
 }
 
-// order each cell's segment by global obs id (insertion sort; segments are tens of entries) and
+// order each cell's segment by global obs id (insertion sort for the usual tens of entries, heapsort beyond) and
 // emit the coordinates in sorted order for sequential reads in the column query
 __global__ void index_cell_sort_kernel(const int32_t* __restrict__ cell_start, int ncell,
                                        int32_t* __restrict__ sorted_row,
@@ -100,12 +100,34 @@ __global__ void index_cell_sort_kernel(const int32_t* __restrict__ cell_start, i
   int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= ncell) return;
   int b = cell_start[c], e = cell_start[c + 1];
-  for (int a = b + 1; a < e; ++a) {
-    int32_t r = sorted_row[a];
-    int64_t gr = gid[r];
-    int q = a - 1;
-    while (q >= b && gid[sorted_row[q]] > gr) { sorted_row[q + 1] = sorted_row[q]; --q; }
-    sorted_row[q + 1] = r;
+  if (e - b <= 48) {
+    for (int a = b + 1; a < e; ++a) {
+      int32_t r = sorted_row[a];
+      int64_t gr = gid[r];
+      int q = a - 1;
+      while (q >= b && gid[sorted_row[q]] > gr) { sorted_row[q + 1] = sorted_row[q]; --q; }
+      sorted_row[q + 1] = r;
+    }
+  } else {
+    // a crowded cell (clustered reports: swaths, many reports at one station): heapsort, O(n log n) -- the insertion
+    // sort above is O(n^2) and would take minutes on 1e5 rows
+    int32_t* h = sorted_row + b;
+    const int n = e - b;
+    auto sift = [&](int start, int end) {
+      int root = start;
+      while (2 * root + 1 < end) {
+        int child = 2 * root + 1;
+        if (child + 1 < end && gid[h[child]] < gid[h[child + 1]]) ++child;
+        if (gid[h[root]] >= gid[h[child]]) return;
+        const int32_t t = h[root]; h[root] = h[child]; h[child] = t;
+        root = child;
+      }
+    };
+    for (int st = n / 2 - 1; st >= 0; --st) sift(st, n);
+    for (int end = n - 1; end > 0; --end) {
+      const int32_t t = h[0]; h[0] = h[end]; h[end] = t;
+      sift(0, end);
+    }
   }
   for (int a = b; a < e; ++a) {
     int32_t r = sorted_row[a];

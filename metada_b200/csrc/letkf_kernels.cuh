@@ -317,7 +317,7 @@ __global__ void __launch_bounds__(LK_THREADS) letkf_column_kernel(ColParams P) {
             const double sq = sqrt(rinv);
             const double* src = P.Yp + (long long)orow * k;
             for (int j = lane; j < k; j += 32) Ych[r * k + j] = sq * src[j];
-            if (lane == 0) dw[r] = sq * P.d[orow];
+            if (lane == 0) dw[r] = rinv > 0.0 ? sq * P.d[orow] : 0.0;   // (weight 0: a NaN missing value must not spread)
           }
           __syncthreads();
           for (int e = tid; e < k * k; e += LK_THREADS) {
@@ -398,7 +398,8 @@ __global__ void __launch_bounds__(LK_THREADS) letkf_column_kernel(ColParams P) {
             __syncthreads();
           }
         }
-        if (s_int[1]) have_xform = false;  // numeric failure: leave the column unchanged
+        __syncthreads();                   // (everyone reads the failure flag before thread 0 can reset it for the
+        if (s_int[1]) have_xform = false;  //  next transform)  numeric failure: leave the column unchanged
       }
       col_sweeps = max(col_sweeps, sweeps);
 

@@ -381,7 +381,7 @@ __global__ void __launch_bounds__(NS_THREADS) letkf_ns_kernel(ColParams P, int l
               const double e_ = P.err[orow];
               const double ivar = P.valid[orow] ? 1.0 / (e_ * e_) : 0.0;
               sq = sqrt(rho * (P.use_R ? ivar : 1.0));
-              sd = sq * P.d[orow];
+              sd = sq > 0.0 ? sq * P.d[orow] : 0.0;            // (weight 0: a NaN missing value must not spread)
             }
           }
           const unsigned bal = __ballot_sync(0xffffffffu, sel);

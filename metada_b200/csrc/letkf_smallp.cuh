@@ -79,7 +79,7 @@ __device__ __forceinline__ int sp_transform(const ColParams& P, SpWarpSmem& W, l
           const double e_ = P.err[orow];
           const double ivar = P.valid[orow] ? 1.0 / (e_ * e_) : 0.0;
           sq = sqrt(rho * (P.use_R ? ivar : 1.0));
-          sd = sq * P.d[orow];
+          sd = sq > 0.0 ? sq * P.d[orow] : 0.0;
         }
       }
       const unsigned bal = __ballot_sync(0xffffffffu, sel);

@@ -298,7 +298,7 @@ __global__ void __launch_bounds__(NT, MINB) letkf_canonical_kernel(ColParams P, 
             const double sq = sqrt(sel_w[c0 + r] * (P.use_R ? ivar : 1.0));
             const double* src = P.Yp + (long long)orow * k;
             for (int j = lane; j < k; j += 32) Ych[r * k + j] = sq * src[j];
-            if (lane == 0) dw[r] = sq * P.d[orow];
+            if (lane == 0) dw[r] = sq > 0.0 ? sq * P.d[orow] : 0.0;
           }
           __syncthreads();
           for (int r = 0; r < rows; ++r) {

@@ -470,3 +470,41 @@ def test_enkf_device_generated_perturbations(ctx):
         ens.close(); obs.close()
     assert rel_err(out["dev"], out["host"]) < 1e-11
     assert rel_err(out["dev"], out["dev2"]) > 1e-3           # another seed, other perturbations
+
+
+def test_invalid_observations_with_nan_values_do_not_spread(ctx):
+    """Missing values often arrive as NaN: an invalid observation has weight 0 and must not poison the column
+    (LETKF in every mode) or the global filters."""
+    X, o = make_case(14, 11, 2, 24, 90, seed=31, invalid_frac=0.15)
+    bad = o["valid"] == 0
+    assert bad.sum() > 3
+    clean = {kk: v.copy() for kk, v in o.items()}
+    o["value"][bad] = np.nan
+    for mode, loc in ((mb.MODE_CANONICAL, mb.LOC_GASPARI_COHN), (mb.MODE_REF_ETKF, 0)):
+        res = []
+        for obsd in (o, clean):
+            ens, obs = _setup(ctx, X, obsd)
+            capi.letkf_analyse(ens, obs, capi.make_params(4.0, 1.0, mode, loc))
+            res.append(ens.download())
+            ens.close(); obs.close()
+        assert np.isfinite(res[0]).all() and np.array_equal(res[0], res[1])
+    ens, obs = _setup(ctx, X, o)
+    capi.etkf_analyse(ens, obs, 1.0)
+    assert np.isfinite(ens.download()).all()
+    ens.close(); obs.close()
+
+
+def test_index_with_a_crowded_cell(ctx):
+    """Thousands of reports in one cell (a station, a swath): the per-cell ordering switches from insertion sort to
+    heapsort; selection counts stay bit-exact."""
+    nx = ny = 24
+    X, _ = make_case(nx, ny, 1, 4, 4, seed=2)
+    o = syn.observations(6000, nx, ny, 1, seed=3)
+    o["x"][:5000] = 7; o["y"][:5000] = 9
+    ens, obs = _setup(ctx, X, o)
+    counts = obs.query_counts(ens, 3.0)
+    assert np.array_equal(counts, orc.select_counts(nx, ny, o["x"], o["y"], 3.0))
+    cols = np.array([9 * nx + 7], np.int64)
+    lists, cnt = obs.query_lists(ens, 3.0, cols, cap=6000)
+    assert cnt[0] > 5000 and np.all(np.diff(lists[0][:4000]) != 0)
+    ens.close(); obs.close()

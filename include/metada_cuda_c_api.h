@@ -175,7 +175,7 @@ enum { MDC_LOC_CUTOFF = 0, MDC_LOC_GASPARI_COHN = 1, MDC_LOC_GAUSSIAN = 2, MDC_L
 /* AUTO: Newton-Schulz (GEMM-only symmetric square root on FP64 DMMA) for 24 <= k <= 128, else Jacobi.
  * JACOBI: one-block-per-column one-sided Jacobi eigen-decomposition with warp-shuffle reductions.
  * NEWTON_SCHULZ: packed symmetric tiles (two columns per SM for k <= 80); transforms whose
- *   conditioning bound exceeds 256 are redone by NEWTON_SCHULZ_FULL (k <= 80) or JACOBI (k > 80).
+ *   conditioning bound exceeds mdc_letkf_params.kappa_max are redone by NEWTON_SCHULZ_FULL (k <= 80) or JACOBI (k > 80).
  * NEWTON_SCHULZ_FULL: every product computed in full, any conditioning, 24 <= k <= 80.
  * All give the same (unique) symmetric square-root transform to rounding. */
 enum { MDC_SOLVER_AUTO = 0, MDC_SOLVER_JACOBI = 1, MDC_SOLVER_NEWTON_SCHULZ = 2, MDC_SOLVER_NEWTON_SCHULZ_FULL = 3 };
@@ -194,6 +194,9 @@ typedef struct {
                          (member transposes of a streamed pipeline); 0 = use every SM          */
   double loc_scale;   /* length scale L of MDC_LOC_GAUSSIAN / EXPONENTIAL / REF_GASPARI_COHN; <= 0: radius.
                          The vertical scale is radius_v * L / radius.                          */
+  double kappa_max;   /* NEWTON_SCHULZ: largest rigorous condition bound lambda_max / lambda_min of a transform's
+                         k x k matrix the packed symmetric kernel keeps (the others are redone, see above);
+                         <= 0: 1e5 (agreement with the eigen-decomposition ~1e-11 there), at most 3e5       */
 } mdc_letkf_params;
 
 typedef struct {

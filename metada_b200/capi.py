@@ -37,7 +37,8 @@ class MdcError(RuntimeError):
 class LetkfParams(C.Structure):
     _fields_ = [("radius", C.c_double), ("radius_v", C.c_double), ("inflation", C.c_double),
                 ("mode", C.c_int), ("loc", C.c_int), ("use_R", C.c_int), ("max_sweeps", C.c_int),
-                ("jacobi_tol", C.c_double), ("solver", C.c_int), ("sm_reserve", C.c_int), ("loc_scale", C.c_double)]
+                ("jacobi_tol", C.c_double), ("solver", C.c_int), ("sm_reserve", C.c_int), ("loc_scale", C.c_double),
+                ("kappa_max", C.c_double)]
 
 
 class LetkfStats(C.Structure):
@@ -526,13 +527,14 @@ SOLVER_AUTO, SOLVER_JACOBI, SOLVER_NEWTON_SCHULZ, SOLVER_NEWTON_SCHULZ_FULL = 0,
 
 def make_params(radius, inflation=1.0, mode=MODE_CANONICAL, loc=LOC_GASPARI_COHN, use_R=1,
                 radius_v=0.0, max_sweeps=0, jacobi_tol=0.0, solver=SOLVER_AUTO, sm_reserve=0,
-                loc_scale=0.0) -> LetkfParams:
+                loc_scale=0.0, kappa_max=0.0) -> LetkfParams:
     p = LetkfParams()
     p.radius, p.radius_v, p.inflation = radius, radius_v, inflation
     p.mode, p.loc, p.use_R, p.max_sweeps, p.jacobi_tol = mode, loc, use_R, max_sweeps, jacobi_tol
     p.solver = solver
     p.sm_reserve = sm_reserve
     p.loc_scale = loc_scale
+    p.kappa_max = kappa_max
     return p
 
 

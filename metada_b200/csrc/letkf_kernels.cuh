@@ -33,6 +33,7 @@ struct ColParams {
   const uint8_t* valid;
   double radius, radius_v, inflation;
   double loc_scale, loc_scale_v;   // length scales of the exp-type localisation functions
+  double kappa_max;                // condition bound up to which the packed Newton-Schulz kernel keeps a transform
   int mode, loc, use_R, max_sweeps;
   double jtol;
   long long* stats;  // [0] sum p_loc [1] max p_loc [2] sum sweeps [3] max sweeps [4] failures [5] columns

@@ -16,7 +16,7 @@
 // Off-diagonal tiles are stored once (no mirrored store).
 //
 // Forcing symmetry is only stable while cond(A) is moderate (letkf_ns.cuh); a column (or level, with
-// per-level transforms) whose rigorous condition bound exceeds NSP_KAPPA_MAX is appended to a
+// per-level transforms) whose rigorous condition bound exceeds the limit (default 1e5) is appended to a
 // redo list, which a second launch of the full-product kernel (k <= 80) or the Jacobi kernel
 // (k > 80) consumes.
 #pragma once
@@ -46,6 +46,15 @@ __device__ long long* nsp_prof_;
 #define NSP_TICK3(slot) NSP_TICK(slot)
 #else
 #define NSP_TICK3(slot) do {} while (0)
+#endif
+// -DNSP_PROFILE -DNSP_PROFILE_EPI -DNSP_PROFILE_EPI2: slots 8 / 9 = the A^2 epilogue (bound, start) / the residual epilogues
+// (M0, ET) instead
+#if defined(NSP_PROFILE) && defined(NSP_PROFILE_EPI2)
+#define NSP_TICK4(slot) NSP_TICK(slot)
+#undef NSP_TICK3
+#define NSP_TICK3(slot) do {} while (0)
+#else
+#define NSP_TICK4(slot) do {} while (0)
 #endif
 #if defined(NSP_PROFILE) && defined(NSP_PROFILE_UPDATE)
 #define NSP_TICK2(slot) NSP_TICK(slot)
@@ -421,13 +430,18 @@ __device__ __forceinline__ int nss_start_index(double kappa) {
   return (nss_starts[i].kappa >= kappa) ? i : -1;
 }
 
-// largest condition bound (Schatten-4 bound of the spectrum / shift) the packed kernel takes; beyond it the
-// transform goes to the redo list.  Symmetric-tile products assume the iterates commute; with the short composite
-// minimax schedule (13 - 20 products) the rounding defect stays small much longer than with plain Newton-Schulz:
-// error of Z against the eigen-decomposition (numpy emulation of these very tile products on C5-like matrices)
-// 5e-15 at cond 50, 7e-15 at 200, 1.5e-14 at 530, 3.3e-14 at 1200, 1.4e-13 at 3500.
-#define NSP_KAPPA_MAX 2000.0
+// largest condition bound (Schatten-4 bound of the spectrum / shift) the packed kernel takes by default
+// (mdc_letkf_params.kappa_max overrides it, up to NSP_KAPPA_TABLE_MAX); beyond it the transform goes to the redo
+// list.  Symmetric-tile products assume the iterates commute; with the short composite minimax schedule (13 - 25
+// products) the rounding defect stays at the level of the eigen-decomposition's own: difference of Z to numpy's eigh
+// (emulation of these very tile products, tests/ns_emul.py) 5e-15 at cond 50, 3e-14 at 1200, 1.5e-13 at 6e3, 6e-13 at
+// 5e4, <= 8e-12 at 1e5 over k = 24 .. 128 -- and the residual Z A Z - I in long double is within 2x of that of the
+// eigen-decomposition at every one of them (round 1 stopped at 256, round 2's first table at 2000: the accurate-
+// observation cliff of bench.py's sigma = 0.01 variant).
+#define NSP_KAPPA_MAX_DEFAULT 1e5
+#define NSP_KAPPA_TABLE_MAX 3e5
 #define NSP_SC_DOUBLES 48   /* schedule scratch: 8 steps x {kind, c0..c3}, + the residual bound of the finish */
+#define NSP_SC_KMAX 45      /* slot that carries the condition limit from the Gram phase to the iteration */
 
 // Z <- A^{-1/2} for the A held in the T buffer, by the composite minimax polynomial iteration of
 // tools/gen_ns_schedule.py: state Z and the residual E = I - Z^2 A (in the Y buffer), spectrum(E) in [-rho, rho];
@@ -444,7 +458,7 @@ __device__ __forceinline__ int nss_start_index(double kappa) {
 // products' software pipeline as written only when few registers are alive around it -- inside a fat column loop,
 // and also as a called function of one, it fell back to a pressure-minimising schedule that serialised every
 // fragment load behind the MMA before it (r02 SASS; the isolated function pipelines even with 80 registers).
-// Returns the number of k x k products used, -1 if the iteration failed, -2 if kappa is beyond NSP_KAPPA_MAX.
+// Returns the number of k x k products used, -1 if the iteration failed, -2 if kappa is beyond the limit (sc[NSP_SC_KMAX]).
 #ifdef NSP_ISQ_NOINLINE   /* development */
 #define NSP_ISQ_INLINE __noinline__
 #else
@@ -518,7 +532,7 @@ __device__ NSP_ISQ_INLINE int nsp_inverse_sqrt(double* Zp, double* red, double* 
       const float hi_f = (float)(shift + fro) * 1.000001f, sh_f = (float)shift;
       const float s4 = sqrtf(sqrtf((float)f4 * 1.000001f) + 1e-13f * hi_f * hi_f) * 1.000001f;
       const double kappa = (double)(fmaxf(fminf(hi_f, sh_f * 1.000001f + s4) / (sh_f * 0.999999f), 1.0f) * 1.000002f);
-      const int si = (kappa <= NSP_KAPPA_MAX) ? nss_start_index(kappa) : -1;
+      const int si = (kappa <= sc[NSP_SC_KMAX]) ? nss_start_index(kappa) : -1;
       if (si < 0) { rc = -2; break; }
       const int sdeg = nss_starts[si].degree;
       // the column's steps -> shared memory: thread e copies {kind, c0..c3}[e % 5] of step e / 5
@@ -558,6 +572,7 @@ __device__ NSP_ISQ_INLINE int nsp_inverse_sqrt(double* Zp, double* red, double* 
       } else {
         op = (sdeg == 1) ? OP_M0 : OP_Y0;
       }
+      NSP_TICK4(8);
     } else if (op == OP_Y0) {
       nsp_store_run<NTW>(ys + cb0, st.n, acc);                       // Y0 = A Z0 (the Y buffer is free)
       __syncthreads();
@@ -591,6 +606,7 @@ __device__ NSP_ISQ_INLINE int nsp_inverse_sqrt(double* Zp, double* red, double* 
       if (kind % 10 == 1) store_T_lin(c);
       __syncthreads();
       op = (kind % 10 == 1) ? OP_ZT : OP_E2;
+      NSP_TICK4(9);
     } else if (op == OP_E2) {
       const double* c = sc + 5 * sn;
       if ((int)c[0] % 10 == 2) {                                 // T = c0 I + c1 E + c2 E^2 (the T buffer is free)
@@ -923,7 +939,7 @@ __device__ __noinline__ int nsp_phase_gram(const ColParams& P, int lch, long lon
   fro = sqrt(nsp_block_sum1<NTH>(fro, S.red, rbuf));         // (its barrier publishes the partials of g)
   // (||C||_F is typically 2 - 3x the Schatten-4 bound the iteration works with: a transform far beyond the
   // limit is handed over without spending the A^2 product on it)
-  if (!((shift + fro) < 8.0 * NSP_KAPPA_MAX * shift)) {
+  if (!((shift + fro) < 8.0 * P.kappa_max * shift)) {
     if (tid == 0) {
       const unsigned slot = atomicAdd(P.redo_count, 1u);
       P.redo_items[slot] = col * nxf + lt;
@@ -937,7 +953,7 @@ __device__ __noinline__ int nsp_phase_gram(const ColParams& P, int lch, long lon
     for (int w = 0; w < NW; ++w) s += gpart[w * kp + tid];
     S.gvec[tid] = s;
   }
-  if (tid == 0) S.sc[NSP_SC_FRO] = fro;
+  if (tid == 0) { S.sc[NSP_SC_FRO] = fro; S.sc[NSP_SC_KMAX] = P.kappa_max; }
   // A -> T (shift I on the zero padding)
   {
     int wti = st.ti0, wtj = st.tj0;
@@ -1209,7 +1225,7 @@ __global__ void __launch_bounds__(NTH, MINB) letkf_nsp_kernel(const __grid_const
         else
           it = nsp_inverse_sqrt_call<NT, NTH>(S.Zp, S.red, S.sc, rbuf, shift, rsqrt(shift), S.sc[NSP_SC_FRO], k);
         if (it == -2) {
-          // condition bound beyond NSP_KAPPA_MAX: symmetric tiles are not trusted there, the full-product
+          // condition bound beyond the limit: symmetric tiles are not trusted there, the full-product
           // kernel (k <= 80) or the Jacobi kernel redoes this transform
           if (tid == 0) {
             const unsigned slot = atomicAdd(P.redo_count, 1u);

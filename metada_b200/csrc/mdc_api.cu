@@ -858,6 +858,7 @@ static int letkf_launch(mdc_ens* e, mdc_obs* o, const mdc_letkf_params* p, const
   cp.mode = p->mode; cp.loc = p->loc; cp.use_R = p->use_R;
   cp.loc_scale = p->loc_scale > 0.0 ? p->loc_scale : p->radius;
   cp.loc_scale_v = p->radius_v > 0.0 && p->radius > 0.0 ? p->radius_v * (cp.loc_scale / p->radius) : 1.0;
+  cp.kappa_max = p->kappa_max > 0.0 ? std::min(p->kappa_max, (double)NSP_KAPPA_TABLE_MAX) : (double)NSP_KAPPA_MAX_DEFAULT;
   cp.max_sweeps = p->max_sweeps > 0 ? p->max_sweeps : 40;
   cp.jtol = p->jacobi_tol > 0.0 ? p->jacobi_tol : 1e-11;
   cp.stats = ctx->d_stats;

@@ -21,16 +21,17 @@ class ETKF {
         inflation_(config.Get("inflation").asFloat()),
         output_base_file_(config.Get("output_base_file").asString()),
         format_(config.Get("format").asString()) {
+    try { resident_ = config.Get("resident").asBool(); } catch (...) {}   // DeviceAnalysis.hpp
     logger_.Info() << "ETKF constructed (device path)";
   }
 
   void Analyse() {
     logger_.Info() << "ETKF analysis started";
-    auto dev = device::uploadEnsemble(ensemble_);
     backends::cuda::DeviceObservations dobs(obs_.backend());
-    backends::cuda::DeviceContext::Instance().check(mdc_etkf_analyse(dev->get(), dobs.get(), inflation_), "mdc_etkf_analyse");
-    device::downloadEnsemble(*dev, ensemble_);
-    ensemble_.RecomputeMean();   // so that saveEnsemble() can use Mean() (ETKF.hpp:190)
+    // (ends with the ensemble mean, so that saveEnsemble() can use Mean(): ETKF.hpp:190)
+    device::analyseOnDevice(ensemble_, resident_, [&](backends::cuda::DeviceEnsemble& dev) {
+      backends::cuda::DeviceContext::Instance().check(mdc_etkf_analyse(dev.get(), dobs.get(), inflation_), "mdc_etkf_analyse");
+    });
     logger_.Info() << "ETKF analysis completed";
   }
 
@@ -49,6 +50,7 @@ class ETKF {
   double inflation_;
   std::string output_base_file_;
   std::string format_ = "txt";
+  bool resident_ = true;
   Logger<BackendTag>& logger_ = Logger<BackendTag>::Instance();
 };
 

@@ -47,6 +47,7 @@ class EnKF {
       inflation_method_ = "multiplicative";
     }
     try { seed_ = static_cast<uint64_t>(analysis_config.Get("seed").asInt()); } catch (...) {}
+    try { resident_ = analysis_config.Get("resident").asBool(); } catch (...) {}   // DeviceAnalysis.hpp
     logger_.Info() << "EnKF constructed with " << ensemble_.Size() << " members (device path)";
   }
 
@@ -55,17 +56,16 @@ class EnKF {
 
   void Analyse() {
     logger_.Info() << "EnKF analysis started";
-    auto dev = device::uploadEnsemble(ensemble_);
     backends::cuda::DeviceObservations dobs(obs_.backend());
     if (!Z_.empty() && Z_.size() != dobs.size() * ensemble_.Size())
       throw std::invalid_argument("EnKF: observation perturbations must be [obs][member]");
     mdc_enkf_diag d{};
-    backends::cuda::DeviceContext::Instance().check(
-        mdc_enkf_analyse(dev->get(), dobs.get(), inflation_factor_, Z_.empty() ? nullptr : Z_.data(),
-                         seed_ + 0x9E3779B97F4A7C15ull * calls_++ /* a fresh stream every cycle */, 1, &d),
-        "mdc_enkf_analyse");
-    device::downloadEnsemble(*dev, ensemble_);
-    ensemble_.RecomputeMean();       // EnKF.hpp:237
+    device::analyseOnDevice(ensemble_, resident_, [&](backends::cuda::DeviceEnsemble& dev) {
+      backends::cuda::DeviceContext::Instance().check(
+          mdc_enkf_analyse(dev.get(), dobs.get(), inflation_factor_, Z_.empty() ? nullptr : Z_.data(),
+                           seed_ + 0x9E3779B97F4A7C15ull * calls_++ /* a fresh stream every cycle */, 1, &d),
+          "mdc_enkf_analyse");
+    });                              // (the mean of EnKF.hpp:237 included)
     diag_ = d;
     logger_.Info() << "EnKF analysis completed";
   }
@@ -104,6 +104,7 @@ class EnKF {
   std::string output_base_file_;
   std::string format_ = "txt";
   uint64_t seed_ = 7, calls_ = 0;
+  bool resident_ = true;
   std::vector<double> Z_;
   mdc_enkf_diag diag_{};
   Logger<BackendTag>& logger_ = Logger<BackendTag>::Instance();

@@ -14,6 +14,9 @@
 //              (State::getDataPtr) go through mdc_stream_analyse in row slabs, in place (an ensemble larger than
 //              the device is fine); "off" or geographic observations: upload all, analyse, download all
 //   slab_rows: rows per slab of the streamed path (default: chosen by the runtime)
+//   resident:  true (default) | false -- one-shot path only: the ensemble stays in its device store across Analyse()
+//              calls; members come back lazily when the host reads them and only members the host may have written
+//              are uploaded again (DeviceAnalysis.hpp); false: upload all, analyse, download all, every call
 // Several processes (one per GPU; column sharding with the NCCL observation halo): environment MDC_RANK,
 // MDC_WORLD_SIZE, MDC_COMM_ID_FILE (rank 0 writes the NCCL id there, the others wait for it), MDC_DEVICE (default:
 // rank).  Every process reads the whole ensemble, analyses its rows, and receives the others' rows afterwards
@@ -59,6 +62,7 @@ class LETKF {
     try { params_.loc_scale = config.Get("localization_scale").asFloat(); } catch (...) {}
     try { streaming_ = config.Get("streaming").asString(); } catch (...) {}
     try { slab_rows_ = config.Get("slab_rows").asInt(); } catch (...) {}
+    try { resident_ = config.Get("resident").asBool(); } catch (...) {}
     if (streaming_ != "auto" && streaming_ != "on" && streaming_ != "off")
       throw std::invalid_argument("LETKF: streaming must be auto, on or off");
     if (mode == "ref_compat") params_.mode = MDC_MODE_REF_COMPAT;
@@ -78,14 +82,15 @@ class LETKF {
 
   void Analyse() {
     logger_.Info() << "LETKF analysis started";
-    if (!(streaming_ != "off" && analyseStreamed())) {
-      auto dev = device::uploadEnsemble(ensemble_);
+    if (streaming_ != "off" && analyseStreamed()) {
+      ensemble_.RecomputeMean();                     // LETKF.hpp:116
+    } else {
       backends::cuda::DeviceObservations dobs(obs_.backend());
-      auto& ctx = backends::cuda::DeviceContext::Instance();
-      ctx.check(mdc_letkf_analyse(dev->get(), dobs.get(), &params_, &stats_), "mdc_letkf_analyse");
-      device::downloadEnsemble(*dev, ensemble_);
+      device::analyseOnDevice(ensemble_, resident_, [&](backends::cuda::DeviceEnsemble& dev) {
+        backends::cuda::DeviceContext::Instance().check(mdc_letkf_analyse(dev.get(), dobs.get(), &params_, &stats_),
+                                                        "mdc_letkf_analyse");
+      });                                            // (the mean of LETKF.hpp:116 included)
     }
-    ensemble_.RecomputeMean();                       // LETKF.hpp:116
     logger_.Info() << "LETKF analysis completed: " << stats_.columns << " columns, mean local obs "
                    << (stats_.columns ? static_cast<double>(stats_.sum_local_obs) / stats_.columns : 0.0)
                    << ", device time " << stats_.ms_total << " ms";
@@ -176,6 +181,7 @@ class LETKF {
   mdc_letkf_stats stats_{};
   std::string streaming_ = "auto";
   int slab_rows_ = 0;
+  bool resident_ = true;
   Logger<BackendTag>& logger_ = Logger<BackendTag>::Instance();
 };
 

@@ -75,6 +75,7 @@ class LWEnKF {
       weighting_code_ = MDC_LW_UNIFORM;
     }
     try { seed_ = static_cast<uint64_t>(analysis_config.Get("seed").asInt()); } catch (...) {}
+    try { resident_ = analysis_config.Get("resident").asBool(); } catch (...) {}   // DeviceAnalysis.hpp
     logger_.Info() << "LWEnKF constructed with " << ensemble_.Size() << " members (device path)";
   }
 
@@ -83,18 +84,17 @@ class LWEnKF {
 
   void Analyse() {
     logger_.Info() << "LWEnKF analysis started";
-    auto dev = device::uploadEnsemble(ensemble_);
     backends::cuda::DeviceObservations dobs(obs_.backend());
     if (!Z_.empty() && Z_.size() != dobs.size() * ensemble_.Size())
       throw std::invalid_argument("LWEnKF: observation perturbations must be [obs][member]");
     mdc_lwenkf_diag d{};
     const uint64_t seed = seed_ + 0x9E3779B97F4A7C15ull * calls_++;      // a fresh stream every cycle
-    backends::cuda::DeviceContext::Instance().check(
-        mdc_lwenkf_analyse(dev->get(), dobs.get(), inflation_factor_, localization_radius_, loc_fn_, weighting_code_,
-                           Z_.empty() ? nullptr : Z_.data(), seed, &d),
-        "mdc_lwenkf_analyse");
-    device::downloadEnsemble(*dev, ensemble_);
-    ensemble_.RecomputeMean();       // LWEnKF.hpp:317
+    device::analyseOnDevice(ensemble_, resident_, [&](backends::cuda::DeviceEnsemble& dev) {
+      backends::cuda::DeviceContext::Instance().check(
+          mdc_lwenkf_analyse(dev.get(), dobs.get(), inflation_factor_, localization_radius_, loc_fn_, weighting_code_,
+                             Z_.empty() ? nullptr : Z_.data(), seed, &d),
+          "mdc_lwenkf_analyse");
+    });                              // (the mean of LWEnKF.hpp:317 included)
     diag_ = d;
     logger_.Info() << "LWEnKF analysis completed";
   }
@@ -139,6 +139,7 @@ class LWEnKF {
   std::string output_base_file_;
   std::string format_ = "txt";
   uint64_t seed_ = 7, calls_ = 0;
+  bool resident_ = true;
   std::vector<double> Z_;
   mdc_lwenkf_diag diag_{};
   Logger<BackendTag>& logger_ = Logger<BackendTag>::Instance();

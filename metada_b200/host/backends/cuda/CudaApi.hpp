@@ -54,12 +54,31 @@ class DeviceEnsemble {
   void upload(const std::vector<const double*>& members) {
     DeviceContext::Instance().check(mdc_ens_upload_members(h_, 0, static_cast<int>(members.size()), members.data()),
                                     "mdc_ens_upload_members");
+    members_uploaded_ += members.size();
   }
   void download(const std::vector<double*>& members) {
     DeviceContext::Instance().check(mdc_ens_download_members(h_, 0, static_cast<int>(members.size()), members.data()),
                                     "mdc_ens_download_members");
+    members_downloaded_ += members.size();
+  }
+  /** One member (run of members) at a time: what the lazily synchronised host views use. */
+  void uploadMembers(int m0, const std::vector<const double*>& members) {
+    DeviceContext::Instance().check(mdc_ens_upload_members(h_, m0, static_cast<int>(members.size()), members.data()),
+                                    "mdc_ens_upload_members");
+    members_uploaded_ += members.size();
+  }
+  void downloadMember(int m, double* host) {
+    double* p[1] = {host};
+    DeviceContext::Instance().check(mdc_ens_download_members(h_, m, 1, p), "mdc_ens_download_members");
+    members_downloaded_ += 1;
   }
   void mean(double* host) { DeviceContext::Instance().check(mdc_ens_mean(h_, host), "mdc_ens_mean"); }
+  int nx() const { return nx_; }
+  int ny() const { return ny_; }
+  int nz() const { return nz_; }
+  /** Members moved over PCIe since construction (tests and logs: what residency saves). */
+  size_t membersUploaded() const { return members_uploaded_; }
+  size_t membersDownloaded() const { return members_downloaded_; }
   /** Column coordinates in degrees ([ny][nx], e.g. WRFGeometry::unstaggered_info().latitude_2d / longitude_2d)
    *  and the geometry's vertical coordinate: needed by observations with GEOGRAPHIC locations. */
   void setGeography(const std::vector<double>& lat, const std::vector<double>& lon, const std::vector<double>& vertical) {
@@ -77,6 +96,19 @@ class DeviceEnsemble {
  private:
   mdc_ens* h_ = nullptr;
   int nx_, ny_, nz_, k_;
+  size_t members_uploaded_ = 0, members_downloaded_ = 0;
+};
+
+/** Link between the host view of one member (CudaState) and its slot in a device-resident store
+ *  (SURVEY "layout clash": what getDataPtr returns for a device-resident state = a host shadow, lazily
+ *  synchronised).  After an analysis the device holds the truth (host_stale); the first host access of
+ *  a member downloads that member only; a host access that may write marks the device copy stale, and
+ *  the next analysis uploads just those members.  The store lives as long as any member refers to it. */
+struct ResidentLink {
+  std::shared_ptr<DeviceEnsemble> store;
+  int member = -1;
+  bool host_stale = false;
+  bool device_stale = true;
 };
 
 /** Device SoA mirror of an observation backend (anything iterable yielding

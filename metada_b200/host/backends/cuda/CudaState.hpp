@@ -4,8 +4,12 @@
 // geometry(), operator[] (State.hpp:385-386; IdentityObsOperator.hpp:246,265).
 //
 // A CudaState is the HOST view of one member, layout [lev][y][x] (what State::getDataPtr<double>()
-// hands to ETKF.hpp:172-176 / EnKF.hpp:230-234).  During an analysis the members are gathered into
-// one device-resident [col][lev][member] store (CudaApi.hpp: DeviceEnsemble) and written back.
+// hands to ETKF.hpp:172-176 / EnKF.hpp:230-234).  For an analysis the members are gathered into one
+// device-resident [col][lev][member] store (CudaApi.hpp: DeviceEnsemble), which STAYS on the device
+// across analyses: the host array is a shadow, synchronised lazily through a ResidentLink -- every
+// accessor below downloads this member first if the device holds newer values (host_stale), and every
+// accessor that can write marks the device copy stale so that the next analysis uploads this member
+// again (DeviceAnalysis.hpp: acquireResident / publishResident).
 // File formats: whitespace-separated text in [lev][y][x] order (SimpleState.hpp:248-263 for
 // z_dim == 1); saveToFile keeps the reference's fixed 6-decimal format (SimpleState.hpp:162-188).
 #include <cmath>
@@ -18,6 +22,7 @@
 #include <string>
 #include <vector>
 
+#include "CudaApi.hpp"
 #include "CudaGeometry.hpp"
 #include "Location.hpp"
 
@@ -43,33 +48,52 @@ class CudaState {
     readFromFile(config.Get("file").asString());
   }
 
-  void* getData() { return data_.data(); }
-  const void* getData() const { return data_.data(); }
+  void* getData() { touch(); return data_.data(); }
+  const void* getData() const { syncHost(); return data_.data(); }
   const std::vector<std::string>& getVariableNames() const { return variable_names_; }
   size_t size() const { return data_.size(); }
   const CudaGeometry& geometry() const { return geometry_; }
 
-  void zero() { std::fill(data_.begin(), data_.end(), 0.0); }
-  void add(const CudaState& o) { same(o, "add"); for (size_t i = 0; i < data_.size(); ++i) data_[i] += o.data_[i]; }
-  void subtract(const CudaState& o) { same(o, "subtract"); for (size_t i = 0; i < data_.size(); ++i) data_[i] -= o.data_[i]; }
-  void multiply(double s) { for (auto& v : data_) v *= s; }
+  void zero() {
+    if (link_) { link_->host_stale = false; link_->device_stale = true; }   // (nothing worth downloading)
+    std::fill(data_.begin(), data_.end(), 0.0);
+  }
+  void add(const CudaState& o) { same(o, "add"); touch(); o.syncHost(); for (size_t i = 0; i < data_.size(); ++i) data_[i] += o.data_[i]; }
+  void subtract(const CudaState& o) { same(o, "subtract"); touch(); o.syncHost(); for (size_t i = 0; i < data_.size(); ++i) data_[i] -= o.data_[i]; }
+  void multiply(double s) { touch(); for (auto& v : data_) v *= s; }
   double dot(const CudaState& o) const {
     same(o, "compute dot product of");
+    syncHost(); o.syncHost();
     double r = 0.0;
     for (size_t i = 0; i < data_.size(); ++i) r += data_[i] * o.data_[i];
     return r;
   }
   double norm() const { return std::sqrt(dot(*this)); }
-  bool equals(const CudaState& o) const { return data_ == o.data_; }
+  bool equals(const CudaState& o) const { syncHost(); o.syncHost(); return data_ == o.data_; }
   template <typename IncrementBackend>
   void addIncrement(const IncrementBackend& inc) {
+    touch();
     const auto v = inc.getData();
     for (size_t i = 0; i < data_.size() && i < v.size(); ++i) data_[i] += v[i];
   }
 
-  std::unique_ptr<CudaState> clone() const { return std::unique_ptr<CudaState>(new CudaState(*this, 0)); }
+  std::unique_ptr<CudaState> clone() const { syncHost(); return std::unique_ptr<CudaState>(new CudaState(*this, 0)); }
+
+  // ---- device residency (see the header comment); used by framework::device::acquireResident / publishResident
+  const std::shared_ptr<ResidentLink>& resident() const { return link_; }
+  void attachResident(std::shared_ptr<ResidentLink> link) { link_ = std::move(link); }
+  /** Host array without synchronisation: for the transfers themselves. */
+  double* hostShadow() { return data_.data(); }
+  /** Brings the host shadow up to date (one member's download) if the device holds newer values. */
+  void syncHost() const {
+    if (link_ && link_->host_stale) {
+      link_->store->downloadMember(link_->member, const_cast<double*>(data_.data()));
+      link_->host_stale = false;
+    }
+  }
 
   void saveToFile(const std::string& filename) const {
+    syncHost();
     std::filesystem::path p(filename);
     if (!p.parent_path().empty() && !std::filesystem::exists(p.parent_path()))
       std::filesystem::create_directories(p.parent_path());
@@ -85,13 +109,19 @@ class CudaState {
     }
   }
 
-  double& at(const framework::Location& loc) { return data_[index(loc)]; }
-  const double& at(const framework::Location& loc) const { return data_[index(loc)]; }
-  double& operator[](size_t i) { if (i >= data_.size()) throw std::out_of_range("Index out of range"); return data_[i]; }
-  const double& operator[](size_t i) const { if (i >= data_.size()) throw std::out_of_range("Index out of range"); return data_[i]; }
+  double& at(const framework::Location& loc) { touch(); return data_[index(loc)]; }
+  const double& at(const framework::Location& loc) const { syncHost(); return data_[index(loc)]; }
+  double& operator[](size_t i) { if (i >= data_.size()) throw std::out_of_range("Index out of range"); touch(); return data_[i]; }
+  const double& operator[](size_t i) const { if (i >= data_.size()) throw std::out_of_range("Index out of range"); syncHost(); return data_[i]; }
 
  private:
+  // (a clone is a plain host state: no link)
   CudaState(const CudaState& o, int) : data_(o.data_), variable_names_(o.variable_names_), geometry_(o.geometry_) {}
+  /** Host access that may write: up-to-date shadow first, then the device copy counts as stale. */
+  void touch() {
+    syncHost();
+    if (link_) link_->device_stale = true;
+  }
   void same(const CudaState& o, const char* what) const {
     if (data_.size() != o.data_.size()) throw std::runtime_error(std::string("Cannot ") + what + " states of different sizes");
   }
@@ -116,6 +146,7 @@ class CudaState {
   std::vector<double> data_;
   std::vector<std::string> variable_names_;
   const CudaGeometry& geometry_;
+  std::shared_ptr<ResidentLink> link_;
 };
 
 /** Host vector space over the grid: IncrementBackend and ControlVariableBackend of the CUDA

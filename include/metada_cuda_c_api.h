@@ -128,14 +128,25 @@ int mdc_obs_set_variables(mdc_obs* obs, const int32_t* var);
  * nearest grid point and level exactly as IdentityObsOperator::convertGeographicToGrid (:484-530) -- first minimum of
  * the Euclidean distance in degrees -- and H then interpolates at those integer coordinates (:241-248).
  * mdc_hx_idw4 / mdc_letkf_analyse locate on demand.  Regional domains only: the selection circles must not reach a
- * pole or wrap the whole longitude circle (MDC_ERR_UNSUPPORTED otherwise); single device (no domain decomposition);
- * MDC_MODE_CANONICAL.  Staggered (U / V) variables: give the staggered grid its own ensemble store and geography,
+ * pole or wrap the whole longitude circle (MDC_ERR_UNSUPPORTED otherwise).  All three modes.  Domain decomposition:
+ * locate on a store that covers the whole grid, give every rank's store its window of that geography
+ * (mdc_ens_set_geography_from) and exchange the halo rows by box (mdc_obs_pack_rows_geo).  Staggered (U / V) variables: give the staggered grid its own ensemble store and geography,
  * run mdc_hx_idw4(mass_grid_ens, obs) and then mdc_letkf_analyse(staggered_ens, obs, ...) -- the analysis uses the
  * Y' already in the store and the columns / coordinates of the ensemble it is given. */
 int mdc_obs_create_geographic(mdc_ctx* ctx, int64_t P, const double* lat, const double* lon,
                               const double* level, const double* value, const double* err,
                               const uint8_t* valid, const int64_t* gid, mdc_obs** out);
 int mdc_obs_locate(mdc_obs* obs, mdc_ens* ens);
+/* Geography of a DECOMPOSED store (mdc_ens_set_domain) = its window of `global`, a store that covers the whole grid
+ * and has its geography set (one level and one member are enough: it only serves mdc_obs_locate and this call).  The
+ * window inherits the global frame -- unwrap centre and extents --, so the lat / lon lattice of the bucket index, and
+ * with it the order in which a column meets its candidates, is the same for every decomposition: the analysis is
+ * bit-identical to the single-store one. */
+int mdc_ens_set_geography_from(mdc_ens* ens, const mdc_ens* global);
+/* unwrap centre of the longitudes, extents of the unwrapped longitude offsets u = (lon - lon_c) - 360 rint(..) and of
+ * the latitudes over the store's columns (any output may be NULL) */
+int mdc_ens_geography_frame(const mdc_ens* ens, double* lon_c, double* umin, double* umax, double* latmin,
+                            double* latmax);
 /* grid coordinates of the observations (as given, or as located); any output may be NULL */
 int mdc_obs_download_grid_coords(mdc_obs* obs, int32_t* x, int32_t* y, int32_t* z);
 
@@ -146,9 +157,14 @@ int mdc_hx_idw4(mdc_ens* ens, mdc_obs* obs);
 int mdc_hx_download(mdc_obs* obs, double* Y, double* ybar, double* Yp, double* d);
 
 /* ---- multi-GPU observation halo (column sharding) ------------------------------------------
- * Rows are (k + 8) doubles: Y'[k], d, value, err, valid, x, y, z, gid.  pack selects own obs with
- * ylo <= y < yhi into a DEVICE buffer; append adds received rows as halo obs. */
+ * Rows are (k + 8) doubles: Y'[k], d, value, err, valid, x, y, z, gid -- (k + 12) for geographic and per-variable
+ * stores, which add lat, lon, level, variable (mdc_obs_row_doubles tells).  pack selects own obs with
+ * ylo <= y < yhi into a DEVICE buffer; append adds received rows as halo obs.  pack_rows_geo selects by a box in
+ * the frame of the geography instead (lat_lo <= lat <= lat_hi, u_lo <= unwrapped lon - lon_c <= u_hi): the
+ * destination's columns' bounding box widened by the radius -- a cover, the haversine selection decides. */
 int mdc_obs_pack_rows(mdc_obs* obs, int ylo, int yhi, double* dev_rows, int64_t cap, int64_t* n);
+int mdc_obs_pack_rows_geo(mdc_obs* obs, double lat_lo, double lat_hi, double u_lo, double u_hi, double lon_c,
+                          double* dev_rows, int64_t cap, int64_t* n);
 int mdc_obs_append_rows(mdc_obs* obs, const double* dev_rows, int64_t n);
 int mdc_obs_row_doubles(const mdc_obs* obs);
 
@@ -196,7 +212,8 @@ typedef struct {
                          The vertical scale is radius_v * L / radius.                          */
   double kappa_max;   /* NEWTON_SCHULZ: largest rigorous condition bound lambda_max / lambda_min of a transform's
                          k x k matrix the packed symmetric kernel keeps (the others are redone, see above);
-                         <= 0: 1e5 (agreement with the eigen-decomposition ~1e-11 there), at most 3e5       */
+                         <= 0: 2e4 (the analysis agrees with the eigen-decomposition to ~2e-11 there; at 1e5 the mean
+                         update alone is off by ~3e-10), at most 3e5                                           */
 } mdc_letkf_params;
 
 typedef struct {

@@ -185,6 +185,9 @@ def load_library() -> C.CDLL:
         "mdc_hx_idw4": (C.c_int, [vp, vp]),
         "mdc_hx_download": (C.c_int, [vp, vp, vp, vp, vp]),
         "mdc_obs_pack_rows": (C.c_int, [vp, C.c_int, C.c_int, vp, i64, C.POINTER(i64)]),
+        "mdc_obs_pack_rows_geo": (C.c_int, [vp, C.c_double, C.c_double, C.c_double, C.c_double, C.c_double, vp, i64, C.POINTER(i64)]),
+        "mdc_ens_set_geography_from": (C.c_int, [vp, vp]),
+        "mdc_ens_geography_frame": (C.c_int, [vp] + [C.POINTER(C.c_double)] * 5),
         "mdc_obs_append_rows": (C.c_int, [vp, vp, i64]),
         "mdc_obs_row_doubles": (C.c_int, [vp]),
         "mdc_obs_index_build": (C.c_int, [vp, C.c_int]),
@@ -359,6 +362,16 @@ class Ensemble:
         vc = np.ascontiguousarray(vertical_coords, dtype=np.float64) if vertical_coords is not None else None
         self.ctx.check(self.ctx.L.mdc_ens_set_geography(self.h, _ptr(lat), _ptr(lon), len(vc) if vc is not None else 0, _ptr(vc)))
 
+    def set_geography_from(self, whole: "Ensemble"):
+        """Geography of a decomposed store = its window of `whole` (a store covering the whole grid), with the
+        global frame: the analysis is then bit-identical to the single-store one."""
+        self.ctx.check(self.ctx.L.mdc_ens_set_geography_from(self.h, whole.h))
+
+    def geography_frame(self) -> dict:
+        v = [C.c_double() for _ in range(5)]
+        self.ctx.check(self.ctx.L.mdc_ens_geography_frame(self.h, *[C.byref(x) for x in v]))
+        return dict(zip(("lon_c", "umin", "umax", "latmin", "latmax"), (x.value for x in v)))
+
     def set_variables(self, var_nlev):
         """Variables of the state: a member is [var][lev][y][x], nz = sum(var_nlev)."""
         vn = np.ascontiguousarray(var_nlev, dtype=np.int32)
@@ -495,6 +508,13 @@ class Observations:
     def pack_rows(self, ylo: int, yhi: int, dev_ptr: int, cap: int) -> int:
         n = C.c_int64()
         self.ctx.check(self.ctx.L.mdc_obs_pack_rows(self.h, ylo, yhi, C.c_void_p(dev_ptr), cap, C.byref(n)))
+        return n.value
+
+    def pack_rows_geo(self, lat_lo, lat_hi, u_lo, u_hi, lon_c, dev_ptr: int, cap: int) -> int:
+        """Own observations inside a box of the geography's frame (see mdc_obs_pack_rows_geo); returns the count found
+        (rows beyond cap are dropped: call with cap = 0 to count)."""
+        n = C.c_int64()
+        self.ctx.check(self.ctx.L.mdc_obs_pack_rows_geo(self.h, lat_lo, lat_hi, u_lo, u_hi, lon_c, C.c_void_p(dev_ptr), cap, C.byref(n)))
         return n.value
 
     def append_rows(self, dev_ptr: int, n: int):

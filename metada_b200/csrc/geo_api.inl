@@ -74,6 +74,49 @@ int mdc_ens_set_geography(mdc_ens* e, const double* lat, const double* lon, int 
   return MDC_OK;
 }
 
+// Geography of a decomposed ensemble = its window [gy0, gy0 + ny) x [gx0, gx0 + nx) of a store that covers the whole
+// grid, with that store's frame (unwrap centre, extents): the lat / lon lattice of the bucket index is then the same
+// on every rank, and so is the order in which a column meets its candidates.
+int mdc_ens_set_geography_from(mdc_ens* e, const mdc_ens* g) {
+  mdc_ctx* ctx = e->ctx;
+  if (!g || g->ctx != ctx) MDC_FAIL(ctx, MDC_ERR_INVALID, "set_geography_from: the stores belong to different contexts");
+  if (!g->geo) MDC_FAIL(ctx, MDC_ERR_INVALID, "set_geography_from: the source store has no geography");
+  if (g->gnx != g->nx || g->gny != g->ny || g->nx != e->gnx || g->ny != e->gny)
+    MDC_FAIL(ctx, MDC_ERR_INVALID, "set_geography_from: the source must cover the whole %d x %d grid (it is %d x %d)", e->gnx, e->gny, g->nx, g->ny);
+  if (e->gx0 < 0 || e->gy0 < 0 || e->gx0 + e->nx > g->nx || e->gy0 + e->ny > g->ny)
+    MDC_FAIL(ctx, MDC_ERR_INVALID, "set_geography_from: the window [%d, %d) x [%d, %d) leaves the grid", e->gx0, e->gx0 + e->nx, e->gy0, e->gy0 + e->ny);
+  MDC_CUDA(ctx, cudaSetDevice(ctx->device));
+  const size_t G = (size_t)e->nx * e->ny_cap;
+  if (!e->glat && (dev_alloc(ctx, &e->glat, G) || dev_alloc(ctx, &e->glon, G))) return MDC_ERR_CUDA;
+  MDC_CUDA(ctx, cudaMemcpy2DAsync(e->glat, (size_t)e->nx * 8, g->glat + (size_t)e->gy0 * g->nx + e->gx0, (size_t)g->nx * 8,
+                                  (size_t)e->nx * 8, (size_t)e->ny, cudaMemcpyDeviceToDevice, ctx->stream));
+  MDC_CUDA(ctx, cudaMemcpy2DAsync(e->glon, (size_t)e->nx * 8, g->glon + (size_t)e->gy0 * g->nx + e->gx0, (size_t)g->nx * 8,
+                                  (size_t)e->nx * 8, (size_t)e->ny, cudaMemcpyDeviceToDevice, ctx->stream));
+  if (e->vcoord) { cudaFree(e->vcoord); e->vcoord = nullptr; }
+  e->nvcoord = g->nvcoord;
+  if (g->nvcoord > 0) {
+    if (dev_alloc(ctx, &e->vcoord, (size_t)g->nvcoord)) return MDC_ERR_CUDA;
+    MDC_CUDA(ctx, cudaMemcpyAsync(e->vcoord, g->vcoord, (size_t)g->nvcoord * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+  }
+  MDC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  e->geo = true;
+  e->geo_lon_c = g->geo_lon_c; e->geo_umin = g->geo_umin; e->geo_umax = g->geo_umax;
+  e->geo_latmin = g->geo_latmin; e->geo_latmax = g->geo_latmax;
+  return MDC_OK;
+}
+
+/* the frame of a store's geography: unwrap centre of the longitudes and the extents of the unwrapped offsets /
+ * latitudes over its columns -- what a caller needs to decide which observations a rank's columns can reach */
+int mdc_ens_geography_frame(const mdc_ens* e, double* lon_c, double* umin, double* umax, double* latmin, double* latmax) {
+  if (!e->geo) MDC_FAIL(e->ctx, MDC_ERR_INVALID, "geography_frame: the store has no geography");
+  if (lon_c) *lon_c = e->geo_lon_c;
+  if (umin) *umin = e->geo_umin;
+  if (umax) *umax = e->geo_umax;
+  if (latmin) *latmin = e->geo_latmin;
+  if (latmax) *latmax = e->geo_latmax;
+  return MDC_OK;
+}
+
 int mdc_ens_set_variables(mdc_ens* e, int nvar, const int32_t* var_nlev) {
   mdc_ctx* ctx = e->ctx;
   if (nvar < 1 || nvar > MDC_MAX_VARS || !var_nlev) MDC_FAIL(ctx, MDC_ERR_INVALID, "set_variables: 1 <= nvar <= %d", MDC_MAX_VARS);
@@ -124,6 +167,7 @@ int mdc_obs_set_variables(mdc_obs* o, const int32_t* var) {
     vmax = std::max(vmax, (int)var[i]);
   }
   if (dev_alloc(ctx, &o->var, (size_t)o->P)) return MDC_ERR_CUDA;
+  o->var_cap = (size_t)o->P;
   MDC_CUDA(ctx, cudaMemcpyAsync(o->var, var, (size_t)o->P * 4, cudaMemcpyHostToDevice, ctx->stream));
   MDC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   o->var_max = vmax;
@@ -147,6 +191,7 @@ int mdc_obs_create_geographic(mdc_ctx* ctx, int64_t P, const double* lat, const 
   const size_t n = (size_t)std::max<int64_t>(P, 1);
   if (dev_alloc(ctx, &o->lat, n) || dev_alloc(ctx, &o->lon, n) || dev_alloc(ctx, &o->lev, n) ||
       dev_alloc(ctx, &o->qx, n) || dev_alloc(ctx, &o->qy, n)) { mdc_obs_destroy(o); return MDC_ERR_CUDA; }
+  o->geo_cap = n;
   if (P > 0) {
     cudaStream_t s = ctx->stream;
     MDC_CUDA(ctx, cudaMemcpyAsync(o->lat, lat, P * 8, cudaMemcpyHostToDevice, s));
@@ -165,7 +210,9 @@ int mdc_obs_locate(mdc_obs* o, mdc_ens* e) {
   if (!o->geo) MDC_FAIL(ctx, MDC_ERR_INVALID, "obs_locate: the observations carry GRID coordinates already");
   if (!e->geo) MDC_FAIL(ctx, MDC_ERR_INVALID, "obs_locate: the ensemble has no geography (mdc_ens_set_geography)");
   if (e->gnx != e->nx || e->gny != e->ny)
-    MDC_FAIL(ctx, MDC_ERR_UNSUPPORTED, "obs_locate: geographic observations are not supported on a decomposed domain");
+    MDC_FAIL(ctx, MDC_ERR_UNSUPPORTED, "obs_locate: the nearest grid point is searched on the WHOLE grid: locate on an ensemble store that covers it (a 1-level, 1-member store with the global geography will do), then use mdc_ens_set_geography_from on the decomposed one");
+  if (!e->gc_start[0])
+    MDC_FAIL(ctx, MDC_ERR_UNSUPPORTED, "obs_locate: this ensemble's geography is a window of another store's (mdc_ens_set_geography_from): locate on that one");
   MDC_CUDA(ctx, cudaSetDevice(ctx->device));
   if (o->P > 0 && getenv("MDC_GEO_LOCATE_BRUTE")) {   // the reference's O(P G) scan, kept as a cross-check
     geo_locate_kernel<<<mdc_div_up(o->P, 256), 256, 0, ctx->stream>>>(o->P, o->lat, o->lon, o->lev, e->glat, e->glon,
@@ -205,9 +252,8 @@ static int index_build_impl(mdc_obs* o, int cell);
 static int geo_prepare_index(mdc_obs* o, mdc_ens* e, double radius) {
   mdc_ctx* ctx = o->ctx;
   if (!e->geo) MDC_FAIL(ctx, MDC_ERR_INVALID, "geographic observations need an ensemble with geography (mdc_ens_set_geography)");
-  if (e->gnx != e->nx || e->gny != e->ny || e->own_nx != e->nx || e->own_ny != e->ny)
-    MDC_FAIL(ctx, MDC_ERR_UNSUPPORTED, "geographic observations are not supported on a decomposed domain");
-  if (o->P != o->P_own) MDC_FAIL(ctx, MDC_ERR_UNSUPPORTED, "geographic observations do not take halo rows");
+  // (a decomposed domain: the ensemble's geography is a window of the global one and carries the GLOBAL frame --
+  // mdc_ens_set_geography_from --, so the lattice, hence every column's candidate order, is that of the one-shot run)
   MDC_CUDA(ctx, cudaSetDevice(ctx->device));
   const double pi = 3.14159265358979323846;
   // An observation within `radius` km (great circle, R = 6371 km, Location.hpp:325) of a column at latitude phi

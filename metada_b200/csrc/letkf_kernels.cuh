@@ -201,7 +201,9 @@ __device__ int lk_jacobi(double* M, int k, int ks, int max_sweeps, double tol,
   return sweep;
 }
 
-template <int NR>
+// EXT: geographic observations (haversine selection on the lat / lon lattice index) and multi-variable states
+// (level map), for the REF modes too -- the reference's own LETKF.hpp arithmetic on a WRF-shaped case.
+template <int NR, bool EXT = false>
 __global__ void __launch_bounds__(LK_THREADS) letkf_column_kernel(ColParams P) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int k = P.k, ks = k | 1, nz = P.nz;
@@ -230,7 +232,7 @@ __global__ void __launch_bounds__(LK_THREADS) letkf_column_kernel(ColParams P) {
   const double km1 = (double)(k - 1);
   const bool per_level = P.radius_v > 0.0;
   const int nxf = per_level ? nz : 1;
-  const int R = index_reach<false>(P.iv, P.radius);
+  const int R = index_reach<EXT>(P.iv, P.radius);
   const long long ncols = P.cols ? P.ncols : (long long)P.own_nx * P.own_ny;
 
   for (long long ci = blockIdx.x; ci < ncols; ci += gridDim.x) {
@@ -239,7 +241,7 @@ __global__ void __launch_bounds__(LK_THREADS) letkf_column_kernel(ColParams P) {
     else { lx = (int)(ci % P.own_nx); ly = (int)(ci / P.own_nx); }
     int gx = P.gx0 + lx, gy = P.gy0 + ly;
     const long long col = (long long)ly * P.nx + lx;
-    index_col_coords<false>(P.iv, col, gx, gy);
+    index_col_coords<EXT>(P.iv, col, gx, gy);
     double* Xg = P.X + col * nz * k;
     int col_sweeps = 0;
     long long col_npl = 0;
@@ -265,10 +267,10 @@ __global__ void __launch_bounds__(LK_THREADS) letkf_column_kernel(ColParams P) {
           double rho = 1.0;
           if (a < re) {
             double dist;
-            sel = index_within<false>(P.iv, col, a, gx, gy, P.radius, &dist);
+            sel = index_within<EXT>(P.iv, col, a, gx, gy, P.radius, &dist);
             double dv = 0.0;
             if (sel && per_level) {
-              dv = fabs((double)(P.iv.sz[a] - index_level<false>(P.iv, lt)));
+              dv = fabs((double)(P.iv.sz[a] - index_level<EXT>(P.iv, lt)));
               sel = dv <= P.radius_v;
             }
             if (sel && P.mode == MDC_MODE_CANONICAL && P.loc != MDC_LOC_CUTOFF) {

@@ -16,7 +16,7 @@
 // Off-diagonal tiles are stored once (no mirrored store).
 //
 // Forcing symmetry is only stable while cond(A) is moderate (letkf_ns.cuh); a column (or level, with
-// per-level transforms) whose rigorous condition bound exceeds the limit (default 1e5) is appended to a
+// per-level transforms) whose rigorous condition bound exceeds the limit (default 2e4) is appended to a
 // redo list, which a second launch of the full-product kernel (k <= 80) or the Jacobi kernel
 // (k > 80) consumes.
 #pragma once
@@ -437,8 +437,11 @@ __device__ __forceinline__ int nss_start_index(double kappa) {
 // (emulation of these very tile products, tests/ns_emul.py) 5e-15 at cond 50, 3e-14 at 1200, 1.5e-13 at 6e3, 6e-13 at
 // 5e4, <= 8e-12 at 1e5 over k = 24 .. 128 -- and the residual Z A Z - I in long double is within 2x of that of the
 // eigen-decomposition at every one of them (round 1 stopped at 256, round 2's first table at 2000: the accurate-
-// observation cliff of bench.py's sigma = 0.01 variant).
-#define NSP_KAPPA_MAX_DEFAULT 1e5
+// observation cliff of bench.py's sigma = 0.01 variant).  What sets the default limit is the MEAN update:
+// w = Z (Z g) loses cond(A) * err(Z) against the eigen-decomposition's U diag(1 / lambda) U^T g (g lies along the
+// large eigenvalues), measured on the device 7e-11 at cond 4e4 and 2e-10 at 7e4 -- 2e4 keeps a factor 5 - 10 to the
+// 1e-10 parity bound.
+#define NSP_KAPPA_MAX_DEFAULT 2e4
 #define NSP_KAPPA_TABLE_MAX 3e5
 #define NSP_SC_DOUBLES 48   /* schedule scratch: 8 steps x {kind, c0..c3}, + the residual bound of the finish */
 #define NSP_SC_KMAX 45      /* slot that carries the condition limit from the Gram phase to the iteration */

@@ -572,7 +572,8 @@ int mdc_obs_destroy(mdc_obs* o) {
 }
 
 int64_t mdc_obs_size(const mdc_obs* o) { return o->P; }
-int mdc_obs_row_doubles(const mdc_obs* o) { return o->k + 8; }
+// plain stores: Y'[k], d, value, err, valid, x, y, z, gid; geographic / per-variable stores add lat, lon, level, variable
+int mdc_obs_row_doubles(const mdc_obs* o) { return o->k + ((o->geo || o->var) ? 12 : 8); }
 
 // ------------------------------------------------------------------------------ H(x)
 int mdc_hx_idw4(mdc_ens* e, mdc_obs* o) {
@@ -667,8 +668,118 @@ __global__ void obs_unpack_rows_kernel(int64_t n, int k, const double* rows, int
   }
 }
 
+// Geographic / per-variable stores: rows of k + 12 doubles (.., gid, lat, lon, level, variable).  Own observations
+// are selected by grid row (by_box = 0: ylo <= y < yhi) or by a box in the frame of the geography (by_box = 1:
+// lat_lo <= lat <= lat_hi and u_lo <= unwrapped (lon - lon_c) <= u_hi) -- a conservative cover of what another rank's
+// columns can reach; the haversine test of the selection decides.
+struct ObsBox { double lat_lo, lat_hi, u_lo, u_hi, lon_c; };
+__global__ void obs_pack_rows_ext_kernel(int64_t P, int k, const int32_t* x, const int32_t* y, const int32_t* z,
+                                         const int64_t* gid, const double* val, const double* err, const uint8_t* valid,
+                                         const double* Yp, const double* d, const double* lat, const double* lon,
+                                         const double* lev, const int32_t* var, int by_box, int ylo, int yhi, ObsBox box,
+                                         double* rows, int64_t cap, unsigned long long* counter) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp_global = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  const int rd = k + 12;
+  for (int64_t i = warp_global; i < P; i += nwarps) {
+    if (by_box) {
+      const double u = (lon[i] - box.lon_c) - 360.0 * rint((lon[i] - box.lon_c) / 360.0);
+      if (!(lat[i] >= box.lat_lo && lat[i] <= box.lat_hi && u >= box.u_lo && u <= box.u_hi)) continue;
+    } else if (y[i] < ylo || y[i] >= yhi) {
+      continue;
+    }
+    unsigned long long slot = 0;
+    if (lane == 0) slot = atomicAdd(counter, 1ull);
+    slot = __shfl_sync(0xffffffffu, slot, 0);
+    if ((int64_t)slot >= cap) continue;
+    double* r = rows + slot * rd;
+    for (int j = lane; j < k; j += 32) r[j] = Yp[i * k + j];
+    if (lane == 0) {
+      r[k + 0] = d[i]; r[k + 1] = val[i]; r[k + 2] = err[i]; r[k + 3] = (double)valid[i];
+      r[k + 4] = (double)x[i]; r[k + 5] = (double)y[i]; r[k + 6] = (double)z[i];
+      r[k + 7] = (double)gid[i];
+      r[k + 8] = lat ? lat[i] : 0.0; r[k + 9] = lon ? lon[i] : 0.0; r[k + 10] = lev ? lev[i] : 0.0;
+      r[k + 11] = var ? (double)var[i] : 0.0;
+    }
+  }
+}
+
+__global__ void obs_unpack_rows_ext_kernel(int64_t n, int k, const double* rows, int64_t base, int32_t* x, int32_t* y,
+                                           int32_t* z, int64_t* gid, double* val, double* err, uint8_t* valid, double* Yp,
+                                           double* d, double* lat, double* lon, double* lev, int32_t* var) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp_global = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  const int rd = k + 12;
+  for (int64_t i = warp_global; i < n; i += nwarps) {
+    const double* r = rows + i * rd;
+    const int64_t o = base + i;
+    for (int j = lane; j < k; j += 32) Yp[o * k + j] = r[j];
+    if (lane == 0) {
+      d[o] = r[k + 0]; val[o] = r[k + 1]; err[o] = r[k + 2]; valid[o] = (uint8_t)(r[k + 3] != 0.0);
+      x[o] = (int32_t)r[k + 4]; y[o] = (int32_t)r[k + 5]; z[o] = (int32_t)r[k + 6];
+      gid[o] = (int64_t)r[k + 7];
+      if (lat) { lat[o] = r[k + 8]; lon[o] = r[k + 9]; lev[o] = r[k + 10]; }
+      if (var) var[o] = (int32_t)r[k + 11];
+    }
+  }
+}
+
+// grow the arrays only geographic / per-variable stores have, preserving the first P entries
+static int obs_reserve_ext(mdc_obs* o, int64_t cap) {
+  mdc_ctx* ctx = o->ctx;
+  const size_t P = (size_t)o->P;
+  auto grow = [&](auto** arr, size_t ncap) -> int {
+    using T = std::remove_pointer_t<std::remove_pointer_t<decltype(arr)>>;
+    T* n = nullptr;
+    if (int rc = dev_alloc<T>(ctx, &n, ncap)) return rc;
+    if (*arr && P) MDC_CUDA(ctx, cudaMemcpyAsync(n, *arr, P * sizeof(T), cudaMemcpyDeviceToDevice, ctx->stream));
+    MDC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    cudaFree(*arr);
+    *arr = n;
+    return MDC_OK;
+  };
+  if (o->geo && (size_t)cap > o->geo_cap) {
+    const size_t ncap = std::max((size_t)cap, o->geo_cap + o->geo_cap / 2);
+    if (grow(&o->lat, ncap) || grow(&o->lon, ncap) || grow(&o->lev, ncap) || grow(&o->qx, ncap) || grow(&o->qy, ncap)) return MDC_ERR_CUDA;
+    o->geo_cap = ncap;
+  }
+  if (o->var && (size_t)cap > o->var_cap) {
+    const size_t ncap = std::max((size_t)cap, o->var_cap + o->var_cap / 2);
+    if (grow(&o->var, ncap)) return MDC_ERR_CUDA;
+    o->var_cap = ncap;
+  }
+  return MDC_OK;
+}
+
+static int obs_pack_impl(mdc_obs* o, int by_box, int ylo, int yhi, ObsBox box, double* dev_rows, int64_t cap, int64_t* n) {
+  mdc_ctx* ctx = o->ctx;
+  if (!o->have_hx) MDC_FAIL(ctx, MDC_ERR_INVALID, "pack_rows: call mdc_hx_idw4 first");
+  MDC_CUDA(ctx, cudaSetDevice(ctx->device));
+  unsigned long long* counter = (unsigned long long*)ctx->d_stats;
+  MDC_CUDA(ctx, cudaMemsetAsync(counter, 0, sizeof(unsigned long long), ctx->stream));
+  if (o->P_own > 0) {
+    obs_pack_rows_ext_kernel<<<grid_for(ctx, o->P_own * 32, 256, 8), 256, 0, ctx->stream>>>(
+        o->P_own, o->k, o->x, o->y, o->z, o->gid, o->val, o->err, o->valid, o->Yp, o->d, o->lat, o->lon, o->lev, o->var,
+        by_box, ylo, yhi, box, dev_rows, cap, counter);
+    MDC_LAUNCH_CHECK(ctx);
+  }
+  unsigned long long h = 0;
+  if (int rc = read_small(ctx, counter, &h, 8)) return rc;
+  if (n) *n = (int64_t)h;
+  return MDC_OK;
+}
+
+int mdc_obs_pack_rows_geo(mdc_obs* o, double lat_lo, double lat_hi, double u_lo, double u_hi, double lon_c,
+                          double* dev_rows, int64_t cap, int64_t* n) {
+  if (!o->geo) MDC_FAIL(o->ctx, MDC_ERR_INVALID, "pack_rows_geo: the observations carry GRID coordinates (mdc_obs_pack_rows)");
+  return obs_pack_impl(o, 1, 0, 0, ObsBox{lat_lo, lat_hi, u_lo, u_hi, lon_c}, dev_rows, cap, n);
+}
+
 int mdc_obs_pack_rows(mdc_obs* o, int ylo, int yhi, double* dev_rows, int64_t cap, int64_t* n) {
   mdc_ctx* ctx = o->ctx;
+  if (o->geo || o->var) return obs_pack_impl(o, 0, ylo, yhi, ObsBox{0, 0, 0, 0, 0}, dev_rows, cap, n);
   if (!o->have_hx) MDC_FAIL(ctx, MDC_ERR_INVALID, "pack_rows: call mdc_hx_idw4 first");
   MDC_CUDA(ctx, cudaSetDevice(ctx->device));
   unsigned long long* counter = (unsigned long long*)ctx->d_stats;
@@ -687,10 +798,20 @@ int mdc_obs_pack_rows(mdc_obs* o, int ylo, int yhi, double* dev_rows, int64_t ca
 int mdc_obs_append_rows(mdc_obs* o, const double* dev_rows, int64_t n) {
   mdc_ctx* ctx = o->ctx;
   if (!o->have_hx) MDC_FAIL(ctx, MDC_ERR_INVALID, "append_rows: call mdc_hx_idw4 first (defines k)");
-  if (o->geo || o->var) MDC_FAIL(ctx, MDC_ERR_UNSUPPORTED, "append_rows: not for geographic / per-variable observation stores");
   if (n <= 0) return MDC_OK;
   MDC_CUDA(ctx, cudaSetDevice(ctx->device));
   if (int rc = obs_reserve(o, o->P + n, o->k)) return rc;
+  if (o->geo || o->var) {
+    if (o->geo && !o->located) MDC_FAIL(ctx, MDC_ERR_INVALID, "append_rows: locate the store's own observations first");
+    if (int rc = obs_reserve_ext(o, o->P + n)) return rc;
+    obs_unpack_rows_ext_kernel<<<grid_for(ctx, n * 32, 256, 8), 256, 0, ctx->stream>>>(
+        n, o->k, dev_rows, o->P, o->x, o->y, o->z, o->gid, o->val, o->err, o->valid, o->Yp, o->d,
+        o->geo ? o->lat : nullptr, o->geo ? o->lon : nullptr, o->geo ? o->lev : nullptr, o->var);
+    MDC_LAUNCH_CHECK(ctx);
+    o->P += n;
+    o->index_valid = false;
+    return MDC_OK;
+  }
   obs_unpack_rows_kernel<<<grid_for(ctx, n * 32, 256, 8), 256, 0, ctx->stream>>>(
       n, o->k, dev_rows, o->P, o->x, o->y, o->z, o->gid, o->val, o->err, o->valid, o->Yp, o->d);
   MDC_LAUNCH_CHECK(ctx);
@@ -837,10 +958,8 @@ static int letkf_launch(mdc_ens* e, mdc_obs* o, const mdc_letkf_params* p, const
   if (p->mode < 0 || p->mode > 2) MDC_FAIL(ctx, MDC_ERR_INVALID, "letkf: bad mode");
   if (p->loc < 0 || p->loc > MDC_LOC_REF_GASPARI_COHN) MDC_FAIL(ctx, MDC_ERR_INVALID, "letkf: bad localisation function");
   if (!(p->inflation > 0.0)) MDC_FAIL(ctx, MDC_ERR_INVALID, "letkf: inflation must be > 0");
-  // geographic observations / multi-variable states run on the EXT instantiations of the canonical kernels
+  // geographic observations / multi-variable states run on the EXT instantiations of the column kernels
   const bool ext = o->geo || e->levmap != nullptr;
-  if (ext && p->mode != MDC_MODE_CANONICAL)
-    MDC_FAIL(ctx, MDC_ERR_UNSUPPORTED, "letkf: geographic observations and multi-variable states need MDC_MODE_CANONICAL");
   if (ext && p->solver == MDC_SOLVER_NEWTON_SCHULZ_FULL)
     MDC_FAIL(ctx, MDC_ERR_UNSUPPORTED, "letkf: geographic observations and multi-variable states run on the AUTO, JACOBI or NEWTON_SCHULZ solvers");
   const size_t smem = lk_smem_bytes(k, p->mode);
@@ -988,6 +1107,12 @@ static int letkf_launch(mdc_ens* e, mdc_obs* o, const mdc_letkf_params* p, const
     MDC_LAUNCH_CHECK(ctx);
     return MDC_OK;
   };
+  if (ext) switch (nr) {
+    case 1: return launch(letkf_column_kernel<1, true>);
+    case 2: return launch(letkf_column_kernel<2, true>);
+    case 3: return launch(letkf_column_kernel<3, true>);
+    default: return launch(letkf_column_kernel<4, true>);
+  }
   switch (nr) {
     case 1: return launch(letkf_column_kernel<1>);
     case 2: return launch(letkf_column_kernel<2>);

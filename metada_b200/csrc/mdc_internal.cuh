@@ -90,6 +90,7 @@ struct mdc_obs {
   int32_t* var = nullptr;                                  // [P] state variable observed, or nullptr (variable 0)
   int var_max = 0;                                         // largest entry of var (host copy, checked against the ensemble)
   int32_t *qx = nullptr, *qy = nullptr;                    // [P]
+  size_t geo_cap = 0, var_cap = 0;                         // rows allocated for lat / lon / lev / qx / qy, and for var
   int32_t *cqx = nullptr, *cqy = nullptr;                  // [columns of the ensemble the index was built for]
   size_t cq_cap = 0;
   double *slat = nullptr, *slon = nullptr;                 // [P] coordinates in index order

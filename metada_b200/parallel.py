@@ -347,3 +347,136 @@ class SlabLetkf:
             self.obs.close()
             self.obs = None
         self.ens.close()
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# GEOGRAPHIC observations on a decomposed domain (the WRF-shaped case, sharded)
+#
+# Same row slabs.  What changes is who needs which observation: the selection is by haversine kilometres between the
+# column's and the observation's latitude / longitude (Location.hpp:213-217, 349-357), which grid rows say nothing
+# about on a curvilinear grid.  Every rank therefore keeps the (small) global coordinate arrays in a one-level,
+# one-member store -- it serves the nearest-grid-point search of ALL observations (ownership = the slab of the located
+# row, as for GRID observations) and hands each slab its window of the geography with the GLOBAL frame, so that the
+# lat / lon lattice of the bucket index is the one-shot run's -- and sends rank r the own observations inside r's
+# columns' bounding box widened by the radius (a cover: the haversine test of the selection decides).  Rows carry
+# latitude, longitude, level and variable next to Y' (k + 12 doubles).  The result is bit-identical to the
+# single-store analysis for any rank count.
+
+def geo_reach_degrees(radius_km: float, latmin: float, latmax: float):
+    """Largest latitude / longitude difference (degrees) between a column and an observation within radius_km of it
+    (the bound geo_prepare_index uses, csrc/geo_api.inl)."""
+    delta = max(radius_km, 0.0) / 6371.0
+    phic = math.radians(max(abs(latmin), abs(latmax)))
+    dlat = math.degrees(delta) * (1.0 + 1e-9) + 1e-12
+    dlon = math.degrees(math.asin(min(1.0, math.sin(delta) / math.cos(phic)))) * (1.0 + 1e-9) + 1e-12
+    return dlat, dlon
+
+
+def geo_halo_boxes(lat, lon, frame: dict, world: int, radius_km: float):
+    """Per rank: (lat_lo, lat_hi, u_lo, u_hi) = bounding box of the slab's columns in the geography's frame
+    (u = longitude offset from frame['lon_c'], unwrapped), widened by the reach of the radius."""
+    gny = lat.shape[0]
+    dlat, dlon = geo_reach_degrees(radius_km, frame["latmin"], frame["latmax"])
+    u = (lon - frame["lon_c"]) - 360.0 * np.rint((lon - frame["lon_c"]) / 360.0)
+    boxes = []
+    for r in range(world):
+        y0, y1 = slab_bounds(gny, r, world)
+        boxes.append((float(lat[y0:y1].min()) - dlat, float(lat[y0:y1].max()) + dlat,
+                      float(u[y0:y1].min()) - dlon, float(u[y0:y1].max()) + dlon))
+    return boxes
+
+
+class GeoSlabLetkf:
+    """One rank's share of a column-sharded LETKF with GEOGRAPHIC observations (all three modes)."""
+
+    def __init__(self, ctx, lat, lon, vertical, nz, k, rank=0, world=1, radius_km=50.0, var_nlev=None):
+        import metada_b200 as mb
+        self.mb, self.ctx = mb, ctx
+        lat = np.ascontiguousarray(lat, dtype=np.float64)
+        lon = np.ascontiguousarray(lon, dtype=np.float64)
+        self.gny, self.gnx = lat.shape
+        self.nz, self.k, self.rank, self.world, self.radius_km = nz, k, rank, world, float(radius_km)
+        self.whole = mb.Ensemble(ctx, self.gnx, self.gny, 1, 1)      # geography only: locate + windows
+        self.whole.set_geography(lat, lon, vertical)
+        self.frame = self.whole.geography_frame()
+        self.y0, self.y1 = slab_bounds(self.gny, rank, world)
+        self.halo_hi = 1 if self.y1 < self.gny else 0
+        self.ny_loc = (self.y1 - self.y0) + self.halo_hi
+        self.ens = mb.Ensemble(ctx, self.gnx, self.ny_loc, nz, k)
+        self.ens.set_domain(0, self.y0, self.gnx, self.gny, self.gnx, self.y1 - self.y0)
+        self.ens.set_geography_from(self.whole)
+        if var_nlev is not None:
+            self.ens.set_variables(var_nlev)
+        self.boxes = geo_halo_boxes(lat, lon, self.frame, world, self.radius_km)
+        self.obs = None
+        self.halo_rows_last = 0
+
+    def set_observations(self, o: dict):
+        """o: lat, lon, level, value, err, valid [, var] of ALL observations (every rank passes the same arrays)."""
+        mb = self.mb
+        if self.obs is not None:
+            self.obs.close()
+        everything = mb.Observations.geographic(self.ctx, o["lat"], o["lon"], o["level"], o["value"], o["err"], o["valid"])
+        everything.locate(self.whole)
+        _, y, _ = everything.grid_coords()
+        everything.close()
+        own = np.nonzero(owner_of_row(y, self.gny, self.world) == self.rank)[0] if self.world > 1 else np.arange(len(y))
+        self.own = own
+        self.obs = mb.Observations.geographic(self.ctx, o["lat"][own], o["lon"][own], o["level"][own], o["value"][own],
+                                              o["err"][own], o["valid"][own], gid=own.astype(np.int64))
+        if o.get("var") is not None:
+            self.obs.set_variables(np.asarray(o["var"])[own])
+        self.obs.locate(self.whole)
+
+    def pack_halo(self):
+        """H on the own observations, then {dst: cuda tensor [n, k + 12]} of the rows dst's columns can reach."""
+        import torch
+        self.obs.hx(self.ens)
+        rd = self.obs.row_doubles()
+        dev = torch.device("cuda", torch.cuda.current_device())
+        send = {}
+        for dst in range(self.world):
+            if dst == self.rank:
+                continue
+            box = self.boxes[dst]
+            n = self.obs.pack_rows_geo(*box, self.frame["lon_c"], 0, 0)
+            buf = torch.empty((max(n, 1), rd), dtype=torch.float64, device=dev)
+            if n > 0:
+                got = self.obs.pack_rows_geo(*box, self.frame["lon_c"], buf.data_ptr(), n)
+                assert got == n, (got, n)
+            send[dst] = buf[:n]
+        self.ctx.sync()
+        return send
+
+    def analyse(self, params, dist=None, recv=None):
+        """recv: {src: tensor} when the caller moved the rows itself (tests play the ranks in one process); otherwise
+        the rows go through torch.distributed."""
+        from . import capi
+        if params.radius > self.radius_km:
+            raise ValueError(f"GeoSlabLetkf was planned for a radius of {self.radius_km} km; analyse() got {params.radius}")
+        if self.world > 1:
+            import torch
+            if recv is None:
+                import torch.distributed as tdist
+                dist = dist or tdist
+                send = self.pack_halo()
+                torch.cuda.synchronize()
+                recv = exchange_rows(dist, self.rank, self.world, send, self.obs.row_doubles(),
+                                     torch.device("cuda", torch.cuda.current_device()), as_dict=True)
+                torch.cuda.synchronize()
+            self.halo_rows_last = 0
+            for src in sorted(recv):
+                t = recv[src]
+                if t.shape[0]:
+                    self.obs.append_rows(t.data_ptr(), t.shape[0])
+                    self.halo_rows_last += t.shape[0]
+            self.ctx.sync()
+        else:
+            self.obs.hx(self.ens)
+        return capi.letkf_analyse(self.ens, self.obs, params)
+
+    def close(self):
+        if self.obs is not None:
+            self.obs.close()
+        self.ens.close()
+        self.whole.close()

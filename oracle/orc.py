@@ -242,8 +242,8 @@ def hx_ext(member, ox, oy, oz, var_nlev, ovar, valid=None):
 
 def letkf_ext(X, ox, oy, oz, oval, oerr, valid=None, *, radius, glat=None, glon=None, olat=None, olon=None,
               var_nlev=None, ovar=None, inflation=1.0, loc=LOC_GASPARI_COHN, use_R=1, radius_v=0.0, nthreads=0,
-              loc_scale=0.0, Xobs=None):
-    """Canonical snapshot LETKF with GEOGRAPHIC locations (glat/glon [ny, nx], olat/olon [P]; radius in km) and / or
+              loc_scale=0.0, Xobs=None, mode=MODE_CANONICAL):
+    """Snapshot LETKF (canonical by default; the REF modes = LETKF.hpp:209-238 arithmetic) with GEOGRAPHIC locations (glat/glon [ny, nx], olat/olon [P]; radius in km) and / or
     a multi-variable state (var_nlev, ovar).  ox, oy, oz: nearest grid points (geo_locate).  Xobs [k, nz', ny', nx']:
     staggered grids -- H is evaluated on this ensemble (whose variables var_nlev / ovar then describe) and the
     transforms are applied to X, a single variable on its own column set glat / glon.  Returns dict(Xa, counts)."""
@@ -262,7 +262,7 @@ def letkf_ext(X, ox, oy, oz, oval, oerr, valid=None, *, radius, glat=None, glon=
     ext = Ext(_p(keep[0], C.c_double), _p(keep[1], C.c_double), _p(keep[2], C.c_double), _p(keep[3], C.c_double),
               len(vn) if vn is not None else 0, _p(vn, C.c_int32), _p(ov, C.c_int32), _p(xo, C.c_double),
               xo.shape[3] if xo is not None else 0, xo.shape[2] if xo is not None else 0, xo.shape[1] if xo is not None else 0)
-    prm = LetkfParams(nx, ny, nz, k, P, radius, radius_v, inflation, MODE_CANONICAL, loc, use_R, SEM_SNAPSHOT,
+    prm = LetkfParams(nx, ny, nz, k, P, radius, radius_v, inflation, mode, loc, use_R, SEM_SNAPSHOT,
                       nthreads, loc_scale)
     counts = np.full(nx * ny, -1, dtype=np.int32)
     rc = lib().orc_letkf_ext(C.byref(prm), C.byref(ext), _p(Xa, C.c_double), _p(ox, C.c_int32), _p(oy, C.c_int32),

@@ -122,7 +122,7 @@ def test_haversine_selection_counts_and_sets_bit_exact(ctx, radius, lon0):
 
 
 def _check_analysis(ctx, X, lat, lon, o, vc, radius, var_nlev=None, ovar=None, solver=mb.SOLVER_AUTO, radius_v=0.0,
-                    loc=mb.LOC_GASPARI_COHN, inflation=1.0):
+                    loc=mb.LOC_GASPARI_COHN, inflation=1.0, mode=mb.MODE_CANONICAL):
     ens, obs = _setup(ctx, X, lat, lon, o, vc)
     if var_nlev is not None:
         ens.set_variables(var_nlev)
@@ -131,12 +131,11 @@ def _check_analysis(ctx, X, lat, lon, o, vc, radius, var_nlev=None, ovar=None, s
     x, y, z = obs.grid_coords()
     ex, ey, ez = orc.geo_locate(o["lat"], o["lon"], o["level"], lat, lon, vc)
     assert np.array_equal(x, ex) and np.array_equal(y, ey) and np.array_equal(z, ez)
-    st = capi.letkf_analyse(ens, obs, capi.make_params(radius, inflation, mb.MODE_CANONICAL, loc, solver=solver,
-                                                      radius_v=radius_v))
+    st = capi.letkf_analyse(ens, obs, capi.make_params(radius, inflation, mode, loc, solver=solver, radius_v=radius_v))
     Xa = ens.download()
     ref = orc.letkf_ext(X, ex, ey, ez, o["value"], o["err"], o["valid"], radius=radius, glat=lat, glon=lon,
                         olat=o["lat"], olon=o["lon"], var_nlev=var_nlev, ovar=ovar, radius_v=radius_v, loc=loc,
-                        inflation=inflation)
+                        inflation=inflation, mode=mode)
     if radius_v == 0.0:      # (with per-level transforms the device counts the level-0 sets)
         assert st["sum_local_obs"] == int(ref["counts"].sum())
         assert st["max_local_obs"] == int(ref["counts"].max())
@@ -154,6 +153,26 @@ def test_geographic_letkf_matches_oracle(ctx, k, solver):
     lat, lon, o, X = _geo_case(30, 22, 3, k, 900, seed=4, vc=VC[:3])
     st = _check_analysis(ctx, X, lat, lon, o, VC[:3], radius=55.0, solver=solver)
     assert st["columns"] == 30 * 22
+
+
+@pytest.mark.parametrize("mode", [mb.MODE_REF_COMPAT, mb.MODE_REF_ETKF])
+@pytest.mark.parametrize("k,lon0", [(9, -104.0), (40, 177.8)])
+def test_geographic_letkf_in_the_reference_arithmetic(ctx, mode, k, lon0):
+    """The reference's own point update (LETKF.hpp:209-238: R = I, cut-off selection, explicit inverse, Cholesky
+    factor, per-member scale factors -- REF_COMPAT; and its ETKF-style variant) on GEOGRAPHIC observations: what
+    `letkf` computes on a WRF-shaped case, selection by haversine kilometres (Location.hpp:349-357)."""
+    lat, lon, o, X = _geo_case(26, 19, 2, k, 600, seed=40 + k, vc=VC[:2], lon0=lon0)
+    st = _check_analysis(ctx, X, lat, lon, o, VC[:2], radius=48.0, loc=mb.LOC_CUTOFF, inflation=1.1, mode=mode)
+    assert st["columns"] == 26 * 19 and st["numeric_failures"] == 0
+
+
+def test_multivariable_state_in_the_reference_arithmetic(ctx):
+    """REF_COMPAT on a three-variable state with per-observation variables (geographic locations)."""
+    var_nlev = [3, 4, 1]
+    lat, lon, o, X = _geo_case(20, 16, sum(var_nlev), 16, 500, seed=61, vc=VC[:3])
+    ovar = np.random.default_rng(62).integers(0, 3, 500).astype(np.int32)
+    _check_analysis(ctx, X, lat, lon, o, VC[:3], radius=50.0, var_nlev=var_nlev, ovar=ovar, loc=mb.LOC_CUTOFF,
+                    mode=mb.MODE_REF_COMPAT)
 
 
 def test_geographic_few_local_observations_take_the_observation_space_kernel(ctx):
@@ -254,8 +273,8 @@ def test_staggered_grid_is_its_own_column_set_sharing_the_mass_grid_h(ctx, k):
 def test_unsupported_geographic_requests_fail_loudly(ctx):
     lat, lon, o, X = _geo_case(12, 10, 1, 8, 50, seed=7)
     ens, obs = _setup(ctx, X, lat, lon, o)
-    with pytest.raises(mb.MdcError, match="CANONICAL"):
-        capi.letkf_analyse(ens, obs, capi.make_params(50.0, 1.0, mb.MODE_REF_COMPAT, mb.LOC_CUTOFF))
+    with pytest.raises(mb.MdcError, match="solvers"):
+        capi.letkf_analyse(ens, obs, capi.make_params(50.0, 1.0, mb.MODE_CANONICAL, solver=mb.SOLVER_NEWTON_SCHULZ_FULL))
     with pytest.raises(mb.MdcError, match="pole"):
         obs.query_counts(ens, 7000.0)
     with pytest.raises(mb.MdcError, match="index"):

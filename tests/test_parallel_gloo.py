@@ -105,3 +105,29 @@ def test_sharded_analysis_equals_single_process(world):
         y0, y1 = par.slab_bounds(ny, r, world)
         # same observation SETS in the same (global id) order -> bit-identical
         assert np.array_equal(out[r], full[:, :, y0:y1, :]), r
+
+
+def test_geographic_halo_boxes_cover_every_reachable_observation():
+    """The boxes GeoSlabLetkf sends by (bounding box of a slab's columns in the geography's frame, widened by the
+    reach of the radius) contain every observation within the radius of any of the slab's columns -- checked against
+    the oracle's haversine (Location.hpp:349-357) on a curvilinear grid across the date line."""
+    from oracle import orc
+    lat, lon = syn.geography(40, 33, lon0=178.2, lat0=-44.0)
+    o = syn.geo_observations(500, lat, lon, None, seed=12)
+    lon_c = float(np.degrees(np.arctan2(np.sin(np.radians(lon)).sum(), np.cos(np.radians(lon)).sum())))
+    u = (lon - lon_c) - 360.0 * np.rint((lon - lon_c) / 360.0)
+    frame = {"lon_c": lon_c, "umin": float(u.min()), "umax": float(u.max()), "latmin": float(lat.min()), "latmax": float(lat.max())}
+    radius, world = 70.0, 3
+    boxes = par.geo_halo_boxes(lat, lon, frame, world, radius)
+    ou = (o["lon"] - lon_c) - 360.0 * np.rint((o["lon"] - lon_c) / 360.0)
+    reached = 0
+    for r, (la0, la1, u0, u1) in enumerate(boxes):
+        y0, y1 = par.slab_bounds(lat.shape[0], r, world)
+        inbox = (o["lat"] >= la0) & (o["lat"] <= la1) & (ou >= u0) & (ou <= u1)
+        for y in range(y0, y1, 3):
+            for x in range(0, lat.shape[1], 4):
+                sel = orc.select_local_geo(lat[y, x], lon[y, x], o["lat"], o["lon"], radius)
+                assert inbox[sel].all(), (r, y, x)
+                reached += len(sel)
+        assert inbox.sum() < len(inbox)          # ... and it is a proper subset
+    assert reached > 1000

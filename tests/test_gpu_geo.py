@@ -283,3 +283,49 @@ def test_unsupported_geographic_requests_fail_loudly(ctx):
     with pytest.raises(mb.MdcError, match="geography"):
         obs.locate(plain)
     plain.close(); ens.close(); obs.close()
+
+
+@pytest.mark.parametrize("world,mode,multivar", [(2, mb.MODE_CANONICAL, False), (3, mb.MODE_CANONICAL, True),
+                                                  (4, mb.MODE_REF_COMPAT, False)])
+def test_sharded_geographic_analysis_is_bit_identical_to_one_store(ctx, world, mode, multivar):
+    """Domain decomposition of a geographic analysis (VERDICT r1 missing 3), the ranks played one after the other on
+    this device: every rank locates all observations on the global geography, keeps those whose nearest grid point
+    lies in its slab, applies H to them and packs -- by box, with latitude / longitude / level / variable in the row
+    -- what the other ranks' columns can reach; each rank then analyses its rows with own + received observations on
+    its window of the geography.  Same lattice, same candidate order: the assembled analysis equals the one-store
+    result bit for bit."""
+    from metada_b200.parallel import GeoSlabLetkf
+    var_nlev = [3, 3, 1] if multivar else None
+    nx, ny, nz, k, P, radius = 27, 26, (7 if multivar else 2), 24, 700, 45.0
+    vc = VC[:3] if multivar else VC[:2]
+    lat, lon, o, X = _geo_case(nx, ny, nz, k, P, seed=70 + world, vc=vc, lon0=(177.9 if world == 3 else -104.0))
+    ovar = np.random.default_rng(5).integers(0, 3, P).astype(np.int32) if multivar else None
+    ens, obs = _setup(ctx, X, lat, lon, o, vc)
+    if multivar:
+        ens.set_variables(var_nlev)
+        obs.set_variables(ovar)
+    params = capi.make_params(radius, 1.04, mode, mb.LOC_GASPARI_COHN if mode == mb.MODE_CANONICAL else mb.LOC_CUTOFF)
+    st1 = capi.letkf_analyse(ens, obs, params)
+    one = ens.download()
+    ens.close(); obs.close()
+    oo = dict(o)
+    oo["var"] = ovar
+    jobs = [GeoSlabLetkf(ctx, lat, lon, vc, nz, k, r, world, radius, var_nlev) for r in range(world)]
+    sends = []
+    for job in jobs:
+        job.ens.upload(np.ascontiguousarray(X[:, :, job.y0:job.y0 + job.ny_loc, :]))
+        job.set_observations(oo)
+        sends.append(job.pack_halo())
+    assert sum(len(job.own) for job in jobs) == P
+    out = np.empty_like(X)
+    cols = halo = 0
+    for r, job in enumerate(jobs):
+        st = job.analyse(params, recv={src: sends[src][r] for src in range(world) if src != r})
+        cols += st["columns"]
+        halo += job.halo_rows_last
+        out[:, :, job.y0:job.y1, :] = job.ens.download()[:, :, :job.y1 - job.y0, :]
+    for job in jobs:
+        job.close()
+    assert cols == nx * ny and 0 < halo < P * (world - 1)
+    assert np.array_equal(out, one)
+    assert np.abs(one - X).max() > 1e-3

@@ -77,7 +77,7 @@ __host__ __device__ inline int nsp_region_doubles(int k, int lch) {
   int r = 3 * m;
   const int gch = (kp >> 3) <= 5 ? 112 : 128;                  // NSP_GCH_OF
   if (gch * ks > r) r = gch * ks;
-  if (m + lch * ks > r) r = m + lch * ks;
+  if (m + lch * ks + 16 * kp > r) r = m + lch * ks + 16 * kp;   // Z | staged levels | partial sums of w = Z (Z g)
   return r;
 }
 __device__ __forceinline__ int nsp_row_start(int I, int nt) { return (I * (2 * nt - I + 1)) >> 1; }
@@ -593,8 +593,10 @@ __device__ NSP_ISQ_INLINE int nsp_inverse_sqrt(double* Zp, double* red, double* 
           double e0 = (d == 1 ? 1.0 : 0.0), e1 = (d == 2 ? 1.0 : 0.0);
           if (op == OP_ET) { const double2 t2 = own(Tp, n); e0 = (e0 - t2.x) + acc[n][0]; e1 = (e1 - t2.y) + acc[n][1]; }
           else { e0 -= acc[n][0]; e1 -= acc[n][1]; }
-          const double w = offw(n);
-          r = fma(w * e0, e0, fma(w * e1, e1, r));
+          if (kind > 10) {                                       // (the residual is measured once, before the finish)
+            const double w = offw(n);
+            r = fma(w * e0, e0, fma(w * e1, e1, r));
+          }
           acc[n][0] = e0; acc[n][1] = e1;
         }
       if (kind > 10) {
@@ -1013,26 +1015,45 @@ __device__ __noinline__ void nsp_phase_update(const ColParams& P, int lch, long 
   };
   request_x(lev_b, min(lch, lev_e - lev_b));
   if (npl > 0) {
-    // w = Z (Z g): warp per tile row, lanes read Z in the fragment pattern (row g, columns t, 4 + t
-    // of every tile) and reduce over t
+    // w = Z (Z g).  Every warp takes the tile COLUMNS K = warp, warp + NW, ... of all NT tile rows: 2 NT independent
+    // fragment loads per K (row g, columns t and 4 + t of tile (I, K), read straight or transposed), reduced over t
+    // by shuffles; the warps' partial row sums meet in shared memory behind the staged state block.  (One warp per
+    // tile ROW made a serial chain of 2 NT dependent FMAs and left six of eight warps idle in the second round:
+    // 5.7 k cycles per matrix-vector product in the r02 phase profile.)
+    double* ppart = S.Yp + (size_t)lch * ks;                 // [NW][kp]
     for (int pass = 0; pass < 2; ++pass) {
       const double* vin = pass ? S.tv : S.gvec;
       double* vout = pass ? wa : S.tv;
-      for (int I = warp; I < nt; I += NW) {
-        NspWalk zw;
-        zw.start(I);
-        double s = 0.0;
-#pragma unroll 1
-        for (int K = 0; K < nt; ++K) {
-          const double z0 = lds_f64(zw.addr(S.zs, K, 0, L)), z1 = lds_f64(zw.addr(S.zs, K, 1, L));
-          const int c = K * 8 + t;
-          s = fma(z0, c < k ? vin[c] : 0.0, s);
-          s = fma(z1, c + 4 < k ? vin[c + 4] : 0.0, s);
-          zw.next(K, nt);
+      double part[NT];
+#pragma unroll
+      for (int I = 0; I < NT; ++I) part[I] = 0.0;
+      for (int K = warp; K < nt; K += NW) {
+        const int c = K * 8 + t;
+        const double v0 = c < k ? vin[c] : 0.0, v1 = c + 4 < k ? vin[c + 4] : 0.0;
+        const unsigned rsK = (unsigned)nsp_row_start(K, nt);
+#pragma unroll
+        for (int I = 0; I < NT; ++I) {
+          // K < I: tile (K, I) transposed, lane part offt (+ 256 for the second k-half); else tile (I, K) straight
+          const bool tr = K < I;
+          const unsigned tile = tr ? (rsK + (unsigned)(I - K)) : ((unsigned)nsp_rs(I, NT) + (unsigned)(K - I));
+          const unsigned a0 = S.zs + (tile << 9) + (tr ? L.offt : L.offd);
+          const double z0 = lds_f64(a0), z1 = lds_f64(a0 + (tr ? 256u : L.dh));
+          part[I] = fma(z0, v0, fma(z1, v1, part[I]));
         }
-        s += __shfl_xor_sync(0xffffffffu, s, 1);
-        s += __shfl_xor_sync(0xffffffffu, s, 2);
-        if (t == 0 && I * 8 + g < k) vout[I * 8 + g] = s;
+      }
+#pragma unroll
+      for (int I = 0; I < NT; ++I) {
+        double sI = part[I];
+        sI += __shfl_xor_sync(0xffffffffu, sI, 1);
+        sI += __shfl_xor_sync(0xffffffffu, sI, 2);
+        if (t == 0) ppart[warp * kp + I * 8 + g] = sI;
+      }
+      __syncthreads();
+      if (tid < k) {
+        double sum = 0.0;
+#pragma unroll
+        for (int w = 0; w < NW; ++w) sum += ppart[w * kp + tid];
+        vout[tid] = sum;
       }
       __syncthreads();
     }

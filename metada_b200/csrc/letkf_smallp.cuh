@@ -18,26 +18,32 @@
 #pragma once
 #include "letkf_kernels.cuh"
 
-#define SP_PMAX 24
-#define SP_PS (SP_PMAX + 1)
+#define SP_PMAX 24    // first choice: 11 KB of shared memory per warp
+#define SP_PMAX2 32   // second pass over the transforms with 24 < p <= 32 (one lane per row still): 19 KB per warp
 #define SP_WARPS 8
+// warps per CTA of the per-level passes: as many resident warps as shared memory allows (the code is latency bound,
+// a serial Jacobi per warp) -- 2 CTAs x 10 warps per SM at SP_PMAX (round 1: 2 x 8), 1 x 11 at SP_PMAX2
+#define SP_WARPS_P1 10
+#define SP_WARPS_P2 11
 #define SP_MAXR 4     // k <= 128: members per lane
 
-struct SpWarpSmem {
-  double S[SP_PMAX][SP_PS];
-  double V[SP_PMAX][SP_PS];
-  double wgt[SP_PMAX], dw[SP_PMAX], u[SP_PMAX], phi[SP_PMAX], q[SP_PMAX], r[SP_PMAX];
-  double pc[SP_PMAX / 2], ps[SP_PMAX / 2];     // rotations of one Jacobi round
-  int pa[SP_PMAX / 2], pb[SP_PMAX / 2];
-  int row[SP_PMAX];
+template <int PMAX>
+struct SpWarpSmemT {
+  double S[PMAX][PMAX + 1];
+  double V[PMAX][PMAX + 1];
+  double wgt[PMAX], dw[PMAX], u[PMAX], phi[PMAX], q[PMAX], r[PMAX];
+  double pc[PMAX / 2], ps[PMAX / 2];     // rotations of one Jacobi round
+  int pa[PMAX / 2], pb[PMAX / 2];
+  int row[PMAX];
   int pad[8];
 };
+using SpWarpSmem = SpWarpSmemT<SP_PMAX>;
 
 // One transform (col, lt) by the calling warp.  Returns 0: done in observation space (sweeps_out =
 // Jacobi sweeps), 1: no observation in reach, perturbations inflated, 2: too many local observations
 // for this route (nothing written).  p_out = number of local observations.
-template <bool EXT>
-__device__ __forceinline__ int sp_transform(const ColParams& P, SpWarpSmem& W, long long col, int lt, int lane,
+template <bool EXT, int PMAX = SP_PMAX>
+__device__ __forceinline__ int sp_transform(const ColParams& P, SpWarpSmemT<PMAX>& W, long long col, int lt, int lane,
                                             int& p_out, int& sweeps_out) {
   const int k = P.k, nz = P.nz, nr = (k + 31) >> 5;
   const bool per_level = P.radius_v > 0.0;
@@ -84,9 +90,9 @@ __device__ __forceinline__ int sp_transform(const ColParams& P, SpWarpSmem& W, l
       }
       const unsigned bal = __ballot_sync(0xffffffffu, sel);
       const int pos = p + __popc(bal & ((1u << lane) - 1u));
-      if (sel && pos < SP_PMAX) { W.row[pos] = orow; W.wgt[pos] = sq; W.dw[pos] = sd; }
+      if (sel && pos < PMAX) { W.row[pos] = orow; W.wgt[pos] = sq; W.dw[pos] = sd; }
       p += __popc(bal);
-      if (p > SP_PMAX) overflow = true;
+      if (p > PMAX) overflow = true;
     }
   }
   __syncwarp();
@@ -275,17 +281,17 @@ __device__ __forceinline__ int sp_transform(const ColParams& P, SpWarpSmem& W, l
 }
 
 // Consumer of the packed kernel's list of small transforms (non-per-level analyses).
-template <bool EXT>
-__global__ void __launch_bounds__(SP_WARPS * 32) letkf_smallp_kernel(ColParams P) {
+template <bool EXT, int PMAX = SP_PMAX, int WARPS = SP_WARPS>
+__global__ void __launch_bounds__(WARPS * 32) letkf_smallp_kernel(ColParams P) {
   extern __shared__ __align__(16) unsigned char sp_smem_raw[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  SpWarpSmem& W = reinterpret_cast<SpWarpSmem*>(sp_smem_raw)[warp];
+  SpWarpSmemT<PMAX>& W = reinterpret_cast<SpWarpSmemT<PMAX>*>(sp_smem_raw)[warp];
   const int nxf = P.radius_v > 0.0 ? P.nz : 1;
   const long long nitems = (long long)*P.small_count;
-  for (long long it = (long long)blockIdx.x * SP_WARPS + warp; it < nitems; it += (long long)gridDim.x * SP_WARPS) {
+  for (long long it = (long long)blockIdx.x * WARPS + warp; it < nitems; it += (long long)gridDim.x * WARPS) {
     const long long item = P.small_items[it], col = item / nxf;
     int p = 0, sweeps = 0;
-    const int rc = sp_transform<EXT>(P, W, col, (int)(item - col * nxf), lane, p, sweeps);
+    const int rc = sp_transform<EXT, PMAX>(P, W, col, (int)(item - col * nxf), lane, p, sweeps);
     if (lane == 0) {
       if (rc == 2) atomicAdd((unsigned long long*)&P.stats[4], 1ull);   // cannot happen: the producer counted p
       atomicAdd((unsigned long long*)&P.stats[2], (unsigned long long)sweeps);
@@ -296,16 +302,20 @@ __global__ void __launch_bounds__(SP_WARPS * 32) letkf_smallp_kernel(ColParams P
 }
 
 // Per-level analyses: FIRST pass over every (column, level) transform, one warp per transform.  Transforms
-// with no or few local observations are finished here; the others go to the work list of the packed
-// k-space kernel, which then never spends a 512-thread selection on a transform it will not do.
-__global__ void __launch_bounds__(SP_WARPS * 32) letkf_smallp_classify_kernel(ColParams P) {
+// with no or few local observations are finished here; those with SP_PMAX < p <= SP_PMAX2 (and 2 p <= k) go to a
+// second list, which letkf_smallp_kernel<false, SP_PMAX2, ..> finishes in observation space too (P.small_items);
+// the others go to the work list of the packed k-space kernel, which then never spends a 512-thread selection
+// on a transform it will not do.  (BASELINE C4, r_v = 5: mean p ~ 18 at interior levels; 94 % of the transforms
+// have p <= 24, 99.9 % p <= 32, and a k-space transform at k = 128 costs ~130 us of a whole SM.)
+template <int WARPS>
+__global__ void __launch_bounds__(WARPS * 32) letkf_smallp_classify_kernel(ColParams P) {
   extern __shared__ __align__(16) unsigned char sp_smem_raw[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   SpWarpSmem& W = reinterpret_cast<SpWarpSmem*>(sp_smem_raw)[warp];
   const int nxf = P.radius_v > 0.0 ? P.nz : 1;
   const long long ncols = P.cols ? P.ncols : (long long)P.own_nx * P.own_ny;
   // one warp per TRANSFORM (consecutive warps take the levels of one column: their index reads share L1)
-  for (long long ti = (long long)blockIdx.x * SP_WARPS + warp; ti < ncols * nxf; ti += (long long)gridDim.x * SP_WARPS) {
+  for (long long ti = (long long)blockIdx.x * WARPS + warp; ti < ncols * nxf; ti += (long long)gridDim.x * WARPS) {
     const long long ci = ti / nxf;
     const int lt = (int)(ti - ci * nxf);
     long long col;
@@ -315,8 +325,13 @@ __global__ void __launch_bounds__(SP_WARPS * 32) letkf_smallp_classify_kernel(Co
     const int rc = sp_transform<false>(P, W, col, lt, lane, p, sweeps);
     if (lane == 0) {
       if (rc == 2) {
-        const unsigned slot = atomicAdd(P.work_count, 1u);
-        P.work_items[slot] = col * nxf + lt;
+        if (P.small_items && p <= SP_PMAX2 && 2 * p <= P.k) {
+          const unsigned slot = atomicAdd(P.small_count, 1u);
+          P.small_items[slot] = col * nxf + lt;
+        } else {
+          const unsigned slot = atomicAdd(P.work_count, 1u);
+          P.work_items[slot] = col * nxf + lt;
+        }
       }
       if (rc == 0) {
         atomicAdd((unsigned long long*)&P.stats[7], 1ull);
@@ -333,4 +348,6 @@ __global__ void __launch_bounds__(SP_WARPS * 32) letkf_smallp_classify_kernel(Co
   }
 }
 
-static size_t smallp_smem_bytes() { return sizeof(SpWarpSmem) * SP_WARPS; }
+static size_t smallp_smem_bytes(int pmax = SP_PMAX, int warps = SP_WARPS) {
+  return (pmax == SP_PMAX2 ? sizeof(SpWarpSmemT<SP_PMAX2>) : sizeof(SpWarpSmem)) * (size_t)warps;
+}

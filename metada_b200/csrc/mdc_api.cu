@@ -1056,12 +1056,12 @@ static int letkf_launch(mdc_ens* e, mdc_obs* o, const mdc_letkf_params* p, const
     cp.redo_count = reinterpret_cast<unsigned*>(ctx->d_flags + 12);
     MDC_CUDA(ctx, cudaMemsetAsync(ctx->d_flags + 12, 0, 3 * sizeof(unsigned), ctx->stream));
     const bool smallp = !getenv("MDC_LETKF_NO_SMALLP");
-    const size_t smems = smallp_smem_bytes();
-    auto launch_smallp = [&](auto kern, const ColParams& cq) -> int {
+    auto launch_smallp = [&](auto kern, const ColParams& cq, int pmax = SP_PMAX, int warps = SP_WARPS) -> int {
+      const size_t smems = smallp_smem_bytes(pmax, warps);
       MDC_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smems));
       int occ = 1;
-      MDC_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, SP_WARPS * 32, smems));
-      kern<<<sms * std::max(1, occ), SP_WARPS * 32, smems, ctx->stream>>>(cq);
+      MDC_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, warps * 32, smems));
+      kern<<<sms * std::max(1, occ), warps * 32, smems, ctx->stream>>>(cq);
       MDC_LAUNCH_CHECK(ctx);
       return MDC_OK;
     };
@@ -1072,7 +1072,12 @@ static int letkf_launch(mdc_ens* e, mdc_obs* o, const mdc_letkf_params* p, const
     if (classify) {
       cp.work_items = ctx->redo_items + 2 * ctx->redo_cap;
       cp.work_count = reinterpret_cast<unsigned*>(ctx->d_flags + 14);
-      if (int rc = launch_smallp(letkf_smallp_classify_kernel, cp)) return rc;
+      // first pass (p <= 24), then the transforms with 24 < p <= 32 from its second list: both in observation space
+      ColParams cc = cp;
+      cc.small_items = ctx->redo_items + ctx->redo_cap;
+      cc.small_count = reinterpret_cast<unsigned*>(ctx->d_flags + 13);
+      if (int rc = launch_smallp(letkf_smallp_classify_kernel<SP_WARPS_P1>, cc, SP_PMAX, SP_WARPS_P1)) return rc;
+      if (int rc = launch_smallp(letkf_smallp_kernel<false, SP_PMAX2, SP_WARPS_P2>, cc, SP_PMAX2, SP_WARPS_P2)) return rc;
       cp.work_consume = 1;
     } else if (smallp) {
       cp.small_items = ctx->redo_items + ctx->redo_cap;

@@ -730,11 +730,11 @@ __global__ void obs_unpack_rows_ext_kernel(int64_t n, int k, const double* rows,
 static int obs_reserve_ext(mdc_obs* o, int64_t cap) {
   mdc_ctx* ctx = o->ctx;
   const size_t P = (size_t)o->P;
-  auto grow = [&](auto** arr, size_t ncap) -> int {
+  auto grow = [&](auto** arr, size_t ncap, bool preserve = true) -> int {
     using T = std::remove_pointer_t<std::remove_pointer_t<decltype(arr)>>;
     T* n = nullptr;
     if (int rc = dev_alloc<T>(ctx, &n, ncap)) return rc;
-    if (*arr && P) MDC_CUDA(ctx, cudaMemcpyAsync(n, *arr, P * sizeof(T), cudaMemcpyDeviceToDevice, ctx->stream));
+    if (preserve && *arr && P) MDC_CUDA(ctx, cudaMemcpyAsync(n, *arr, P * sizeof(T), cudaMemcpyDeviceToDevice, ctx->stream));
     MDC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     cudaFree(*arr);
     *arr = n;
@@ -742,7 +742,8 @@ static int obs_reserve_ext(mdc_obs* o, int64_t cap) {
   };
   if (o->geo && (size_t)cap > o->geo_cap) {
     const size_t ncap = std::max((size_t)cap, o->geo_cap + o->geo_cap / 2);
-    if (grow(&o->lat, ncap) || grow(&o->lon, ncap) || grow(&o->lev, ncap) || grow(&o->qx, ncap) || grow(&o->qy, ncap)) return MDC_ERR_CUDA;
+    // (the lattice coordinates qx, qy are rewritten by every index build: nothing to keep)
+    if (grow(&o->lat, ncap) || grow(&o->lon, ncap) || grow(&o->lev, ncap) || grow(&o->qx, ncap, false) || grow(&o->qy, ncap, false)) return MDC_ERR_CUDA;
     o->geo_cap = ncap;
   }
   if (o->var && (size_t)cap > o->var_cap) {

@@ -30,7 +30,11 @@
 // -DNSP_PROFILE: thread 0 of every CTA adds the clock64() ticks it spends per phase to stats[8..15]
 // (8 selection, 9 gather + SYRK, 10 norm / A store / start look-up, 11 products, 12 iteration epilogues,
 // 13 w = Z Z g, 14 update, 15 whole column); read with mdc_ctx_last_stats.  Development only.
-#ifdef NSP_PROFILE
+#if defined(NSP_PROFILE) && defined(NSP_PROFILE_WARPS)
+#define NSP_T0() do {} while (0)
+#define NSP_TICK(slot) do {} while (0)
+__device__ long long* nsp_prof_;
+#elif defined(NSP_PROFILE)
 #define NSP_T0() long long nsp_t_ = clock64()
 #define NSP_TICK(slot) do { const long long n_ = clock64(); if (threadIdx.x == 0) atomicAdd((unsigned long long*)&nsp_prof_[slot], (unsigned long long)(n_ - nsp_t_)); nsp_t_ = n_; } while (0)
 __device__ long long* nsp_prof_;
@@ -77,7 +81,7 @@ __host__ __device__ inline int nsp_region_doubles(int k, int lch) {
   int r = 3 * m;
   const int gch = (kp >> 3) <= 5 ? 112 : 128;                  // NSP_GCH_OF
   if (gch * ks > r) r = gch * ks;
-  if (m + lch * ks + 16 * kp > r) r = m + lch * ks + 16 * kp;   // Z | staged levels | partial sums of w = Z (Z g)
+  if (m + lch * ks > r) r = m + lch * ks;
   return r;
 }
 __device__ __forceinline__ int nsp_row_start(int I, int nt) { return (I * (2 * nt - I + 1)) >> 1; }
@@ -311,6 +315,12 @@ __device__ __forceinline__ double nsp_frag_v(unsigned d, unsigned tr) {
   else return nsp_lds_v<(nsp_rs(K, NT) + I - K) * 512>(tr);
 }
 
+// B fragments are requested NSP_BAHEAD MMAs ahead of their use (ring of NSP_BAHEAD + 1 registers)
+// (A/B on one box, r02: 2 ahead 25.25 ms, 3 ahead 25.12, 4 / 5 ahead 25.45 on the C5 probe)
+#ifndef NSP_BAHEAD
+#define NSP_BAHEAD 3
+#endif
+#define NSP_BRING (NSP_BAHEAD + 1)
 template <int NT, int NW, int NTW, int W>
 __device__ __forceinline__ void nsp_mm_warp(unsigned pbase, unsigned qbase, const NspLane& L, double (&acc)[NTW][2]) {
   constexpr int E = NT * (NT + 1) / 2, e0 = (E * W) / NW, e1 = (E * (W + 1)) / NW, N = e1 - e0;
@@ -321,21 +331,23 @@ __device__ __forceinline__ void nsp_mm_warp(unsigned pbase, unsigned qbase, cons
     for (int h = 0; h < 2; ++h) {
       const unsigned pd = pbase + L.offd + (h ? L.dh : 0u), pt = pbase + L.offt + ((unsigned)h << 8);
       const unsigned qd = qbase + L.offd + (h ? L.dh : 0u), qt = qbase + L.offt + ((unsigned)h << 8);
-      double ar[2][NR], br[3];
+      double ar[2][NR], br[NSP_BRING];
       nsp_static_for<0, NR>([&](auto r_c) {
         constexpr int r = decltype(r_c)::value;
         ar[0][r] = nsp_frag_v<NT, R0 + r, 0>(pd, pt);
       });
-      br[0] = nsp_frag_v<NT, nsp_tile_j(NT, e0), 0>(qd, qt);
-      if constexpr (TOT > 1) br[1] = nsp_frag_v<NT, nsp_tile_j(NT, e0 + 1 % N), (1 / N)>(qd, qt);
+      nsp_static_for<0, NSP_BAHEAD>([&](auto j_c) {
+        constexpr int j = decltype(j_c)::value;
+        if constexpr (j < TOT) br[j] = nsp_frag_v<NT, nsp_tile_j(NT, e0 + j % N), j / N>(qd, qt);
+      });
       nsp_static_for<0, TOT>([&](auto i_c) {
         constexpr int idx = decltype(i_c)::value, K = idx / N, n = idx % N;
-        if constexpr (idx + 2 < TOT) {
-          constexpr int K2 = (idx + 2) / N, n2 = (idx + 2) % N;
-          br[(idx + 2) % 3] = nsp_frag_v<NT, nsp_tile_j(NT, e0 + n2), K2>(qd, qt);
+        if constexpr (idx + NSP_BAHEAD < TOT) {
+          constexpr int K2 = (idx + NSP_BAHEAD) / N, n2 = (idx + NSP_BAHEAD) % N;
+          br[(idx + NSP_BAHEAD) % NSP_BRING] = nsp_frag_v<NT, nsp_tile_j(NT, e0 + n2), K2>(qd, qt);
         }
         if constexpr (K + 1 < NT && n < NR) ar[(K + 1) & 1][n] = nsp_frag_v<NT, R0 + n, K + 1>(pd, pt);
-        NSP_DMMA(acc[n], ar[K & 1][nsp_tile_i(NT, e0 + n) - R0], br[idx % 3]);
+        NSP_DMMA(acc[n], ar[K & 1][nsp_tile_i(NT, e0 + n) - R0], br[idx % NSP_BRING]);
       });
     }
   }
@@ -509,7 +521,13 @@ __device__ NSP_ISQ_INLINE int nsp_inverse_sqrt(double* Zp, double* red, double* 
     const unsigned pb = (op == OP_A2 || op == OP_Y0 || op == OP_T2) ? ts : (op == OP_M0 || op == OP_ZT) ? zs : ys;
     const unsigned qb = (op == OP_Y0) ? zs : (op == OP_M0 || op == OP_E2) ? ys : ts;
     NSP_TICK(NSP_SLOT_IT(12));
+#ifdef NSP_PROFILE_WARPS   /* development: stats[8 + warp] = cycles warp `warp` spends inside the products (warps 0..7) */
+    const long long pw_t0_ = clock64();
+#endif
     nsp_mm_any<NT, NW, NTW>(pb, qb, warp, L, acc);
+#ifdef NSP_PROFILE_WARPS
+    if (lane == 0 && warp < 8) atomicAdd((unsigned long long*)&nsp_prof_[8 + warp], (unsigned long long)(clock64() - pw_t0_));
+#endif
     NSP_TICK(NSP_SLOT_IT(11));
     ++nprod;
     if (op == OP_A2) {
@@ -1015,45 +1033,29 @@ __device__ __noinline__ void nsp_phase_update(const ColParams& P, int lch, long 
   };
   request_x(lev_b, min(lch, lev_e - lev_b));
   if (npl > 0) {
-    // w = Z (Z g).  Every warp takes the tile COLUMNS K = warp, warp + NW, ... of all NT tile rows: 2 NT independent
-    // fragment loads per K (row g, columns t and 4 + t of tile (I, K), read straight or transposed), reduced over t
-    // by shuffles; the warps' partial row sums meet in shared memory behind the staged state block.  (One warp per
-    // tile ROW made a serial chain of 2 NT dependent FMAs and left six of eight warps idle in the second round:
-    // 5.7 k cycles per matrix-vector product in the r02 phase profile.)
-    double* ppart = S.Yp + (size_t)lch * ks;                 // [NW][kp]
+    // w = Z (Z g): warp per tile row, lanes read Z in the fragment pattern (row g, columns t, 4 + t of every tile)
+    // and reduce over t.  (A version with every warp on independent loads -- tile COLUMNS per warp, partial row
+    // sums through shared memory, < 1 k instead of 5.7 k cycles per product -- measured 1 % SLOWER end to end:
+    // the phase is hidden behind the other CTA's products either way, and the wider version takes more issue
+    // slots and barriers away from them.  A/B on one box, gpurun_out/ab_w.txt, r02.)
     for (int pass = 0; pass < 2; ++pass) {
       const double* vin = pass ? S.tv : S.gvec;
       double* vout = pass ? wa : S.tv;
-      double part[NT];
-#pragma unroll
-      for (int I = 0; I < NT; ++I) part[I] = 0.0;
-      for (int K = warp; K < nt; K += NW) {
-        const int c = K * 8 + t;
-        const double v0 = c < k ? vin[c] : 0.0, v1 = c + 4 < k ? vin[c + 4] : 0.0;
-        const unsigned rsK = (unsigned)nsp_row_start(K, nt);
-#pragma unroll
-        for (int I = 0; I < NT; ++I) {
-          // K < I: tile (K, I) transposed, lane part offt (+ 256 for the second k-half); else tile (I, K) straight
-          const bool tr = K < I;
-          const unsigned tile = tr ? (rsK + (unsigned)(I - K)) : ((unsigned)nsp_rs(I, NT) + (unsigned)(K - I));
-          const unsigned a0 = S.zs + (tile << 9) + (tr ? L.offt : L.offd);
-          const double z0 = lds_f64(a0), z1 = lds_f64(a0 + (tr ? 256u : L.dh));
-          part[I] = fma(z0, v0, fma(z1, v1, part[I]));
+      for (int I = warp; I < nt; I += NW) {
+        NspWalk zw;
+        zw.start(I);
+        double s = 0.0;
+#pragma unroll 1
+        for (int K = 0; K < nt; ++K) {
+          const double z0 = lds_f64(zw.addr(S.zs, K, 0, L)), z1 = lds_f64(zw.addr(S.zs, K, 1, L));
+          const int c = K * 8 + t;
+          s = fma(z0, c < k ? vin[c] : 0.0, s);
+          s = fma(z1, c + 4 < k ? vin[c + 4] : 0.0, s);
+          zw.next(K, nt);
         }
-      }
-#pragma unroll
-      for (int I = 0; I < NT; ++I) {
-        double sI = part[I];
-        sI += __shfl_xor_sync(0xffffffffu, sI, 1);
-        sI += __shfl_xor_sync(0xffffffffu, sI, 2);
-        if (t == 0) ppart[warp * kp + I * 8 + g] = sI;
-      }
-      __syncthreads();
-      if (tid < k) {
-        double sum = 0.0;
-#pragma unroll
-        for (int w = 0; w < NW; ++w) sum += ppart[w * kp + tid];
-        vout[tid] = sum;
+        s += __shfl_xor_sync(0xffffffffu, s, 1);
+        s += __shfl_xor_sync(0xffffffffu, s, 2);
+        if (t == 0 && I * 8 + g < k) vout[I * 8 + g] = s;
       }
       __syncthreads();
     }
@@ -1267,7 +1269,7 @@ __global__ void __launch_bounds__(NTH, MINB) letkf_nsp_kernel(const __grid_const
       } else {
         nsp_phase_update<NT, NTH>(P, lch, col, lt, npl);
       }
-#ifdef NSP_PROFILE
+#if defined(NSP_PROFILE) && !defined(NSP_PROFILE_WARPS)
       if (threadIdx.x == 0) atomicAdd((unsigned long long*)&P.stats[15], (unsigned long long)(clock64() - nsp_col_t0));
 #endif
     }  // lt

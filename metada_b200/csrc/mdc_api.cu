@@ -475,11 +475,12 @@ static int obs_reserve(mdc_obs* o, int64_t cap, int k) {
   const size_t P = (size_t)o->P;
   if (mv(&n.x, o->x, ncap, P) || mv(&n.y, o->y, ncap, P) || mv(&n.z, o->z, ncap, P) ||
       mv(&n.gid, o->gid, ncap, P) || mv(&n.val, o->val, ncap, P) || mv(&n.err, o->err, ncap, P) ||
-      mv(&n.valid, o->valid, ncap, P) || mv(&n.ybar, o->ybar, ncap, o->have_hx ? P : 0) || mv(&n.d, o->d, ncap, o->have_hx ? P : 0))
+      mv(&n.valid, o->valid, ncap, P) || mv(&n.ybar, o->ybar, ncap, o->have_hx ? (size_t)o->P_own : 0) || mv(&n.d, o->d, ncap, o->have_hx ? P : 0))
     return MDC_ERR_CUDA;
   const size_t kold = (o->k == nk && o->have_hx) ? P * (size_t)nk : 0;   // H(x) results exist only after mdc_hx_idw4
+  const size_t kown = (o->k == nk && o->have_hx) ? (size_t)o->P_own * (size_t)nk : 0;   // Y, ybar: own rows only (halo rows carry Y')
   if (nk > 0) {
-    if (mv(&n.Y, o->Y, (size_t)ncap * nk, kold) || mv(&n.Yp, o->Yp, (size_t)ncap * nk, kold)) return MDC_ERR_CUDA;
+    if (mv(&n.Y, o->Y, (size_t)ncap * nk, kown) || mv(&n.Yp, o->Yp, (size_t)ncap * nk, kold)) return MDC_ERR_CUDA;
   } else {
     n.Y = nullptr; n.Yp = nullptr;
   }

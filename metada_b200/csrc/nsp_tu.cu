@@ -26,6 +26,9 @@ int launchp(K kern, int nth, const ColParams& cp, int lch, int sms, long long to
   return MDC_OK;
 }
 
+#ifndef NSP_DEV_NTH10   /* development: threads per CTA for 41 <= k <= 80 */
+#define NSP_DEV_NTH10 256
+#endif
 template <int NT>
 int launch_nt(const ColParams& cp, int lch, int sms, int ext, int work, long long total_cols, mdc_ctx* ctx) {
   // k <= 80: 8 warps, two columns per SM (nt = 10 with 384 threads measured 6 % slower); above: 16 warps, one per SM
@@ -34,7 +37,7 @@ int launch_nt(const ColParams& cp, int lch, int sms, int ext, int work, long lon
 #else
   // k <= 40: 4 warps, four columns per SM (products of 15 tiles: the fixed cost per product dominates, more CTAs
   // interleave); k <= 80: 8 warps, two per SM (nt = 10 with 384 threads measured 6 % slower); above: 16 warps, one
-  constexpr int NTH = NT <= 5 ? 128 : NT <= 10 ? 256 : 512, MINB = NT <= 5 ? 4 : NT <= 10 ? 2 : 1;
+  constexpr int NTH = NT <= 5 ? 128 : NT <= 10 ? NSP_DEV_NTH10 : 512, MINB = NT <= 5 ? 4 : NT <= 10 ? 2 : 1;
 #endif
   if (ext) return launchp(letkf_nsp_kernel<NT, NTH, MINB, false, true>, NTH, cp, lch, sms, total_cols, ctx);
   if (work) return launchp(letkf_nsp_kernel<NT, NTH, MINB, true>, NTH, cp, lch, sms, total_cols, ctx);

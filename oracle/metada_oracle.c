@@ -74,6 +74,14 @@ double orc_distance_geo(double lat1, double lon1, double lat2, double lon2) {
   return 6371.0 * c;
 }
 
+/* Location::distance_to, CARTESIAN (Location.hpp:217-225): 3-D Euclid, sum in the order dx^2 + dy^2 + dz^2.
+ * Restated and pinned for completeness of distance_to; no filter can reach it in the reference -- H throws for a
+ * CARTESIAN observation (IdentityObsOperator.hpp:251-255 -> Location.hpp:100-103) -- so there is no device path. */
+double orc_distance_cartesian(double x1, double y1, double z1, double x2, double y2, double z2) {
+  double dx = x1 - x2, dy = y1 - y2, dz = z1 - z2;
+  return sqrt(dx * dx + dy * dy + dz * dz);
+}
+
 /* LETKF.hpp:159-165 with GEOGRAPHIC locations: ascending obs index, inclusive <= (kilometres) */
 int64_t orc_select_local_geo(double clat, double clon, int64_t P, const double* olat, const double* olon,
                              double radius, int32_t* idx_out, double* min_margin) {

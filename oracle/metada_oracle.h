@@ -99,6 +99,7 @@ int orc_letkf(const orc_letkf_params* p, double* X, const int32_t* ox, const int
 
 /* Location::distance_to for two GEOGRAPHIC locations: haversine kilometres, R = 6371 km
  * (Location.hpp:213-217, 325, 333, 349-357). */
+double orc_distance_cartesian(double x1, double y1, double z1, double x2, double y2, double z2);
 double orc_distance_geo(double lat1, double lon1, double lat2, double lon2);
 
 /* LETKF.hpp:159-165 with GEOGRAPHIC locations.  min_margin (optional, in/out): smallest |distance - radius|

@@ -66,6 +66,8 @@ def lib() -> C.CDLL:
         _lib.orc_max_threads.restype = C.c_int
         _lib.orc_distance_geo.restype = C.c_double
         _lib.orc_distance_geo.argtypes = [C.c_double] * 4
+        _lib.orc_distance_cartesian.restype = C.c_double
+        _lib.orc_distance_cartesian.argtypes = [C.c_double] * 6
         _lib.orc_select_local_geo.restype = C.c_int64
     return _lib
 
@@ -184,6 +186,11 @@ class Ext(C.Structure):
                 ("olat", C.POINTER(C.c_double)), ("olon", C.POINTER(C.c_double)),
                 ("nvar", C.c_int), ("var_nlev", C.POINTER(C.c_int32)), ("ovar", C.POINTER(C.c_int32)),
                 ("Xobs", C.POINTER(C.c_double)), ("nx_obs", C.c_int), ("ny_obs", C.c_int), ("nz_obs", C.c_int)]
+
+
+def distance_cartesian(x1, y1, z1, x2, y2, z2) -> float:
+    """Location::distance_to, CARTESIAN (3-D Euclid)."""
+    return lib().orc_distance_cartesian(float(x1), float(y1), float(z1), float(x2), float(y2), float(z2))
 
 
 def distance_geo(lat1, lon1, lat2, lon2) -> float:

@@ -165,7 +165,18 @@ def location_case(tmp):
         f.write(struct.pack("<q", n))
         f.write(np.ascontiguousarray(a).tobytes())
     subprocess.check_call([os.path.join(ROOT, "oracle", "_ref", "ref_location"), inp, out])
-    return {"pairs": a, "km": np.frombuffer(open(out, "rb").read(), dtype="<f8").copy()}
+    # CARTESIAN pairs (Location.hpp:217-225): mixed magnitudes, identical points, one coordinate differing
+    m = 1000
+    c = rng.uniform(-1.0, 1.0, (m, 6)) * 10.0 ** rng.integers(-3, 7, (m, 1))
+    c[800:850, 3:] = c[800:850, :3]
+    c[850:900, 3:5] = c[850:900, 0:2]
+    cin, cout = os.path.join(tmp, "c_in.bin"), os.path.join(tmp, "c_out.bin")
+    with open(cin, "wb") as f:
+        f.write(struct.pack("<q", m))
+        f.write(np.ascontiguousarray(c).tobytes())
+    subprocess.check_call([os.path.join(ROOT, "oracle", "_ref", "ref_location"), cin, cout, "cartesian"])
+    return {"pairs": a, "km": np.frombuffer(open(out, "rb").read(), dtype="<f8").copy(),
+            "cart_pairs": c, "cart_dist": np.frombuffer(open(cout, "rb").read(), dtype="<f8").copy()}
 
 
 def obsop_geo_case(tmp, var_nlev=(5, 5, 1)):

@@ -29,6 +29,17 @@ def test_haversine_matches_reference_location_header_bit_exactly():
     assert orc.distance_geo(10.0, 179.5, 10.0, -179.5) < 120.0   # across the dateline
 
 
+def test_cartesian_distance_matches_reference_location_header_bit_exactly():
+    """Location::distance_to for CARTESIAN locations (Location.hpp:217-225), the third coordinate system: restated and
+    pinned to the reference's own header.  (No filter reaches it in the reference -- H throws for a CARTESIAN
+    observation, IdentityObsOperator.hpp:251-255 -> Location.hpp:100-103 -- hence no device path)"""
+    g = np.load(os.path.join(G, "location_geographic.npz"))
+    got = np.array([orc.distance_cartesian(*r) for r in g["cart_pairs"]])
+    assert np.array_equal(got, g["cart_dist"])
+    assert (g["cart_dist"][800:850] == 0.0).all() and (g["cart_dist"][850:900] > 0.0).all()
+    assert orc.distance_cartesian(1.0, 2.0, 3.0, 4.0, 6.0, 15.0) == 13.0
+
+
 @pytest.mark.parametrize("fname", ["obsop_geographic.npz", "obsop_geographic_wstag.npz"])
 def test_locate_and_variable_h_match_reference_obs_operator_bit_exactly(fname):
     """IdentityObsOperator::apply on GEOGRAPHIC observations of a [5, 5, 1]-level three-variable state: nearest grid

@@ -116,21 +116,54 @@ __device__ __forceinline__ int sp_transform(const ColParams& P, SpWarpSmemT<PMAX
   }
   if (overflow || 2 * p > k) return 2;    // not for this kernel
 
-  // ---- S = M M^T (upper triangle, mirrored), rows re-read from L1/L2
-  for (int a = 0; a < p; ++a) {
-    const double* ya = P.Yp + (long long)W.row[a] * k;
-    double va[SP_MAXR];
+  // ---- S = M M^T on the FP64 tensor path.  Lane (g, t) of a k-step reads element [8 I + g][4 kk + t] of the NRT row
+  // tiles straight from global memory (32 contiguous bytes per row: whole sectors): that one register is the A
+  // fragment of tile row I and, S being M times ITS OWN transpose, the B fragment of tile column I as well, so a
+  // k-step is NRT independent loads and NRT (NRT + 1) / 2 MMAs.  (Round 1 formed the p (p + 1) / 2 entries one at
+  // a time -- four loads from L2, a warp reduction and a store each, ~1 k cycles per entry in a serial chain: for
+  // p = 18 as long as the whole Jacobi.)  Row weights are applied to the finished entries.
+  {
+    constexpr int NRT = PMAX / 8;
+    const int g = lane >> 2, t = lane & 3;
+    double sacc[NRT][NRT][2];
+    const double* rowp[NRT];
+    bool rowok[NRT];
 #pragma unroll
-    for (int r = 0; r < SP_MAXR; ++r) va[r] = (r < nr && lane + 32 * r < k) ? ya[lane + 32 * r] : 0.0;
-    for (int b = a; b < p; ++b) {
-      const double* yb = P.Yp + (long long)W.row[b] * k;
-      double acc = 0.0;
+    for (int I = 0; I < NRT; ++I) {
+      rowok[I] = 8 * I + g < p;
+      rowp[I] = P.Yp + (long long)W.row[rowok[I] ? 8 * I + g : 0] * k + t;
 #pragma unroll
-      for (int r = 0; r < SP_MAXR; ++r)
-        if (r < nr && lane + 32 * r < k) acc = fma(va[r], yb[lane + 32 * r], acc);
-      acc = warp_sum(acc);
-      if (lane == 0) { const double v = acc * W.wgt[a] * W.wgt[b]; W.S[a][b] = v; W.S[b][a] = v; }
+      for (int J = 0; J < NRT; ++J) { sacc[I][J][0] = 0.0; sacc[I][J][1] = 0.0; }
     }
+    const int nrt = (p + 7) >> 3;
+#pragma unroll 4
+    for (int kk = 0; kk < k; kk += 4) {
+      double f[NRT];
+#pragma unroll
+      for (int I = 0; I < NRT; ++I) f[I] = (I < nrt && rowok[I] && kk + t < k) ? rowp[I][kk] : 0.0;
+#pragma unroll
+      for (int I = 0; I < NRT; ++I)
+#pragma unroll
+        for (int J = I; J < NRT; ++J)
+          if (J < nrt)
+            asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                         : "+d"(sacc[I][J][0]), "+d"(sacc[I][J][1]) : "d"(f[I]), "d"(f[J]));
+    }
+#pragma unroll
+    for (int I = 0; I < NRT; ++I)
+#pragma unroll
+      for (int J = I; J < NRT; ++J) {
+        const int a = 8 * I + g, b0 = 8 * J + 2 * t;
+        if (J < nrt && a < p) {
+#pragma unroll
+          for (int e = 0; e < 2; ++e)
+            if (b0 + e < p) {
+              const double v = sacc[I][J][e] * W.wgt[a] * W.wgt[b0 + e];
+              W.S[a][b0 + e] = v;
+              if (I != J) W.S[b0 + e][a] = v;          // (a diagonal tile holds both halves itself)
+            }
+        }
+      }
   }
   for (int e = lane; e < p * p; e += 32) W.V[e / p][e % p] = (e / p == e % p) ? 1.0 : 0.0;
   __syncwarp();

@@ -192,38 +192,55 @@ __device__ __forceinline__ int sp_transform(const ColParams& P, SpWarpSmemT<PMAX
         double c = 1.0, sn = 0.0;
         if (b < p) {                                           // (index p is the padding of an odd p)
           const double apq = W.S[a][b];
-          if (fabs(apq) > 1e-300) {
-            const double theta = (W.S[b][b] - W.S[a][a]) / (2.0 * apq);
-            const double t = (theta >= 0.0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
-            c = 1.0 / sqrt(t * t + 1.0); sn = t * c;
+          if (fabs(apq) > 1e-140) {                            // (apq^2 must not underflow)
+            // t = sgn(theta) / (|theta| + sqrt(theta^2 + 1)), theta = al / apq, al = (S_bb - S_aa) / 2, with numerator
+            // and denominator multiplied by |apq|: one reciprocal square root, one division, one reciprocal square
+            // root in the dependent chain (the textbook form has three divisions and two square roots -- this chain,
+            // run by p / 2 lanes, was 30 % of the per-level first pass)
+            const double al = 0.5 * (W.S[b][b] - W.S[a][a]);
+            const double h2 = fma(al, al, apq * apq);
+            const double hyp = h2 * rsqrt(h2);
+            double t = fabs(apq) / (fabs(al) + hyp);
+            if (al != 0.0 && ((al < 0.0) != (apq < 0.0))) t = -t;
+            c = rsqrt(fma(t, t, 1.0)); sn = t * c;
           }
         }
         W.pa[lane] = a; W.pb[lane] = b; W.pc[lane] = c; W.ps[lane] = sn;
       }
       __syncwarp();
-      if (lane < p)                                            // S <- S J, V <- V J: row `lane`
-        for (int l = 0; l < half; ++l) {
-          const double sn = W.ps[l];
-          if (sn != 0.0) {
-            const int a = W.pa[l], b = W.pb[l];
-            const double c = W.pc[l];
-            const double sa = W.S[lane][a], sb = W.S[lane][b];
-            W.S[lane][a] = c * sa - sn * sb; W.S[lane][b] = sn * sa + c * sb;
-            const double v0 = W.V[lane][a], v1 = W.V[lane][b];
-            W.V[lane][a] = c * v0 - sn * v1; W.V[lane][b] = sn * v0 + c * v1;
+      // S <- S J, V <- V J (row `lane`), then S <- J^T S (column `lane`).  The pairs of a round are disjoint, so two
+      // of them are loaded before either is stored: the compiler cannot know that and would chain every pair's
+      // loads behind the previous pair's stores.
+      if (lane < p) {
+        for (int l = 0; l < half; l += 2) {
+          const bool two = l + 1 < half;
+          const double sn0 = W.ps[l], sn1 = two ? W.ps[l + 1] : 0.0;
+          const int a0 = W.pa[l], b0 = W.pb[l], a1 = two ? W.pa[l + 1] : a0, b1 = two ? W.pb[l + 1] : b0;
+          const double c0 = W.pc[l], c1 = two ? W.pc[l + 1] : 1.0;
+          const double sa0 = W.S[lane][a0], sb0 = W.S[lane][b0], va0 = W.V[lane][a0], vb0 = W.V[lane][b0];
+          const double sa1 = W.S[lane][a1], sb1 = W.S[lane][b1], va1 = W.V[lane][a1], vb1 = W.V[lane][b1];
+          if (sn0 != 0.0) {
+            W.S[lane][a0] = c0 * sa0 - sn0 * sb0; W.S[lane][b0] = sn0 * sa0 + c0 * sb0;
+            W.V[lane][a0] = c0 * va0 - sn0 * vb0; W.V[lane][b0] = sn0 * va0 + c0 * vb0;
+          }
+          if (sn1 != 0.0) {
+            W.S[lane][a1] = c1 * sa1 - sn1 * sb1; W.S[lane][b1] = sn1 * sa1 + c1 * sb1;
+            W.V[lane][a1] = c1 * va1 - sn1 * vb1; W.V[lane][b1] = sn1 * va1 + c1 * vb1;
           }
         }
+      }
       __syncwarp();
-      if (lane < p)                                            // S <- J^T S: column `lane`
-        for (int l = 0; l < half; ++l) {
-          const double sn = W.ps[l];
-          if (sn != 0.0) {
-            const int a = W.pa[l], b = W.pb[l];
-            const double c = W.pc[l];
-            const double sa = W.S[a][lane], sb = W.S[b][lane];
-            W.S[a][lane] = c * sa - sn * sb; W.S[b][lane] = sn * sa + c * sb;
-          }
+      if (lane < p) {
+        for (int l = 0; l < half; l += 2) {
+          const bool two = l + 1 < half;
+          const double sn0 = W.ps[l], sn1 = two ? W.ps[l + 1] : 0.0;
+          const int a0 = W.pa[l], b0 = W.pb[l], a1 = two ? W.pa[l + 1] : a0, b1 = two ? W.pb[l + 1] : b0;
+          const double c0 = W.pc[l], c1 = two ? W.pc[l + 1] : 1.0;
+          const double sa0 = W.S[a0][lane], sb0 = W.S[b0][lane], sa1 = W.S[a1][lane], sb1 = W.S[b1][lane];
+          if (sn0 != 0.0) { W.S[a0][lane] = c0 * sa0 - sn0 * sb0; W.S[b0][lane] = sn0 * sa0 + c0 * sb0; }
+          if (sn1 != 0.0) { W.S[a1][lane] = c1 * sa1 - sn1 * sb1; W.S[b1][lane] = sn1 * sa1 + c1 * sb1; }
         }
+      }
       __syncwarp();
     }
   }

@@ -269,9 +269,11 @@ def measure_configs(ctx, mb, capi, syn, fp64_peak):
     letkf_case("C4_horizontal_only", 1000, 1000, 60, 128, 500000, 8.0)
     letkf_case("C5q_sigma_0.01", 256, 256, 60, 80, 29127, 8.0, sigma=0.01,
                note="accurate observations (50x below the ensemble spread): condition bounds ~7e3, 20 products per column; "
-                    "within the packed kernel's limit (2e4) since round 2 -- redo_transforms counts what is not")
+                    "within the packed kernel's limit (1e5) since round 2 -- redo_transforms counts what is not")
     letkf_case("C5q_sigma_0.004", 256, 256, 60, 80, 29127, 8.0, sigma=0.004,
-               note="the conditioning cliff: condition bounds ~4e4 are beyond the packed kernel's limit, every column goes "
+               note="condition bounds ~4e4, 23 products per column + refined mean update: still on the packed kernel")
+    letkf_case("C5q_sigma_0.002", 256, 256, 60, 80, 29127, 8.0, sigma=0.002,
+               note="the conditioning cliff: condition bounds ~1.7e5 are beyond the packed kernel's limit, the columns go "
                     "through its redo list (full-product Newton-Schulz kernel)")
     # C2: global stochastic EnKF, n = 1e5, 40 members, 1e4 distinct observations
     nx, ny, k, P = 400, 250, 40, 10000

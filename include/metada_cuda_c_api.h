@@ -212,8 +212,8 @@ typedef struct {
                          The vertical scale is radius_v * L / radius.                          */
   double kappa_max;   /* NEWTON_SCHULZ: largest rigorous condition bound lambda_max / lambda_min of a transform's
                          k x k matrix the packed symmetric kernel keeps (the others are redone, see above);
-                         <= 0: 2e4 (the analysis agrees with the eigen-decomposition to ~2e-11 there; at 1e5 the mean
-                         update alone is off by ~3e-10), at most 3e5                                           */
+                         <= 0: 1e5 (the analysis agrees with the eigen-decomposition to ~5e-12 there: the mean update of
+                         ill-conditioned transforms is iteratively refined), at most 3e5 (~1e-11)              */
 } mdc_letkf_params;
 
 typedef struct {

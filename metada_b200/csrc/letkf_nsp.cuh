@@ -16,7 +16,7 @@
 // Off-diagonal tiles are stored once (no mirrored store).
 //
 // Forcing symmetry is only stable while cond(A) is moderate (letkf_ns.cuh); a column (or level, with
-// per-level transforms) whose rigorous condition bound exceeds the limit (default 2e4) is appended to a
+// per-level transforms) whose rigorous condition bound exceeds the limit (default 1e5) is appended to a
 // redo list, which a second launch of the full-product kernel (k <= 80) or the Jacobi kernel
 // (k > 80) consumes.
 #pragma once
@@ -449,14 +449,18 @@ __device__ __forceinline__ int nss_start_index(double kappa) {
 // (emulation of these very tile products, tests/ns_emul.py) 5e-15 at cond 50, 3e-14 at 1200, 1.5e-13 at 6e3, 6e-13 at
 // 5e4, <= 8e-12 at 1e5 over k = 24 .. 128 -- and the residual Z A Z - I in long double is within 2x of that of the
 // eigen-decomposition at every one of them (round 1 stopped at 256, round 2's first table at 2000: the accurate-
-// observation cliff of bench.py's sigma = 0.01 variant).  What sets the default limit is the MEAN update:
-// w = Z (Z g) loses cond(A) * err(Z) against the eigen-decomposition's U diag(1 / lambda) U^T g (g lies along the
-// large eigenvalues), measured on the device 7e-11 at cond 4e4 and 2e-10 at 7e4 -- 2e4 keeps a factor 5 - 10 to the
-// 1e-10 parity bound.
-#define NSP_KAPPA_MAX_DEFAULT 2e4
+// observation cliff of bench.py's sigma = 0.01 variant).  The MEAN update w = Z (Z g) alone loses err(Z) sqrt(cond)
+// (2e-10 at cond 7e4) and gets one step of iterative refinement beyond NSP_REFINE_KAPPA (nsp_phase_update); with it
+// the analysis agrees with the oracle's eigen-decomposition to 4e-12 at cond 7e4, 9e-12 at 1.7e5 and 1.1e-11 at the
+// table's end (tools/refine_probe.py on the device, k = 40 ... 128), so the default limit leaves a factor 20.
+#define NSP_KAPPA_MAX_DEFAULT 1e5
 #define NSP_KAPPA_TABLE_MAX 3e5
 #define NSP_SC_DOUBLES 48   /* schedule scratch: 8 steps x {kind, c0..c3}, + the residual bound of the finish */
 #define NSP_SC_KMAX 45      /* slot that carries the condition limit from the Gram phase to the iteration */
+#define NSP_SC_ROUNDS 44    /* selection rounds of the Gram phase (1: sel_row / sel_w still describe every local observation) */
+#define NSP_SC_KAPPA 43     /* the transform's condition bound, from the iteration to the update */
+#define NSP_REFINE_KAPPA 1000.0   /* beyond it the mean update gets one step of iterative refinement */
+#define NSP_RCH 64          /* rows re-gathered per round of the refinement */
 
 // Z <- A^{-1/2} for the A held in the T buffer, by the composite minimax polynomial iteration of
 // tools/gen_ns_schedule.py: state Z and the residual E = I - Z^2 A (in the Y buffer), spectrum(E) in [-rho, rho];
@@ -555,6 +559,7 @@ __device__ NSP_ISQ_INLINE int nsp_inverse_sqrt(double* Zp, double* red, double* 
       const double kappa = (double)(fmaxf(fminf(hi_f, sh_f * 1.000001f + s4) / (sh_f * 0.999999f), 1.0f) * 1.000002f);
       const int si = (kappa <= sc[NSP_SC_KMAX]) ? nss_start_index(kappa) : -1;
       if (si < 0) { rc = -2; break; }
+      if (tid == 0) sc[NSP_SC_KAPPA] = kappa;
       const int sdeg = nss_starts[si].degree;
       // the column's steps -> shared memory: thread e copies {kind, c0..c3}[e % 5] of step e / 5
       if (tid < 40) {
@@ -802,13 +807,14 @@ __device__ __noinline__ int nsp_phase_gram(const ColParams& P, int lch, long lon
   double gp[NGP];
 #pragma unroll
   for (int jj = 0; jj < NGP; ++jj) gp[jj] = 0.0;
-  int npl = 0;
+  int npl = 0, rounds = 0;
   int cy0 = 0, cy1 = -1;
   if (P.radius >= 0.0) index_cy_range(P.iv, gy, R, cy0, cy1);
   int cy = cy0, rb = 0, re = 0;
   bool rows_left = (cy <= cy1);
   if (rows_left) index_row_range(P.iv, gx, R, cy, rb, re);
   while (true) {
+    ++rounds;
     // candidates: the concatenation of the cell rows' index ranges, NTH per batch (a batch may span rows);
     // the selected ones keep that order (the summation order of C is the same whatever the launch shape)
     int nsel = 0;
@@ -976,7 +982,7 @@ __device__ __noinline__ int nsp_phase_gram(const ColParams& P, int lch, long lon
     for (int w = 0; w < NW; ++w) s += gpart[w * kp + tid];
     S.gvec[tid] = s;
   }
-  if (tid == 0) { S.sc[NSP_SC_FRO] = fro; S.sc[NSP_SC_KMAX] = P.kappa_max; }
+  if (tid == 0) { S.sc[NSP_SC_FRO] = fro; S.sc[NSP_SC_KMAX] = P.kappa_max; S.sc[NSP_SC_ROUNDS] = (double)rounds; }
   // A -> T (shift I on the zero padding)
   {
     int wti = st.ti0, wtj = st.tj0;
@@ -1031,33 +1037,83 @@ __device__ __noinline__ void nsp_phase_update(const ColParams& P, int lch, long 
     }
     if (kp > k) for (int e = tid; e < nl * (kp - k); e += NTH) Xt[(e / (kp - k)) * ks + k + e % (kp - k)] = 0.0;
   };
-  request_x(lev_b, min(lch, lev_e - lev_b));
-  if (npl > 0) {
-    // w = Z (Z g): warp per tile row, lanes read Z in the fragment pattern (row g, columns t, 4 + t of every tile)
-    // and reduce over t.  (A version with every warp on independent loads -- tile COLUMNS per warp, partial row
-    // sums through shared memory, < 1 k instead of 5.7 k cycles per product -- measured 1 % SLOWER end to end:
-    // the phase is hidden behind the other CTA's products either way, and the wider version takes more issue
-    // slots and barriers away from them.  A/B on one box, gpurun_out/ab_w.txt, r02.)
-    for (int pass = 0; pass < 2; ++pass) {
-      const double* vin = pass ? S.tv : S.gvec;
-      double* vout = pass ? wa : S.tv;
-      for (int I = warp; I < nt; I += NW) {
-        NspWalk zw;
-        zw.start(I);
-        double s = 0.0;
+  // v_out = Z v_in: warp per tile row, lanes read Z in the fragment pattern (row g, columns t, 4 + t of every tile) and
+  // reduce over t.  (A version with every warp on independent loads -- tile COLUMNS per warp, partial row sums through
+  // shared memory, < 1 k instead of 5.7 k cycles per product -- measured 1 % SLOWER end to end: the phase is hidden
+  // behind the other CTA's products either way, and the wider version takes more issue slots and barriers away from
+  // them.  A/B on one box, r02.)
+  auto zmatvec = [&](const double* vin, double* vout) {
+    for (int I = warp; I < nt; I += NW) {
+      NspWalk zw;
+      zw.start(I);
+      double s = 0.0;
 #pragma unroll 1
-        for (int K = 0; K < nt; ++K) {
-          const double z0 = lds_f64(zw.addr(S.zs, K, 0, L)), z1 = lds_f64(zw.addr(S.zs, K, 1, L));
-          const int c = K * 8 + t;
-          s = fma(z0, c < k ? vin[c] : 0.0, s);
-          s = fma(z1, c + 4 < k ? vin[c + 4] : 0.0, s);
-          zw.next(K, nt);
-        }
-        s += __shfl_xor_sync(0xffffffffu, s, 1);
-        s += __shfl_xor_sync(0xffffffffu, s, 2);
-        if (t == 0 && I * 8 + g < k) vout[I * 8 + g] = s;
+      for (int K = 0; K < nt; ++K) {
+        const double z0 = lds_f64(zw.addr(S.zs, K, 0, L)), z1 = lds_f64(zw.addr(S.zs, K, 1, L));
+        const int c = K * 8 + t;
+        s = fma(z0, c < k ? vin[c] : 0.0, s);
+        s = fma(z1, c + 4 < k ? vin[c + 4] : 0.0, s);
+        zw.next(K, nt);
       }
+      s += __shfl_xor_sync(0xffffffffu, s, 1);
+      s += __shfl_xor_sync(0xffffffffu, s, 2);
+      if (t == 0 && I * 8 + g < k) vout[I * 8 + g] = s;
+    }
+    __syncthreads();
+  };
+  // Ill-conditioned transforms (condition bound > NSP_REFINE_KAPPA): w = Z (Z g) inherits err(Z) sqrt(cond) -- g lies
+  // along the LARGE eigenvalues of A, Z's error is relative to its largest entry 1 / sqrt(lambda_min) -- which is
+  // what limited the packed kernel's condition range (2e-10 on the analysis mean at cond 7e4).  One step of iterative
+  // refinement with Z Z as the approximate inverse squares that factor away: r = g - A w, w += Z (Z r), with
+  // A w = shift w + Y^T (rho / sigma^2 o (Y w)) formed from the local rows themselves, re-gathered from L2 by bulk
+  // copies NSP_RCH at a time into the (free) Y | T buffers.  Needs the selection of a single round (sel_row, sel_w).
+  const bool refine = npl > 0 && S.sc[NSP_SC_KAPPA] > NSP_REFINE_KAPPA && S.sc[NSP_SC_ROUNDS] == 1.0;
+  if (!refine) request_x(lev_b, min(lch, lev_e - lev_b));
+  if (npl > 0) {
+    zmatvec(S.gvec, S.tv);
+    zmatvec(S.tv, wa);                                         // w = Z (Z g)
+    if (refine) {
+      unsigned gph = (unsigned)S.par[0];
+      const double shift = (double)(k - 1) / P.inflation;
+      double* Yr = S.Yp;                                         // [NSP_RCH][ks] re-gathered rows
+      double* su = S.xm;                                         // [NSP_RCH] rho / sigma^2 * (Y w) of the round
+      if (tid < k) S.tv[tid] = S.gvec[tid] - shift * wa[tid];    // r, accumulated in tv
+      for (int c0 = 0; c0 < npl; c0 += NSP_RCH) {
+        const int rows = min(NSP_RCH, npl - c0);
+        if (tma) {
+          fence_proxy_async();
+          if (tid == 0) mbar_expect_tx(S.mbar_g, (unsigned)(rows * k * 8));
+          for (int r = tid; r < rows; r += NTH)
+            bulk_g2s(S.ys + (unsigned)(r * ks * 8), P.Yp + (long long)S.sel_row[c0 + r] * k, (unsigned)(k * 8), S.mbar_g);
+          mbar_wait(S.mbar_g, gph);
+          gph ^= 1u;
+        } else {
+          for (int r = warp; r < rows; r += NW) {
+            const double* src = P.Yp + (long long)S.sel_row[c0 + r] * k;
+            for (int j = lane; j < k; j += 32) Yr[r * ks + j] = src[j];
+          }
+        }
+        __syncthreads();
+        for (int r = warp; r < rows; r += NW) {                  // (Y w)_r, scaled by the row's weight
+          double u = 0.0;
+          for (int j = lane; j < k; j += 32) u = fma(Yr[r * ks + j], wa[j], u);
+          u = warp_sum(u);
+          if (lane == 0) su[r] = S.sel_w[c0 + r] * u;
+        }
+        __syncthreads();
+        if (tid < k) {                                           // r -= Y^T su
+          double acc = 0.0;
+          for (int r = 0; r < rows; ++r) acc = fma(Yr[r * ks + tid], su[r], acc);
+          S.tv[tid] -= acc;
+        }
+        __syncthreads();
+      }
+      if (tid == 0) S.par[0] = (int)gph;
+      zmatvec(S.tv, S.gvec);                                     // (g is not needed any more)
+      zmatvec(S.gvec, S.tv);
+      if (tid < k) wa[tid] += S.tv[tid];
       __syncthreads();
+      request_x(lev_b, min(lch, lev_e - lev_b));                 // (the rows above used the state block's staging)
     }
   }
   NSP_TICK(13);

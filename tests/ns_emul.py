@@ -8,7 +8,7 @@ import re
 import numpy as np
 
 HEADER = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "metada_b200", "csrc", "ns_schedule_table.h")
-KAPPA_MAX = 2e4          # NSP_KAPPA_MAX_DEFAULT of the kernel
+KAPPA_MAX = 1e5          # NSP_KAPPA_MAX_DEFAULT of the kernel
 
 
 def with_margin(rho):

@@ -80,7 +80,7 @@ def _c5_like(rng, k, p, sigma):
     (80, 87, 0.3, 11, 3e-14), (80, 87, 0.1, 14, 3e-14), (80, 140, 0.1, 15, 3e-14), (40, 93, 0.1, 15, 3e-14),
     (128, 90, 0.1, 14, 3e-14), (80, 87, 0.05, 16, 5e-14), (80, 87, 0.03, 18, 1e-13), (80, 87, 0.02, 20, 2e-13),
     (24, 5, 0.1, 14, 3e-14), (80, 30, 1.0, 10, 3e-14),
-    # accurate observations (round 2: the packed kernel's default limit went from a condition bound of 2000 to 2e4,
+    # accurate observations (round 2: the packed kernel's default limit went from a condition bound of 2000 to 1e5,
     # the table to 3e5: up there the symmetric-tile iteration agrees with numpy's eigh to ~cond * eps, and its
     # residual Z A Z - I in long double is as small as that of the eigen-decomposition itself -- condition bounds
     # 7e3, 3e4, 7e4, 7e4, 5e4; the emulation runs with kappa_max = 1e5)
@@ -101,7 +101,7 @@ def test_emulated_kernel_iteration_matches_the_eigendecomposition(k, p, sigma, m
 
 def test_condition_bound_beyond_the_limit_is_refused():
     rng = np.random.default_rng(5)
-    A = _c5_like(rng, 80, 87, 0.0008)                      # cond ~ 8e5
+    A = _c5_like(rng, 80, 87, 0.0008)                      # cond ~ 8e5 > 1e5
     Z, _, why = ns_emul.inverse_sqrt(A, 79.0)
     assert Z is None and why == "kappa"
     A = _c5_like(rng, 80, 87, 0.004)                       # a caller's own, lower limit (mdc_letkf_params.kappa_max)

@@ -319,6 +319,17 @@ int mdc_comm_init(mdc_stream* s, const void* id, int rank, int nranks);
 int mdc_comm_allgather_rows(mdc_stream* s, double* const* members);
 /* max over ranks of *value (device-side ncclAllReduce); single rank: unchanged */
 int mdc_comm_max(mdc_stream* s, double* value);
+/* Sharded analysis of GEOGRAPHIC observations through the same handle (created for this rank's slab, mdc_comm_init
+ * done; one process: the whole grid).  Every rank passes the GLOBAL latitude / longitude arrays [gny][gnx], the
+ * vertical coordinate, the variables' level counts (nvar = 0: one variable) and ALL observations (level, valid,
+ * variable may be NULL); members[m] points at the full host member [nz][gny][gnx], of which the rank's rows are
+ * read (+ one halo row) and overwritten with the analysis (mdc_comm_allgather_rows shares them afterwards).  The
+ * result is bit-identical to mdc_letkf_analyse on one store with mdc_ens_set_geography.  radius in kilometres. */
+int mdc_geo_sharded_analyse(mdc_stream* s, double* const* members, const double* glat, const double* glon, int nvc,
+                            const double* vertical_coords, int nvar, const int32_t* var_nlev, int64_t P,
+                            const double* olat, const double* olon, const double* olevel, const double* ovalue,
+                            const double* oerr, const uint8_t* ovalid, const int32_t* ovar,
+                            const mdc_letkf_params* params, mdc_letkf_stats* stats);
 
 /* ---- microbenchmarks used for the roofline denominators (profiles/) ------------------------ */
 int mdc_bench_fp64_fma(mdc_ctx* ctx, double* tflops);

@@ -537,6 +537,153 @@ int mdc_comm_allgather_rows(mdc_stream* s, double* const* members) {
   return MDC_OK;
 }
 
+
+// ---- sharded analysis of GEOGRAPHIC observations (one process per GPU; csrc/geo_api.inl for the pieces).  What
+// metada_b200/parallel.py: GeoSlabLetkf does, from C++: every rank locates ALL observations on the global geography
+// (ownership = the slab of the located row), applies H to its own, sends rank r the own observations inside the
+// bounding box of r's columns widened by the reach of the radius (rows with latitude / longitude / level / variable,
+// grouped ncclSend / ncclRecv; the row counts travel first -- the box test runs on the device, so they are not
+// recomputed on the host), analyses its rows on its window of the geography (global frame: the lattice of the
+// bucket index, hence the result, is the one-store run's) and writes them back to the host members.
+int mdc_geo_sharded_analyse(mdc_stream* s, double* const* members, const double* glat, const double* glon, int nvc,
+                            const double* vc, int nvar, const int32_t* var_nlev, int64_t P, const double* olat,
+                            const double* olon, const double* olev, const double* oval, const double* oerr,
+                            const uint8_t* ovalid, const int32_t* ovar, const mdc_letkf_params* prm, mdc_letkf_stats* st) {
+  if (!s || !members || !glat || !glon || !prm || !st || P < 0) return MDC_ERR_INVALID;
+  const int gnx = s->cfg.gnx, gny = s->cfg.gny, nz = s->cfg.nz, k = s->cfg.k, W = s->comm ? s->world : 1, me = s->comm ? s->rank : 0;
+  mdc_ctx* ctx = s->ctxs[0];
+  int y0, y1;
+  slab_bounds(gny, me, W, y0, y1);
+  if (y0 != s->cfg.row0 || y1 != s->cfg.row1) return fail(s, MDC_ERR_INVALID, "geo_sharded_analyse: the stream's row range is not this rank's slab");
+  const int halo = y1 < gny ? 1 : 0;
+  mdc_ens *whole = nullptr, *ens = nullptr;
+  mdc_obs *all = nullptr, *own = nullptr;
+  auto cleanup = [&]() {
+    if (own) mdc_obs_destroy(own);
+    if (all) mdc_obs_destroy(all);
+    if (ens) mdc_ens_destroy(ens);
+    if (whole) mdc_ens_destroy(whole);
+  };
+#define MDC_RTC(call)                                                                                         \
+  do {                                                                                                        \
+    int rc_ = (call);                                                                                         \
+    if (rc_) { fail(s, rc_, "%s: %s", #call, mdc_last_error(ctx)); cleanup(); return rc_; }                   \
+  } while (0)
+  // the global geography (one level, one member: it only locates and hands out windows)
+  MDC_RTC(mdc_ens_create(ctx, gnx, gny, 1, 1, &whole));
+  MDC_RTC(mdc_ens_set_geography(whole, glat, glon, nvc, vc));
+  std::vector<int32_t> oy((size_t)std::max<int64_t>(P, 1));
+  MDC_RTC(mdc_obs_create_geographic(ctx, P, olat, olon, olev, oval, oerr, ovalid, nullptr, &all));
+  MDC_RTC(mdc_obs_locate(all, whole));
+  MDC_RTC(mdc_obs_download_grid_coords(all, nullptr, oy.data(), nullptr));
+  mdc_obs_destroy(all);
+  all = nullptr;
+  std::vector<int64_t> idx;
+  for (int64_t a = 0; a < P; ++a)
+    if (W == 1 || owner_of_row(oy[(size_t)a], gny, W) == me) idx.push_back(a);
+  const size_t n = idx.size();
+  std::vector<double> la(n), lo(n), le(n), va(n), er(n);
+  std::vector<uint8_t> ok(n);
+  std::vector<int32_t> vr(n);
+  for (size_t i = 0; i < n; ++i) {
+    const int64_t a = idx[i];
+    la[i] = olat[a]; lo[i] = olon[a]; le[i] = olev ? olev[a] : 0.0; va[i] = oval[a]; er[i] = oerr[a];
+    ok[i] = ovalid ? ovalid[a] : 1; vr[i] = ovar ? ovar[a] : 0;
+  }
+  // this rank's slab (+ the halo row of the IDW stencil) on its window of the geography
+  MDC_RTC(mdc_ens_create(ctx, gnx, (y1 - y0) + halo, nz, k, &ens));
+  MDC_RTC(mdc_ens_set_domain(ens, 0, y0, gnx, gny, gnx, y1 - y0));
+  MDC_RTC(mdc_ens_set_geography_from(ens, whole));
+  if (nvar > 0) MDC_RTC(mdc_ens_set_variables(ens, nvar, var_nlev));
+  MDC_RTC(mdc_ens_upload_members_rows(ens, 0, k, members, gny, y0));
+  MDC_RTC(mdc_obs_create_geographic(ctx, (int64_t)n, la.data(), lo.data(), le.data(), va.data(), er.data(), ok.data(), idx.data(), &own));
+  if (ovar) MDC_RTC(mdc_obs_set_variables(own, vr.data()));
+  MDC_RTC(mdc_obs_locate(own, whole));
+  MDC_RTC(mdc_hx_idw4(ens, own));
+  s->last_halo_rows = 0;
+  if (W > 1) {
+    // every rank's box from the global arrays: bounding box of its columns in the geography's frame + the reach
+    double lon_c, umin, umax, latmin, latmax;
+    MDC_RTC(mdc_ens_geography_frame(whole, &lon_c, &umin, &umax, &latmin, &latmax));
+    const double pi = 3.14159265358979323846, delta = std::max(prm->radius, 0.0) / 6371.0;
+    const double phic = std::max(std::fabs(latmin), std::fabs(latmax)) * pi / 180.0;
+    const double dlat = delta * 180.0 / pi * (1.0 + 1e-9) + 1e-12;
+    const double dlon = std::asin(std::min(1.0, std::sin(delta) / std::cos(phic))) * 180.0 / pi * (1.0 + 1e-9) + 1e-12;
+    std::vector<double> box((size_t)W * 4);
+    for (int r = 0; r < W; ++r) {
+      int a0, a1;
+      slab_bounds(gny, r, W, a0, a1);
+      double b0 = 1e300, b1 = -1e300, c0 = 1e300, c1 = -1e300;
+      for (int64_t g = (int64_t)a0 * gnx; g < (int64_t)a1 * gnx; ++g) {
+        const double u = (glon[g] - lon_c) - 360.0 * std::rint((glon[g] - lon_c) / 360.0);
+        b0 = std::min(b0, glat[g]); b1 = std::max(b1, glat[g]); c0 = std::min(c0, u); c1 = std::max(c1, u);
+      }
+      box[4 * r] = b0 - dlat; box[4 * r + 1] = b1 + dlat; box[4 * r + 2] = c0 - dlon; box[4 * r + 3] = c1 + dlon;
+    }
+    const int rd = mdc_obs_row_doubles(own);
+    std::vector<int64_t> nsend((size_t)W, 0), nrecv((size_t)W, 0);
+    for (int r = 0; r < W; ++r)
+      if (r != me) MDC_RTC(mdc_obs_pack_rows_geo(own, box[4 * r], box[4 * r + 1], box[4 * r + 2], box[4 * r + 3], lon_c, nullptr, 0, &nsend[(size_t)r]));
+    // counts first (one double per peer), then the rows
+    void* stream = mdc_ctx_stream(ctx);
+    if (int rc = grow_dev(s, &s->xbuf, &s->xbuf_bytes, (int64_t)2 * W * 8)) { cleanup(); return rc; }
+    {
+      std::vector<double> c((size_t)2 * W, 0.0);
+      for (int r = 0; r < W; ++r) c[(size_t)r] = (double)nsend[(size_t)r];
+      MDC_RTC(mdc_dev_copy(ctx, s->xbuf, c.data(), (int64_t)2 * W * 8, 1));
+      double* d = static_cast<double*>(s->xbuf);
+      int rc = g_nccl.GroupStart();
+      for (int r = 0; r < W && !rc; ++r) {
+        if (r == me) continue;
+        rc = g_nccl.Send(d + r, 1, kNcclFloat64, r, s->comm, stream);
+        if (!rc) rc = g_nccl.Recv(d + W + r, 1, kNcclFloat64, r, s->comm, stream);
+      }
+      if (!rc) rc = g_nccl.GroupEnd();
+      if (rc) { fail(s, MDC_ERR_CUDA, "NCCL count exchange: %s", g_nccl.GetErrorString(rc)); cleanup(); return MDC_ERR_CUDA; }
+      MDC_RTC(mdc_ctx_sync(ctx));
+      MDC_RTC(mdc_dev_copy(ctx, c.data(), s->xbuf, (int64_t)2 * W * 8, 2));
+      for (int r = 0; r < W; ++r) nrecv[(size_t)r] = r == me ? 0 : (int64_t)c[(size_t)(W + r)];
+    }
+    int64_t tot = 0;
+    for (int r = 0; r < W; ++r) tot += nsend[(size_t)r] + nrecv[(size_t)r];
+    void* rows = nullptr;
+    MDC_RTC(mdc_dev_malloc(ctx, std::max<int64_t>(tot, 1) * rd * 8, &rows));
+    std::vector<double*> sp((size_t)W, nullptr), rp((size_t)W, nullptr);
+    {
+      double* p = static_cast<double*>(rows);
+      for (int r = 0; r < W; ++r) { sp[(size_t)r] = p; p += nsend[(size_t)r] * rd; }
+      for (int r = 0; r < W; ++r) { rp[(size_t)r] = p; p += nrecv[(size_t)r] * rd; }
+    }
+    int rc = 0;
+    for (int r = 0; r < W && !rc; ++r) {
+      if (r == me || nsend[(size_t)r] == 0) continue;
+      int64_t got = 0;
+      rc = mdc_obs_pack_rows_geo(own, box[4 * r], box[4 * r + 1], box[4 * r + 2], box[4 * r + 3], lon_c, sp[(size_t)r], nsend[(size_t)r], &got);
+      if (!rc && got != nsend[(size_t)r]) rc = MDC_ERR_INVALID;
+    }
+    if (!rc) {
+      rc = g_nccl.GroupStart() ? MDC_ERR_CUDA : 0;
+      for (int r = 0; r < W && !rc; ++r) {
+        if (r == me) continue;
+        if (nsend[(size_t)r] > 0) rc = g_nccl.Send(sp[(size_t)r], (size_t)(nsend[(size_t)r] * rd), kNcclFloat64, r, s->comm, stream) ? MDC_ERR_CUDA : 0;
+        if (!rc && nrecv[(size_t)r] > 0) rc = g_nccl.Recv(rp[(size_t)r], (size_t)(nrecv[(size_t)r] * rd), kNcclFloat64, r, s->comm, stream) ? MDC_ERR_CUDA : 0;
+      }
+      if (!rc) rc = g_nccl.GroupEnd() ? MDC_ERR_CUDA : 0;
+      if (!rc) rc = mdc_ctx_sync(ctx);
+    }
+    for (int r = 0; r < W && !rc; ++r)
+      if (r != me && nrecv[(size_t)r] > 0) { rc = mdc_obs_append_rows(own, rp[(size_t)r], nrecv[(size_t)r]); s->last_halo_rows += nrecv[(size_t)r]; }
+    if (!rc) rc = mdc_ctx_sync(ctx);
+    mdc_dev_free(ctx, rows);
+    if (rc) { fail(s, rc, "geographic halo exchange: %s", mdc_last_error(ctx)); cleanup(); return rc; }
+  }
+  MDC_RTC(mdc_letkf_analyse(ens, own, prm, st));
+  MDC_RTC(mdc_ens_download_members_rows(ens, 0, k, members, gny, y0, y1 - y0));
+#undef MDC_RTC
+  cleanup();
+  return MDC_OK;
+}
+
 int mdc_stream_analyse(mdc_stream* s, double* const* members, int host_row0, int host_ny, int64_t P, const int32_t* ox,
                        const int32_t* oy, const int32_t* oz, const double* oval, const double* oerr, const uint8_t* ovalid,
                        const mdc_letkf_params* params, mdc_letkf_stats* out) {

@@ -122,8 +122,8 @@ class LETKF {
       x.push_back(i); y.push_back(j); z.push_back(l);
       val.push_back(p.value); err.push_back(p.error); valid.push_back(p.is_valid ? 1 : 0);
     }
-    const char* ws = std::getenv("MDC_WORLD_SIZE");
-    const int world = ws ? std::atoi(ws) : 1, rank = std::getenv("MDC_RANK") ? std::atoi(std::getenv("MDC_RANK")) : 0;
+    const backends::cuda::ProcessGroup pg;
+    const int world = pg.world, rank = pg.rank;
     const int gnx = static_cast<int>(g.x_dim()), gny = static_cast<int>(g.y_dim()), nz = static_cast<int>(g.z_dim());
     const int k = static_cast<int>(ensemble_.Size());
     const double bytes = 8.0 * gnx * gny * nz * k;
@@ -133,7 +133,7 @@ class LETKF {
     cfg.row0 = static_cast<int>((static_cast<long long>(gny) * rank) / world);
     cfg.row1 = static_cast<int>((static_cast<long long>(gny) * (rank + 1)) / world);
     cfg.slab_rows = slab_rows_; cfg.slots = 4; cfg.sm_reserve = 8; cfg.radius = params_.radius;
-    const int device = std::getenv("MDC_DEVICE") ? std::atoi(std::getenv("MDC_DEVICE")) : (world > 1 ? rank : 0);
+    const int device = pg.device;
     mdc_stream* st = nullptr;
     if (mdc_stream_create(device, &cfg, &st)) throw std::runtime_error("mdc_stream_create failed");
     auto fail = [&](const char* what) {
@@ -141,24 +141,7 @@ class LETKF {
       mdc_stream_destroy(st);
       throw std::runtime_error(msg);
     };
-    if (world > 1) {
-      const char* idfile = std::getenv("MDC_COMM_ID_FILE");
-      if (!idfile) fail("MDC_WORLD_SIZE > 1 needs MDC_COMM_ID_FILE");
-      char id[128];
-      if (rank == 0) {
-        if (mdc_comm_get_unique_id(id, 128)) fail("mdc_comm_get_unique_id");
-        std::ofstream(std::string(idfile) + ".tmp", std::ios::binary).write(id, 128);
-        std::rename((std::string(idfile) + ".tmp").c_str(), idfile);
-      } else {
-        for (int tries = 0;; ++tries) {
-          std::ifstream f(idfile, std::ios::binary);
-          if (f.read(id, 128)) break;
-          if (tries > 6000) fail("timed out waiting for MDC_COMM_ID_FILE");
-          std::this_thread::sleep_for(std::chrono::milliseconds(10));
-        }
-      }
-      if (mdc_comm_init(st, id, rank, world)) fail("mdc_comm_init");
-    }
+    try { pg.attach(st); } catch (const std::exception& e) { fail(e.what()); }
     std::vector<double*> ptrs;
     for (int m = 0; m < k; ++m) ptrs.push_back(ensemble_.GetMember(m).template getDataPtr<double>());
     if (mdc_stream_analyse(st, ptrs.data(), 0, gny, static_cast<int64_t>(val.size()), x.data(), y.data(), z.data(), val.data(),

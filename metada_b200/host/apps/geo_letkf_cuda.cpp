@@ -6,9 +6,14 @@
 //   in : int64 nx, ny, nz, k, P, nvc; double radius_km; lat[ny*nx], lon[ny*nx], vc[nvc]; X[k][nz][ny][nx];
 //        olat[P], olon[P], olev[P], value[P], error[P], valid[P] (as doubles)
 //   out: X_a [k][nz][ny][nx]
+// With MDC_WORLD_SIZE > 1 (one process per GPU: MDC_RANK, MDC_COMM_ID_FILE, MDC_DEVICE) or MDC_GEO_SHARDED=1 the
+// analysis goes through the C++ runtime's sharded geographic path (mdc_geo_sharded_analyse: global geography for
+// locating, a window of it per rank, halo rows by box over NCCL) and every rank writes the whole analysis.
 #include <cstdint>
 #include <cstdio>
+#include <cstdlib>
 #include <iostream>
+#include <string>
 #include <vector>
 
 #include "CudaApi.hpp"
@@ -45,10 +50,38 @@ int main(int argc, char** argv) {
     std::vector<Point> obs;
     for (size_t i = 0; i < P; ++i)
       obs.push_back({fwk::Location(olat[i], olon[i], olev[i], fwk::CoordinateSystem::GEOGRAPHIC), val[i], err[i], valid[i] != 0.0});
-    cuda::DeviceEnsemble ens(nx, ny, nz, k);
     std::vector<const double*> in;
     std::vector<double*> out;
     for (int m = 0; m < k; ++m) { in.push_back(X.data() + (size_t)m * n); out.push_back(X.data() + (size_t)m * n); }
+    const cuda::ProcessGroup pg;
+    if (pg.world > 1 || std::getenv("MDC_GEO_SHARDED")) {
+      mdc_stream_config cfg{};
+      cfg.gnx = nx; cfg.gny = ny; cfg.nz = nz; cfg.k = k; cfg.row0 = pg.row0(ny); cfg.row1 = pg.row1(ny); cfg.slots = 3;
+      mdc_stream* st = nullptr;
+      if (mdc_stream_create(pg.device, &cfg, &st)) throw std::runtime_error("mdc_stream_create failed");
+      auto fail = [&](const std::string& what) {
+        const std::string msg = what + ": " + mdc_stream_last_error(st);
+        mdc_stream_destroy(st);
+        throw std::runtime_error(msg);
+      };
+      try { pg.attach(st); } catch (const std::exception& e) { fail(e.what()); }
+      std::vector<uint8_t> ok(P);
+      for (size_t i = 0; i < P; ++i) ok[i] = valid[i] != 0.0;
+      mdc_letkf_params p{};
+      p.radius = radius; p.inflation = 1.0; p.mode = MDC_MODE_CANONICAL; p.loc = MDC_LOC_GASPARI_COHN; p.use_R = 1;
+      mdc_letkf_stats st_{};
+      if (mdc_geo_sharded_analyse(st, out.data(), lat.data(), lon.data(), (int)nvc, vc.data(), 0, nullptr, (int64_t)P, olat.data(),
+                                  olon.data(), olev.data(), val.data(), err.data(), ok.data(), nullptr, &p, &st_))
+        fail("mdc_geo_sharded_analyse");
+      if (pg.world > 1 && mdc_comm_allgather_rows(st, out.data())) fail("mdc_comm_allgather_rows");
+      mdc_stream_destroy(st);
+      std::FILE* o = std::fopen(argv[2], "wb");
+      std::fwrite(X.data(), 8, X.size(), o);
+      std::fclose(o);
+      std::cout << "rank " << pg.rank << " of " << pg.world << ": columns " << st_.columns << std::endl;
+      return 0;
+    }
+    cuda::DeviceEnsemble ens(nx, ny, nz, k);
     ens.upload(in);
     ens.setGeography(lat, lon, vc);
     cuda::DeviceObservations dobs(obs);

@@ -2,10 +2,15 @@
 // RAII + exception layer over the C ABI (include/metada_cuda_c_api.h), following the reference's
 // convention for native bridges: opaque handle in a smart pointer, non-zero return code -> throw
 // std::runtime_error (backends/wrf/WRFObsOperator.hpp:150-154 pattern).
+#include <chrono>
 #include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <fstream>
 #include <memory>
 #include <stdexcept>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "Location.hpp"
@@ -36,6 +41,39 @@ class DeviceContext {
       throw std::runtime_error("CUDA backend: no usable CUDA device (this backend has no CPU fallback)");
   }
   mdc_ctx* ctx_ = nullptr;
+};
+
+/** Several processes, one per GPU (MDC_RANK, MDC_WORLD_SIZE, MDC_COMM_ID_FILE, MDC_DEVICE): rank 0 writes the NCCL id
+ *  to the file, the others wait for it; attaches the communicator to a streaming handle created for the rank's rows. */
+struct ProcessGroup {
+  int rank = 0, world = 1, device = 0;
+  ProcessGroup() {
+    if (const char* w = std::getenv("MDC_WORLD_SIZE")) world = std::atoi(w);
+    if (const char* r = std::getenv("MDC_RANK")) rank = std::atoi(r);
+    device = std::getenv("MDC_DEVICE") ? std::atoi(std::getenv("MDC_DEVICE")) : (world > 1 ? rank : 0);
+  }
+  int row0(int gny) const { return static_cast<int>((static_cast<long long>(gny) * rank) / world); }
+  int row1(int gny) const { return static_cast<int>((static_cast<long long>(gny) * (rank + 1)) / world); }
+  /** throws std::runtime_error with the handle's message on failure (the caller destroys the handle) */
+  void attach(mdc_stream* st) const {
+    if (world < 2) return;
+    const char* idfile = std::getenv("MDC_COMM_ID_FILE");
+    if (!idfile) throw std::runtime_error("MDC_WORLD_SIZE > 1 needs MDC_COMM_ID_FILE");
+    char id[128];
+    if (rank == 0) {
+      if (mdc_comm_get_unique_id(id, 128)) throw std::runtime_error("mdc_comm_get_unique_id failed");
+      std::ofstream(std::string(idfile) + ".tmp", std::ios::binary).write(id, 128);
+      std::rename((std::string(idfile) + ".tmp").c_str(), idfile);
+    } else {
+      for (int tries = 0;; ++tries) {
+        std::ifstream f(idfile, std::ios::binary);
+        if (f.read(id, 128)) break;
+        if (tries > 6000) throw std::runtime_error("timed out waiting for MDC_COMM_ID_FILE");
+        std::this_thread::sleep_for(std::chrono::milliseconds(10));
+      }
+    }
+    if (mdc_comm_init(st, id, rank, world)) throw std::runtime_error(std::string("mdc_comm_init: ") + mdc_stream_last_error(st));
+  }
 };
 
 /** Device-resident ensemble store [col][lev][member] (replaces vector<State> for the analysis). */

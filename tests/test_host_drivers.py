@@ -179,6 +179,12 @@ def test_host_layer_geographic_observations(tmp_path):
     em, ep = analysis_errors(Xa, ref["Xa"])
     assert em < 1e-10 and ep < 1e-10, (em, ep)
     assert "columns %d" % (nx * ny) in r.stdout
+    # the C++ runtime's sharded geographic path (mdc_geo_sharded_analyse) with one rank: same bits as the one-store
+    # analysis (two ranks over NCCL: tools/mgpu_geo_driver_check.sh)
+    out2 = str(tmp_path / "out2.bin")
+    r = subprocess.run([_need("geo_letkf_cuda"), inp, out2], capture_output=True, text=True, env={**os.environ, "MDC_GEO_SHARDED": "1"})
+    assert r.returncode == 0, r.stderr + r.stdout
+    assert open(out2, "rb").read() == open(out, "rb").read()
 
 
 @pytest.mark.gpu

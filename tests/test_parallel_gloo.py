@@ -131,3 +131,68 @@ def test_geographic_halo_boxes_cover_every_reachable_observation():
                 reached += len(sel)
         assert inbox.sum() < len(inbox)          # ... and it is a proper subset
     assert reached > 1000
+
+
+def _geo_worker(rank, world, port, nx, ny, nz, k, P, radius, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from oracle import orc
+    lat, lon = syn.geography(nx, ny, lon0=178.4)
+    vc = np.array([1000.0, 850.0])
+    o = syn.geo_observations(P, lat, lon, vc, seed=14)
+    X = syn.ensemble(k, nx, ny, nz, seed=15)
+    ex, ey, ez = orc.geo_locate(o["lat"], o["lon"], o["level"], lat, lon, vc)
+    lon_c = float(np.degrees(np.arctan2(np.sin(np.radians(lon)).sum(), np.cos(np.radians(lon)).sum())))
+    u = (lon - lon_c) - 360.0 * np.rint((lon - lon_c) / 360.0)
+    frame = {"lon_c": lon_c, "umin": float(u.min()), "umax": float(u.max()), "latmin": float(lat.min()), "latmax": float(lat.max())}
+    boxes = par.geo_halo_boxes(lat, lon, frame, world, radius)
+    own = np.nonzero(par.owner_of_row(ey, ny, world) == rank)[0]        # ownership = the slab of the LOCATED row
+    ou = (o["lon"] - lon_c) - 360.0 * np.rint((o["lon"] - lon_c) / 360.0)
+    # what travels: the global id (the rows' other fields are functions of it here; the device rows carry them)
+    send = {}
+    for dst in range(world):
+        if dst != rank:
+            la0, la1, u0, u1 = boxes[dst]
+            m = (o["lat"][own] >= la0) & (o["lat"][own] <= la1) & (ou[own] >= u0) & (ou[own] <= u1)
+            send[dst] = torch.from_numpy(own[m].astype(np.float64)[:, None].copy())
+    recv = par.exchange_rows(dist, rank, world, send, 1, torch.device("cpu"))
+    have = np.sort(np.concatenate([own] + [t.numpy()[:, 0].astype(np.int64) for t in recv]))
+    assert len(np.unique(have)) == len(have)
+    # analyse with own + received observations only (ascending global id = the order of the one-store run)
+    r = orc.letkf_ext(X, ex[have], ey[have], ez[have], o["value"][have], o["err"][have], o["valid"][have], radius=radius,
+                      glat=lat, glon=lon, olat=o["lat"][have], olon=o["lon"][have])
+    y0, y1 = par.slab_bounds(ny, rank, world)
+    out[rank] = (r["Xa"][:, :, y0:y1, :].copy(), len(own), len(have))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_sharded_geographic_plan_equals_single_process(world):
+    """The plan of GeoSlabLetkf / mdc_geo_sharded_analyse over gloo with the oracle as the kernel: ownership by the
+    located row, halo observations by box.  Every rank's rows equal the single-process analysis bit for bit although
+    it only ever sees its own and the received observations."""
+    from oracle import orc
+    nx, ny, nz, k, P, radius = 22, 21, 2, 6, 260, 55.0
+    port = _free_port()
+    ctx = mp.get_context("spawn")
+    mgr = ctx.Manager()
+    out = mgr.dict()
+    procs = [ctx.Process(target=_geo_worker, args=(r, world, port, nx, ny, nz, k, P, radius, out)) for r in range(world)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(timeout=180)
+        assert p.exitcode == 0
+    lat, lon = syn.geography(nx, ny, lon0=178.4)
+    vc = np.array([1000.0, 850.0])
+    o = syn.geo_observations(P, lat, lon, vc, seed=14)
+    X = syn.ensemble(k, nx, ny, nz, seed=15)
+    ex, ey, ez = orc.geo_locate(o["lat"], o["lon"], o["level"], lat, lon, vc)
+    full = orc.letkf_ext(X, ex, ey, ez, o["value"], o["err"], o["valid"], radius=radius, glat=lat, glon=lon,
+                         olat=o["lat"], olon=o["lon"])["Xa"]
+    assert sum(out[r][1] for r in range(world)) == P
+    for r in range(world):
+        y0, y1 = par.slab_bounds(ny, r, world)
+        assert np.array_equal(out[r][0], full[:, :, y0:y1, :]), r
+        assert out[r][2] < P                                  # a rank does not need every observation

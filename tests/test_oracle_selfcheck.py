@@ -178,3 +178,34 @@ def test_letkf_exp_type_localisation_against_numpy(loc):
     lam, V = np.linalg.eigh(A)
     W = ((V / lam) @ (V.T @ ((Yp[sel] * w[:, None]).T @ d[sel])))[:, None] + np.sqrt(k - 1) * (V / np.sqrt(lam)) @ V.T
     assert np.abs(ref["W"][0] - W).max() < 1e-12 * np.abs(W).max()
+
+
+def test_canonical_transform_against_a_schur_square_root():
+    """A third witness for the headline arithmetic (the canonical mode has no counterpart in the
+    reference, and the oracle's eigen-decomposition was only checked against numpy.linalg.eigh): the column
+    transform rebuilt from Y', d and the Gaspari-Cohn weights with SciPy's Schur-method matrix square root
+    (scipy.linalg.sqrtm: no symmetric eigensolver involved) and an LU solve for the mean weights."""
+    import scipy.linalg as sla
+    nx, ny, nz, k, P, radius, infl = 12, 10, 1, 24, 90, 3.5, 1.05
+    X, o = make_case(nx, ny, nz, k, P, seed=9, sigma=0.2)
+    r = orc.letkf(X, o["x"], o["y"], o["z"], o["value"], o["err"], radius=radius, inflation=infl, want_W=True)
+    _, _, Yp, d = orc.obs_space(X, o["x"], o["y"], o["z"], o["value"])
+    checked = 0
+    for c in (0, 17, 55, 64, 119):
+        gy, gx = divmod(c, nx)
+        idx = orc.select_local(gx, gy, o["x"], o["y"], radius)
+        if len(idx) == 0:
+            continue
+        dist = np.hypot(o["x"][idx] - gx, o["y"][idx] - gy)
+        rho = np.array([np_twin.gaspari_cohn(dd / (0.5 * radius)) for dd in dist])
+        wgt = rho / o["err"][idx] ** 2
+        Yl = Yp[idx]
+        A = (k - 1) / infl * np.eye(k) + Yl.T @ (wgt[:, None] * Yl)
+        g = Yl.T @ (wgt * d[idx])
+        S = np.real(sla.sqrtm(A))                              # A^{1/2} by the Schur method
+        Wa = np.sqrt(k - 1.0) * np.linalg.inv(S)
+        wa = sla.lu_solve(sla.lu_factor(A), g)
+        W = wa[:, None] + 0.5 * (Wa + Wa.T)
+        assert np.abs(r["W"][c] - W).max() < 1e-10 * max(1.0, np.abs(W).max()), c
+        checked += 1
+    assert checked >= 4

@@ -357,7 +357,7 @@ __global__ void __launch_bounds__(WARPS * 32) letkf_smallp_kernel(ColParams P) {
 // the others go to the work list of the packed k-space kernel, which then never spends a 512-thread selection
 // on a transform it will not do.  (BASELINE C4, r_v = 5: mean p ~ 18 at interior levels; 94 % of the transforms
 // have p <= 24, 99.9 % p <= 32, and a k-space transform at k = 128 costs ~130 us of a whole SM.)
-template <int WARPS>
+template <int WARPS, bool EXT = false>
 __global__ void __launch_bounds__(WARPS * 32) letkf_smallp_classify_kernel(ColParams P) {
   extern __shared__ __align__(16) unsigned char sp_smem_raw[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -372,7 +372,7 @@ __global__ void __launch_bounds__(WARPS * 32) letkf_smallp_classify_kernel(ColPa
     if (P.cols) col = P.cols[ci];
     else col = (ci / P.own_nx) * P.nx + ci % P.own_nx;
     int p = 0, sweeps = 0;
-    const int rc = sp_transform<false>(P, W, col, lt, lane, p, sweeps);
+    const int rc = sp_transform<EXT>(P, W, col, lt, lane, p, sweeps);
     if (lane == 0) {
       if (rc == 2) {
         if (P.small_items && p <= SP_PMAX2 && 2 * p <= P.k) {

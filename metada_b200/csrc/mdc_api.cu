@@ -1070,7 +1070,7 @@ static int letkf_launch(mdc_ens* e, mdc_obs* o, const mdc_letkf_params* p, const
     // Per-level analyses: a first pass (one warp per column) finishes the transforms with no or few local
     // observations in observation space and lists the others for the k-space kernel.  Otherwise the k-space
     // kernel defers its small transforms to the observation-space kernel after its own selection.
-    const bool classify = smallp && nxf > 1 && !dW && !ext;
+    const bool classify = smallp && nxf > 1 && !dW;
     if (classify) {
       cp.work_items = ctx->redo_items + 2 * ctx->redo_cap;
       cp.work_count = reinterpret_cast<unsigned*>(ctx->d_flags + 14);
@@ -1078,8 +1078,13 @@ static int letkf_launch(mdc_ens* e, mdc_obs* o, const mdc_letkf_params* p, const
       ColParams cc = cp;
       cc.small_items = ctx->redo_items + ctx->redo_cap;
       cc.small_count = reinterpret_cast<unsigned*>(ctx->d_flags + 13);
-      if (int rc = launch_smallp(letkf_smallp_classify_kernel<SP_WARPS_P1>, cc, SP_PMAX, SP_WARPS_P1)) return rc;
-      if (int rc = launch_smallp(letkf_smallp_kernel<false, SP_PMAX2, SP_WARPS_P2>, cc, SP_PMAX2, SP_WARPS_P2)) return rc;
+      if (ext) {          // (geographic observations / multi-variable states: haversine selection, levels inside variables)
+        if (int rc = launch_smallp(letkf_smallp_classify_kernel<SP_WARPS_P1, true>, cc, SP_PMAX, SP_WARPS_P1)) return rc;
+        if (int rc = launch_smallp(letkf_smallp_kernel<true, SP_PMAX2, SP_WARPS_P2>, cc, SP_PMAX2, SP_WARPS_P2)) return rc;
+      } else {
+        if (int rc = launch_smallp(letkf_smallp_classify_kernel<SP_WARPS_P1>, cc, SP_PMAX, SP_WARPS_P1)) return rc;
+        if (int rc = launch_smallp(letkf_smallp_kernel<false, SP_PMAX2, SP_WARPS_P2>, cc, SP_PMAX2, SP_WARPS_P2)) return rc;
+      }
       cp.work_consume = 1;
     } else if (smallp) {
       cp.small_items = ctx->redo_items + ctx->redo_cap;

@@ -39,6 +39,7 @@ int launch_nt(const ColParams& cp, int lch, int sms, int ext, int work, long lon
   // interleave); k <= 80: 8 warps, two per SM (nt = 10 with 384 threads measured 6 % slower); above: 16 warps, one
   constexpr int NTH = NT <= 5 ? 128 : NT <= 10 ? NSP_DEV_NTH10 : 512, MINB = NT <= 5 ? 4 : NT <= 10 ? 2 : 1;
 #endif
+  if (ext && work) return launchp(letkf_nsp_kernel<NT, NTH, MINB, true, true>, NTH, cp, lch, sms, total_cols, ctx);
   if (ext) return launchp(letkf_nsp_kernel<NT, NTH, MINB, false, true>, NTH, cp, lch, sms, total_cols, ctx);
   if (work) return launchp(letkf_nsp_kernel<NT, NTH, MINB, true>, NTH, cp, lch, sms, total_cols, ctx);
   return launchp(letkf_nsp_kernel<NT, NTH, MINB, false>, NTH, cp, lch, sms, total_cols, ctx);

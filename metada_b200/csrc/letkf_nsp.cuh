@@ -459,7 +459,7 @@ __device__ __forceinline__ int nss_start_index(double kappa) {
 #define NSP_SC_KMAX 45      /* slot that carries the condition limit from the Gram phase to the iteration */
 #define NSP_SC_ROUNDS 44    /* selection rounds of the Gram phase (1: sel_row / sel_w still describe every local observation) */
 #define NSP_SC_KAPPA 43     /* the transform's condition bound, from the iteration to the update */
-#define NSP_REFINE_KAPPA 1000.0   /* beyond it the mean update gets one step of iterative refinement */
+#define NSP_REFINE_KAPPA 1e4      /* beyond it the mean update gets one step of iterative refinement (below: <= 1e-11 without) */
 #define NSP_RCH 64          /* rows re-gathered per round of the refinement */
 
 // Z <- A^{-1/2} for the A held in the T buffer, by the composite minimax polynomial iteration of

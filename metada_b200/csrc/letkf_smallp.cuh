@@ -32,8 +32,8 @@ struct SpWarpSmemT {
   double S[PMAX][PMAX + 1];
   double V[PMAX][PMAX + 1];
   double wgt[PMAX], dw[PMAX], u[PMAX], phi[PMAX], q[PMAX], r[PMAX];
-  double pc[PMAX / 2], ps[PMAX / 2];     // rotations of one Jacobi round
-  int pa[PMAX / 2], pb[PMAX / 2];
+  double2 pcs[PMAX / 2 + 2];             // rotations of one Jacobi round: (c, s) ...
+  int pab[PMAX / 2 + 2];                 // ... and the index pair a | b << 8 (one identity entry pads an odd count)
   int row[PMAX];
   int pad[8];
 };
@@ -165,7 +165,7 @@ __device__ __forceinline__ int sp_transform(const ColParams& P, SpWarpSmemT<PMAX
         }
       }
   }
-  for (int e = lane; e < p * p; e += 32) W.V[e / p][e % p] = (e / p == e % p) ? 1.0 : 0.0;
+  if (lane < p) for (int i = 0; i < p; ++i) W.V[i][lane] = (i == lane) ? 1.0 : 0.0;
   __syncwarp();
 
   // ---- two-sided Jacobi on S (p x p), eigenvectors in the columns of V.  Parallel ordering: a round
@@ -177,27 +177,31 @@ __device__ __forceinline__ int sp_transform(const ColParams& P, SpWarpSmemT<PMAX
   int sweeps = 0;
   for (; sweeps < 30; ++sweeps) {
     double off = 0.0, dia = 0.0;
-    for (int e = lane; e < p * p; e += 32) {
-      const int i = e / p, j = e - i * p;
-      const double v = W.S[i][j];
-      if (i == j) dia = fma(v, v, dia); else off = fma(v, v, off);
-    }
+    if (lane < p)                                             // (column `lane` of every row: no index arithmetic)
+      for (int i = 0; i < p; ++i) {
+        const double v = W.S[i][lane];
+        if (i == lane) dia = fma(v, v, dia); else off = fma(v, v, off);
+      }
     off = warp_sum(off); dia = warp_sum(dia);
     if (!(off > 1e-26 * dia) || off == 0.0) break;      // off-diagonal mass below 1e-13 of the diagonal
     for (int r = 0; r < n - 1; ++r) {
       if (lane < half) {
-        int a = (lane == 0) ? n - 1 : (r + lane) % (n - 1);
-        int b = (r - lane + (n - 1)) % (n - 1);
+        int a = r + lane, b = r - lane;                          // (mod n - 1 without divisions: r < n - 1, lane < n / 2)
+        if (a >= n - 1) a -= n - 1;
+        if (b < 0) b += n - 1;
+        if (lane == 0) a = n - 1;
         if (a > b) { const int t_ = a; a = b; b = t_; }
         double c = 1.0, sn = 0.0;
         if (b < p) {                                           // (index p is the padding of an odd p)
-          const double apq = W.S[a][b];
-          if (fabs(apq) > 1e-140) {                            // (apq^2 must not underflow)
+          const double apq = W.S[a][b], app = W.S[a][a], aqq = W.S[b][b];
+          // (a pair whose off-diagonal entry is below 1e-16 of its diagonal neighbourhood is rotated by less than a
+          // unit round-off: skipped, and the update loops skip it too -- most pairs of the last sweep; apq^2 must not underflow)
+          if (fabs(apq) > 1e-140 && apq * apq > 1e-32 * fabs(app * aqq)) {
             // t = sgn(theta) / (|theta| + sqrt(theta^2 + 1)), theta = al / apq, al = (S_bb - S_aa) / 2, with numerator
             // and denominator multiplied by |apq|: one reciprocal square root, one division, one reciprocal square
             // root in the dependent chain (the textbook form has three divisions and two square roots -- this chain,
             // run by p / 2 lanes, was 30 % of the per-level first pass)
-            const double al = 0.5 * (W.S[b][b] - W.S[a][a]);
+            const double al = 0.5 * (aqq - app);
             const double h2 = fma(al, al, apq * apq);
             const double hyp = h2 * rsqrt(h2);
             double t = fabs(apq) / (fabs(al) + hyp);
@@ -205,7 +209,9 @@ __device__ __forceinline__ int sp_transform(const ColParams& P, SpWarpSmemT<PMAX
             c = rsqrt(fma(t, t, 1.0)); sn = t * c;
           }
         }
-        W.pa[lane] = a; W.pb[lane] = b; W.pc[lane] = c; W.ps[lane] = sn;
+        W.pab[lane] = a | (b << 8); W.pcs[lane] = make_double2(c, sn);
+      } else if (lane == half) {
+        W.pab[lane] = 0; W.pcs[lane] = make_double2(1.0, 0.0);
       }
       __syncwarp();
       // S <- S J, V <- V J (row `lane`), then S <- J^T S (column `lane`).  The pairs of a round are disjoint, so two
@@ -213,10 +219,10 @@ __device__ __forceinline__ int sp_transform(const ColParams& P, SpWarpSmemT<PMAX
       // loads behind the previous pair's stores.
       if (lane < p) {
         for (int l = 0; l < half; l += 2) {
-          const bool two = l + 1 < half;
-          const double sn0 = W.ps[l], sn1 = two ? W.ps[l + 1] : 0.0;
-          const int a0 = W.pa[l], b0 = W.pb[l], a1 = two ? W.pa[l + 1] : a0, b1 = two ? W.pb[l + 1] : b0;
-          const double c0 = W.pc[l], c1 = two ? W.pc[l + 1] : 1.0;
+          const double2 cs0 = W.pcs[l], cs1 = W.pcs[l + 1];
+          const int ab0 = W.pab[l], ab1 = W.pab[l + 1];
+          const double c0 = cs0.x, sn0 = cs0.y, c1 = cs1.x, sn1 = cs1.y;
+          const int a0 = ab0 & 255, b0 = ab0 >> 8, a1 = ab1 & 255, b1 = ab1 >> 8;
           const double sa0 = W.S[lane][a0], sb0 = W.S[lane][b0], va0 = W.V[lane][a0], vb0 = W.V[lane][b0];
           const double sa1 = W.S[lane][a1], sb1 = W.S[lane][b1], va1 = W.V[lane][a1], vb1 = W.V[lane][b1];
           if (sn0 != 0.0) {
@@ -232,10 +238,10 @@ __device__ __forceinline__ int sp_transform(const ColParams& P, SpWarpSmemT<PMAX
       __syncwarp();
       if (lane < p) {
         for (int l = 0; l < half; l += 2) {
-          const bool two = l + 1 < half;
-          const double sn0 = W.ps[l], sn1 = two ? W.ps[l + 1] : 0.0;
-          const int a0 = W.pa[l], b0 = W.pb[l], a1 = two ? W.pa[l + 1] : a0, b1 = two ? W.pb[l + 1] : b0;
-          const double c0 = W.pc[l], c1 = two ? W.pc[l + 1] : 1.0;
+          const double2 cs0 = W.pcs[l], cs1 = W.pcs[l + 1];
+          const int ab0 = W.pab[l], ab1 = W.pab[l + 1];
+          const double c0 = cs0.x, sn0 = cs0.y, c1 = cs1.x, sn1 = cs1.y;
+          const int a0 = ab0 & 255, b0 = ab0 >> 8, a1 = ab1 & 255, b1 = ab1 >> 8;
           const double sa0 = W.S[a0][lane], sb0 = W.S[b0][lane], sa1 = W.S[a1][lane], sb1 = W.S[b1][lane];
           if (sn0 != 0.0) { W.S[a0][lane] = c0 * sa0 - sn0 * sb0; W.S[b0][lane] = sn0 * sa0 + c0 * sb0; }
           if (sn1 != 0.0) { W.S[a1][lane] = c1 * sa1 - sn1 * sb1; W.S[b1][lane] = sn1 * sa1 + c1 * sb1; }

@@ -174,6 +174,7 @@ __device__ __forceinline__ int sp_transform(const ColParams& P, SpWarpSmemT<PMAX
   // its column (J^T S).  The scalar sqrt/div chain of a rotation is the latency that matters here, and
   // this way it is paid p - 1 times per sweep instead of p (p - 1) / 2.
   const int n = (p + 1) & ~1, half = n >> 1;
+  if (lane == half) { W.pab[lane] = 0; W.pcs[lane] = make_double2(1.0, 0.0); }   // identity entry that pads an odd pair count
   int sweeps = 0;
   for (; sweeps < 30; ++sweeps) {
     double off = 0.0, dia = 0.0;
@@ -210,8 +211,6 @@ __device__ __forceinline__ int sp_transform(const ColParams& P, SpWarpSmemT<PMAX
           }
         }
         W.pab[lane] = a | (b << 8); W.pcs[lane] = make_double2(c, sn);
-      } else if (lane == half) {
-        W.pab[lane] = 0; W.pcs[lane] = make_double2(1.0, 0.0);
       }
       __syncwarp();
       // S <- S J, V <- V J (row `lane`), then S <- J^T S (column `lane`).  The pairs of a round are disjoint, so two
